@@ -1,0 +1,186 @@
+/*
+ * k2b_b200.h -- C ABI of the B200-native keypoints2body fitting path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The
+ * Python host (keypoints2body_b200/_native.py) binds it with ctypes; a
+ * maintainer of the reference would bind the same symbols.
+ *
+ * Reference interfaces replaced (paths into /root/reference/keypoints2body):
+ *   k2b_model_create      <- per-call setup in core/fitters/world_space.py:56-91
+ *                            (index tables, MaxMixturePrior load, core/prior.py:101-176)
+ *                            plus the body-model buffers smplx keeps
+ *   k2b_fit_batch         <- WorldSpaceFitter.fit_frame, core/fitters/world_space.py:93-257
+ *                            (compute_loss :173-212, L-BFGS :231-247, Adam :248-256),
+ *                            called per frame from api/sequence.py:214-281
+ *   k2b_evaluate_batch    <- one compute_loss()+backward(), world_space.py:173-212,239-243
+ *   k2b_mesh_batch        <- the final body-model forward, world_space.py:258-278
+ *   k2b_shape_pass        <- optimize_shape_multi_frame, core/shape.py:10-115
+ *
+ * Conventions
+ *   - all arrays are dense row-major float32 unless stated; "dev" pointers live
+ *     on the current CUDA device, "host" pointers in host memory;
+ *   - every call returns 0 on success, a negative K2B_E* code otherwise, and
+ *     k2b_last_error() returns a thread-local message;
+ *   - calls taking a stream enqueue work on it and do not synchronise; the
+ *     *_host variants copy in, run, copy out and synchronise the stream.
+ */
+#ifndef K2B_B200_H_
+#define K2B_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define K2B_OK 0
+#define K2B_EINVAL (-1)   /* bad argument */
+#define K2B_ECUDA (-2)    /* CUDA runtime error */
+#define K2B_ENOMEM (-3)   /* workspace too small */
+#define K2B_EUNSUPPORTED (-4)
+
+#define K2B_POSE_DIM 72   /* global_orient(3) + body_pose(69) */
+#define K2B_BODY_POSE_DIM 69
+#define K2B_NUM_BETAS 10
+#define K2B_NUM_EXPR 10
+#define K2B_GMM_COMPONENTS 8
+#define K2B_MAX_FIT_JOINTS 24 /* kinematic joints a fit can observe (SMPL-24 / AMASS-22) */
+
+typedef struct k2b_model k2b_model; /* opaque: device-resident constants of one body model */
+
+/* Host-side description of a body model + pose prior; all pointers are HOST memory
+ * and are copied (pre-contracted where useful) by k2b_model_create. */
+typedef struct k2b_model_desc {
+  int32_t num_joints;      /* n_j: 24 (SMPL) / 52 (SMPL-H) / 55 (SMPL-X) */
+  int32_t num_vertices;    /* V: 6890 / 6890 / 10475 */
+  int32_t num_shape;       /* 10 (betas) or 20 (betas + expression) */
+  int32_t num_extra;       /* vertex-picked extra joints appended after the n_j kinematic ones */
+  const int32_t* parents;  /* [n_j], parents[0] = -1, parents[j] < j */
+  const float* v_template; /* [V][3] */
+  const float* shapedirs;  /* [V][3][num_shape] */
+  const float* posedirs;   /* [9*(n_j-1)][3V] */
+  const float* J_regressor;/* [n_j][V] */
+  const float* lbs_weights;/* [V][n_j] */
+  const int32_t* extra_vertex_ids; /* [num_extra] */
+  /* max-mixture pose prior (core/prior.py:101-176), 69-D, K2B_GMM_COMPONENTS comps */
+  const float* gmm_means;      /* [8][69] */
+  const float* gmm_chol;       /* [8][69][69] lower-triangular L with sym(P) = L L^T */
+  const float* gmm_neg_log_w;  /* [8] = -log(nll_weights) */
+} k2b_model_desc;
+/* k2b_model_create pre-contracts the rest joints once, in float64:
+ *   J0 = J_regressor . v_template,  JS = J_regressor . shapedirs,
+ * so the fitting loop never touches vertices (the reference recomputes the full mesh on
+ * every evaluation, world_space.py:192). */
+
+int k2b_model_create(const k2b_model_desc* desc, k2b_model** out);
+void k2b_model_destroy(k2b_model* m);
+
+enum { K2B_OPT_ADAM = 0, K2B_OPT_LBFGS = 1 };
+
+/* One batched fit = B independent WorldSpaceFitter.fit_frame calls.
+ * Flat parameter blocks follow the reference's optimiser order
+ * (world_space.py:215-229) restricted to blocks that receive gradient from
+ * body keypoints: global_orient, body_pose, transl, [expression], [betas]. */
+typedef struct k2b_fit_args {
+  int64_t num_frames;        /* B */
+  int32_t num_obs;           /* K: 22 (AMASS) or 24 (SMPL24, SMPL only) */
+  int32_t optimizer;         /* K2B_OPT_* */
+  int32_t num_iters;         /* iteration budget (max_iter for L-BFGS) when frame_iters == NULL */
+  int32_t freeze_betas;      /* betas kept at their initial value */
+  int32_t conf_per_frame;    /* conf is [B][K] (1) or [K] shared (0) */
+  float lr;                  /* step_size, reference default 1e-2 */
+  float joint_loss_weight;   /* reference default 600 */
+  float pose_preserve_weight;/* reference default 5; applied where preserve is on */
+  /* inputs (device) */
+  const float* targets;      /* [B][K][3] */
+  const float* conf;         /* [B][K] or [K]; NULL = ones */
+  const float* init_pose;    /* [B][72] */
+  const float* init_betas;   /* [B][10] */
+  const float* init_transl;  /* [B][3] */
+  const float* init_expr;    /* [B][10] or NULL (required iff model num_shape == 20) */
+  const float* preserve_pose;/* [B][69] or NULL = init body pose (world_space.py:159) */
+  const int32_t* frame_iters;   /* [B] per-frame budget or NULL */
+  const uint8_t* frame_preserve;/* [B] 1 = temporal term on (seq_ind > 0), or NULL = preserve_all */
+  int32_t preserve_all;      /* used when frame_preserve == NULL */
+  /* outputs (device) */
+  float* out_pose;           /* [B][72] */
+  float* out_betas;          /* [B][10] */
+  float* out_transl;         /* [B][3] */
+  float* out_expr;           /* [B][10] or NULL */
+  float* out_loss;           /* [B] (L-BFGS: loss at the returned params; Adam: loss of the
+                                last iteration before its step, world_space.py:246-256) */
+  float* out_joints;         /* [B][K][3] posed kinematic joints incl. transl, or NULL */
+  int32_t* out_evals;        /* [B] closure evaluations performed, or NULL */
+  /* scratch (device) */
+  void* workspace;
+  size_t workspace_bytes;    /* >= k2b_fit_workspace_bytes(...) */
+} k2b_fit_args;
+
+size_t k2b_fit_workspace_bytes(const k2b_model* m, int64_t num_frames, int32_t optimizer,
+                               int32_t max_iters);
+int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* args, void* cuda_stream);
+
+/* Same arguments with HOST pointers for every input/output array; workspace may be
+ * NULL (allocated internally and cached on the model).  Performs H2D copies, the fit,
+ * D2H copies, then synchronises. */
+int k2b_fit_batch_host(k2b_model* m, const k2b_fit_args* host_args, void* cuda_stream);
+
+/* One evaluation of loss and gradient at given parameters (parity / debugging). */
+typedef struct k2b_eval_args {
+  int64_t num_frames;
+  int32_t num_obs;
+  int32_t conf_per_frame;
+  int32_t preserve_all;
+  float joint_loss_weight;
+  float pose_preserve_weight;
+  const float* targets;      /* [B][K][3] */
+  const float* conf;         /* [B][K] or [K] or NULL */
+  const float* pose;         /* [B][72] */
+  const float* betas;        /* [B][10] */
+  const float* transl;       /* [B][3] */
+  const float* expr;         /* [B][10] or NULL */
+  const float* preserve_pose;/* [B][69] or NULL = pose */
+  float* out_loss;           /* [B] */
+  float* out_grad_pose;      /* [B][72] */
+  float* out_grad_betas;     /* [B][10] */
+  float* out_grad_transl;    /* [B][3] */
+  float* out_grad_expr;      /* [B][10] or NULL */
+  float* out_joints;         /* [B][K][3] or NULL */
+  int32_t* out_gmm_component;/* [B] arg-min mixture component, or NULL */
+  void* workspace;
+  size_t workspace_bytes;
+} k2b_eval_args;
+
+int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* args, void* cuda_stream);
+
+/* Final mesh: vertices [B][V][3] and joints [B][n_j + num_extra][3] for fitted parameters.
+ * full_pose is [B][3*n_j] axis-angle in the model's own joint order. */
+typedef struct k2b_mesh_args {
+  int64_t num_frames;
+  const float* full_pose;    /* [B][3*n_j] */
+  const float* shape;        /* [B][num_shape] (betas, then expression) */
+  const float* transl;       /* [B][3] or NULL */
+  float* out_vertices;       /* [B][V][3] or NULL (joints only) */
+  float* out_joints;         /* [B][n_j + num_extra][3] */
+  void* workspace;
+  size_t workspace_bytes;
+} k2b_mesh_args;
+
+size_t k2b_mesh_workspace_bytes(const k2b_model* m, int64_t num_frames);
+int k2b_mesh_batch(const k2b_model* m, const k2b_mesh_args* args, void* cuda_stream);
+
+/* FP32-FMA micro-benchmark used as the roofline denominator of the fit kernel:
+ * returns achieved TFLOP/s (2 flop per FMA) over `iters` dependent-chain rounds. */
+int k2b_fma_peak(int iters, double* out_tflops, double* out_ms, void* cuda_stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t k2b_launch_count(void);
+
+const char* k2b_last_error(void);
+const char* k2b_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* K2B_B200_H_ */

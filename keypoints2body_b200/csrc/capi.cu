@@ -1,0 +1,405 @@
+// capi.cu -- C ABI (include/k2b_b200.h) over the CUDA kernels.  No torch types.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/k2b_b200.h"
+#include "fit_kernel.cuh"
+#include "mesh_kernel.cuh"
+
+using namespace k2b;
+
+namespace {
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(K2B_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+template <class T>
+cudaError_t upload(const std::vector<T>& h, T** d) {
+  cudaError_t e = cudaMalloc((void**)d, h.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+}  // namespace
+
+struct k2b_model {
+  int num_joints = 0, num_vertices = 0, num_shape = 0, num_extra = 0;
+  bool smpl24_ok = false;
+  int device = 0, num_sms = 0;
+  float *chol = nullptr, *mu = nullptr, *nlw = nullptr, *rel = nullptr;
+  MeshModel mesh;
+  // cached device staging for the *_host entry points
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+extern "C" const char* k2b_last_error(void) { return g_err.c_str(); }
+extern "C" const char* k2b_version(void) { return "k2b_b200 0.1 (sm_100a)"; }
+extern "C" int64_t k2b_launch_count(void) { return g_launches.load(); }
+
+extern "C" void k2b_model_destroy(k2b_model* m) {
+  if (!m) return;
+  cudaFree(m->chol); cudaFree(m->mu); cudaFree(m->nlw); cudaFree(m->rel);
+  mesh_model_free(m->mesh);
+  cudaFree(m->stage); cudaFree(m->ws);
+  delete m;
+}
+
+extern "C" int k2b_model_create(const k2b_model_desc* d, k2b_model** out) {
+  if (!d || !out) return fail(K2B_EINVAL, "null argument");
+  if (d->num_shape != 10 && d->num_shape != 20) return fail(K2B_EINVAL, "num_shape must be 10 or 20");
+  if (d->num_joints < 22) return fail(K2B_EINVAL, "need at least the 22 body joints");
+  static const int body[22] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
+  for (int j = 0; j < 22; ++j)
+    if (d->parents[j] != body[j]) return fail(K2B_EUNSUPPORTED, "first 22 parents are not the SMPL body tree");
+  k2b_model* m = new k2b_model();
+  m->num_joints = d->num_joints;
+  m->num_vertices = d->num_vertices;
+  m->num_shape = d->num_shape;
+  m->num_extra = d->num_extra;
+  m->smpl24_ok = d->num_joints >= 24 && d->parents[22] == 20 && d->parents[23] == 21;
+  cudaGetDevice(&m->device);
+  cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device);
+
+  const int NS = d->num_shape;
+  // packed Cholesky rows
+  std::vector<float> chol((size_t)kGmmM * kCholStride, 0.f), mu((size_t)kGmmM * kMuStride, 0.f), nlw(kGmmM);
+  for (int c = 0; c < kGmmM; ++c) {
+    for (int j = 0; j < kBodyDim; ++j) {
+      for (int i = 0; i <= j; ++i)
+        chol[(size_t)c * kCholStride + chol_row_off(j) + i] = d->gmm_chol[((size_t)c * kBodyDim + j) * kBodyDim + i];
+      mu[(size_t)c * kMuStride + j] = d->gmm_means[(size_t)c * kBodyDim + j];
+    }
+    nlw[c] = d->gmm_neg_log_w[c];
+  }
+  // rest-pose offsets relative to the parent, and their shape derivatives (float64 contraction)
+  if (!d->v_template || !d->shapedirs || !d->J_regressor || !d->posedirs || !d->lbs_weights) {
+    delete m;
+    return fail(K2B_EINVAL, "missing body-model buffer");
+  }
+  std::vector<double> J0, JS;
+  rest_joint_tables(*d, J0, JS);
+  const int nfit = d->num_joints < kMaxFitJoints ? d->num_joints : kMaxFitJoints;
+  std::vector<float> rel((size_t)kMaxFitJoints * (1 + NS) * 4, 0.f);
+  for (int j = 0; j < nfit; ++j) {
+    const int pj = d->parents[j];
+    for (int k = 0; k < 3; ++k) {
+      double v = J0[j * 3 + k];
+      if (pj >= 0) v -= J0[pj * 3 + k];
+      rel[((size_t)j * (1 + NS)) * 4 + k] = (float)v;
+      for (int s = 0; s < NS; ++s) {
+        double w = JS[((size_t)j * 3 + k) * NS + s];
+        if (pj >= 0) w -= JS[((size_t)pj * 3 + k) * NS + s];
+        rel[((size_t)j * (1 + NS) + 1 + s) * 4 + k] = (float)w;
+      }
+    }
+  }
+  cudaError_t e;
+  if ((e = upload(chol, &m->chol)) != cudaSuccess || (e = upload(mu, &m->mu)) != cudaSuccess ||
+      (e = upload(nlw, &m->nlw)) != cudaSuccess || (e = upload(rel, &m->rel)) != cudaSuccess) {
+    k2b_model_destroy(m);
+    return fail(K2B_ECUDA, std::string("table upload: ") + cudaGetErrorString(e));
+  }
+  {
+    std::string err;
+    if (!mesh_model_build(*d, J0, JS, m->mesh, err)) {
+      k2b_model_destroy(m);
+      return fail(K2B_ECUDA, "mesh tables: " + err);
+    }
+  }
+  *out = m;
+  return K2B_OK;
+}
+
+namespace {
+int fit_grid(const k2b_model* m, long num_frames) {
+  const long tiles = (num_frames + kFitThreads - 1) / kFitThreads;
+  return (int)(tiles < m->num_sms ? tiles : m->num_sms);
+}
+
+template <int NS, int K, int MODE>
+int launch_fit(const FitParams& p, const AdamTable& at, int grid, cudaStream_t st) {
+  auto kern = fit_kernel<NS, K, MODE>;
+  const size_t smem = fit_smem_bytes<NS>();
+  static bool configured = false;   // per template instantiation
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  kern<<<grid, kFitThreads, smem, st>>>(p, at);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return K2B_OK;
+}
+
+template <int MODE>
+int launch_fit_ns(int ns, const FitParams& p, const AdamTable& at, int grid, cudaStream_t st) {
+  if (p.num_obs == 24) return launch_fit<10, 24, MODE>(p, at, grid, st);   // SMPL24 exists for SMPL only
+  return ns == 20 ? launch_fit<20, 22, MODE>(p, at, grid, st) : launch_fit<10, 22, MODE>(p, at, grid, st);
+}
+
+void fill_adam_table(AdamTable& at, double lr) {
+  for (int k = 1; k <= kAdamTable; ++k) {
+    at.step[k - 1] = (float)(lr / (1.0 - std::pow(0.9, (double)k)));
+    at.bc2[k - 1] = (float)std::sqrt(1.0 - std::pow(0.999, (double)k));
+  }
+}
+
+int check_common(const k2b_model* m, long B, int num_obs, const void* expr) {
+  if (!m) return fail(K2B_EINVAL, "null model");
+  if (B <= 0) return fail(K2B_EINVAL, "num_frames must be positive");
+  if (num_obs != 22 && num_obs != 24) return fail(K2B_EINVAL, "num_obs must be 22 (AMASS) or 24 (SMPL24)");
+  if (num_obs == 24 && !m->smpl24_ok)
+    return fail(K2B_EUNSUPPORTED, "SMPL24 observations need the SMPL joint tree (parents[22:24] == 20, 21)");
+  if (num_obs == 24 && m->num_shape != 10) return fail(K2B_EUNSUPPORTED, "SMPL24 observations are SMPL-only");
+  if (m->num_shape == 20 && !expr) return fail(K2B_EINVAL, "expression is required for a 20-component shape space");
+  return K2B_OK;
+}
+}  // namespace
+
+extern "C" size_t k2b_fit_workspace_bytes(const k2b_model* m, int64_t num_frames, int32_t optimizer,
+                                          int32_t max_iters) {
+  if (!m || num_frames <= 0) return 0;
+  const int grid = fit_grid(m, num_frames);
+  const int mode = optimizer == K2B_OPT_LBFGS ? kModeLbfgs : kModeAdam;
+  const long rows = scratch_rows(m->num_shape, mode, lbfgs_history_capacity(max_iters));
+  return (size_t)rows * grid * kFitThreads * sizeof(float);
+}
+
+extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* stream) {
+  if (!a) return fail(K2B_EINVAL, "null args");
+  int rc = check_common(m, a->num_frames, a->num_obs, a->init_expr);
+  if (rc) return rc;
+  if (a->optimizer != K2B_OPT_ADAM && a->optimizer != K2B_OPT_LBFGS) return fail(K2B_EINVAL, "unknown optimizer");
+  if (!a->targets || !a->init_pose || !a->init_betas || !a->init_transl || !a->out_pose || !a->out_betas ||
+      !a->out_transl || !a->out_loss)
+    return fail(K2B_EINVAL, "missing required array");
+  if (a->num_iters < 0) return fail(K2B_EINVAL, "num_iters must be >= 0");
+  // the largest per-frame budget bounds the L-BFGS history; callers passing frame_iters must
+  // pass num_iters = max(frame_iters)
+  const size_t need = k2b_fit_workspace_bytes(m, a->num_frames, a->optimizer, a->num_iters);
+  if (!a->workspace || a->workspace_bytes < need) return fail(K2B_ENOMEM, "workspace too small");
+
+  FitParams p{};
+  p.tab = DeviceTables{m->chol, m->mu, m->nlw, m->rel};
+  p.num_frames = a->num_frames;
+  const int grid = fit_grid(m, a->num_frames);
+  p.stride = (long)grid * kFitThreads;
+  p.num_obs = a->num_obs;
+  p.num_iters = a->num_iters;
+  p.freeze_betas = a->freeze_betas;
+  p.conf_per_frame = a->conf_per_frame;
+  p.preserve_all = a->preserve_all;
+  p.lr = a->lr;
+  p.joint_w2 = a->joint_loss_weight * a->joint_loss_weight;
+  p.keep_w2 = a->pose_preserve_weight * a->pose_preserve_weight;
+  p.targets = a->targets; p.conf = a->conf;
+  p.init_pose = a->init_pose; p.init_betas = a->init_betas; p.init_transl = a->init_transl; p.init_expr = a->init_expr;
+  p.preserve_pose = a->preserve_pose;
+  p.frame_iters = a->frame_iters; p.frame_preserve = a->frame_preserve;
+  p.out_pose = a->out_pose; p.out_betas = a->out_betas; p.out_transl = a->out_transl; p.out_expr = a->out_expr;
+  p.out_loss = a->out_loss; p.out_joints = a->out_joints; p.out_evals = a->out_evals;
+  p.scratch = (float*)a->workspace;
+  p.lbfgs_hmax = lbfgs_history_capacity(a->num_iters);
+  AdamTable at;
+  fill_adam_table(at, (double)a->lr);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->optimizer == K2B_OPT_ADAM) return launch_fit_ns<kModeAdam>(m->num_shape, p, at, grid, st);
+  return launch_fit_ns<kModeLbfgs>(m->num_shape, p, at, grid, st);
+}
+
+extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, void* stream) {
+  if (!a) return fail(K2B_EINVAL, "null args");
+  int rc = check_common(m, a->num_frames, a->num_obs, a->expr);
+  if (rc) return rc;
+  if (!a->targets || !a->pose || !a->betas || !a->transl || !a->out_loss || !a->out_grad_pose ||
+      !a->out_grad_betas || !a->out_grad_transl)
+    return fail(K2B_EINVAL, "missing required array");
+  const int grid = fit_grid(m, a->num_frames);
+  const size_t need = (size_t)scratch_rows(m->num_shape, kModeEval, 0) * grid * kFitThreads * sizeof(float);
+  if (!a->workspace || a->workspace_bytes < need) return fail(K2B_ENOMEM, "workspace too small");
+  FitParams p{};
+  p.tab = DeviceTables{m->chol, m->mu, m->nlw, m->rel};
+  p.num_frames = a->num_frames;
+  p.stride = (long)grid * kFitThreads;
+  p.num_obs = a->num_obs;
+  p.conf_per_frame = a->conf_per_frame;
+  p.preserve_all = a->preserve_all;
+  p.joint_w2 = a->joint_loss_weight * a->joint_loss_weight;
+  p.keep_w2 = a->pose_preserve_weight * a->pose_preserve_weight;
+  p.targets = a->targets; p.conf = a->conf;
+  p.init_pose = a->pose; p.init_betas = a->betas; p.init_transl = a->transl; p.init_expr = a->expr;
+  p.preserve_pose = a->preserve_pose;
+  p.out_loss = a->out_loss; p.out_joints = a->out_joints;
+  p.out_grad_pose = a->out_grad_pose; p.out_grad_betas = a->out_grad_betas;
+  p.out_grad_transl = a->out_grad_transl; p.out_grad_expr = a->out_grad_expr;
+  p.out_gmm_component = a->out_gmm_component;
+  p.scratch = (float*)a->workspace;
+  AdamTable at{};
+  return launch_fit_ns<kModeEval>(m->num_shape, p, at, grid, (cudaStream_t)stream);
+}
+
+// ---- host-buffer variant: H2D, fit, D2H, synchronise ---------------------------------------
+namespace {
+struct Stager {
+  char* base;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = (T*)(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+};
+}  // namespace
+
+extern "C" int k2b_fit_batch_host(k2b_model* m, const k2b_fit_args* h, void* stream) {
+  if (!m || !h) return fail(K2B_EINVAL, "null argument");
+  const long B = h->num_frames;
+  const int K = h->num_obs;
+  if (B <= 0 || (K != 22 && K != 24)) return fail(K2B_EINVAL, "bad num_frames / num_obs");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ws_need = k2b_fit_workspace_bytes(m, B, h->optimizer, h->num_iters);
+  // staging size (upper bound incl. alignment slack)
+  size_t need = 4096 + 256 * 24;
+  need += sizeof(float) * B * (size_t)(K * 3 + K + 72 + 10 + 3 + 10 + 69);
+  need += sizeof(int32_t) * B + B;
+  need += sizeof(float) * B * (size_t)(72 + 10 + 3 + 10 + 1 + K * 3) + sizeof(int32_t) * B;
+  if (m->stage_bytes < need) {
+    cudaFree(m->stage);
+    m->stage = nullptr; m->stage_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->stage, need));
+    m->stage_bytes = need;
+  }
+  if (m->ws_bytes < ws_need) {
+    cudaFree(m->ws);
+    m->ws = nullptr; m->ws_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->ws, ws_need));
+    m->ws_bytes = ws_need;
+  }
+  Stager sg{(char*)m->stage};
+  k2b_fit_args d = *h;
+  auto h2d = [&](auto*& dst, const auto* src, size_t count) -> cudaError_t {
+    using T = std::remove_const_t<std::remove_pointer_t<std::remove_reference_t<decltype(dst)>>>;
+    if (!src) { dst = nullptr; return cudaSuccess; }
+    T* p = sg.take<T>(count);
+    dst = p;
+    return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st);
+  };
+  CUDA_TRY(h2d(d.targets, h->targets, (size_t)B * K * 3));
+  CUDA_TRY(h2d(d.conf, h->conf, h->conf_per_frame ? (size_t)B * K : (size_t)K));
+  CUDA_TRY(h2d(d.init_pose, h->init_pose, (size_t)B * 72));
+  CUDA_TRY(h2d(d.init_betas, h->init_betas, (size_t)B * 10));
+  CUDA_TRY(h2d(d.init_transl, h->init_transl, (size_t)B * 3));
+  CUDA_TRY(h2d(d.init_expr, h->init_expr, (size_t)B * 10));
+  CUDA_TRY(h2d(d.preserve_pose, h->preserve_pose, (size_t)B * 69));
+  CUDA_TRY(h2d(d.frame_iters, h->frame_iters, (size_t)B));
+  CUDA_TRY(h2d(d.frame_preserve, h->frame_preserve, (size_t)B));
+  d.out_pose = sg.take<float>((size_t)B * 72);
+  d.out_betas = sg.take<float>((size_t)B * 10);
+  d.out_transl = sg.take<float>((size_t)B * 3);
+  d.out_expr = h->out_expr ? sg.take<float>((size_t)B * 10) : nullptr;
+  d.out_loss = sg.take<float>((size_t)B);
+  d.out_joints = h->out_joints ? sg.take<float>((size_t)B * K * 3) : nullptr;
+  d.out_evals = h->out_evals ? sg.take<int32_t>((size_t)B) : nullptr;
+  d.workspace = m->ws;
+  d.workspace_bytes = m->ws_bytes;
+  int rc = k2b_fit_batch(m, &d, stream);
+  if (rc) return rc;
+  auto d2h = [&](auto* dst, const auto* src, size_t count) -> cudaError_t {
+    if (!dst) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, count * sizeof(*dst), cudaMemcpyDeviceToHost, st);
+  };
+  CUDA_TRY(d2h(h->out_pose, d.out_pose, (size_t)B * 72));
+  CUDA_TRY(d2h(h->out_betas, d.out_betas, (size_t)B * 10));
+  CUDA_TRY(d2h(h->out_transl, d.out_transl, (size_t)B * 3));
+  CUDA_TRY(d2h(h->out_expr, d.out_expr, (size_t)B * 10));
+  CUDA_TRY(d2h(h->out_loss, d.out_loss, (size_t)B));
+  CUDA_TRY(d2h(h->out_joints, d.out_joints, (size_t)B * K * 3));
+  CUDA_TRY(d2h(h->out_evals, d.out_evals, (size_t)B));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return K2B_OK;
+}
+
+// ---- mesh ------------------------------------------------------------------------------------
+extern "C" size_t k2b_mesh_workspace_bytes(const k2b_model* m, int64_t num_frames) {
+  if (!m) return 0;
+  return mesh_workspace_bytes(m->mesh, num_frames);
+}
+
+extern "C" int k2b_mesh_batch(const k2b_model* m, const k2b_mesh_args* a, void* stream) {
+  if (!m || !a) return fail(K2B_EINVAL, "null argument");
+  if (!m->mesh.ready) return fail(K2B_EUNSUPPORTED, "model was created without mesh buffers");
+  if (a->num_frames <= 0 || !a->full_pose || !a->shape || !a->out_joints) return fail(K2B_EINVAL, "missing required array");
+  if (!a->workspace || a->workspace_bytes < mesh_workspace_bytes(m->mesh, a->num_frames))
+    return fail(K2B_ENOMEM, "workspace too small");
+  std::string err;
+  int launches = 0;
+  if (!mesh_forward(m->mesh, *a, (cudaStream_t)stream, err, launches)) return fail(K2B_ECUDA, err);
+  g_launches.fetch_add(launches);
+  return K2B_OK;
+}
+
+// ---- FP32 FMA micro-benchmark (roofline denominator of the fit kernel) ---------------------
+namespace {
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3f + i;
+  const float b = 1.0000001f, c = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) out[0] = s;  // never true; keeps the chain alive
+}
+}  // namespace
+
+extern "C" int k2b_fma_peak(int iters, double* out_tflops, double* out_ms, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  float* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 4));
+  const int grid = sms * 8, block = 256;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  fma_peak_kernel<<<grid, block, 0, st>>>(d, iters / 4 + 1);  // warm-up
+  CUDA_TRY(cudaEventRecord(e0, st));
+  fma_peak_kernel<<<grid, block, 0, st>>>(d, iters);
+  CUDA_TRY(cudaEventRecord(e1, st));
+  g_launches.fetch_add(2);
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  const double flops = 2.0 * 128.0 * (double)iters * (double)grid * block;
+  if (out_tflops) *out_tflops = flops / (ms * 1e-3) / 1e12;
+  if (out_ms) *out_ms = ms;
+  return K2B_OK;
+}

@@ -1,0 +1,269 @@
+// fit_kernel.cuh -- the fused, persistent fitting kernel (K1).
+//
+// Mapping: one thread = one frame, one CTA = kFitThreads frames, grid = #SMs, CTAs loop
+// over frame tiles.  Shared memory holds (a) the tables every frame shares -- the packed
+// Cholesky factors of the 8 mixture precisions, the mixture means, the rest-pose joint
+// offset table -- loaded once per CTA, and (b) the per-frame parameter vector x and
+// gradient g as columns [element][thread] (bank-conflict free, no block-level
+// synchronisation after the table load).  Iterations run inside the kernel, so x never
+// leaves shared memory between optimiser steps; Adam moments / L-BFGS vectors and the
+// per-frame observations live in a transposed (coalesced) global scratch that stays
+// L2-resident for the frames in flight.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "fit_core.cuh"
+#include "lbfgs_core.cuh"
+
+namespace k2b {
+
+constexpr int kFitThreads = 128;
+constexpr int kAdamTable = 256;
+
+enum FitMode { kModeEval = 0, kModeAdam = 1, kModeLbfgs = 2 };
+
+struct DeviceTables {      // global-memory copies owned by k2b_model
+  const float* chol;       // [8][kCholStride]
+  const float* mu;         // [8][kMuStride]
+  const float* nlw;        // [8]
+  const float* rel;        // [24][1+NS][4]
+};
+
+struct FitParams {
+  DeviceTables tab;
+  long num_frames;
+  long stride;             // scratch column stride = gridDim.x * kFitThreads (scratch is per resident thread)
+  int num_obs;
+  int num_iters;
+  int freeze_betas;
+  int conf_per_frame;
+  int preserve_all;
+  float lr, joint_w2, keep_w2;
+  const float* targets; const float* conf;
+  const float* init_pose; const float* init_betas; const float* init_transl; const float* init_expr;
+  const float* preserve_pose;
+  const int* frame_iters; const unsigned char* frame_preserve;
+  float* out_pose; float* out_betas; float* out_transl; float* out_expr;
+  float* out_loss; float* out_joints; int* out_evals;
+  // evaluate-only outputs
+  float* out_grad_pose; float* out_grad_betas; float* out_grad_transl; float* out_grad_expr;
+  int* out_gmm_component;
+  float* scratch;          // transposed per-frame scratch, see scratch_floats_per_frame
+  int lbfgs_hmax;
+};
+
+struct AdamTable {
+  float step[kAdamTable];  // lr / (1 - 0.9^k), k = 1..
+  float bc2[kAdamTable];   // sqrt(1 - 0.999^k)
+};
+
+// scratch rows (each row is `stride` floats): targets 72, weights 24, preserve 69, then
+// optimiser state.
+constexpr int kScrTgt = 0;
+constexpr int kScrWgt = 72;
+constexpr int kScrKeep = 96;
+constexpr int kScrOpt = 165;
+
+inline long scratch_rows(int ns, int mode, int hmax) {
+  const int n = 75 + ns;
+  if (mode == kModeAdam) return kScrOpt + 2 * n;
+  if (mode == kModeLbfgs) return kScrOpt + Vecs::floats_per_frame(n, hmax);
+  return kScrOpt;
+}
+
+template <int NS>
+constexpr size_t fit_smem_bytes() {
+  return sizeof(float) * (size_t)(kGmmM * kCholStride + kGmmM * kMuStride + kGmmM +
+                                  kMaxFitJoints * (1 + NS) * 4 + 2 * (75 + NS) * kFitThreads);
+}
+
+template <int NS, int K, int MODE>
+__global__ void __launch_bounds__(kFitThreads, 1)
+fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTable at) {
+  constexpr int NX = 75 + NS;
+  extern __shared__ __align__(16) float smem[];
+  float* s_chol = smem;
+  float* s_mu = s_chol + kGmmM * kCholStride;
+  float* s_nlw = s_mu + kGmmM * kMuStride;
+  float* s_rel = s_nlw + kGmmM;
+  float* s_x = s_rel + kMaxFitJoints * (1 + NS) * 4;
+  float* s_g = s_x + NX * kFitThreads;
+
+  const int tid = threadIdx.x;
+  // ---- tables: one cooperative, vectorised copy per CTA --------------------------------
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.tab.chol);
+    float4* dst = reinterpret_cast<float4*>(s_chol);
+    for (int i = tid; i < kGmmM * kCholStride / 4; i += kFitThreads) dst[i] = src[i];
+    src = reinterpret_cast<const float4*>(p.tab.mu);
+    dst = reinterpret_cast<float4*>(s_mu);
+    for (int i = tid; i < kGmmM * kMuStride / 4; i += kFitThreads) dst[i] = src[i];
+    if (tid < kGmmM) s_nlw[tid] = p.tab.nlw[tid];
+    src = reinterpret_cast<const float4*>(p.tab.rel);
+    dst = reinterpret_cast<float4*>(s_rel);
+    for (int i = tid; i < kMaxFitJoints * (1 + NS); i += kFitThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+
+  FitTables tb;
+  tb.chol = s_chol;
+  tb.mu = s_mu;
+  tb.nlw = s_nlw;
+  tb.rel = reinterpret_cast<const float4*>(s_rel);
+  Cols c{s_x + tid, s_g + tid, kFitThreads};
+
+  const long num_tiles = (p.num_frames + kFitThreads - 1) / kFitThreads;
+  for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const long f = tile * kFitThreads + tid;
+    const bool valid = f < p.num_frames;
+    const long fr = valid ? f : p.num_frames - 1;   // padding lanes mirror the last frame
+    float* scr = p.scratch + (long)blockIdx.x * kFitThreads + tid;
+
+    // ---- load this frame: parameters -> smem columns, observations -> scratch ---------
+    {
+      const float* ip = p.init_pose + fr * kPoseDim;
+#pragma unroll 8
+      for (int i = 0; i < kPoseDim; ++i) c.X(i) = ip[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) c.X(kTranslOff + i) = p.init_transl[fr * 3 + i];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) c.X(kShapeOff + i) = p.init_betas[fr * 10 + i];
+      if (NS == 20) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) c.X(kShapeOff + 10 + i) = p.init_expr[fr * 10 + i];
+      }
+      const float* tg = p.targets + fr * K * 3;
+#pragma unroll 6
+      for (int i = 0; i < K * 3; ++i) scr[(kScrTgt + i) * p.stride] = tg[i];
+#pragma unroll 2
+      for (int j = 0; j < K; ++j) {
+        const float cf = p.conf ? (p.conf_per_frame ? p.conf[fr * K + j] : p.conf[j]) : 1.f;
+        scr[(kScrWgt + j) * p.stride] = p.joint_w2 * cf * cf;
+      }
+      const float* kp = p.preserve_pose ? p.preserve_pose + fr * kBodyDim : p.init_pose + fr * kPoseDim + 3;
+#pragma unroll 3
+      for (int i = 0; i < kBodyDim; ++i) scr[(kScrKeep + i) * p.stride] = kp[i];
+    }
+    FrameConsts fc;
+    fc.tgt = scr + kScrTgt * p.stride;
+    fc.wgt = scr + kScrWgt * p.stride;
+    fc.keep = scr + kScrKeep * p.stride;
+    fc.stride = p.stride;
+    const bool keep_on = p.frame_preserve ? (p.frame_preserve[fr] != 0) : (p.preserve_all != 0);
+    fc.keep_w2 = keep_on ? p.keep_w2 : 0.f;
+    const bool freeze_betas = p.freeze_betas != 0;
+
+    float out_loss = 0.f;
+    int evals = 0;
+
+    int iters = p.frame_iters ? p.frame_iters[fr] : p.num_iters;
+    if (!valid) iters = 0;
+    float* jout = (p.out_joints && valid) ? p.out_joints + f * K * 3 : nullptr;
+
+    // Every mode funnels through ONE eval_frame call site (one copy of the evaluation code):
+    // each round evaluates at the current x, then the mode-specific (cheap) update runs.
+    if (MODE == kModeEval) {
+      int comp = 0;
+      out_loss = eval_frame<NS, K>(c, tb, fc, true, true, jout, &comp);
+      if (valid) {
+        for (int i = 0; i < kPoseDim; ++i) p.out_grad_pose[f * kPoseDim + i] = c.G(i);
+        for (int i = 0; i < 3; ++i) p.out_grad_transl[f * 3 + i] = c.G(kTranslOff + i);
+        for (int i = 0; i < 10; ++i) p.out_grad_betas[f * 10 + i] = c.G(kShapeOff + i);
+        if (NS == 20 && p.out_grad_expr)
+          for (int i = 0; i < 10; ++i) p.out_grad_expr[f * 10 + i] = c.G(kShapeOff + 10 + i);
+        if (p.out_gmm_component) p.out_gmm_component[f] = comp;
+        p.out_loss[f] = out_loss;
+      }
+      continue;
+    }
+
+    if (MODE == kModeAdam) {
+      float* m1 = scr + kScrOpt * p.stride;
+      float* m2 = m1 + (long)NX * p.stride;
+#pragma unroll 5
+      for (int i = 0; i < NX; ++i) {
+        m1[i * p.stride] = 0.f;
+        m2[i * p.stride] = 0.f;
+      }
+      const int warp_iters = __reduce_max_sync(0xffffffffu, iters);
+      // rounds 1..warp_iters: loss + gradient + Adam step; round warp_iters+1: joints-only
+      // forward at the final parameters (world_space.py:258-278)
+      const int rounds = warp_iters + (p.out_joints ? 1 : 0);
+      for (int k = 1; k <= rounds; ++k) {
+        const bool last = k > warp_iters;
+        const float loss = eval_frame<NS, K>(c, tb, fc, !last, !last, last ? jout : nullptr, nullptr);
+        if (!last && k <= iters) {
+          out_loss = loss;   // loss of the last iteration, before its step (world_space.py:250-256)
+          ++evals;
+          float step_k, bc2_k;
+          if (k <= kAdamTable) {
+            step_k = at.step[k - 1];
+            bc2_k = at.bc2[k - 1];
+          } else {
+            step_k = (float)((double)p.lr / (1.0 - pow(0.9, (double)k)));
+            bc2_k = (float)sqrt(1.0 - pow(0.999, (double)k));
+          }
+#pragma unroll 5
+          for (int i = 0; i < NX; ++i) {
+            if (freeze_betas && i >= kShapeOff && i < kShapeOff + 10) continue;
+            float mm = m1[i * p.stride], vv = m2[i * p.stride], x = c.X(i);
+            adam_update(x, mm, vv, c.G(i), step_k, bc2_k);
+            c.X(i) = x;
+            m1[i * p.stride] = mm;
+            m2[i * p.stride] = vv;
+          }
+        }
+      }
+    }
+
+    if (MODE == kModeLbfgs) {
+      Vecs v;
+      v.base = scr + kScrOpt * p.stride;
+      v.stride = p.stride;
+      v.n = NX;
+      v.hmax = p.lbfgs_hmax;
+      Lbfgs st;
+      st.done = false;
+      // round 0: closure at the initial parameters; rounds while any lane is searching: one
+      // closure per round; final round: loss (+ joints) at the returned parameters
+      // (world_space.py:246-247)
+      int stage = 0;   // 0 first closure, 1 searching, 2 final loss
+      while (true) {
+        const bool fin = stage == 2;
+        const float loss = eval_frame<NS, K>(c, tb, fc, !fin, true, fin ? jout : nullptr, nullptr);
+        if (fin) {
+          out_loss = loss;
+          break;
+        }
+        if (freeze_betas)
+          for (int i = 0; i < 10; ++i) c.G(kShapeOff + i) = 0.f;
+        if (stage == 0) {
+          st.begin(c, v, loss, iters, p.lr);
+          stage = 1;
+        } else if (!st.done) {
+          st.after_eval(c, v, loss);
+        }
+        if (!__any_sync(0xffffffffu, !st.done)) {
+          stage = 2;
+          for (int i = 0; i < NX; ++i) c.X(i) = v.at(i);
+        }
+      }
+      evals = st.evals;
+    }
+
+    if (valid) {
+      float* op = p.out_pose + f * kPoseDim;
+#pragma unroll 8
+      for (int i = 0; i < kPoseDim; ++i) op[i] = c.X(i);
+      for (int i = 0; i < 3; ++i) p.out_transl[f * 3 + i] = c.X(kTranslOff + i);
+      for (int i = 0; i < 10; ++i) p.out_betas[f * 10 + i] = c.X(kShapeOff + i);
+      if (NS == 20 && p.out_expr)
+        for (int i = 0; i < 10; ++i) p.out_expr[f * 10 + i] = c.X(kShapeOff + 10 + i);
+      p.out_loss[f] = out_loss;
+      if (p.out_evals) p.out_evals[f] = evals;
+    }
+  }
+}
+
+}  // namespace k2b

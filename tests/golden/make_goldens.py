@@ -157,9 +157,23 @@ def main():
             import torch.optim.lbfgs as L
             outs = {k: [] for k in ("pose", "betas", "transl", "joints", "loss", "nevals")}
             traces = []
+            ls_records = []
             for b in range(B):
                 tr = []
+                ls = []
                 orig = L.LBFGS._directional_evaluate
+                orig_sw = L._strong_wolfe
+
+                def rec_sw(obj_func, x, t, d, f, g, gtd, c1=1e-4, c2=0.9, tolerance_change=1e-9,
+                           max_ls=25, _o=orig_sw, _ls=ls, _tr=tr):
+                    start = len(_tr)
+                    out = _o(obj_func, x, t, d, f, g, gtd, c1, c2, tolerance_change, max_ls)
+                    # t_in, f, gtd, d_norm, max_ls, first trace row, n_evals, t_out, f_out, t_is_tensor
+                    _ls.append((float(t), float(f), float(gtd), float(d.abs().max()), max_ls, start,
+                                out[3], float(out[2]), float(out[0]), float(isinstance(t, torch.Tensor))))
+                    return out
+
+                L._strong_wolfe = rec_sw
 
                 def rec(self, closure, x, t, d, _orig=orig, _tr=tr):
                     loss, fg = _orig(self, closure, x, t, d)
@@ -173,6 +187,10 @@ def main():
                     res = fitter.fit_frame(sub, tgt[b:b + 1], conf, seq_ind=seq_ind, freeze_betas=freeze)
                 finally:
                     L.LBFGS._directional_evaluate = orig
+                    L._strong_wolfe = orig_sw
+                ls_arr = np.full((40, 10), np.nan)
+                ls_arr[: len(ls)] = np.asarray(ls, dtype=np.float64)
+                ls_records.append(ls_arr)
                 outs["pose"].append(res.params.pose)
                 outs["betas"].append(res.params.betas)
                 outs["transl"].append(res.params.transl)
@@ -185,6 +203,7 @@ def main():
             for k, v in outs.items():
                 put(f"{tag}_{k}", torch.cat(v))
             put(tag + "_trace", np.stack(traces))
+            put(tag + "_linesearch", np.stack(ls_records))
 
         for n in (5, 10, 30):
             run_fitter("smpl", False, n, n, 0, False, 4, seed=11, tag=f"adam_smpl_n{n}")
