@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- frames fitted / second (SMPL, AMASS-22, reference iteration schedule).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # CPU oracle port on the host cores
+
+Workload (BASELINE.json configs[3] sharded; every sequence is configs[1]): per GPU
+`--frames-per-gpu` frames (default 1 048 576 = 256 sequences x 4 096 frames; at 8 GPUs that is the
+8M-frame config) of synthetic AMASS-22 keypoints generated from the synthetic SMPL model, fitted
+with the frame-parallel two-sweep schedule S2 (sweep 0: 30-iteration budget, sweep 1: 10-iteration
+budget + temporal pose-preserve term), reference default optimiser (L-BFGS / strong Wolfe), followed
+by the full-mesh output (6 890 vertices + 45 joints per frame).  One step = one pass over the batch.
+The sequence grid is shifted by half a sequence so every shard boundary falls inside a sequence
+and the one-frame halo exchange is really used.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames fitted/sec (SMPL, AMASS-22, fixed iters)"
+UNIT = "frames/s"
+SEQ_LEN = 4096
+EVAL_FLOP = {"smpl": 98e3, "smplh": 110e3, "smplx": 115e3}   # algorithmic flop / evaluation, SURVEY.md 8(d)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=256 * SEQ_LEN)
+    ap.add_argument("--optimizer", default="lbfgs", choices=["lbfgs", "adam"])
+    ap.add_argument("--no-vertices", action="store_true", help="skip the vertex output (joints only)")
+    ap.add_argument("--cpu-sample-frames", type=int, default=0, help="0 = choose for ~20 s of CPU work")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def seq_index(lo: int, hi: int, device) -> torch.Tensor:
+    """Index of global frames [lo, hi) inside their sequence: a first half-length sequence, then
+    back-to-back sequences of SEQ_LEN frames (so multiples of 2^20 frames fall mid-sequence)."""
+    g = torch.arange(lo, hi, device=device, dtype=torch.int64)
+    half = SEQ_LEN // 2
+    return torch.where(g < half, g, (g - half) % SEQ_LEN).to(torch.int32)
+
+
+def make_targets(weights, lo: int, hi: int, device, chunk=1 << 16) -> torch.Tensor:
+    """Synthetic keypoints of global frames [lo, hi): smooth random motions through the synthetic model
+    (SURVEY.md 8(d)); deterministic per 65 536-frame chunk of the global frame axis."""
+    from keypoints2body_b200 import synthetic as syn
+
+    out = torch.empty(hi - lo, 22, 3, device=device)
+    c0 = lo // chunk
+    pos = lo
+    while pos < hi:
+        c = pos // chunk
+        mo = syn.make_motion(SEQ_LEN, seed=1000 + c, num_sequences=chunk // SEQ_LEN)
+        a, b = pos - c * chunk, min(hi, (c + 1) * chunk) - c * chunk
+        sl = {k: v[a:b].to(device) for k, v in mo.items()}
+        j = syn.kinematic_joints(weights, sl["pose"][:, :66], sl["betas"], sl["transl"], 22)
+        g = torch.Generator(device="cpu").manual_seed(5000 + c)
+        noise = 0.005 * torch.randn(chunk, 22, 3, generator=g)[a:b].to(device)
+        out[pos - lo: pos - lo + (b - a)] = j + noise
+        pos += b - a
+    del c0
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(frames: int, threads: int, optimizer: str, seed: int = 77):
+    """Times the oracle port (the reference's algorithm on torch CPU, B = 1 per frame like the API,
+    full-mesh forward per evaluation like smplx) on `frames` frames with schedule S2."""
+    from keypoints2body_b200 import synthetic as syn
+    from oracle import reference_port as rp
+    from oracle.smplx_shim import BodyModelShim
+
+    torch.set_num_threads(threads)
+    weights = syn.make_body_model("smpl", seed=0)
+    model, prior = BodyModelShim(weights), rp.GMMPrior(syn.make_gmm(seed=0))
+    mo = syn.make_motion(frames, seed=seed)
+    tgt = syn.kinematic_joints(weights, mo["pose"][:, :66], mo["betas"], mo["transl"], 22)
+    lbfgs = optimizer == "lbfgs"
+    conf = torch.ones(22)
+    root0 = model(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10)).joints[:, 0]
+
+    def one_pass():
+        s0 = []
+        for t in range(frames):
+            init = {k: None for k in rp.PARAM_ORDER}
+            init.update(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10),
+                        transl=tgt[t:t + 1, 0] - root0)
+            s0.append(rp.fit_frame(model, prior, init, tgt[t:t + 1], conf, seq_ind=0, use_lbfgs=lbfgs))
+        for t in range(1, frames):
+            rp.fit_frame(model, prior, s0[t - 1]["params"], tgt[t:t + 1], conf, seq_ind=t, use_lbfgs=lbfgs)
+
+    return one_pass
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    probe = cpu_reference_rate(2, threads, args.optimizer)
+    t0 = time.perf_counter()
+    probe()
+    per_frame = (time.perf_counter() - t0) / 2
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n = args.cpu_sample_frames or int(max(2, min(64, budget / per_frame)))
+    one_pass = cpu_reference_rate(n, threads, args.optimizer)
+    for _ in range(args.warmup):
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_pass()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt
+    sample = (f"{n} frames/step, schedule S2 (30 + 10 iteration budgets), {args.optimizer}, B=1 per frame, "
+              f"torch {torch.__version__} CPU, full-mesh forward per evaluation")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "bounded sample of the ours-arm workload: " + sample, "optimizer": args.optimizer},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from keypoints2body_b200 import _native as nat
+    from keypoints2body_b200 import synthetic as syn
+    from keypoints2body_b200.api.batch import SequenceBatchFitter
+    from keypoints2body_b200.core.config import FrameOptimizeConfig
+    from keypoints2body_b200.core.fitters.world_space import WorldSpaceFitter
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F = args.frames_per_gpu
+    lo, hi = rank * F, (rank + 1) * F
+
+    weights = syn.make_body_model("smpl", seed=0)
+    fitter = WorldSpaceFitter(weights, joints_category="AMASS", use_lbfgs=args.optimizer == "lbfgs",
+                              model_type="smpl", gmm=syn.make_gmm(seed=0), device=dev)
+    cfg = FrameOptimizeConfig()
+    sf = SequenceBatchFitter(fitter, F, cfg, with_vertices=not args.no_vertices)
+    targets = make_targets(weights, lo, hi, dev)
+    seq_ind = seq_index(lo, hi, dev)
+    lib = fitter.native.lib
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t) / steps
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------
+    def step_device():
+        return sf.run(targets, seq_ind)
+
+    for _ in range(args.warmup):
+        step_device()
+    sf.kernel_events = []
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.k2b_launch_count()
+    ms_step = timed(step_device, args.steps)
+    launches = (lib.k2b_launch_count() - launches0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    torch.cuda.synchronize()
+    fit_ms = [a.elapsed_time(b) for a, b in sf.kernel_events]          # two fit launches per step
+    sf.kernel_events = None
+    out = step_device()
+    evals_total = float(out["evals"].sum())
+    evals0, evals1 = float(sf.evals0.sum()), float(sf.evals1.sum())
+    mean_err = float((out["joints"][:, :22] - targets).norm(dim=-1).mean())
+
+    # ---- e2e: pinned host inputs -> device, fit, results -> pinned host ----------------------------
+    h_targets = torch.empty(targets.shape, pin_memory=True).copy_(targets)
+    d_targets = torch.empty_like(targets)
+    n_j = out["joints"].shape[1]
+    h_pose = torch.empty(F, 72, pin_memory=True)
+    h_betas = torch.empty(F, 10, pin_memory=True)
+    h_transl = torch.empty(F, 3, pin_memory=True)
+    h_loss = torch.empty(F, pin_memory=True)
+    h_joints = torch.empty(F, n_j, 3, pin_memory=True)
+
+    def step_host():
+        d_targets.copy_(h_targets, non_blocking=True)
+        o = sf.run(d_targets, seq_ind)
+        h_pose.copy_(o["pose"], non_blocking=True)
+        h_betas.copy_(o["params"]["betas"], non_blocking=True)
+        h_transl.copy_(o["params"]["transl"], non_blocking=True)
+        h_loss.copy_(o["loss"], non_blocking=True)
+        h_joints.copy_(o["joints"], non_blocking=True)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    ms_e2e = timed(step_host, args.steps)
+    h2d = h_targets.numel() * 4
+    d2h = 4 * (h_pose.numel() + h_betas.numel() + h_transl.numel() + h_loss.numel() + h_joints.numel())
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (fused fit kernel, two launches per step) -------------------
+    tf = ctypes_double()
+    peak_tflops, _ = fma_peak(lib)
+    flop_step = (evals0 + evals1 + F) * EVAL_FLOP["smpl"]     # + one final (loss / joints) forward per frame/sweep
+    fit_ms_step = sum(fit_ms) / max(1, args.steps)
+    achieved = flop_step / (fit_ms_step * 1e-3) / 1e12 if fit_ms_step > 0 else None
+    nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    mesh_ms = ms_step - fit_ms_step
+    mesh_bytes = F * (6890 * 3 * 4 + n_j * 3 * 4) if not args.no_vertices else F * n_j * 12
+    line = {
+        "metric": METRIC, "value": world * F / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": (f"SMPL AMASS-22 sequence fit, {F} frames/GPU ({F // SEQ_LEN} sequences x {SEQ_LEN}; "
+                         "BASELINE configs[3] shard, each sequence = configs[1]), schedule S2: sweep0 30-iteration "
+                         f"budget + sweep1 10-iteration budget with pose-preserve, {args.optimizer}, "
+                         + ("full mesh (6890 verts + 45 joints) per frame" if not args.no_vertices else "joints only")),
+            "optimizer": args.optimizer, "frames_per_gpu": F, "seq_len": SEQ_LEN,
+            "l2_policy": "inputs larger than L2 (targets %.0f MB/GPU, outputs %.1f GB/GPU)" % (h2d / 1e6, mesh_bytes / 1e9),
+            "evals_per_frame": evals_total / F, "mean_joint_error_m": mean_err,
+        },
+        "e2e": {"value": world * F / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                "note": "vertices stay in HBM (%.1f GB/GPU); params, loss and 45 joints are copied back" % (mesh_bytes / 1e9)},
+        "gpu_launches": int(launches) * args.steps,
+        "clocks": clocks,
+        "roofline": {
+            "kernel": "fit_kernel<10,22,%s> (sweep 0 + sweep 1)" % ("lbfgs" if args.optimizer == "lbfgs" else "adam"),
+            "bound": "fp32_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": achieved / peak_tflops if achieved and peak_tflops else None,
+            "peak_source": "in-run FFMA micro-benchmark (k2b_fma_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f" % nominal,
+            "frac_of_nominal": achieved / nominal if achieved else None,
+            "flop_per_eval": EVAL_FLOP["smpl"], "evals_per_launch": [evals0 + F, evals1 + F],
+            "ms_per_launch_pair": fit_ms_step, "share_of_step": fit_ms_step / ms_step, "traffic": None,
+        },
+        "roofline_mesh": {
+            "kernel": "mesh_pose_kernel + mesh_skin_kernel", "bound": "hbm",
+            "achieved": mesh_bytes / (mesh_ms * 1e-3) / 1e9 if mesh_ms > 0 else None,
+            "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+            "frac": (mesh_bytes / (mesh_ms * 1e-3) / 1e9) / peaks.get("hbm_gbs", 6650.0) if mesh_ms > 0 else None,
+            "ms": mesh_ms, "traffic": None,
+        },
+    }
+    del tf
+    if world == 1 and not args.skip_cpu_baseline:
+        threads = os.cpu_count() or 1
+        probe = cpu_reference_rate(2, threads, args.optimizer)
+        t0 = time.perf_counter()
+        probe()
+        per_frame = (time.perf_counter() - t0) / 2
+        n = args.cpu_sample_frames or int(max(2, min(64, 20.0 / per_frame)))
+        one_pass = cpu_reference_rate(n, threads, args.optimizer)
+        t0 = time.perf_counter()
+        one_pass()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} frames, schedule S2 (30 + 10 budgets), {args.optimizer}, B=1 per frame, torch CPU, "
+                      "full-mesh forward per evaluation like the reference"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ctypes_double():
+    import ctypes
+
+    return ctypes.c_double()
+
+
+def fma_peak(lib):
+    import ctypes
+
+    tf, ms = ctypes.c_double(), ctypes.c_double()
+    rc = lib.k2b_fma_peak(20000, ctypes.byref(tf), ctypes.byref(ms), None)
+    return (tf.value, ms.value) if rc == 0 else (None, None)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -170,6 +170,32 @@ typedef struct k2b_mesh_args {
 size_t k2b_mesh_workspace_bytes(const k2b_model* m, int64_t num_frames);
 int k2b_mesh_batch(const k2b_model* m, const k2b_mesh_args* args, void* cuda_stream);
 
+/* Shared-betas pre-pass (core/shape.py:10-115): for each of S sequences, L-BFGS over betas on
+ * the root-aligned squared joint error of its first T frames at fixed poses. */
+typedef struct k2b_shape_args {
+  int32_t num_sequences;       /* S */
+  int32_t frames_per_sequence; /* T frames used per sequence (reference default 50) */
+  int64_t sequence_stride;     /* frames between consecutive sequences in targets / poses */
+  int32_t num_obs;             /* K: 22 or 24 */
+  int32_t pose_per_frame;      /* poses are [S][stride][72] (1) or one [S][72] per sequence (0) */
+  int32_t conf_per_sequence;   /* conf is [S][K] (1) or [K] (0) */
+  int32_t num_iters;           /* L-BFGS max_iter (reference default 40) */
+  float lr;                    /* reference: 0.1 */
+  float shape_prior_weight;    /* reference default 5 */
+  const float* targets;        /* [S][stride][K][3] (device) */
+  const float* poses;          /* see pose_per_frame */
+  const float* conf;           /* or NULL = ones */
+  const float* init_betas;     /* [S][10] */
+  float* out_betas;            /* [S][10] */
+  float* out_loss;             /* [S] */
+  int32_t* out_evals;          /* [S] or NULL */
+  void* workspace;
+  size_t workspace_bytes;      /* >= k2b_shape_workspace_bytes */
+} k2b_shape_args;
+
+size_t k2b_shape_workspace_bytes(const k2b_model* m, int32_t num_sequences, int32_t num_iters);
+int k2b_shape_pass(const k2b_model* m, const k2b_shape_args* args, void* cuda_stream);
+
 /* FP32-FMA micro-benchmark used as the roofline denominator of the fit kernel:
  * returns achieved TFLOP/s (2 flop per FMA) over `iters` dependent-chain rounds. */
 int k2b_fma_peak(int iters, double* out_tflops, double* out_ms, void* cuda_stream);

@@ -72,10 +72,21 @@ class MeshArgs(C.Structure):
     ]
 
 
+class ShapeArgs(C.Structure):
+    _fields_ = [
+        ("num_sequences", C.c_int32), ("frames_per_sequence", C.c_int32), ("sequence_stride", C.c_int64),
+        ("num_obs", C.c_int32), ("pose_per_frame", C.c_int32), ("conf_per_sequence", C.c_int32),
+        ("num_iters", C.c_int32), ("lr", C.c_float), ("shape_prior_weight", C.c_float),
+        ("targets", C.c_void_p), ("poses", C.c_void_p), ("conf", C.c_void_p), ("init_betas", C.c_void_p),
+        ("out_betas", C.c_void_p), ("out_loss", C.c_void_p), ("out_evals", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 EXPORTS = (
     "k2b_model_create", "k2b_model_destroy", "k2b_fit_workspace_bytes", "k2b_fit_batch",
     "k2b_fit_batch_host", "k2b_evaluate_batch", "k2b_mesh_workspace_bytes", "k2b_mesh_batch",
-    "k2b_fma_peak", "k2b_launch_count", "k2b_last_error", "k2b_version",
+    "k2b_shape_workspace_bytes", "k2b_shape_pass", "k2b_fma_peak", "k2b_launch_count", "k2b_last_error", "k2b_version",
 )
 
 _lib = None
@@ -99,10 +110,13 @@ def load_library():
     lib.k2b_fit_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
     lib.k2b_fit_workspace_bytes.restype = C.c_size_t
     for name, st in (("k2b_fit_batch", FitArgs), ("k2b_fit_batch_host", FitArgs),
-                     ("k2b_evaluate_batch", EvalArgs), ("k2b_mesh_batch", MeshArgs)):
+                     ("k2b_evaluate_batch", EvalArgs), ("k2b_mesh_batch", MeshArgs),
+                     ("k2b_shape_pass", ShapeArgs)):
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p, C.POINTER(st), C.c_void_p]
         fn.restype = C.c_int
+    lib.k2b_shape_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.k2b_shape_workspace_bytes.restype = C.c_size_t
     lib.k2b_mesh_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
     lib.k2b_mesh_workspace_bytes.restype = C.c_size_t
     lib.k2b_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]

@@ -1,0 +1,363 @@
+"""World-space fitter backed by the fused CUDA kernel.
+
+Drop-in for the reference's ``WorldSpaceFitter``
+(/root/reference/keypoints2body/core/fitters/world_space.py:53-323): same
+constructor arguments, same ``fit_frame`` signature / result contract.  What
+differs is the execution: the body model's weights are uploaded once
+(``NativeModel``), and a whole batch of frames is fitted by ONE persistent kernel
+launch (``k2b_fit_batch``) that runs forward, analytic backward, all priors and
+the Adam / L-BFGS update for every iteration on chip, followed by one mesh pass
+(``k2b_mesh_batch``) for the returned vertices / joints.
+
+``fit_batch`` is the batched entry the sequence driver and the benchmark use;
+``fit_frame`` is the reference-shaped call (it also accepts B > 1 like the
+reference does, with the reference's quirk that a 2-D confidence collapses to
+its first row, world_space.py:163-164).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from ... import _native as nat
+from ...body_model import BodyModelWeights, extract_weights, full_pose_from_params
+from ...models.smpl_data import BodyModelFitResult, SMPLData, SMPLHData, SMPLXData
+from ..constants import AMASS_JOINT_MAP, JOINT_MAP
+from ..prior import GMMConstants, load_gmm, prepare_gmm
+
+_EXTRA_BLOCKS = ("left_hand_pose", "right_hand_pose", "expression", "jaw_pose", "leye_pose", "reye_pose")
+
+
+def _f32(t, device):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)       # numpy prev_params are accepted (the reference crashes on them)
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def guess_init_transl_from_root(fitter_or_model, pose_aa, betas, j3d_world_frame, joints_category="SMPL24"):
+    """Root-joint alignment (world_space.py:13-50): ``target_root - model_root``.
+
+    The model root at the given pose / shape comes from the mesh kernel's skeleton pass.
+    """
+    if joints_category not in ("SMPL24", "AMASS"):
+        raise ValueError(f"Unknown joints category: {joints_category}")
+    root = (JOINT_MAP if joints_category == "SMPL24" else AMASS_JOINT_MAP)["MidHip"]
+    fitter = fitter_or_model
+    pose_aa = _f32(pose_aa, fitter.device)
+    out = fitter.forward_batch(
+        {"global_orient": pose_aa[:, :3], "body_pose": pose_aa[:, 3:], "betas": _f32(betas, fitter.device)},
+        with_vertices=False,
+    )
+    return (_f32(j3d_world_frame, fitter.device)[:, root, :] - out["joints"][:, root, :]).detach()
+
+
+class WorldSpaceFitter:
+    """Per-frame optimiser in world coordinates, B frames per kernel launch."""
+
+    def __init__(
+        self,
+        smpl_model,
+        step_size=1e-2,
+        num_iters_first=30,
+        num_iters_followup=10,
+        use_lbfgs=True,
+        joints_category="SMPL24",
+        device=None,
+        pose_prior_num_gaussians=8,
+        *,
+        model_type: Optional[str] = None,
+        prior_folder: str = "./data/models/",
+        gmm: Optional[dict] = None,
+    ):
+        if not torch.cuda.is_available():
+            raise RuntimeError("keypoints2body_b200 needs a CUDA device (there is no CPU fallback)")
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if device.type != "cuda":
+            raise ValueError(f"keypoints2body_b200 runs on CUDA devices only, got device={device}")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if joints_category == "GENERIC":
+            raise NotImplementedError(
+                "GENERIC / dict-block observations need vertex-picked joints inside the loop; "
+                "not built yet (SURVEY.md section 8f row 2)")
+        if joints_category not in ("SMPL24", "AMASS"):
+            raise ValueError("No such joints category!")
+        self.smpl = smpl_model
+        self.step_size = float(step_size)
+        self.num_iters_first = int(num_iters_first)
+        self.num_iters_followup = int(num_iters_followup)
+        self.use_lbfgs = bool(use_lbfgs)
+        self.device = device
+        self.joints_category = joints_category
+        self.num_obs = 24 if joints_category == "SMPL24" else 22
+
+        if isinstance(smpl_model, nat.NativeModel):
+            self.native = smpl_model
+        else:
+            cached = getattr(smpl_model, "_k2b_native", None)
+            key = (str(device), int(pose_prior_num_gaussians), prior_folder if gmm is None else id(gmm))
+            if cached is not None and cached[0] == key:
+                self.native = cached[1]
+            else:
+                weights = smpl_model if isinstance(smpl_model, BodyModelWeights) else extract_weights(smpl_model, model_type)
+                consts: GMMConstants = prepare_gmm(gmm if gmm is not None else load_gmm(prior_folder, pose_prior_num_gaussians))
+                self.native = nat.NativeModel(weights, consts, device)
+                try:   # upload once per model object (the reference re-unpickles the prior per call)
+                    smpl_model._k2b_native = (key, self.native)
+                except Exception:
+                    pass
+        self.model_type = self.native.weights.model_type
+        self.has_expr = self.native.num_shape == 20
+
+    # ------------------------------------------------------------------ kernels
+    def _run_fit(self, B, targets, conf, conf_per_frame, pose, betas, transl, expr, preserve, frame_iters,
+                 frame_preserve, preserve_all, num_iters, optimizer, joint_loss_weight, pose_preserve_weight,
+                 freeze_betas, want_joints=True):
+        dev = self.device
+        out_pose = torch.empty(B, 72, device=dev)
+        out_betas = torch.empty(B, 10, device=dev)
+        out_transl = torch.empty(B, 3, device=dev)
+        out_expr = torch.empty(B, 10, device=dev) if self.has_expr else None
+        out_loss = torch.empty(B, device=dev)
+        out_joints = torch.empty(B, self.num_obs, 3, device=dev) if want_joints else None
+        out_evals = torch.empty(B, dtype=torch.int32, device=dev)
+        lib = self.native.lib
+        ws_bytes = lib.k2b_fit_workspace_bytes(self.native.handle, B, optimizer, int(num_iters))
+        ws = self.native.workspace("fit", ws_bytes)
+        a = nat.FitArgs(
+            num_frames=B, num_obs=self.num_obs, optimizer=optimizer, num_iters=int(num_iters),
+            freeze_betas=int(bool(freeze_betas)), conf_per_frame=int(conf_per_frame), lr=self.step_size,
+            joint_loss_weight=float(joint_loss_weight), pose_preserve_weight=float(pose_preserve_weight),
+            targets=nat.ptr(targets), conf=nat.ptr(conf), init_pose=nat.ptr(pose), init_betas=nat.ptr(betas),
+            init_transl=nat.ptr(transl), init_expr=nat.ptr(expr), preserve_pose=nat.ptr(preserve),
+            frame_iters=nat.ptr(frame_iters), frame_preserve=nat.ptr(frame_preserve),
+            preserve_all=int(preserve_all),
+            out_pose=nat.ptr(out_pose), out_betas=nat.ptr(out_betas), out_transl=nat.ptr(out_transl),
+            out_expr=nat.ptr(out_expr), out_loss=nat.ptr(out_loss), out_joints=nat.ptr(out_joints),
+            out_evals=nat.ptr(out_evals), workspace=nat.ptr(ws), workspace_bytes=ws.numel(),
+        )
+        with torch.cuda.device(dev):
+            nat.check(lib.k2b_fit_batch(self.native.handle, C.byref(a), nat.current_stream()))
+        return dict(pose=out_pose, betas=out_betas, transl=out_transl, expression=out_expr, loss=out_loss,
+                    fit_joints=out_joints, evals=out_evals)
+
+    def evaluate_batch(self, params: dict, j3d, conf=None, preserve_pose=None, preserve_on=False,
+                       joint_loss_weight=600.0, pose_preserve_weight=5.0):
+        """One evaluation of the loss and its gradient (parity / debugging entry)."""
+        dev = self.device
+        pose = torch.cat([_f32(params["global_orient"], dev), _f32(params["body_pose"], dev)], dim=1).contiguous()
+        B = pose.shape[0]
+        targets = _f32(j3d, dev)[:, : self.num_obs].contiguous()
+        conf = _f32(conf, dev)
+        conf_pf = conf is not None and conf.dim() == 2
+        if conf is not None:
+            conf = conf[..., : self.num_obs].contiguous()
+        expr = _f32(params.get("expression"), dev)
+        if self.has_expr and expr is None:
+            expr = torch.zeros(B, 10, device=dev)
+        outs = dict(loss=torch.empty(B, device=dev), grad_pose=torch.empty(B, 72, device=dev),
+                    grad_betas=torch.empty(B, 10, device=dev), grad_transl=torch.empty(B, 3, device=dev),
+                    grad_expression=torch.empty(B, 10, device=dev) if self.has_expr else None,
+                    joints=torch.empty(B, self.num_obs, 3, device=dev),
+                    gmm_component=torch.empty(B, dtype=torch.int32, device=dev))
+        lib = self.native.lib
+        ws = self.native.workspace("fit", lib.k2b_fit_workspace_bytes(self.native.handle, B, nat.OPT_ADAM, 1))
+        a = nat.EvalArgs(
+            num_frames=B, num_obs=self.num_obs, conf_per_frame=int(conf_pf), preserve_all=int(bool(preserve_on)),
+            joint_loss_weight=float(joint_loss_weight), pose_preserve_weight=float(pose_preserve_weight),
+            targets=nat.ptr(targets), conf=nat.ptr(conf), pose=nat.ptr(pose),
+            betas=nat.ptr(_f32(params["betas"], dev)), transl=nat.ptr(_f32(params["transl"], dev)),
+            expr=nat.ptr(expr), preserve_pose=nat.ptr(_f32(preserve_pose, dev)),
+            out_loss=nat.ptr(outs["loss"]), out_grad_pose=nat.ptr(outs["grad_pose"]),
+            out_grad_betas=nat.ptr(outs["grad_betas"]), out_grad_transl=nat.ptr(outs["grad_transl"]),
+            out_grad_expr=nat.ptr(outs["grad_expression"]), out_joints=nat.ptr(outs["joints"]),
+            out_gmm_component=nat.ptr(outs["gmm_component"]), workspace=nat.ptr(ws), workspace_bytes=ws.numel(),
+        )
+        with torch.cuda.device(dev):
+            nat.check(lib.k2b_evaluate_batch(self.native.handle, C.byref(a), nat.current_stream()))
+        return outs
+
+    def forward_batch(self, params: dict, with_vertices=True, out_vertices=None):
+        """Body-model forward (mesh kernels): joints ``(B, n_j + extras, 3)`` and vertices ``(B,V,3)``."""
+        dev = self.device
+        go = _f32(params["global_orient"], dev)
+        B = go.shape[0]
+        extras = {k: _f32(params.get(k), dev) for k in _EXTRA_BLOCKS}
+        full_pose = full_pose_from_params(self.model_type, go, _f32(params["body_pose"], dev), extras).contiguous()
+        betas = _f32(params["betas"], dev)
+        if betas.shape[0] != B:
+            betas = betas.expand(B, -1)
+        shape = betas
+        if self.has_expr:
+            expr = extras.get("expression")
+            shape = torch.cat([betas, expr if expr is not None else torch.zeros(B, 10, device=dev)], dim=1)
+        shape = shape.contiguous()
+        transl = _f32(params.get("transl"), dev)
+        n_out = self.native.num_joints + self.native.num_extra
+        joints = torch.empty(B, n_out, 3, device=dev)
+        verts = None
+        if with_vertices:
+            verts = out_vertices if out_vertices is not None else torch.empty(B, self.native.num_vertices, 3, device=dev)
+        lib = self.native.lib
+        ws = self.native.workspace("mesh", lib.k2b_mesh_workspace_bytes(self.native.handle, B))
+        a = nat.MeshArgs(num_frames=B, full_pose=nat.ptr(full_pose), shape=nat.ptr(shape), transl=nat.ptr(transl),
+                         out_vertices=nat.ptr(verts), out_joints=nat.ptr(joints), workspace=nat.ptr(ws),
+                         workspace_bytes=ws.numel())
+        with torch.cuda.device(dev):
+            nat.check(lib.k2b_mesh_batch(self.native.handle, C.byref(a), nat.current_stream()))
+        return {"joints": joints, "vertices": verts}
+
+    def shape_pass(self, init_betas, pose_init, j3d_world, *, frame_indices=None, conf=None, num_iters=40,
+                   step_size=1e-1, shape_prior_weight=5.0, num_sequences=1):
+        """Shared-betas L-BFGS pre-pass (core/shape.py:10-115) for ``num_sequences`` sequences.
+
+        ``j3d_world`` is (S*T, K, 3) with sequences back to back, ``pose_init`` (S*T, 72) the fixed
+        poses; ``frame_indices`` must be a prefix ``range(n)`` (what the reference's driver passes,
+        engine.py:244-248).  Returns betas (S,10) -- (1,10) for a single sequence.
+        """
+        dev = self.device
+        targets = _f32(j3d_world, dev)[:, : self.num_obs].contiguous()
+        S = int(num_sequences)
+        T = targets.shape[0] // S
+        n_use = T if frame_indices is None else len(frame_indices)
+        if frame_indices is not None and list(frame_indices) != list(range(n_use)):
+            raise NotImplementedError("shape pass supports a leading range of frames only")
+        poses = _f32(pose_init, dev).contiguous()
+        betas0 = _f32(init_betas, dev)
+        if betas0.shape[0] != S:
+            betas0 = betas0.expand(S, -1)
+        betas0 = betas0.contiguous()
+        conf = _f32(conf, dev)
+        conf_ps = conf is not None and conf.dim() == 2
+        if conf is not None:
+            conf = conf[..., : self.num_obs].contiguous()
+        out_betas = torch.empty(S, 10, device=dev)
+        out_loss = torch.empty(S, device=dev)
+        out_evals = torch.empty(S, dtype=torch.int32, device=dev)
+        lib = self.native.lib
+        ws = self.native.workspace("shape", lib.k2b_shape_workspace_bytes(self.native.handle, S, int(num_iters)))
+        a = nat.ShapeArgs(num_sequences=S, frames_per_sequence=n_use, sequence_stride=T, num_obs=self.num_obs,
+                          pose_per_frame=1, conf_per_sequence=int(conf_ps), num_iters=int(num_iters),
+                          lr=float(step_size), shape_prior_weight=float(shape_prior_weight),
+                          targets=nat.ptr(targets), poses=nat.ptr(poses), conf=nat.ptr(conf),
+                          init_betas=nat.ptr(betas0), out_betas=nat.ptr(out_betas), out_loss=nat.ptr(out_loss),
+                          out_evals=nat.ptr(out_evals), workspace=nat.ptr(ws), workspace_bytes=ws.numel())
+        with torch.cuda.device(dev):
+            nat.check(lib.k2b_shape_pass(self.native.handle, C.byref(a), nat.current_stream()))
+        self.last_shape_evals = out_evals
+        return out_betas
+
+    # ------------------------------------------------------------------ public
+    def fit_batch(self, init: dict, j3d, conf=None, *, seq_ind=0, preserve_pose=None, num_iters=None,
+                  joint_loss_weight=600.0, pose_preserve_weight=5.0, freeze_betas=False, use_lbfgs=None,
+                  with_mesh=True, out_vertices=None):
+        """Fit B independent frames in one launch.
+
+        ``init``: dict of (B,dim) arrays with keys global_orient, body_pose, betas, transl
+        (+ SMPL-H / SMPL-X blocks).  ``seq_ind``: int or (B,) integer tensor; 0 selects the
+        first-frame budget without the temporal term, > 0 the follow-up budget with it
+        (world_space.py:211,214).  ``preserve_pose``: (B,69) temporal anchor, default the
+        initial body pose (world_space.py:159).  Returns a dict of device tensors.
+        """
+        dev = self.device
+        go, bp = _f32(init["global_orient"], dev), _f32(init["body_pose"], dev)
+        transl = init.get("transl")
+        if transl is None:
+            raise ValueError("init_params.transl must be provided")
+        pose = torch.cat([go, bp], dim=1).contiguous()
+        B = pose.shape[0]
+        betas = _f32(init["betas"], dev)
+        if betas.shape[0] != B:
+            betas = betas.expand(B, -1).contiguous()
+        transl = _f32(transl, dev)
+        targets = _f32(j3d, dev)
+        if targets.dim() != 3 or targets.shape[0] != B or targets.shape[1] < self.num_obs:
+            raise ValueError(f"j3d must be (B={B}, K>={self.num_obs}, 3), got {tuple(targets.shape)}")
+        targets = targets[:, : self.num_obs].contiguous()
+        conf = _f32(conf, dev)
+        conf_pf = conf is not None and conf.dim() == 2
+        if conf is not None:
+            conf = conf[..., : self.num_obs].contiguous()
+        extras = {k: _f32(init.get(k), dev) for k in _EXTRA_BLOCKS}
+        expr = extras["expression"]
+        if self.has_expr and expr is None:
+            expr = torch.zeros(B, 10, device=dev)
+
+        frame_iters = frame_preserve = None
+        if isinstance(seq_ind, torch.Tensor):
+            seq = seq_ind.to(dev)
+            first = seq == 0
+            n_first = self.num_iters_first if num_iters is None else num_iters
+            n_follow = self.num_iters_followup if num_iters is None else num_iters
+            frame_iters = torch.where(first, n_first, n_follow).to(torch.int32).contiguous()
+            frame_preserve = (~first).to(torch.uint8).contiguous()
+            budget, preserve_all = max(n_first, n_follow), 0
+        else:
+            budget = num_iters if num_iters is not None else (
+                self.num_iters_first if seq_ind == 0 else self.num_iters_followup)
+            preserve_all = int(seq_ind > 0)
+        lbfgs = self.use_lbfgs if use_lbfgs is None else use_lbfgs
+        res = self._run_fit(B, targets, conf, conf_pf, pose, betas, transl, expr if self.has_expr else None,
+                            _f32(preserve_pose, dev), frame_iters, frame_preserve, preserve_all, budget,
+                            nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight, pose_preserve_weight,
+                            freeze_betas)
+        params = {"global_orient": res["pose"][:, :3], "body_pose": res["pose"][:, 3:], "betas": res["betas"],
+                  "transl": res["transl"]}
+        for k in _EXTRA_BLOCKS:
+            if extras[k] is not None:
+                params[k] = extras[k]      # receive no gradient from body keypoints: passed through
+        if self.has_expr:
+            params["expression"] = res["expression"]
+        out = {"params": params, "loss": res["loss"], "evals": res["evals"], "fit_joints": res["fit_joints"]}
+        if with_mesh:
+            out.update(self.forward_batch(params, with_vertices=True, out_vertices=out_vertices))
+        return out
+
+    def fit_frame(
+        self,
+        init_params: SMPLData,
+        j3d: torch.Tensor,
+        conf_3d: Optional[torch.Tensor] = None,
+        seq_ind: int = 0,
+        target_model_indices: Optional[torch.Tensor] = None,
+        joint_loss_weight: float = 600.0,
+        pose_preserve_weight: float = 5.0,
+        freeze_betas: bool = False,
+    ) -> BodyModelFitResult:
+        """Reference-shaped single call (world_space.py:93-323)."""
+        if init_params.transl is None:
+            raise ValueError("init_params.transl must be provided")
+        if target_model_indices is not None:
+            raise NotImplementedError("explicit target_model_indices (GENERIC observations) are not built yet")
+        init = {k: getattr(init_params, k) for k in ("global_orient", "body_pose", "betas", "transl")}
+        if isinstance(init_params, SMPLHData):
+            init["left_hand_pose"] = init_params.left_hand_pose
+            init["right_hand_pose"] = init_params.right_hand_pose
+        if isinstance(init_params, SMPLXData):
+            for k in ("expression", "jaw_pose", "leye_pose", "reye_pose"):
+                init[k] = getattr(init_params, k)
+        if self.has_expr and not isinstance(init_params, SMPLXData):
+            raise ValueError("an SMPL-X model needs SMPLXData init_params")
+        if conf_3d is not None:
+            conf_3d = _f32(conf_3d, self.device)
+            if conf_3d.dim() == 2:
+                conf_3d = conf_3d[0]       # reference quirk, world_space.py:163-164
+        out = self.fit_batch(init, j3d, conf_3d, seq_ind=int(seq_ind), joint_loss_weight=joint_loss_weight,
+                             pose_preserve_weight=pose_preserve_weight, freeze_betas=freeze_betas)
+        p = out["params"]
+        base = dict(betas=p["betas"], global_orient=p["global_orient"], body_pose=p["body_pose"], transl=p["transl"])
+        if isinstance(init_params, SMPLXData):
+            fitted = SMPLXData(**base, left_hand_pose=p.get("left_hand_pose"), right_hand_pose=p.get("right_hand_pose"),
+                               expression=p.get("expression") if init_params.expression is not None else None,
+                               jaw_pose=p.get("jaw_pose"), leye_pose=p.get("leye_pose"), reye_pose=p.get("reye_pose"))
+        elif isinstance(init_params, SMPLHData):
+            fitted = SMPLHData(**base, left_hand_pose=p.get("left_hand_pose"), right_hand_pose=p.get("right_hand_pose"))
+        else:
+            fitted = SMPLData(**base)
+        loss = out["loss"].sum()   # losses.py:67 sums over the batch
+        return BodyModelFitResult(params=fitted, vertices=out["vertices"], joints=out["joints"], loss=loss)

@@ -10,7 +10,9 @@
 
 #include "../../include/k2b_b200.h"
 #include "fit_kernel.cuh"
+#include "fit_launch.h"
 #include "mesh_kernel.cuh"
+#include "shape_kernel.cuh"
 
 using namespace k2b;
 
@@ -134,25 +136,15 @@ int fit_grid(const k2b_model* m, long num_frames) {
   return (int)(tiles < m->num_sms ? tiles : m->num_sms);
 }
 
-template <int NS, int K, int MODE>
-int launch_fit(const FitParams& p, const AdamTable& at, int grid, cudaStream_t st) {
-  auto kern = fit_kernel<NS, K, MODE>;
-  const size_t smem = fit_smem_bytes<NS>();
-  static bool configured = false;   // per template instantiation
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  kern<<<grid, kFitThreads, smem, st>>>(p, at);
-  g_launches.fetch_add(1);
-  CUDA_TRY(cudaGetLastError());
-  return K2B_OK;
-}
-
 template <int MODE>
 int launch_fit_ns(int ns, const FitParams& p, const AdamTable& at, int grid, cudaStream_t st) {
-  if (p.num_obs == 24) return launch_fit<10, 24, MODE>(p, at, grid, st);   // SMPL24 exists for SMPL only
-  return ns == 20 ? launch_fit<20, 22, MODE>(p, at, grid, st) : launch_fit<10, 22, MODE>(p, at, grid, st);
+  cudaError_t e;
+  if (p.num_obs == 24) e = launch_fit<10, 24, MODE>(p, at, grid, st);   // SMPL24 exists for SMPL only
+  else if (ns == 20) e = launch_fit<20, 22, MODE>(p, at, grid, st);
+  else e = launch_fit<10, 22, MODE>(p, at, grid, st);
+  g_launches.fetch_add(1);
+  if (e != cudaSuccess) return fail(K2B_ECUDA, std::string("fit kernel launch: ") + cudaGetErrorString(e));
+  return K2B_OK;
 }
 
 void fill_adam_table(AdamTable& at, double lr) {
@@ -355,6 +347,44 @@ extern "C" int k2b_mesh_batch(const k2b_model* m, const k2b_mesh_args* a, void* 
   int launches = 0;
   if (!mesh_forward(m->mesh, *a, (cudaStream_t)stream, err, launches)) return fail(K2B_ECUDA, err);
   g_launches.fetch_add(launches);
+  return K2B_OK;
+}
+
+// ---- shape pre-pass ---------------------------------------------------------------------------
+extern "C" size_t k2b_shape_workspace_bytes(const k2b_model* m, int32_t num_sequences, int32_t num_iters) {
+  if (!m || num_sequences <= 0) return 0;
+  return sizeof(float) * (size_t)num_sequences * (size_t)Vecs::floats_per_frame(10, lbfgs_history_capacity(num_iters));
+}
+
+extern "C" int k2b_shape_pass(const k2b_model* m, const k2b_shape_args* a, void* stream) {
+  if (!m || !a) return fail(K2B_EINVAL, "null argument");
+  int rc = check_common(m, a->num_sequences, a->num_obs, (const void*)1);
+  if (rc) return rc;
+  if (a->frames_per_sequence <= 0 || !a->targets || !a->poses || !a->init_betas || !a->out_betas || !a->out_loss)
+    return fail(K2B_EINVAL, "missing required array");
+  if (!a->workspace || a->workspace_bytes < k2b_shape_workspace_bytes(m, a->num_sequences, a->num_iters))
+    return fail(K2B_ENOMEM, "workspace too small");
+  ShapeParams p{};
+  p.rel = m->rel;
+  p.parents = m->mesh.parents;
+  p.ns = m->num_shape;
+  p.K = a->num_obs;
+  p.num_seq = a->num_sequences;
+  p.frames_per_seq = a->frames_per_sequence;
+  p.seq_stride_frames = a->sequence_stride;
+  p.pose_per_frame = a->pose_per_frame;
+  p.conf_per_seq = a->conf_per_sequence;
+  p.num_iters = a->num_iters;
+  p.lr = a->lr;
+  p.w2 = a->shape_prior_weight * a->shape_prior_weight;
+  p.targets = a->targets; p.poses = a->poses; p.conf = a->conf; p.init_betas = a->init_betas;
+  p.out_betas = a->out_betas; p.out_loss = a->out_loss; p.out_evals = a->out_evals;
+  p.scratch = (float*)a->workspace;
+  p.hmax = lbfgs_history_capacity(a->num_iters);
+  const int grid = (a->num_sequences + kShapeWarps - 1) / kShapeWarps;
+  shape_pass_kernel<<<grid, 32 * kShapeWarps, shape_smem_bytes(m->num_shape), (cudaStream_t)stream>>>(p);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
   return K2B_OK;
 }
 

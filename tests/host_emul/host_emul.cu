@@ -13,6 +13,7 @@
 
 #include "../../keypoints2body_b200/csrc/fit_core.cuh"
 #include "../../keypoints2body_b200/csrc/lbfgs_core.cuh"
+#include "../../keypoints2body_b200/csrc/shape_kernel.cuh"
 
 using namespace k2b;
 
@@ -158,4 +159,37 @@ extern "C" int emu_linesearch_replay(double t0, double f0, float gtd0, double d_
   out_final[1] = st.loss;
   out_final[2] = (double)st.ls_evals;
   return k;
+}
+
+// Shape pre-pass for ONE sequence: frames evaluated sequentially, same machine as the kernel.
+extern "C" int emu_shape_pass(void* model, const int* parents, int K, int T, int iters, float lr, float w,
+                              const float* targets, const float* poses, const float* conf, const float* betas0,
+                              float* out_betas, float* out_loss) {
+  EmuModel* m = (EmuModel*)model;
+  float x[10], g[10];
+  for (int s = 0; s < 10; ++s) x[s] = betas0[s];
+  Cols c{x, g, 1};
+  const int hmax = lbfgs_history_capacity(iters);
+  std::vector<float> scratch(Vecs::floats_per_frame(10, hmax), 0.f);
+  Vecs v{scratch.data(), 1, 10, hmax};
+  Lbfgs st;
+  st.done = false;
+  int stage = 0;
+  while (true) {
+    float grad[10] = {0};
+    float loss = 0.f;
+    for (int t = 0; t < T; ++t)
+      loss += shape_frame_eval((const float4*)m->rel.data(), m->ns, parents, K, poses + (size_t)t * 72,
+                               targets + (size_t)t * K * 3, conf, x, grad);
+    float bb = 0.f;
+    for (int s = 0; s < 10; ++s) bb += x[s] * x[s];
+    loss += (float)T * w * w * bb;
+    for (int s = 0; s < 10; ++s) g[s] = grad[s] + 2.f * (float)T * w * w * x[s];
+    if (stage == 0) st.begin(c, v, loss, iters, lr); else st.after_eval(c, v, loss);
+    stage = 1;
+    if (st.done) break;
+  }
+  for (int s = 0; s < 10; ++s) out_betas[s] = v.at(s);
+  *out_loss = (float)st.loss;
+  return st.evals;
 }

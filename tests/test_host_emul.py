@@ -34,7 +34,8 @@ def _stale():
     if not os.path.exists(EMU_LIB):
         return True
     t = os.path.getmtime(EMU_LIB)
-    srcs = [os.path.join(EMU_DIR, "host_emul.cu")] + [os.path.join(CSRC, f) for f in ("fit_core.cuh", "lbfgs_core.cuh")]
+    srcs = [os.path.join(EMU_DIR, "host_emul.cu")] + [os.path.join(CSRC, f) for f in
+                                                      ("fit_core.cuh", "lbfgs_core.cuh", "shape_kernel.cuh")]
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
@@ -48,6 +49,7 @@ def emu():
     lib.emu_model_destroy.argtypes = [C.c_void_p]
     lib.emu_fit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                             C.c_float, C.POINTER(C.c_uint8), fp, fp, C.c_int, fp, fp, fp, fp, fp, ip, ip, fp]
+    lib.emu_shape_pass.argtypes = [C.c_void_p, ip, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, fp, fp, fp, fp, fp, fp]
     lib.emu_sincos.argtypes = [C.c_int, fp, fp, fp]
     lib.emu_linesearch_replay.argtypes = [C.c_double, C.c_double, C.c_float, C.c_double, C.c_int, C.c_int,
                                           C.c_int, dp, fp, dp, dp]
@@ -244,3 +246,16 @@ def test_lbfgs_end_to_end_statistics(goldens, emu_models, tag):
     ref_loss = g[tag + "_loss"].reshape(-1)
     assert np.median(out["loss"]) <= 1.5 * np.median(ref_loss)
     print(tag, "agreeing trials/frame", agree, "evals", out["evals"], "ref", g[tag + "_nevals"].reshape(-1))
+
+
+def test_shape_pass_matches_reference(goldens, emu, emu_models, weights):
+    """Shared-betas pre-pass (core/shape.py) vs the reference's optimize_shape_multi_frame."""
+    g = goldens
+    tgt = f32(g["seq_in_target"][:5])
+    poses = np.zeros((5, 72), np.float32)
+    par = np.ascontiguousarray(weights("smpl").parents.numpy().astype(np.int32))
+    out, loss = np.zeros(10, np.float32), np.zeros(1, np.float32)
+    emu.emu_shape_pass(emu_models("smpl").h, par.ctypes.data_as(ip), 22, 5, 40, 0.1, 5.0, tgt.ctypes.data_as(fp),
+                       poses.ctypes.data_as(fp), None, np.zeros(10, np.float32).ctypes.data_as(fp),
+                       out.ctypes.data_as(fp), loss.ctypes.data_as(fp))
+    np.testing.assert_allclose(out, g["shape_pass_betas"].reshape(-1), atol=1e-4)
