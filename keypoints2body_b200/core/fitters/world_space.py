@@ -160,6 +160,8 @@ class WorldSpaceFitter:
         expr = _f32(params.get("expression"), dev)
         if self.has_expr and expr is None:
             expr = torch.zeros(B, 10, device=dev)
+        # keep every converted input alive until the launch has been enqueued
+        betas, transl, keep = _f32(params["betas"], dev), _f32(params["transl"], dev), _f32(preserve_pose, dev)
         outs = dict(loss=torch.empty(B, device=dev), grad_pose=torch.empty(B, 72, device=dev),
                     grad_betas=torch.empty(B, 10, device=dev), grad_transl=torch.empty(B, 3, device=dev),
                     grad_expression=torch.empty(B, 10, device=dev) if self.has_expr else None,
@@ -171,8 +173,7 @@ class WorldSpaceFitter:
             num_frames=B, num_obs=self.num_obs, conf_per_frame=int(conf_pf), preserve_all=int(bool(preserve_on)),
             joint_loss_weight=float(joint_loss_weight), pose_preserve_weight=float(pose_preserve_weight),
             targets=nat.ptr(targets), conf=nat.ptr(conf), pose=nat.ptr(pose),
-            betas=nat.ptr(_f32(params["betas"], dev)), transl=nat.ptr(_f32(params["transl"], dev)),
-            expr=nat.ptr(expr), preserve_pose=nat.ptr(_f32(preserve_pose, dev)),
+            betas=nat.ptr(betas), transl=nat.ptr(transl), expr=nat.ptr(expr), preserve_pose=nat.ptr(keep),
             out_loss=nat.ptr(outs["loss"]), out_grad_pose=nat.ptr(outs["grad_pose"]),
             out_grad_betas=nat.ptr(outs["grad_betas"]), out_grad_transl=nat.ptr(outs["grad_transl"]),
             out_grad_expr=nat.ptr(outs["grad_expression"]), out_joints=nat.ptr(outs["joints"]),
@@ -302,8 +303,9 @@ class WorldSpaceFitter:
                 self.num_iters_first if seq_ind == 0 else self.num_iters_followup)
             preserve_all = int(seq_ind > 0)
         lbfgs = self.use_lbfgs if use_lbfgs is None else use_lbfgs
+        keep_pose = _f32(preserve_pose, dev)
         res = self._run_fit(B, targets, conf, conf_pf, pose, betas, transl, expr if self.has_expr else None,
-                            _f32(preserve_pose, dev), frame_iters, frame_preserve, preserve_all, budget,
+                            keep_pose, frame_iters, frame_preserve, preserve_all, budget,
                             nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight, pose_preserve_weight,
                             freeze_betas)
         params = {"global_orient": res["pose"][:, :3], "body_pose": res["pose"][:, 3:], "betas": res["betas"],

@@ -132,7 +132,8 @@ extern "C" int k2b_model_create(const k2b_model_desc* d, k2b_model** out) {
 
 namespace {
 int fit_grid(const k2b_model* m, long num_frames) {
-  const long tiles = (num_frames + kFitThreads - 1) / kFitThreads;
+  const int nt = fit_threads_rt(m->num_shape);
+  const long tiles = (num_frames + nt - 1) / nt;
   return (int)(tiles < m->num_sms ? tiles : m->num_sms);
 }
 
@@ -172,7 +173,7 @@ extern "C" size_t k2b_fit_workspace_bytes(const k2b_model* m, int64_t num_frames
   const int grid = fit_grid(m, num_frames);
   const int mode = optimizer == K2B_OPT_LBFGS ? kModeLbfgs : kModeAdam;
   const long rows = scratch_rows(m->num_shape, mode, lbfgs_history_capacity(max_iters));
-  return (size_t)rows * grid * kFitThreads * sizeof(float);
+  return (size_t)rows * grid * fit_threads_rt(m->num_shape) * sizeof(float);
 }
 
 extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* stream) {
@@ -193,7 +194,7 @@ extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* st
   p.tab = DeviceTables{m->chol, m->mu, m->nlw, m->rel};
   p.num_frames = a->num_frames;
   const int grid = fit_grid(m, a->num_frames);
-  p.stride = (long)grid * kFitThreads;
+  p.stride = (long)grid * fit_threads_rt(m->num_shape);
   p.num_obs = a->num_obs;
   p.num_iters = a->num_iters;
   p.freeze_betas = a->freeze_betas;
@@ -225,12 +226,12 @@ extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, vo
       !a->out_grad_betas || !a->out_grad_transl)
     return fail(K2B_EINVAL, "missing required array");
   const int grid = fit_grid(m, a->num_frames);
-  const size_t need = (size_t)scratch_rows(m->num_shape, kModeEval, 0) * grid * kFitThreads * sizeof(float);
+  const size_t need = (size_t)scratch_rows(m->num_shape, kModeEval, 0) * grid * fit_threads_rt(m->num_shape) * sizeof(float);
   if (!a->workspace || a->workspace_bytes < need) return fail(K2B_ENOMEM, "workspace too small");
   FitParams p{};
   p.tab = DeviceTables{m->chol, m->mu, m->nlw, m->rel};
   p.num_frames = a->num_frames;
-  p.stride = (long)grid * kFitThreads;
+  p.stride = (long)grid * fit_threads_rt(m->num_shape);
   p.num_obs = a->num_obs;
   p.conf_per_frame = a->conf_per_frame;
   p.preserve_all = a->preserve_all;

@@ -35,12 +35,13 @@ constexpr int kMaxFitJoints = 24;
 constexpr int kTranslOff = 72;   // x layout: [go 3 | body 69 | transl 3 | shape NS]
 constexpr int kShapeOff = 75;    // shape = [betas 10 | expression 10 (NS == 20)]
 
-// Packed lower-triangular Cholesky factor: row j holds L[j][0..j], padded to a
-// multiple of 4 floats so every row starts 16-byte aligned.
-K2B_HD constexpr int chol_row_off(int j) {
-  return 8 * (j / 4) * (j / 4 + 1) + 4 * (j % 4) * (j / 4 + 1);
-}
-constexpr int kCholStride = 2520;  // chol_row_off(68) + 72
+// Packed lower-triangular Cholesky factor in 9 row panels of 8 rows (the last has 5): every
+// row of panel p stores L[j][0 .. 8(p+1)-1] (structural zeros above the diagonal kept), so a
+// panel is a dense 8 x 8(p+1) block and the kernels walk it with a rolled row loop and a
+// statically unrolled column loop.  2664 floats per component (2415 non-zeros).
+K2B_HD constexpr int chol_panel_off(int p) { return 32 * p * (p + 1); }
+K2B_HD constexpr int chol_row_off(int j) { return chol_panel_off(j / 8) + (j % 8) * 8 * (j / 8 + 1); }
+constexpr int kCholStride = 2664;
 constexpr int kMuStride = 72;
 
 constexpr float kSigma2 = 100.f * 100.f;               // gmof sigma^2 (losses.py:33)
@@ -203,90 +204,144 @@ struct FrameConsts {
   float keep_w2;         // pose_preserve_weight^2 or 0
 };
 
-// Column accessor: element i of this frame's x / g vector.
+// Column accessor: element i of this frame's parameter vector x (shared memory on the device,
+// column stride xs) and gradient vector g (coalesced global scratch, column stride gs).
 struct Cols {
   float* x;
   float* g;
-  int stride;
-  K2B_HD float& X(int i) const { return x[i * stride]; }
-  K2B_HD float& G(int i) const { return g[i * stride]; }
+  int xs;
+  long gs;
+  K2B_HD float& X(int i) const { return x[i * xs]; }
+  K2B_HD float& G(int i) const { return g[(long)i * gs]; }
 };
 
 // ---------------------------------------------------------------------------------
 // GMM max-mixture prior on body pose (prior.py:182-195) with P_m = L_m L_m^T:
 //   q_m = ||L_m^T d||^2, d = x - mu_m;  m* = argmin(0.5 q_m + nlw_m)
 //   gradient = L_m* (L_m*^T d)
-// The best candidate's z = L^T d is parked in the (not yet used) gradient column
-// G(3..71) so only one 72-register accumulator set is live.  With with_grad the
-// final G(3..71) = kPosePriorW2 * gradient.  Returns kPosePriorW2 * min.
+// z = L^T d is accumulated in 72 registers by a rolled loop over the rows of each panel; the
+// arg-min component's z is recomputed in a 9th pass (cheaper than keeping a second register
+// set alive), then G(3..71) = kPosePriorW2 * L z.  Returns kPosePriorW2 * min.
 // ---------------------------------------------------------------------------------
+template <int P>
+K2B_HD void gmm_zpanel(const Cols& c, const float* __restrict__ Lm, const float* __restrict__ mum, float (&z)[72]) {
+  constexpr int W = 8 * (P + 1);
+  constexpr int ROWS = P < 8 ? 8 : 5;
+  const float* row = Lm + chol_panel_off(P);
+#pragma unroll 1
+  for (int r = 0; r < ROWS; ++r, row += W) {
+    const int j = 8 * P + r;
+    const float dj = c.X(3 + j) - mum[j];
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 l = r4[q];
+      z[4 * q + 0] = fmaf(l.x, dj, z[4 * q + 0]);
+      z[4 * q + 1] = fmaf(l.y, dj, z[4 * q + 1]);
+      z[4 * q + 2] = fmaf(l.z, dj, z[4 * q + 2]);
+      z[4 * q + 3] = fmaf(l.w, dj, z[4 * q + 3]);
+    }
+  }
+}
+
+template <int P>
+K2B_HD void gmm_gpanel(const Cols& c, const float* __restrict__ Lb, const float (&z)[72]) {
+  constexpr int W = 8 * (P + 1);
+  constexpr int ROWS = P < 8 ? 8 : 5;
+  const float* row = Lb + chol_panel_off(P);
+#pragma unroll 1
+  for (int r = 0; r < ROWS; ++r, row += W) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 l = r4[q];
+      a0 = fmaf(l.x, z[4 * q + 0], a0);
+      a1 = fmaf(l.y, z[4 * q + 1], a1);
+      a2 = fmaf(l.z, z[4 * q + 2], a2);
+      a3 = fmaf(l.w, z[4 * q + 3], a3);
+    }
+    c.G(3 + 8 * P + r) = kPosePriorW2 * ((a0 + a1) + (a2 + a3));
+  }
+}
+
 K2B_HD float gmm_prior(const Cols& c, const FitTables& tb, bool with_grad, int* best_m_out) {
   float best = INFINITY;
   int best_m = 0;
+  float z[72];
+  const int passes = with_grad ? kGmmM + 1 : kGmmM;
 #pragma unroll 1
-  for (int m = 0; m < kGmmM; ++m) {
+  for (int it = 0; it < passes; ++it) {
+    const int m = it < kGmmM ? it : best_m;   // last pass: recompute z of the arg-min component
     const float* __restrict__ Lm = tb.chol + m * kCholStride;
     const float* __restrict__ mum = tb.mu + m * kMuStride;
-    float z[72];
 #pragma unroll
     for (int i = 0; i < 72; ++i) z[i] = 0.f;
+    gmm_zpanel<0>(c, Lm, mum, z); gmm_zpanel<1>(c, Lm, mum, z); gmm_zpanel<2>(c, Lm, mum, z);
+    gmm_zpanel<3>(c, Lm, mum, z); gmm_zpanel<4>(c, Lm, mum, z); gmm_zpanel<5>(c, Lm, mum, z);
+    gmm_zpanel<6>(c, Lm, mum, z); gmm_zpanel<7>(c, Lm, mum, z); gmm_zpanel<8>(c, Lm, mum, z);
+    if (it < kGmmM) {
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-    for (int j = 0; j < kBodyDim; ++j) {
-      const float dj = c.X(3 + j) - mum[j];
-      const float4* row = reinterpret_cast<const float4*>(Lm + chol_row_off(j));
-#pragma unroll
-      for (int ib = 0; ib <= j / 4; ++ib) {
-        const float4 l = row[ib];
-        if (4 * ib + 0 <= j) z[4 * ib + 0] = fmaf(l.x, dj, z[4 * ib + 0]);
-        if (4 * ib + 1 <= j) z[4 * ib + 1] = fmaf(l.y, dj, z[4 * ib + 1]);
-        if (4 * ib + 2 <= j) z[4 * ib + 2] = fmaf(l.z, dj, z[4 * ib + 2]);
-        if (4 * ib + 3 <= j) z[4 * ib + 3] = fmaf(l.w, dj, z[4 * ib + 3]);
+      for (int i = 0; i < 68; i += 4) {
+        q0 = fmaf(z[i], z[i], q0); q1 = fmaf(z[i + 1], z[i + 1], q1);
+        q2 = fmaf(z[i + 2], z[i + 2], q2); q3 = fmaf(z[i + 3], z[i + 3], q3);
       }
-    }
-    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 68; i += 4) {
-      q0 = fmaf(z[i], z[i], q0); q1 = fmaf(z[i + 1], z[i + 1], q1);
-      q2 = fmaf(z[i + 2], z[i + 2], q2); q3 = fmaf(z[i + 3], z[i + 3], q3);
-    }
-    q0 = fmaf(z[68], z[68], q0);
-    const float ll = fmaf(0.5f, (q0 + q1) + (q2 + q3), tb.nlw[m]);
-    if (ll < best) {   // strict: first minimum wins, like torch.min
-      best = ll;
-      best_m = m;
-      if (with_grad) {
-#pragma unroll
-        for (int i = 0; i < kBodyDim; ++i) c.G(3 + i) = z[i];
+      q0 = fmaf(z[68], z[68], q0);
+      const float ll = fmaf(0.5f, (q0 + q1) + (q2 + q3), tb.nlw[m]);
+      if (ll < best) {   // strict: first minimum wins, like torch.min
+        best = ll;
+        best_m = m;
       }
     }
   }
   if (best_m_out) *best_m_out = best_m;
   if (with_grad) {
-    float zb[72];
-#pragma unroll
-    for (int i = 0; i < kBodyDim; ++i) zb[i] = c.G(3 + i);
     const float* __restrict__ Lb = tb.chol + best_m * kCholStride;
-#pragma unroll
-    for (int i = 0; i < kBodyDim; ++i) {
-      const float4* row = reinterpret_cast<const float4*>(Lb + chol_row_off(i));
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int ib = 0; ib <= i / 4; ++ib) {
-        const float4 l = row[ib];
-        if (4 * ib + 0 <= i) a0 = fmaf(l.x, zb[4 * ib + 0], a0);
-        if (4 * ib + 1 <= i) a1 = fmaf(l.y, zb[4 * ib + 1], a1);
-        if (4 * ib + 2 <= i) a2 = fmaf(l.z, zb[4 * ib + 2], a2);
-        if (4 * ib + 3 <= i) a3 = fmaf(l.w, zb[4 * ib + 3], a3);
-      }
-      c.G(3 + i) = kPosePriorW2 * ((a0 + a1) + (a2 + a3));
-    }
+    gmm_gpanel<0>(c, Lb, z); gmm_gpanel<1>(c, Lb, z); gmm_gpanel<2>(c, Lb, z);
+    gmm_gpanel<3>(c, Lb, z); gmm_gpanel<4>(c, Lb, z); gmm_gpanel<5>(c, Lb, z);
+    gmm_gpanel<6>(c, Lb, z); gmm_gpanel<7>(c, Lb, z); gmm_gpanel<8>(c, Lb, z);
   }
   return kPosePriorW2 * best;
 }
 
 // ---------------------------------------------------------------------------------
-// Kinematic chain: forward, residuals, world-frame backward.
+// Kinematic tree: rolled walk with O(1) state.
+//
+// A chain is walked forward to its tail keeping only the running (Rw, t); on the way back the
+// parent's state is reconstructed from the child's -- Rw_p = Rw_j R_j^T, t_p = t_j - Rw_p rel_j --
+// so no per-joint state is stored.  Residuals (loss and gradient) are evaluated on the way
+// back, where every joint is visited exactly once.
+// Tree (SMPL body, identical in SMPL / SMPL-H / SMPL-X): root 0; legs {1,4,7,10}+side from the
+// root; spine 3 -> 6 -> 9; neck {12,15} and arms {13,16,18,20,(22)}+side from joint 9.
 // ---------------------------------------------------------------------------------
+enum ChainType { kSpine = 0, kNeck = 1, kArm = 2, kLeg = 3 };
+
+K2B_HD int chain_joint(int type, int side, int k) {
+  if (type == kSpine) return 3 + 3 * k;
+  if (type == kNeck) return 12 + 3 * k;
+  if (type == kLeg) return 1 + side + 3 * k;
+  return 13 + side + (k ? 1 + 2 * k : 0);
+}
+
+struct KinState {
+  M3 R;   // world rotation of the current joint (of its parent while standing on a leaf)
+  V3 t;   // position of the current joint, translation not yet added
+};
+
+template <int NS>
+struct KinCtx {
+  const Cols& c;
+  const FitTables& tb;
+  const FrameConsts& fc;
+  float shape[NS];
+  float shape_bar[NS];
+  V3 transl;
+  float loss;
+  bool with_grad;
+  float* joints_out;
+};
+
 template <int NS>
 K2B_HD V3 rel_offset(const FitTables& tb, int j, const float (&shape)[NS]) {
   const float4* e = tb.rel + j * (1 + NS);
@@ -302,39 +357,35 @@ K2B_HD V3 rel_offset(const FitTables& tb, int j, const float (&shape)[NS]) {
   return v3(x, y, z);
 }
 
-// d loss / d shape accumulates straight into the gradient column (keeps registers free)
 template <int NS>
-K2B_HD void rel_offset_bwd(const Cols& c, const FitTables& tb, int j, V3 rb) {
+K2B_HD void rel_offset_bwd(const FitTables& tb, int j, V3 rb, float (&shape_bar)[NS]) {
   const float4* e = tb.rel + j * (1 + NS);
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const float4 d = e[1 + s];
-    c.G(kShapeOff + s) = fmaf(d.x, rb.x, fmaf(d.y, rb.y, fmaf(d.z, rb.z, c.G(kShapeOff + s))));
+    shape_bar[s] = fmaf(d.x, rb.x, fmaf(d.y, rb.y, fmaf(d.z, rb.z, shape_bar[s])));
   }
 }
 
-struct KinAcc {
-  V3 transl;
-  float loss;
-};
+K2B_HD V3 load_rot(const Cols& c, int j) { return v3(c.X(3 * j), c.X(3 * j + 1), c.X(3 * j + 2)); }
 
-// Residual of joint j at position t (transl not yet added): accumulates the loss, returns
-// the gradient w.r.t. the joint position (zero when !with_grad).
-K2B_HD V3 residual(const FrameConsts& fc, int j, V3 t, KinAcc& ks, bool with_grad, float* joints_out) {
-  const V3 p = t + ks.transl;
-  if (joints_out) {
-    joints_out[3 * j + 0] = p.x;
-    joints_out[3 * j + 1] = p.y;
-    joints_out[3 * j + 2] = p.z;
+// Residual of joint j at position t: accumulates the loss, returns d loss / d position.
+template <int NS>
+K2B_HD V3 residual(KinCtx<NS>& k, int j, V3 t) {
+  const V3 p = t + k.transl;
+  if (k.joints_out) {
+    k.joints_out[3 * j + 0] = p.x;
+    k.joints_out[3 * j + 1] = p.y;
+    k.joints_out[3 * j + 2] = p.z;
   }
+  const FrameConsts& fc = k.fc;
   const float w = fc.wgt[j * fc.stride];
   const float ex = p.x - fc.tgt[(3 * j + 0) * fc.stride];
   const float ey = p.y - fc.tgt[(3 * j + 1) * fc.stride];
   const float ez = p.z - fc.tgt[(3 * j + 2) * fc.stride];
   const float ix = fdiv(1.f, kSigma2 + ex * ex), iy = fdiv(1.f, kSigma2 + ey * ey), iz = fdiv(1.f, kSigma2 + ez * ez);
   const float gx = kSigma2 * ex * ex * ix, gy = kSigma2 * ey * ey * iy, gz = kSigma2 * ez * ez * iz;
-  ks.loss = fmaf(w, (gx + gy) + gz, ks.loss);
-  if (!with_grad) return v3(0.f, 0.f, 0.f);
+  k.loss = fmaf(w, (gx + gy) + gz, k.loss);
   const float c2 = 2.f * kSigma2 * kSigma2 * w;
   return v3(c2 * ex * ix * ix, c2 * ey * iy * iy, c2 * ez * iz * iz);
 }
@@ -348,39 +399,82 @@ K2B_HD M3 rot_grad(const Acc& a, const M3& Rp, const M3& Rw, V3 t) {
   return matmul(matmul_tn(Rp, M), Rw);
 }
 
-K2B_HD V3 load_rot(const Cols& c, int j) { return v3(c.X(3 * j), c.X(3 * j + 1), c.X(3 * j + 2)); }
-K2B_HD void add_rot_grad(const Cols& c, int j, V3 rb) {
-  c.G(3 * j + 0) += rb.x;
-  c.G(3 * j + 1) += rb.y;
-  c.G(3 * j + 2) += rb.z;
+// A B^T
+K2B_HD M3 matmul_nt(const M3& A, const M3& B) {
+  M3 C;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      C.m[3 * i + j] = fmaf(A.m[3 * i], B.m[3 * j], fmaf(A.m[3 * i + 1], B.m[3 * j + 1], A.m[3 * i + 2] * B.m[3 * j + 2]));
+  return C;
+}
+
+// Forward: advance `s` from the chain's base to its tail joint.
+template <int NS>
+K2B_HD void chain_fwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail, KinState& s) {
+#pragma unroll 1
+  for (int i = 0; i < len; ++i) {
+    const int j = chain_joint(type, side, i);
+    s.t = matvec(s.R, rel_offset<NS>(k.tb, j, k.shape)) + s.t;
+    if (!(leaf_tail && i == len - 1)) {
+      Rod o;
+      s.R = matmul(s.R, rodrigues(load_rot(k.c, j), o));
+    }
+  }
+}
+
+// Backward: `s` stands on the tail; `a` holds the subtree sums of the tail's children (zero for a
+// leaf).  Walks back to the base, emitting losses / gradients; returns with `a` = chain sums.
+template <int NS>
+K2B_HD void chain_bwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail, KinState& s, Acc& a) {
+#pragma unroll 1
+  for (int i = len - 1; i >= 0; --i) {
+    const int j = chain_joint(type, side, i);
+    const bool has_rot = !(leaf_tail && i == len - 1);
+    M3 Rp = s.R;
+    V3 r = v3(0.f, 0.f, 0.f);
+    Rod o;
+    if (has_rot) {
+      r = load_rot(k.c, j);
+      Rp = matmul_nt(s.R, rodrigues(r, o));    // Rw_p = Rw_j R_j^T
+    }
+    const V3 g = residual<NS>(k, j, s.t);
+    if (k.with_grad) {
+      acc_point(a, g, s.t);
+      rel_offset_bwd<NS>(k.tb, j, matvec_t(Rp, a.s), k.shape_bar);
+      if (has_rot) {
+        const V3 rb = rodrigues_bwd(rot_grad(a, Rp, s.R, s.t), r, o);
+        k.c.G(3 * j + 0) += rb.x;
+        k.c.G(3 * j + 1) += rb.y;
+        k.c.G(3 * j + 2) += rb.z;
+      }
+    }
+    s.t = s.t - matvec(Rp, rel_offset<NS>(k.tb, j, k.shape));
+    s.R = Rp;
+  }
 }
 
 // ---------------------------------------------------------------------------------
 // One function evaluation for one frame (K observed joints: 22 AMASS / 24 SMPL24).
 // with_grad fills G(0 .. 75+NS) completely; with_priors = false skips every prior term
 // (joints-only final forward).  Returns the total loss (losses.py:41-67).
-// Tree walk: root -> spine (3,6,9) forward -> neck (12,15) -> four limbs in one rolled
-// loop (legs hang from the root, arms from joint 9) -> spine backward -> root backward.
 // ---------------------------------------------------------------------------------
 template <int NS, int K>
 K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& fc, bool with_grad,
                         bool with_priors, float* joints_out, int* gmm_component) {
-  constexpr int LEN = (K == 24) ? 5 : 4;   // joints per limb chain (arms gain the hand joint)
+  constexpr int ARM_LEN = (K == 24) ? 5 : 4;
   float loss = 0.f;
-  float shape[NS];
-#pragma unroll
-  for (int s = 0; s < NS; ++s) shape[s] = c.X(kShapeOff + s);
-
   if (with_priors) {
     loss = gmm_prior(c, tb, with_grad, gmm_component);
     // angle prior (losses.py:13-21) on body-pose entries 52, 55, 9, 12 with signs +,-,-,-
-    const int idx[4] = {52, 55, 9, 12};
-    const float sgn[4] = {1.f, -1.f, -1.f, -1.f};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float e = expf(c.X(3 + idx[q]) * sgn[q]);
+      const int idx = q == 0 ? 52 : (q == 1 ? 55 : (q == 2 ? 9 : 12));
+      const float sgn = q == 0 ? 1.f : -1.f;
+      const float e = expf(c.X(3 + idx) * sgn);
       loss = fmaf(kAnglePriorW2, e * e, loss);
-      if (with_grad) c.G(3 + idx[q]) += 2.f * kAnglePriorW2 * sgn[q] * e * e;
+      if (with_grad) c.G(3 + idx) += 2.f * kAnglePriorW2 * sgn * e * e;
     }
     // temporal pose-preserve term (losses.py:57-59), active when seq_ind > 0
     if (fc.keep_w2 != 0.f) {
@@ -393,133 +487,75 @@ K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& f
       }
       loss = fmaf(fc.keep_w2, acc, loss);
     }
-    // shape prior on betas only (losses.py:56)
-    float acc = 0.f;
-#pragma unroll
-    for (int s = 0; s < 10; ++s) acc = fmaf(shape[s], shape[s], acc);
-    loss = fmaf(kShapePriorW2, acc, loss);
-  }
-  if (with_grad) {
-#pragma unroll
-    for (int s = 0; s < NS; ++s) c.G(kShapeOff + s) = (with_priors && s < 10) ? 2.f * kShapePriorW2 * shape[s] : 0.f;
+  } else if (with_grad) {
+#pragma unroll 3
+    for (int i = 0; i < kBodyDim; ++i) c.G(3 + i) = 0.f;
   }
 
-  KinAcc ks;
-  ks.transl = v3(c.X(kTranslOff), c.X(kTranslOff + 1), c.X(kTranslOff + 2));
-  ks.loss = 0.f;
+  KinCtx<NS> k{c, tb, fc};
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    k.shape[s] = c.X(kShapeOff + s);
+    k.shape_bar[s] = 0.f;
+  }
+  k.transl = v3(c.X(kTranslOff), c.X(kTranslOff + 1), c.X(kTranslOff + 2));
+  k.loss = 0.f;
+  k.with_grad = with_grad;
+  k.joints_out = joints_out;
+  if (with_priors) {   // shape prior on betas only (losses.py:56)
+    float acc = 0.f;
+#pragma unroll
+    for (int s = 0; s < 10; ++s) acc = fmaf(k.shape[s], k.shape[s], acc);
+    loss = fmaf(kShapePriorW2, acc, loss);
+  }
 
   // ---- root ---------------------------------------------------------------------------
   Rod o0;
-  const M3 R0 = rodrigues(load_rot(c, 0), o0);
-  const V3 t0 = rel_offset<NS>(tb, 0, shape);
-  const V3 g0 = residual(fc, 0, t0, ks, with_grad, joints_out);
-  Acc a0{zero3(), v3(0.f, 0.f, 0.f)};
+  const V3 r0 = load_rot(c, 0);
+  KinState root;
+  root.R = rodrigues(r0, o0);
+  root.t = rel_offset<NS>(tb, 0, k.shape);
 
-  // ---- spine forward: 3 -> 6 -> 9 ---------------------------------------------------------
-  M3 Rs[3];
-  V3 ts[3], gs[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int j = 3 + 3 * k;
-    const M3& Rp = k == 0 ? R0 : Rs[k - 1];
-    const V3 tp = k == 0 ? t0 : ts[k - 1];
-    ts[k] = matvec(Rp, rel_offset<NS>(tb, j, shape)) + tp;
-    Rod o;
-    Rs[k] = matmul(Rp, rodrigues(load_rot(c, j), o));
-    gs[k] = residual(fc, j, ts[k], ks, with_grad, joints_out);
-  }
+  // ---- spine forward to joint 9, then everything hanging from it ---------------------------
+  KinState j9 = root;
+  chain_fwd<NS>(k, kSpine, 0, 3, false, j9);
   Acc a9{zero3(), v3(0.f, 0.f, 0.f)};
-
-  // ---- neck 12 -> head 15 (leaf) ----------------------------------------------------------
-  {
-    const V3 t12 = matvec(Rs[2], rel_offset<NS>(tb, 12, shape)) + ts[2];
-    Rod o12;
-    const V3 r12 = load_rot(c, 12);
-    const M3 R12 = matmul(Rs[2], rodrigues(r12, o12));
-    const V3 g12 = residual(fc, 12, t12, ks, with_grad, joints_out);
-    const V3 t15 = matvec(R12, rel_offset<NS>(tb, 15, shape)) + t12;
-    const V3 g15 = residual(fc, 15, t15, ks, with_grad, joints_out);
-    if (with_grad) {
-      Acc a{zero3(), v3(0.f, 0.f, 0.f)};
-      acc_point(a, g15, t15);
-      rel_offset_bwd<NS>(c, tb, 15, matvec_t(R12, a.s));
-      acc_point(a, g12, t12);
-      rel_offset_bwd<NS>(c, tb, 12, matvec_t(Rs[2], a.s));
-      add_rot_grad(c, 12, rodrigues_bwd(rot_grad(a, Rs[2], R12, t12), r12, o12));
-      acc_add(a9, a);
-    }
-  }
-
-  // ---- limbs: legs {1,4,7,10}+side from the root, arms {13,16,18,20,(22)}+side from joint 9 ---
+  Acc a0{zero3(), v3(0.f, 0.f, 0.f)};
 #pragma unroll 1
-  for (int limb = 0; limb < 4; ++limb) {
-    const bool arm = limb >= 2;
-    const int side = limb & 1;
-    int id[LEN];
-    id[0] = (arm ? 13 : 1) + side;
-    id[1] = id[0] + 3;
-    id[2] = id[0] + (arm ? 5 : 6);
-    id[3] = id[0] + (arm ? 7 : 9);
-    if (LEN == 5) id[4] = arm ? id[0] + 9 : id[3];   // legs have no 5th joint: masked below
-    M3 Rp0;
-    V3 tp0;
+  for (int ch = 0; ch < 5; ++ch) {          // neck, left arm, right arm, left leg, right leg
+    const bool from9 = ch < 3;
+    const int type = ch == 0 ? kNeck : (ch < 3 ? kArm : kLeg);
+    const int side = ch == 0 ? 0 : ((ch - 1) & 1);
+    const int len = ch == 0 ? 2 : (ch < 3 ? ARM_LEN : 4);
+    KinState s;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Rp0.m[i] = arm ? Rs[2].m[i] : R0.m[i];
-    tp0 = arm ? ts[2] : t0;
-
-    M3 Rw[LEN - 1];
-    V3 t[LEN], gb[LEN];
-    Rod rod[LEN - 1];
-#pragma unroll
-    for (int k = 0; k < LEN; ++k) {
-      const bool live = (LEN == 4) || k < 4 || arm;   // 5th joint exists on arms only
-      const M3& Rp = k == 0 ? Rp0 : Rw[k - 1];
-      const V3 tp = k == 0 ? tp0 : t[k - 1];
-      t[k] = matvec(Rp, rel_offset<NS>(tb, id[k], shape)) + tp;
-      if (k < LEN - 1) Rw[k] = matmul(Rp, rodrigues(load_rot(c, id[k]), rod[k]));
-      gb[k] = live ? residual(fc, id[k], t[k], ks, with_grad, joints_out) : v3(0.f, 0.f, 0.f);
-    }
+    for (int i = 0; i < 9; ++i) s.R.m[i] = from9 ? j9.R.m[i] : root.R.m[i];
+    s.t = from9 ? j9.t : root.t;
+    chain_fwd<NS>(k, type, side, len, true, s);
+    Acc a{zero3(), v3(0.f, 0.f, 0.f)};
+    chain_bwd<NS>(k, type, side, len, true, s, a);
     if (with_grad) {
-      Acc a{zero3(), v3(0.f, 0.f, 0.f)};
-#pragma unroll
-      for (int k = LEN - 1; k >= 0; --k) {
-        const bool live = (LEN == 4) || k < 4 || arm;
-        const M3& Rp = k == 0 ? Rp0 : Rw[k - 1];
-        acc_point(a, gb[k], t[k]);
-        if (live) rel_offset_bwd<NS>(c, tb, id[k], matvec_t(Rp, a.s));
-        if (k < LEN - 1 && (LEN == 4 || k < 3 || arm))
-          add_rot_grad(c, id[k], rodrigues_bwd(rot_grad(a, Rp, Rw[k], t[k]), load_rot(c, id[k]), rod[k]));
-      }
-      if (arm) acc_add(a9, a); else acc_add(a0, a);
+      if (from9) acc_add(a9, a); else acc_add(a0, a);
     }
   }
-  loss += ks.loss;
-
+  // ---- spine backward 9 -> 6 -> 3, then the root -------------------------------------------
+  chain_bwd<NS>(k, kSpine, 0, 3, false, j9, a9);
+  const V3 g0 = residual<NS>(k, 0, root.t);
+  loss += k.loss;
   if (with_grad) {
-    // ---- spine backward 9 -> 6 -> 3 (Rodrigues terms recomputed: cheaper than holding them) ----
-    Acc a = a9;
-#pragma unroll
-    for (int k = 2; k >= 0; --k) {
-      const int j = 3 + 3 * k;
-      const M3& Rp = k == 0 ? R0 : Rs[k - 1];
-      acc_point(a, gs[k], ts[k]);
-      rel_offset_bwd<NS>(c, tb, j, matvec_t(Rp, a.s));
-      const V3 r = load_rot(c, j);
-      Rod o;
-      (void)rodrigues(r, o);
-      add_rot_grad(c, j, rodrigues_bwd(rot_grad(a, Rp, Rs[k], ts[k]), r, o));
-    }
-    acc_add(a0, a);
-    // ---- root: Rw_p = I, rel_0 = J_0 ----------------------------------------------------
-    acc_point(a0, g0, t0);
-    rel_offset_bwd<NS>(c, tb, 0, a0.s);
-    const V3 rb = rodrigues_bwd(rot_grad(a0, eye3(), R0, t0), load_rot(c, 0), o0);
+    acc_add(a0, a9);
+    acc_point(a0, g0, root.t);
+    rel_offset_bwd<NS>(tb, 0, a0.s, k.shape_bar);           // Rw_p = I, rel_0 = J_0
+    const V3 rb = rodrigues_bwd(rot_grad(a0, eye3(), root.R, root.t), r0, o0);
     c.G(0) = rb.x;
     c.G(1) = rb.y;
     c.G(2) = rb.z;
     c.G(kTranslOff) = a0.s.x;
     c.G(kTranslOff + 1) = a0.s.y;
     c.G(kTranslOff + 2) = a0.s.z;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      c.G(kShapeOff + s) = (with_priors && s < 10) ? fmaf(2.f * kShapePriorW2, k.shape[s], k.shape_bar[s]) : k.shape_bar[s];
   }
   return loss;
 }

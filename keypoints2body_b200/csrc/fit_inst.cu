@@ -19,7 +19,7 @@ cudaError_t launch_fit<K2B_NS, K2B_K, K2B_MODE>(const FitParams& p, const AdamTa
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, kFitThreads, smem, st>>>(p, at);
+  kern<<<grid, fit_threads<K2B_NS>(), smem, st>>>(p, at);
   return cudaGetLastError();
 }
 

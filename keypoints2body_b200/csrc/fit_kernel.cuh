@@ -1,14 +1,15 @@
 // fit_kernel.cuh -- the fused, persistent fitting kernel (K1).
 //
-// Mapping: one thread = one frame, one CTA = kFitThreads frames, grid = #SMs, CTAs loop
-// over frame tiles.  Shared memory holds (a) the tables every frame shares -- the packed
-// Cholesky factors of the 8 mixture precisions, the mixture means, the rest-pose joint
-// offset table -- loaded once per CTA, and (b) the per-frame parameter vector x and
-// gradient g as columns [element][thread] (bank-conflict free, no block-level
-// synchronisation after the table load).  Iterations run inside the kernel, so x never
-// leaves shared memory between optimiser steps; Adam moments / L-BFGS vectors and the
-// per-frame observations live in a transposed (coalesced) global scratch that stays
-// L2-resident for the frames in flight.
+// Mapping: one thread = one frame, one CTA = fit_threads<NS>() frames (384: 12 warps, the most
+// that fits next to the tables), grid = #SMs, CTAs loop over frame tiles.  Shared memory holds
+// (a) the tables every frame shares -- the panel-packed Cholesky factors of the 8 mixture
+// precisions (85 KB), the mixture means, the rest-pose joint offset table -- loaded once per
+// CTA, and (b) the per-frame parameter vector x as columns [element][thread] (bank-conflict
+// free; no block-level synchronisation after the table load, so warps drift apart and overlap
+// each other's latencies).  Iterations run inside the kernel, so x never leaves shared memory
+// between optimiser steps.  The gradient, Adam moments / L-BFGS vectors and the per-frame
+// observations live in a transposed global scratch with one column per RESIDENT thread
+// (coalesced; ~25 MB per GPU for Adam, L2-resident), not per frame.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -18,7 +19,11 @@
 
 namespace k2b {
 
-constexpr int kFitThreads = 128;
+template <int NS>
+struct FitThreads { static constexpr int value = NS == 20 ? 320 : 384; };
+template <int NS>
+__host__ __device__ constexpr int fit_threads() { return FitThreads<NS>::value; }
+inline int fit_threads_rt(int ns) { return ns == 20 ? 320 : 384; }
 constexpr int kAdamTable = 256;
 
 enum FitMode { kModeEval = 0, kModeAdam = 1, kModeLbfgs = 2 };
@@ -33,7 +38,7 @@ struct DeviceTables {      // global-memory copies owned by k2b_model
 struct FitParams {
   DeviceTables tab;
   long num_frames;
-  long stride;             // scratch column stride = gridDim.x * kFitThreads (scratch is per resident thread)
+  long stride;             // scratch column stride = gridDim.x * threads (scratch is per resident thread)
   int num_obs;
   int num_iters;
   int freeze_betas;
@@ -58,12 +63,13 @@ struct AdamTable {
   float bc2[kAdamTable];   // sqrt(1 - 0.999^k)
 };
 
-// scratch rows (each row is `stride` floats): targets 72, weights 24, preserve 69, then
-// optimiser state.
+// scratch rows (each row is `stride` floats): targets 72, weights 24, preserve 69, gradient
+// 95, then optimiser state.
 constexpr int kScrTgt = 0;
 constexpr int kScrWgt = 72;
 constexpr int kScrKeep = 96;
-constexpr int kScrOpt = 165;
+constexpr int kScrGrad = 165;
+constexpr int kScrOpt = 260;
 
 inline long scratch_rows(int ns, int mode, int hmax) {
   const int n = 75 + ns;
@@ -75,20 +81,20 @@ inline long scratch_rows(int ns, int mode, int hmax) {
 template <int NS>
 constexpr size_t fit_smem_bytes() {
   return sizeof(float) * (size_t)(kGmmM * kCholStride + kGmmM * kMuStride + kGmmM +
-                                  kMaxFitJoints * (1 + NS) * 4 + 2 * (75 + NS) * kFitThreads);
+                                  kMaxFitJoints * (1 + NS) * 4 + (75 + NS) * fit_threads<NS>());
 }
 
 template <int NS, int K, int MODE>
-__global__ void __launch_bounds__(kFitThreads, 1)
+__global__ void __launch_bounds__(fit_threads<NS>(), 1)
 fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTable at) {
   constexpr int NX = 75 + NS;
+  constexpr int kFitThreads = fit_threads<NS>();
   extern __shared__ __align__(16) float smem[];
   float* s_chol = smem;
   float* s_mu = s_chol + kGmmM * kCholStride;
   float* s_nlw = s_mu + kGmmM * kMuStride;
   float* s_rel = s_nlw + kGmmM;
   float* s_x = s_rel + kMaxFitJoints * (1 + NS) * 4;
-  float* s_g = s_x + NX * kFitThreads;
 
   const int tid = threadIdx.x;
   // ---- tables: one cooperative, vectorised copy per CTA --------------------------------
@@ -111,19 +117,19 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
   tb.mu = s_mu;
   tb.nlw = s_nlw;
   tb.rel = reinterpret_cast<const float4*>(s_rel);
-  Cols c{s_x + tid, s_g + tid, kFitThreads};
+  float* const scr = p.scratch + (long)blockIdx.x * kFitThreads + tid;   // this thread's scratch column
+  Cols c{s_x + tid, scr + kScrGrad * p.stride, kFitThreads, p.stride};
 
   const long num_tiles = (p.num_frames + kFitThreads - 1) / kFitThreads;
   for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const long f = tile * kFitThreads + tid;
     const bool valid = f < p.num_frames;
     const long fr = valid ? f : p.num_frames - 1;   // padding lanes mirror the last frame
-    float* scr = p.scratch + (long)blockIdx.x * kFitThreads + tid;
 
     // ---- load this frame: parameters -> smem columns, observations -> scratch ---------
     {
       const float* ip = p.init_pose + fr * kPoseDim;
-#pragma unroll 8
+#pragma unroll 4
       for (int i = 0; i < kPoseDim; ++i) c.X(i) = ip[i];
 #pragma unroll
       for (int i = 0; i < 3; ++i) c.X(kTranslOff + i) = p.init_transl[fr * 3 + i];
@@ -134,7 +140,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         for (int i = 0; i < 10; ++i) c.X(kShapeOff + 10 + i) = p.init_expr[fr * 10 + i];
       }
       const float* tg = p.targets + fr * K * 3;
-#pragma unroll 6
+#pragma unroll 2
       for (int i = 0; i < K * 3; ++i) scr[(kScrTgt + i) * p.stride] = tg[i];
 #pragma unroll 2
       for (int j = 0; j < K; ++j) {
@@ -254,7 +260,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
 
     if (valid) {
       float* op = p.out_pose + f * kPoseDim;
-#pragma unroll 8
+#pragma unroll 4
       for (int i = 0; i < kPoseDim; ++i) op[i] = c.X(i);
       for (int i = 0; i < 3; ++i) p.out_transl[f * 3 + i] = c.X(kTranslOff + i);
       for (int i = 0; i < 10; ++i) p.out_betas[f * 10 + i] = c.X(kShapeOff + i);

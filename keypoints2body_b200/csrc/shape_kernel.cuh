@@ -120,7 +120,7 @@ shape_pass_kernel(const __grid_constant__ ShapeParams p) {
   if (lane < 10) x[lane] = p.init_betas[seq * 10 + lane];
   __syncwarp();
 
-  Cols c{x, g, 1};
+  Cols c{x, g, 1, 1};
   Vecs v{p.scratch + (long)seq * Vecs::floats_per_frame(10, p.hmax), 1, 10, p.hmax};
   Lbfgs st;
   st.done = false;

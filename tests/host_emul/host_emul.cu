@@ -77,7 +77,7 @@ extern "C" int emu_fit(void* model, int mode, int B, int K, int iters, int freez
     }
     FrameConsts fc{targets + (size_t)f * K * 3, w.data(), keep_pose + (size_t)f * kBodyDim, 1,
                    (keep_on && keep_on[f]) ? keep_w * keep_w : 0.f};
-    Cols c{x.data(), g.data(), 1};
+    Cols c{x.data(), g.data(), 1, 1};
     float loss = 0.f;
     int evals = 0, comp = 0;
     float* jout = out_joints ? out_joints + (size_t)f * K * 3 : nullptr;
@@ -143,7 +143,7 @@ extern "C" int emu_linesearch_replay(double t0, double f0, float gtd0, double d_
                                      const double* resp_f, const float* resp_gtd, double* out_t, double* out_final) {
   // 1-D surrogate: n = 1, direction d = 1, gradient slot values = gtd.
   float x = 0.f, g = gtd0;
-  Cols c{&x, &g, 1};
+  Cols c{&x, &g, 1, 1};
   std::vector<float> scratch(Vecs::floats_per_frame(1, 1), 0.f);
   Vecs v{scratch.data(), 1, 1, 1};
   Lbfgs st;
@@ -168,7 +168,7 @@ extern "C" int emu_shape_pass(void* model, const int* parents, int K, int T, int
   EmuModel* m = (EmuModel*)model;
   float x[10], g[10];
   for (int s = 0; s < 10; ++s) x[s] = betas0[s];
-  Cols c{x, g, 1};
+  Cols c{x, g, 1, 1};
   const int hmax = lbfgs_history_capacity(iters);
   std::vector<float> scratch(Vecs::floats_per_frame(10, hmax), 0.f);
   Vecs v{scratch.data(), 1, 10, hmax};

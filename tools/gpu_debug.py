@@ -1,0 +1,53 @@
+"""Scratch GPU diagnostics (not part of the product or the tests)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from keypoints2body_b200 import synthetic as syn
+from keypoints2body_b200.core.fitters.world_space import WorldSpaceFitter
+from oracle import reference_port as rp
+
+g = dict(np.load("tests/golden/ref_goldens.npz"))
+w = syn.make_body_model("smpl"); gmm = syn.make_gmm(0)
+T = torch.as_tensor
+what = sys.argv[1] if len(sys.argv) > 1 else "eval"
+if what == "eval":
+    f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm)
+    tag = "eval_smpl_22_w0"
+    params = {k: T(g[f"{tag}_in_{k}"]) for k in rp.PARAM_ORDER if f"{tag}_in_{k}" in g}
+    for conf in (T(g[tag + "_in_conf"]), None, torch.ones(22)):
+        out = f.evaluate_batch(params, T(g[tag + "_in_target"]), conf)
+        print("conf", None if conf is None else conf[:3], "loss", out["loss"].cpu().numpy(), "ref", g[tag + "_loss"].reshape(-1))
+        print(" joints err", np.abs(out["joints"].cpu().numpy() - g[tag + "_joints"][:, :22]).max(), "comp", out["gmm_component"].cpu().numpy())
+    # same frames through the Adam kernel with 0 iterations -> loss not returned; use 1 iteration
+    fa = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=False)
+    o = fa.fit_batch(params, T(g[tag + "_in_target"]), T(g[tag + "_in_conf"]), seq_ind=0, num_iters=1, with_mesh=False)
+    print("adam 1-iter loss (pre-step)", o["loss"].cpu().numpy())
+if what == "time":
+    for opt in ("adam", "lbfgs"):
+        f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=opt == "lbfgs")
+        for B in (128, 148 * 128, 148 * 128 * 4):
+            mo = syn.make_motion(B, seed=3)
+            tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22).cuda()
+            init = dict(global_orient=mo["pose"][:, :3].contiguous(), body_pose=mo["pose"][:, 3:].contiguous() * 0.9,
+                        betas=torch.zeros(B, 10), transl=mo["transl"])
+            init = {k: v.cuda() for k, v in init.items()}
+            for iters in (4, 10):
+                f.fit_batch(init, tgt, None, seq_ind=1, num_iters=iters, with_mesh=False)
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                o = f.fit_batch(init, tgt, None, seq_ind=1, num_iters=iters, with_mesh=False)
+                torch.cuda.synchronize(); dt = time.perf_counter() - t0
+                ev = float(o["evals"].float().mean())
+                print(f"{opt} B={B} iters={iters} evals/frame={ev:.1f} time={dt*1e3:.2f} ms  -> {dt/ (ev+1) * 1e6:.1f} us per eval-round, {B*(ev+1)/dt/1e6:.2f} M frame-evals/s")
+if what == "prof":
+    B = 148 * 128
+    opt = sys.argv[2] if len(sys.argv) > 2 else "adam"
+    f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=opt == "lbfgs")
+    mo = syn.make_motion(B, seed=3)
+    tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22).cuda()
+    init = dict(global_orient=mo["pose"][:, :3].contiguous(), body_pose=mo["pose"][:, 3:].contiguous() * 0.9,
+                betas=torch.zeros(B, 10), transl=mo["transl"])
+    init = {k: v.cuda() for k, v in init.items()}
+    for _ in range(2):
+        o = f.fit_batch(init, tgt, None, seq_ind=1, num_iters=3, with_mesh=True)
+    torch.cuda.synchronize()
+    print("ok", float(o["loss"].mean()))
