@@ -119,6 +119,16 @@ K2B_HD float fdiv(float a, float b) {
 #endif
 }
 
+// Packed pair of FP32 multiply-adds: one FFMA2 instruction on sm_100 (Blackwell's two-wide FP32
+// FMA, half the issue slots of two FFMAs); two fmaf on the host.
+K2B_HD float2 fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+
 // ---- Rodrigues, smplx flavour: angle = ||r + 1e-8||, axis = r / angle ----------
 struct Rod {
   float inv, s, c;   // 1/theta, sin, cos  (axis k = r * inv is recomputed where needed)
@@ -224,51 +234,70 @@ struct Cols {
 // set alive), then G(3..71) = kPosePriorW2 * L z.  Returns kPosePriorW2 * min.
 // ---------------------------------------------------------------------------------
 template <int P>
-K2B_HD void gmm_zpanel(const Cols& c, const float* __restrict__ Lm, const float* __restrict__ mum, float (&z)[72]) {
+K2B_HD void gmm_zpanel(const Cols& c, const float* __restrict__ Lm, const float* __restrict__ mum, float2 (&z)[36]) {
   constexpr int W = 8 * (P + 1);
   constexpr int ROWS = P < 8 ? 8 : 5;
   const float* row = Lm + chol_panel_off(P);
-#pragma unroll 1
+  // narrow panels: unroll rows so the next row's loads overlap this row's multiply-adds
+#pragma unroll (P <= 1 ? 4 : (P <= 4 ? 2 : 1))
   for (int r = 0; r < ROWS; ++r, row += W) {
     const int j = 8 * P + r;
     const float dj = c.X(3 + j) - mum[j];
+    const float2 dj2 = make_float2(dj, dj);
     const float4* r4 = reinterpret_cast<const float4*>(row);
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
       const float4 l = r4[q];
-      z[4 * q + 0] = fmaf(l.x, dj, z[4 * q + 0]);
-      z[4 * q + 1] = fmaf(l.y, dj, z[4 * q + 1]);
-      z[4 * q + 2] = fmaf(l.z, dj, z[4 * q + 2]);
-      z[4 * q + 3] = fmaf(l.w, dj, z[4 * q + 3]);
+      z[2 * q + 0] = fma2(make_float2(l.x, l.y), dj2, z[2 * q + 0]);
+      z[2 * q + 1] = fma2(make_float2(l.z, l.w), dj2, z[2 * q + 1]);
     }
   }
 }
 
+// Rows of panel P of g = L z.  Adds, in the same pass, the other body-pose terms so the
+// gradient column is touched once: G(3+i) = kinematic part (already there) + pose-prior part
+// + temporal pose-preserve part (losses.py:57-59) + angle-prior part (losses.py:13-21).
 template <int P>
-K2B_HD void gmm_gpanel(const Cols& c, const float* __restrict__ Lb, const float (&z)[72]) {
+K2B_HD void gmm_gpanel(const Cols& c, const FrameConsts& fc, const float* __restrict__ Lb, const float2 (&z)[36],
+                       float& extra_loss) {
   constexpr int W = 8 * (P + 1);
   constexpr int ROWS = P < 8 ? 8 : 5;
   const float* row = Lb + chol_panel_off(P);
-#pragma unroll 1
+#pragma unroll (P <= 1 ? 4 : (P <= 4 ? 2 : 1))
   for (int r = 0; r < ROWS; ++r, row += W) {
+    const int i = 8 * P + r;
+    const float gk = c.G(3 + i);                      // issued early, consumed after the dot product
+    const float xi = c.X(3 + i);
+    const float keep = fc.keep_w2 != 0.f ? fc.keep[i * fc.stride] : xi;
     const float4* r4 = reinterpret_cast<const float4*>(row);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
       const float4 l = r4[q];
-      a0 = fmaf(l.x, z[4 * q + 0], a0);
-      a1 = fmaf(l.y, z[4 * q + 1], a1);
-      a2 = fmaf(l.z, z[4 * q + 2], a2);
-      a3 = fmaf(l.w, z[4 * q + 3], a3);
+      a01 = fma2(make_float2(l.x, l.y), z[2 * q + 0], a01);
+      a23 = fma2(make_float2(l.z, l.w), z[2 * q + 1], a23);
     }
-    c.G(3 + 8 * P + r) = kPosePriorW2 * ((a0 + a1) + (a2 + a3));
+    float g = fmaf(kPosePriorW2, (a01.x + a01.y) + (a23.x + a23.y), gk);
+    const float d = xi - keep;
+    extra_loss = fmaf(fc.keep_w2 * d, d, extra_loss);
+    g = fmaf(2.f * fc.keep_w2, d, g);
+    if (i == 9 || i == 12 || i == 52 || i == 55) {
+      const float sgn = i == 52 ? 1.f : -1.f;
+      const float e = expf(xi * sgn);
+      extra_loss = fmaf(kAnglePriorW2, e * e, extra_loss);
+      g = fmaf(2.f * kAnglePriorW2 * sgn, e * e, g);
+    }
+    c.G(3 + i) = g;
   }
 }
 
-K2B_HD float gmm_prior(const Cols& c, const FitTables& tb, bool with_grad, int* best_m_out) {
+// with_grad: also folds the preserve / angle terms in (see gmm_gpanel) and returns their loss in
+// `extra_loss`; without it the caller adds those terms itself.
+K2B_HD float gmm_prior(const Cols& c, const FitTables& tb, const FrameConsts& fc, bool with_grad, int* best_m_out,
+                       float& extra_loss) {
   float best = INFINITY;
   int best_m = 0;
-  float z[72];
+  float2 z[36];
   const int passes = with_grad ? kGmmM + 1 : kGmmM;
 #pragma unroll 1
   for (int it = 0; it < passes; ++it) {
@@ -276,19 +305,19 @@ K2B_HD float gmm_prior(const Cols& c, const FitTables& tb, bool with_grad, int* 
     const float* __restrict__ Lm = tb.chol + m * kCholStride;
     const float* __restrict__ mum = tb.mu + m * kMuStride;
 #pragma unroll
-    for (int i = 0; i < 72; ++i) z[i] = 0.f;
+    for (int i = 0; i < 36; ++i) z[i] = make_float2(0.f, 0.f);
     gmm_zpanel<0>(c, Lm, mum, z); gmm_zpanel<1>(c, Lm, mum, z); gmm_zpanel<2>(c, Lm, mum, z);
     gmm_zpanel<3>(c, Lm, mum, z); gmm_zpanel<4>(c, Lm, mum, z); gmm_zpanel<5>(c, Lm, mum, z);
     gmm_zpanel<6>(c, Lm, mum, z); gmm_zpanel<7>(c, Lm, mum, z); gmm_zpanel<8>(c, Lm, mum, z);
     if (it < kGmmM) {
-      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      float2 q01 = make_float2(0.f, 0.f), q23 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 68; i += 4) {
-        q0 = fmaf(z[i], z[i], q0); q1 = fmaf(z[i + 1], z[i + 1], q1);
-        q2 = fmaf(z[i + 2], z[i + 2], q2); q3 = fmaf(z[i + 3], z[i + 3], q3);
+      for (int i = 0; i < 34; i += 2) {
+        q01 = fma2(z[i], z[i], q01);
+        q23 = fma2(z[i + 1], z[i + 1], q23);
       }
-      q0 = fmaf(z[68], z[68], q0);
-      const float ll = fmaf(0.5f, (q0 + q1) + (q2 + q3), tb.nlw[m]);
+      q01.x = fmaf(z[34].x, z[34].x, q01.x);    // element 68; 69..71 are padding
+      const float ll = fmaf(0.5f, (q01.x + q01.y) + (q23.x + q23.y), tb.nlw[m]);
       if (ll < best) {   // strict: first minimum wins, like torch.min
         best = ll;
         best_m = m;
@@ -298,9 +327,11 @@ K2B_HD float gmm_prior(const Cols& c, const FitTables& tb, bool with_grad, int* 
   if (best_m_out) *best_m_out = best_m;
   if (with_grad) {
     const float* __restrict__ Lb = tb.chol + best_m * kCholStride;
-    gmm_gpanel<0>(c, Lb, z); gmm_gpanel<1>(c, Lb, z); gmm_gpanel<2>(c, Lb, z);
-    gmm_gpanel<3>(c, Lb, z); gmm_gpanel<4>(c, Lb, z); gmm_gpanel<5>(c, Lb, z);
-    gmm_gpanel<6>(c, Lb, z); gmm_gpanel<7>(c, Lb, z); gmm_gpanel<8>(c, Lb, z);
+    gmm_gpanel<0>(c, fc, Lb, z, extra_loss); gmm_gpanel<1>(c, fc, Lb, z, extra_loss);
+    gmm_gpanel<2>(c, fc, Lb, z, extra_loss); gmm_gpanel<3>(c, fc, Lb, z, extra_loss);
+    gmm_gpanel<4>(c, fc, Lb, z, extra_loss); gmm_gpanel<5>(c, fc, Lb, z, extra_loss);
+    gmm_gpanel<6>(c, fc, Lb, z, extra_loss); gmm_gpanel<7>(c, fc, Lb, z, extra_loss);
+    gmm_gpanel<8>(c, fc, Lb, z, extra_loss);
   }
   return kPosePriorW2 * best;
 }
@@ -443,12 +474,11 @@ K2B_HD void chain_bwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail
     if (k.with_grad) {
       acc_point(a, g, s.t);
       rel_offset_bwd<NS>(k.tb, j, matvec_t(Rp, a.s), k.shape_bar);
-      if (has_rot) {
-        const V3 rb = rodrigues_bwd(rot_grad(a, Rp, s.R, s.t), r, o);
-        k.c.G(3 * j + 0) += rb.x;
-        k.c.G(3 * j + 1) += rb.y;
-        k.c.G(3 * j + 2) += rb.z;
-      }
+      V3 rb = v3(0.f, 0.f, 0.f);                      // a leaf's own rotation moves nothing observed
+      if (has_rot) rb = rodrigues_bwd(rot_grad(a, Rp, s.R, s.t), r, o);
+      k.c.G(3 * j + 0) = rb.x;                          // each entry is written exactly once per evaluation
+      k.c.G(3 * j + 1) = rb.y;
+      k.c.G(3 * j + 2) = rb.z;
     }
     s.t = s.t - matvec(Rp, rel_offset<NS>(k.tb, j, k.shape));
     s.R = Rp;
@@ -465,32 +495,6 @@ K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& f
                         bool with_priors, float* joints_out, int* gmm_component) {
   constexpr int ARM_LEN = (K == 24) ? 5 : 4;
   float loss = 0.f;
-  if (with_priors) {
-    loss = gmm_prior(c, tb, with_grad, gmm_component);
-    // angle prior (losses.py:13-21) on body-pose entries 52, 55, 9, 12 with signs +,-,-,-
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = q == 0 ? 52 : (q == 1 ? 55 : (q == 2 ? 9 : 12));
-      const float sgn = q == 0 ? 1.f : -1.f;
-      const float e = expf(c.X(3 + idx) * sgn);
-      loss = fmaf(kAnglePriorW2, e * e, loss);
-      if (with_grad) c.G(3 + idx) += 2.f * kAnglePriorW2 * sgn * e * e;
-    }
-    // temporal pose-preserve term (losses.py:57-59), active when seq_ind > 0
-    if (fc.keep_w2 != 0.f) {
-      float acc = 0.f;
-#pragma unroll 3
-      for (int i = 0; i < kBodyDim; ++i) {
-        const float d = c.X(3 + i) - fc.keep[i * fc.stride];
-        acc = fmaf(d, d, acc);
-        if (with_grad) c.G(3 + i) = fmaf(2.f * fc.keep_w2, d, c.G(3 + i));
-      }
-      loss = fmaf(fc.keep_w2, acc, loss);
-    }
-  } else if (with_grad) {
-#pragma unroll 3
-    for (int i = 0; i < kBodyDim; ++i) c.G(3 + i) = 0.f;
-  }
 
   KinCtx<NS> k{c, tb, fc};
 #pragma unroll
@@ -556,6 +560,36 @@ K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& f
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       c.G(kShapeOff + s) = (with_priors && s < 10) ? fmaf(2.f * kShapePriorW2, k.shape[s], k.shape_bar[s]) : k.shape_bar[s];
+    if (K == 22) {   // body-pose entries of joints 22, 23: prior-only
+#pragma unroll
+      for (int i = 66; i < 72; ++i) c.G(i) = 0.f;
+    }
+  }
+
+  // ---- priors on the body pose (after the kinematic part of the gradient is in place) -------
+  if (with_priors) {
+    float extra = 0.f;
+    loss += gmm_prior(c, tb, fc, with_grad, gmm_component, extra);
+    if (!with_grad) {
+      // angle prior (losses.py:13-21) on body-pose entries 52, 55, 9, 12 with signs +,-,-,-
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = q == 0 ? 52 : (q == 1 ? 55 : (q == 2 ? 9 : 12));
+        const float e = expf(c.X(3 + idx) * (q == 0 ? 1.f : -1.f));
+        extra = fmaf(kAnglePriorW2, e * e, extra);
+      }
+      // temporal pose-preserve term (losses.py:57-59), active when seq_ind > 0
+      if (fc.keep_w2 != 0.f) {
+        float acc = 0.f;
+#pragma unroll 23
+        for (int i = 0; i < kBodyDim; ++i) {
+          const float d = c.X(3 + i) - fc.keep[i * fc.stride];
+          acc = fmaf(d, d, acc);
+        }
+        extra = fmaf(fc.keep_w2, acc, extra);
+      }
+    }
+    loss += extra;
   }
   return loss;
 }

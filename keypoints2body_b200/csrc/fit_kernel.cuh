@@ -210,7 +210,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
             step_k = (float)((double)p.lr / (1.0 - pow(0.9, (double)k)));
             bc2_k = (float)sqrt(1.0 - pow(0.999, (double)k));
           }
-#pragma unroll 5
+#pragma unroll 17
           for (int i = 0; i < NX; ++i) {
             if (freeze_betas && i >= kShapeOff && i < kShapeOff + 10) continue;
             float mm = m1[i * p.stride], vv = m2[i * p.stride], x = c.X(i);
@@ -229,29 +229,28 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       v.stride = p.stride;
       v.n = NX;
       v.hmax = p.lbfgs_hmax;
-      Lbfgs st;
-      st.done = false;
+      Lbfgs<NX> st;
+      st.init();
       // round 0: closure at the initial parameters; rounds while any lane is searching: one
       // closure per round; final round: loss (+ joints) at the returned parameters
-      // (world_space.py:246-247)
+      // (world_space.py:246-247).  Each closure writes its gradient into the slot the machine
+      // designates, so nothing is copied afterwards.
       int stage = 0;   // 0 first closure, 1 searching, 2 final loss
       while (true) {
         const bool fin = stage == 2;
-        const float loss = eval_frame<NS, K>(c, tb, fc, !fin, true, fin ? jout : nullptr, nullptr);
+        const Cols ce = st.eval_cols(c, v);
+        const float loss = eval_frame<NS, K>(ce, tb, fc, !fin, true, fin ? jout : nullptr, nullptr);
         if (fin) {
           out_loss = loss;
           break;
         }
         if (freeze_betas)
-          for (int i = 0; i < 10; ++i) c.G(kShapeOff + i) = 0.f;
-        if (stage == 0) {
-          st.begin(c, v, loss, iters, p.lr);
-          stage = 1;
-        } else if (!st.done) {
-          st.after_eval(c, v, loss);
-        }
+          for (int i = 0; i < 10; ++i) ce.G(kShapeOff + i) = 0.f;
+        if (stage == 0 || !st.done) st.advance(c, v, loss, stage == 0, iters, p.lr);
+        stage = 1;
         if (!__any_sync(0xffffffffu, !st.done)) {
           stage = 2;
+#pragma unroll 17
           for (int i = 0; i < NX; ++i) c.X(i) = v.at(i);
         }
       }

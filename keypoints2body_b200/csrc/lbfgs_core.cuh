@@ -36,12 +36,12 @@ struct Vecs {
   K2B_HD float& at(int e) const { return base[(long)e * stride]; }
   K2B_HD int xk() const { return 0; }
   K2B_HD int d() const { return n; }
-  K2B_HD int gslot(int s) const { return (2 + s) * n; }
-  K2B_HD int y(int h) const { return (5 + h) * n; }
-  K2B_HD int s(int h) const { return (5 + hmax + h) * n; }
-  K2B_HD int ro(int h) const { return (5 + 2 * hmax) * n + h; }
-  K2B_HD int al(int h) const { return (5 + 2 * hmax) * n + hmax + h; }
-  static K2B_HD long floats_per_frame(int n, int hmax) { return (long)(5 + 2 * hmax) * n + 2 * hmax; }
+  K2B_HD int gslot(int s) const { return (2 + s) * n; }          // 4 gradient slots
+  K2B_HD int y(int h) const { return (6 + h) * n; }
+  K2B_HD int s(int h) const { return (6 + hmax + h) * n; }
+  K2B_HD int ro(int h) const { return (6 + 2 * hmax) * n + h; }
+  K2B_HD int al(int h) const { return (6 + 2 * hmax) * n + hmax + h; }
+  static K2B_HD long floats_per_frame(int n, int hmax) { return (long)(6 + 2 * hmax) * n + 2 * hmax; }
 };
 
 K2B_HD int lbfgs_history_capacity(int max_iter) {
@@ -79,6 +79,14 @@ K2B_HD double cubic_interpolate(double x1, double f1, float g1, double x2, doubl
   return (lo + hi) / 2.0;
 }
 
+// N = optimised vector length (compile time).  Vector passes are unrolled 17-fold so a warp keeps
+// 17-34 coalesced loads in flight.
+//
+// Gradient storage: four slots in scratch.  Every evaluation writes its gradient straight into
+// slot `cur` (the caller points Cols::g at it), so keeping a gradient -- as flat_grad, g_prev or a
+// bracket end -- is a matter of remembering the slot index, never a copy.  After each evaluation
+// `cur` moves to a slot that holds nothing still needed (g0 + at most two others are ever kept).
+template <int N>
 struct Lbfgs {
   // configuration
   int max_iter, max_eval;
@@ -88,7 +96,8 @@ struct Lbfgs {
   bool done;
   double loss, prev_loss, t;
   float H_diag;
-  int g0;  // gradient slot holding flat_grad of the current iterate
+  int g0;   // slot holding flat_grad of the current iterate
+  int cur;  // slot the next evaluation writes its gradient to
   // line search
   int phase;  // 0 bracket, 1 zoom
   bool first_eval, ls_done, insuf, t_f32;
@@ -103,33 +112,69 @@ struct Lbfgs {
   int br_slot[2];
   int br_n, low, high;
 
-  K2B_HD int free_slot(int keep1, int keep2) const {
-#pragma unroll
-    for (int s = 0; s < 3; ++s)
-      if (s != g0 && s != keep1 && s != keep2) return s;
-    return (g0 + 1) % 3;  // unreachable when keep1/keep2 follow the analysis in DESIGN.md
+  // Column accessor for the next evaluation: gradient lands in slot `cur`.
+  K2B_HD Cols eval_cols(const Cols& c, const Vecs& v) const {
+    Cols e = c;
+    e.g = &v.at(v.gslot(cur));
+    e.gs = v.stride;
+    return e;
   }
 
-  K2B_HD static void store_grad(const Cols& c, const Vecs& v, int slot) {
-    const int o = v.gslot(slot);
-#pragma unroll 5
-    for (int i = 0; i < v.n; ++i) v.at(o + i) = c.G(i);
+  K2B_HD void pick_cur() {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      bool used = s == g0 || s == slot_prev_grad;
+      if (phase == 0) used = used || s == slot_prev;
+      else used = used || s == br_slot[0] || (br_n == 2 && s == br_slot[1]);
+      if (!used) {
+        cur = s;
+        return;
+      }
+    }
   }
-  K2B_HD static float dot_g_d(const Cols& c, const Vecs& v) {
-    float a = 0.f;
-    const int od = v.d();
-#pragma unroll 5
-    for (int i = 0; i < v.n; ++i) a = fmaf(c.G(i), v.at(od + i), a);
-    return a;
+
+  K2B_HD float dot_cur_d(const Vecs& v) const {
+    const int og = v.gslot(cur), od = v.d();
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) {
+      if (i & 1) a1 = fmaf(v.at(og + i), v.at(od + i), a1);
+      else a0 = fmaf(v.at(og + i), v.at(od + i), a0);
+    }
+    return a0 + a1;
   }
   K2B_HD void set_trial(const Cols& c, const Vecs& v) const {
     const float tf = (float)t;
     const int od = v.d();
-#pragma unroll 5
-    for (int i = 0; i < v.n; ++i) c.X(i) = fmaf(tf, v.at(od + i), v.at(i));
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, v.at(od + i), v.at(i));
   }
 
-  // Called once after the first evaluation at the initial parameters (loss, G valid).
+  // Drive one round after an evaluation: `first` selects begin() vs after_eval(); the outer-iteration
+  // set-up (two-loop recursion etc.) is inlined at exactly one site.
+  K2B_HD void advance(const Cols& c, const Vecs& v, float loss_f, bool first, int max_iter_, float lr_) {
+    need_outer = false;
+    if (first) begin(c, v, loss_f, max_iter_, lr_);
+    else after_eval(c, v, loss_f);
+    if (need_outer) start_outer(c, v);
+  }
+  bool need_outer;
+
+  // Before the first evaluation: its gradient goes to slot 0.
+  K2B_HD void init() {
+    done = false;
+    need_outer = false;
+    replay = false;
+    cur = 0;
+    g0 = 0;
+    slot_prev_grad = 0;
+    slot_prev = 0;
+    phase = 0;
+    br_n = 0;
+    evals = 0;
+  }
+
+  // Called once after the first evaluation at the initial parameters (loss; gradient in slot 0).
   K2B_HD void begin(const Cols& c, const Vecs& v, float loss0, int max_iter_, float lr_) {
     max_iter = max_iter_;
     max_eval = max_iter_ * 5 / 4;
@@ -144,98 +189,104 @@ struct Lbfgs {
     t = 0.0;
     H_diag = 1.f;
     g0 = 0;
-    store_grad(c, v, 0);
+    slot_prev_grad = 0;
     float gmax = 0.f;
-    for (int i = 0; i < v.n; ++i) {
+    const int og = v.gslot(0);
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) {
       v.at(i) = c.X(i);
-      gmax = fmaxf(gmax, fabsf(c.G(i)));
+      gmax = fmaxf(gmax, fabsf(v.at(og + i)));
     }
     if (max_iter_ <= 0 || (double)gmax <= kTolGrad) {
       done = true;
       return;
     }
-    start_outer(c, v);
+    need_outer = true;
   }
 
   // lbfgs.py:388-476: direction update, initial step, line-search setup, first trial point.
+  // The two-loop's running vector q lives in the (idle between evaluations) x column.
   K2B_HD void start_outer(const Cols& c, const Vecs& v) {
-    const int n = v.n, od = v.d(), og = v.gslot(g0);
+    const int od = v.d(), og = v.gslot(g0);
     ++n_iter;
     if (n_iter == 1) {
-#pragma unroll 5
-      for (int i = 0; i < n; ++i) v.at(od + i) = -v.at(og + i);
+#pragma unroll 17
+      for (int i = 0; i < N; ++i) c.X(i) = -v.at(og + i);
       H_diag = 1.f;
       num_old = 0;
       head = 0;
     } else {
-      // y = flat_grad - prev_flat_grad (still in slot g_prev_slot), s = d * t
+      // y = flat_grad - prev_flat_grad (slot slot_prev_grad), s = d * t
       const int op = v.gslot(slot_prev_grad);
       const float tf = (float)t;
-      float ys = 0.f, yy = 0.f;
-#pragma unroll 5
-      for (int i = 0; i < n; ++i) {
-        const float yi = v.at(og + i) - v.at(op + i);
+      int h = (head + num_old) % v.hmax;          // where the pair goes if it is accepted
+      if (num_old == v.hmax) h = head;
+      const int oy = v.y(h), os = v.s(h);
+      float ys0 = 0.f, ys1 = 0.f, yy0 = 0.f, yy1 = 0.f;
+#pragma unroll 17
+      for (int i = 0; i < N; ++i) {
+        const float gi = v.at(og + i);
+        const float yi = gi - v.at(op + i);
         const float si = v.at(od + i) * tf;
-        ys = fmaf(yi, si, ys);
-        yy = fmaf(yi, yi, yy);
+        c.X(i) = -gi;
+        v.at(oy + i) = yi;                        // written speculatively; committed by num_old / head
+        v.at(os + i) = si;
+        if (i & 1) { ys1 = fmaf(yi, si, ys1); yy1 = fmaf(yi, yi, yy1); }
+        else       { ys0 = fmaf(yi, si, ys0); yy0 = fmaf(yi, yi, yy0); }
       }
+      const float ys = ys0 + ys1, yy = yy0 + yy1;
       if (ys > 1e-10f) {
-        int h;
-        if (num_old == v.hmax) {  // drop the oldest pair (ring buffer)
-          h = head;
-          head = (head + 1) % v.hmax;
-        } else {
-          h = (head + num_old) % v.hmax;
-          ++num_old;
-        }
-        const int oy = v.y(h), os = v.s(h);
-#pragma unroll 5
-        for (int i = 0; i < n; ++i) {
-          v.at(oy + i) = v.at(og + i) - v.at(op + i);
-          v.at(os + i) = v.at(od + i) * tf;
-        }
+        if (num_old == v.hmax) head = (head + 1) % v.hmax;   // drop the oldest pair (ring buffer)
+        else ++num_old;
         v.at(v.ro(h)) = 1.f / ys;
         H_diag = ys / yy;
       }
-      // two-loop recursion (lbfgs.py:430-442); q lives in the direction buffer
-#pragma unroll 5
-      for (int i = 0; i < n; ++i) v.at(od + i) = -v.at(og + i);
+      // two-loop recursion (lbfgs.py:430-442)
+#pragma unroll 1
       for (int k = num_old - 1; k >= 0; --k) {
-        const int h = (head + k) % v.hmax;
-        const int oy = v.y(h), os = v.s(h);
-        float a = 0.f;
-#pragma unroll 5
-        for (int i = 0; i < n; ++i) a = fmaf(v.at(os + i), v.at(od + i), a);
-        a *= v.at(v.ro(h));
-        v.at(v.al(h)) = a;
-#pragma unroll 5
-        for (int i = 0; i < n; ++i) v.at(od + i) = fmaf(-a, v.at(oy + i), v.at(od + i));
+        const int hk = (head + k) % v.hmax;
+        const int oyk = v.y(hk), osk = v.s(hk);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 17
+        for (int i = 0; i < N; ++i) {
+          if (i & 1) a1 = fmaf(v.at(osk + i), c.X(i), a1);
+          else a0 = fmaf(v.at(osk + i), c.X(i), a0);
+        }
+        const float a = (a0 + a1) * v.at(v.ro(hk));
+        v.at(v.al(hk)) = a;
+#pragma unroll 17
+        for (int i = 0; i < N; ++i) c.X(i) = fmaf(-a, v.at(oyk + i), c.X(i));
       }
-#pragma unroll 5
-      for (int i = 0; i < n; ++i) v.at(od + i) *= H_diag;
+#pragma unroll 17
+      for (int i = 0; i < N; ++i) c.X(i) *= H_diag;
+#pragma unroll 1
       for (int k = 0; k < num_old; ++k) {
-        const int h = (head + k) % v.hmax;
-        const int oy = v.y(h), os = v.s(h);
-        float b = 0.f;
-#pragma unroll 5
-        for (int i = 0; i < n; ++i) b = fmaf(v.at(oy + i), v.at(od + i), b);
-        b *= v.at(v.ro(h));
-        const float coef = v.at(v.al(h)) - b;
-#pragma unroll 5
-        for (int i = 0; i < n; ++i) v.at(od + i) = fmaf(coef, v.at(os + i), v.at(od + i));
+        const int hk = (head + k) % v.hmax;
+        const int oyk = v.y(hk), osk = v.s(hk);
+        float b0 = 0.f, b1 = 0.f;
+#pragma unroll 17
+        for (int i = 0; i < N; ++i) {
+          if (i & 1) b1 = fmaf(v.at(oyk + i), c.X(i), b1);
+          else b0 = fmaf(v.at(oyk + i), c.X(i), b0);
+        }
+        const float coef = v.at(v.al(hk)) - (b0 + b1) * v.at(v.ro(hk));
+#pragma unroll 17
+        for (int i = 0; i < N; ++i) c.X(i) = fmaf(coef, v.at(osk + i), c.X(i));
       }
     }
     slot_prev_grad = g0;  // prev_flat_grad.copy_(flat_grad)
     prev_loss = loss;
 
-    float gsum = 0.f, gtd = 0.f, dmax = 0.f;
-#pragma unroll 5
-    for (int i = 0; i < n; ++i) {
-      const float gi = v.at(og + i), di = v.at(od + i);
+    float gsum = 0.f, gtd0a = 0.f, gtd1a = 0.f, dmax = 0.f;
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) {
+      const float gi = v.at(og + i), di = c.X(i);
+      v.at(od + i) = di;
       gsum += fabsf(gi);
-      gtd = fmaf(gi, di, gtd);
+      if (i & 1) gtd1a = fmaf(gi, di, gtd1a); else gtd0a = fmaf(gi, di, gtd0a);
       dmax = fmaxf(dmax, fabsf(di));
     }
+    const float gtd = gtd0a + gtd1a;
     if (n_iter == 1) {
       const float inv = 1.f / gsum;
       t_f32 = inv < 1.f;   // Python min(1.0, tensor) keeps the tensor only when it is smaller
@@ -264,14 +315,18 @@ struct Lbfgs {
     ls_done = false;
     insuf = false;
     br_n = 0;
-    set_trial(c, v);
+    pick_cur();
+    // first trial point: x = xk + t d with d still in the x column
+    const float tf = (float)t;
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, c.X(i), v.at(i));
   }
 
   // Process the evaluation at the current trial point (loss f_new, gradient in G).
   // Afterwards either `done` is set (parameters are in v.xk) or X holds the next trial point.
   K2B_HD void after_eval(const Cols& c, const Vecs& v, float f_new_f) {
     const double f_new = (double)f_new_f;
-    const float gtd_new = dot_g_d(c, v);
+    const float gtd_new = dot_cur_d(v);      // the evaluation wrote its gradient to slot `cur`
     ++ls_evals;
     bool finished = false;
 
@@ -281,17 +336,16 @@ struct Lbfgs {
       if (ls_iter < max_ls) {
         const bool armijo_fail = (float)f_new > (float)(f0 + (double)((float)(kC1 * t) * gtd0));
         if (armijo_fail || (ls_iter > 1 && f_new >= f_prev) ) {
-          make_bracket(c, v, f_new, gtd_new);
+          make_bracket(f_new, gtd_new);
         } else if (fabsf(gtd_new) <= -(float)kC2 * gtd0) {
           br_n = 1;
           br_t[0] = t;
           br_f[0] = f_new;
-          br_slot[0] = free_slot(slot_prev, -1);
-          store_grad(c, v, br_slot[0]);
+          br_slot[0] = cur;
           br_gtd[0] = gtd_new;
           ls_done = true;
         } else if (gtd_new >= 0.f) {
-          make_bracket(c, v, f_new, gtd_new);
+          make_bracket(f_new, gtd_new);
         } else {
           // extrapolate (lbfgs.py:76-94)
           double min_step = t + 0.01 * (t - t_prev);
@@ -305,10 +359,9 @@ struct Lbfgs {
           t = cubic_interpolate(t_prev, f_prev, gtd_prev, t, f_new, gtd_new, true, min_step, max_step, t_f32);
           t_prev = tmp;
           f_prev = f_new;
-          const int s = free_slot(-1, -1);  // old g_prev is dropped unless it is g0
-          store_grad(c, v, s);
-          slot_prev = s;
+          slot_prev = cur;                  // g_prev = g_new (the old g_prev slot becomes free)
           gtd_prev = gtd_new;
+          pick_cur();
           set_trial(c, v);
           return;  // evaluate the extrapolated point
         }
@@ -318,8 +371,7 @@ struct Lbfgs {
         br_t[0] = 0.0; br_t[1] = t;
         br_f[0] = f0;  br_f[1] = f_new;
         br_slot[0] = g0;
-        br_slot[1] = free_slot(-1, -1);
-        store_grad(c, v, br_slot[1]);
+        br_slot[1] = cur;
         br_gtd[0] = gtd0; br_gtd[1] = gtd_new;
       }
       phase = 1;
@@ -331,9 +383,7 @@ struct Lbfgs {
       ++ls_iter;
       const bool armijo_fail = (float)f_new > (float)(f0 + (double)((float)(kC1 * t) * gtd0));
       if (armijo_fail || f_new >= br_f[low]) {
-        const int s = (br_slot[high] != g0) ? br_slot[high] : free_slot(br_slot[low], -1);
-        store_grad(c, v, s);
-        br_t[high] = t; br_f[high] = f_new; br_slot[high] = s; br_gtd[high] = gtd_new;
+        br_t[high] = t; br_f[high] = f_new; br_slot[high] = cur; br_gtd[high] = gtd_new;
         low = (br_f[0] <= br_f[1]) ? 0 : 1;
         high = 1 - low;
       } else {
@@ -343,11 +393,8 @@ struct Lbfgs {
           br_t[high] = br_t[low]; br_f[high] = br_f[low];
           br_slot[high] = br_slot[low]; br_gtd[high] = br_gtd[low];
         }
-        // the new point becomes the low end; it may reuse any slot that is neither g0 nor
-        // the (possibly just reassigned) high end
-        const int s = free_slot(br_slot[high], -1);
-        store_grad(c, v, s);
-        br_t[low] = t; br_f[low] = f_new; br_slot[low] = s; br_gtd[low] = gtd_new;
+        // the new point becomes the low end
+        br_t[low] = t; br_f[low] = f_new; br_slot[low] = cur; br_gtd[low] = gtd_new;
       }
     }
 
@@ -371,6 +418,7 @@ struct Lbfgs {
           insuf = false;
         }
         t = tn;
+        pick_cur();
         set_trial(c, v);
         return;  // evaluate the zoom point
       }
@@ -395,38 +443,38 @@ struct Lbfgs {
                               int max_ls_, bool t_is_f32) {
     max_iter = 1; max_eval = max_ls_ + 1; lr = 1.f;
     n_iter = 1; evals = 1; num_old = 0; head = 0; done = false;
-    loss = f0_; prev_loss = f0_; t = t0; H_diag = 1.f; g0 = 0; slot_prev_grad = 0;
+    loss = f0_; prev_loss = f0_; t = t0; H_diag = 1.f; g0 = 0; slot_prev_grad = 0; cur = 1;
     v.at(v.xk()) = 0.f; v.at(v.d()) = 1.f; v.at(v.gslot(0)) = gtd0_;
     d_norm = d_norm_; f0 = f0_; gtd0 = gtd0_; max_ls = max_ls_; ls_evals = 0;
     t_prev = 0.0; f_prev = f0_; gtd_prev = gtd0_; slot_prev = 0; ls_iter = 0; phase = 0;
     first_eval = true; ls_done = false; insuf = false; br_n = 0; ls_replay_finished = false;
     replay = true;
     t_f32 = t_is_f32;
+    pick_cur();
     set_trial(c, v);
   }
-  bool replay = false;
+  bool replay;
 
  private:
   int slot_prev_grad;  // slot holding prev_flat_grad
 
-  K2B_HD void make_bracket(const Cols& c, const Vecs& v, double f_new, float gtd_new) {
+  K2B_HD void make_bracket(double f_new, float gtd_new) {
     br_n = 2;
     br_t[0] = t_prev; br_t[1] = t;
     br_f[0] = f_prev; br_f[1] = f_new;
     br_slot[0] = slot_prev;
-    br_slot[1] = free_slot(slot_prev, -1);
-    store_grad(c, v, br_slot[1]);
+    br_slot[1] = cur;
     br_gtd[0] = gtd_prev; br_gtd[1] = gtd_new;
   }
 
   // Line search returned: move the iterate, account evaluations, test termination,
   // and either stop or start the next outer iteration.
   K2B_HD void g0_next(const Cols& c, const Vecs& v, int new_g_slot) {
-    const int n = v.n, od = v.d();
+    const int od = v.d();
     const float tf = (float)t;
     float dtmax = 0.f;
-#pragma unroll 5
-    for (int i = 0; i < n; ++i) {
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) {
       const float di = v.at(od + i);
       v.at(i) = fmaf(tf, di, v.at(i));      // _add_grad(t, d)
       dtmax = fmaxf(dtmax, fabsf(di * tf));
@@ -436,16 +484,15 @@ struct Lbfgs {
     g0 = new_g_slot;
     float gmax = 0.f;
     const int og = v.gslot(g0);
-#pragma unroll 5
-    for (int i = 0; i < n; ++i) gmax = fmaxf(gmax, fabsf(v.at(og + i)));
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) gmax = fmaxf(gmax, fabsf(v.at(og + i)));
     if (n_iter == max_iter || evals >= max_eval || (double)gmax <= kTolGrad ||
         (double)dtmax <= kTolChange || fabs(loss - prev_loss) < kTolChange) {
       done = true;
       return;
     }
-    // prev_flat_grad (slot_prev_grad) is consumed by start_outer before any store of the next
-    // line search, and free_slot never hands out g0.
-    start_outer(c, v);
+    // prev_flat_grad (slot_prev_grad) is consumed by start_outer before the next evaluation.
+    need_outer = true;
   }
 
 };

@@ -122,8 +122,8 @@ shape_pass_kernel(const __grid_constant__ ShapeParams p) {
 
   Cols c{x, g, 1, 1};
   Vecs v{p.scratch + (long)seq * Vecs::floats_per_frame(10, p.hmax), 1, 10, p.hmax};
-  Lbfgs st;
-  st.done = false;
+  Lbfgs<10> st;
+  st.init();
   const float* conf = p.conf ? (p.conf_per_seq ? p.conf + (long)seq * p.K : p.conf) : nullptr;
   const float T = (float)p.frames_per_seq;
   int stage = 0;
@@ -153,10 +153,10 @@ shape_pass_kernel(const __grid_constant__ ShapeParams p) {
     loss = fmaf(T * p.w2, bb, loss);
     int done = 0;
     if (lane == 0) {
+      const Cols ce = st.eval_cols(c, v);
 #pragma unroll
-      for (int s = 0; s < 10; ++s) g[s] = fmaf(2.f * T * p.w2, betas[s], grad[s]);
-      if (stage == 0) st.begin(c, v, loss, p.num_iters, p.lr);
-      else st.after_eval(c, v, loss);
+      for (int s = 0; s < 10; ++s) ce.G(s) = fmaf(2.f * T * p.w2, betas[s], grad[s]);
+      st.advance(c, v, loss, stage == 0, p.num_iters, p.lr);
       done = st.done;
       if (done) {
         for (int s = 0; s < 10; ++s) x[s] = v.at(s);

@@ -50,6 +50,21 @@ extern "C" void* emu_model_create(int ns, const float* chol69, const float* mean
 }
 extern "C" void emu_model_destroy(void* m) { delete (EmuModel*)m; }
 
+// runtime dispatch over the two vector lengths the fit kernel instantiates (85 / 95)
+struct LbfgsAny {
+  int n;
+  Lbfgs<85> a;
+  Lbfgs<95> b;
+  explicit LbfgsAny(int n_) : n(n_) { a.init(); b.init(); }
+  Cols eval_cols(const Cols& c, const Vecs& v) const { return n == 85 ? a.eval_cols(c, v) : b.eval_cols(c, v); }
+  void begin(const Cols& c, const Vecs& v, float l, int it, float lr) { n == 85 ? a.advance(c, v, l, true, it, lr) : b.advance(c, v, l, true, it, lr); }
+  void after_eval(const Cols& c, const Vecs& v, float l) { n == 85 ? a.advance(c, v, l, false, 0, 0.f) : b.advance(c, v, l, false, 0, 0.f); }
+  bool done_() const { return n == 85 ? a.done : b.done; }
+  double t_() const { return n == 85 ? a.t : b.t; }
+  int evals_() const { return n == 85 ? a.evals : b.evals; }
+  float dot_cur_d(const Vecs& v) const { return n == 85 ? a.dot_cur_d(v) : b.dot_cur_d(v); }
+};
+
 template <int NS, int K>
 static float run_eval(const Cols& c, const FitTables& tb, const FrameConsts& fc, bool g, bool pr, float* j, int* comp) {
   return eval_frame<NS, K>(c, tb, fc, g, pr, j, comp);
@@ -103,24 +118,27 @@ extern "C" int emu_fit(void* model, int mode, int B, int K, int iters, int freez
       const int hmax = lbfgs_history_capacity(iters);
       std::vector<float> scratch(Vecs::floats_per_frame(NX, hmax), 0.f);
       Vecs v{scratch.data(), 1, NX, hmax};
-      Lbfgs st;
-      st.done = false;
-      loss = ev(c, tb, fc, true, true, nullptr, nullptr);
-      if (freeze_betas) for (int i = 0; i < 10; ++i) g[kShapeOff + i] = 0.f;
+      LbfgsAny st(NX);
+      {
+        const Cols ce = st.eval_cols(c, v);
+        loss = ev(ce, tb, fc, true, true, nullptr, nullptr);
+        if (freeze_betas) for (int i = 0; i < 10; ++i) ce.G(kShapeOff + i) = 0.f;
+      }
       st.begin(c, v, loss, iters, lr);
       int ntr = 0;
-      while (!st.done) {
-        const double t_trial = st.t;
-        loss = ev(c, tb, fc, true, true, nullptr, nullptr);
-        if (freeze_betas) for (int i = 0; i < 10; ++i) g[kShapeOff + i] = 0.f;
+      while (!st.done_()) {
+        const double t_trial = st.t_();
+        const Cols ce = st.eval_cols(c, v);
+        loss = ev(ce, tb, fc, true, true, nullptr, nullptr);
+        if (freeze_betas) for (int i = 0; i < 10; ++i) ce.G(kShapeOff + i) = 0.f;
         if (out_trace && ntr < 64) {
           float* tr = out_trace + ((size_t)f * 64 + ntr) * 3;
-          tr[0] = (float)t_trial; tr[1] = loss; tr[2] = Lbfgs::dot_g_d(c, v);
+          tr[0] = (float)t_trial; tr[1] = loss; tr[2] = st.dot_cur_d(v);
           ++ntr;
         }
         st.after_eval(c, v, loss);
       }
-      evals = st.evals;
+      evals = st.evals_();
       for (int i = 0; i < NX; ++i) x[i] = v.at(i);
       loss = ev(c, tb, fc, false, true, jout, nullptr);
       memcpy(out_x + (size_t)f * NX, x.data(), NX * sizeof(float));
@@ -144,14 +162,15 @@ extern "C" int emu_linesearch_replay(double t0, double f0, float gtd0, double d_
   // 1-D surrogate: n = 1, direction d = 1, gradient slot values = gtd.
   float x = 0.f, g = gtd0;
   Cols c{&x, &g, 1, 1};
-  std::vector<float> scratch(Vecs::floats_per_frame(1, 1), 0.f);
+  std::vector<float> scratch(Vecs::floats_per_frame(1, 1) + 8, 0.f);
   Vecs v{scratch.data(), 1, 1, 1};
-  Lbfgs st;
+  Lbfgs<1> st;
+  st.init();
   st.ls_replay_begin(c, v, t0, f0, gtd0, d_norm, max_ls, t_is_f32 != 0);
   int k = 0;
   while (!st.ls_replay_finished && k < n_resp) {
     out_t[k] = st.t;
-    g = resp_gtd[k];
+    st.eval_cols(c, v).G(0) = resp_gtd[k];
     st.after_eval(c, v, (float)resp_f[k]);
     ++k;
   }
@@ -172,8 +191,8 @@ extern "C" int emu_shape_pass(void* model, const int* parents, int K, int T, int
   const int hmax = lbfgs_history_capacity(iters);
   std::vector<float> scratch(Vecs::floats_per_frame(10, hmax), 0.f);
   Vecs v{scratch.data(), 1, 10, hmax};
-  Lbfgs st;
-  st.done = false;
+  Lbfgs<10> st;
+  st.init();
   int stage = 0;
   while (true) {
     float grad[10] = {0};
@@ -184,8 +203,8 @@ extern "C" int emu_shape_pass(void* model, const int* parents, int K, int T, int
     float bb = 0.f;
     for (int s = 0; s < 10; ++s) bb += x[s] * x[s];
     loss += (float)T * w * w * bb;
-    for (int s = 0; s < 10; ++s) g[s] = grad[s] + 2.f * (float)T * w * w * x[s];
-    if (stage == 0) st.begin(c, v, loss, iters, lr); else st.after_eval(c, v, loss);
+    { const Cols ce = st.eval_cols(c, v); for (int s = 0; s < 10; ++s) ce.G(s) = grad[s] + 2.f * (float)T * w * w * x[s]; }
+    st.advance(c, v, loss, stage == 0, iters, lr);
     stage = 1;
     if (st.done) break;
   }

@@ -25,13 +25,13 @@ if what == "eval":
 if what == "time":
     for opt in ("adam", "lbfgs"):
         f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=opt == "lbfgs")
-        for B in (128, 148 * 128, 148 * 128 * 4):
+        for B in (384, 148 * 384, 148 * 384 * 4):
             mo = syn.make_motion(B, seed=3)
             tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22).cuda()
             init = dict(global_orient=mo["pose"][:, :3].contiguous(), body_pose=mo["pose"][:, 3:].contiguous() * 0.9,
                         betas=torch.zeros(B, 10), transl=mo["transl"])
             init = {k: v.cuda() for k, v in init.items()}
-            for iters in (4, 10):
+            for iters in (10, 30):
                 f.fit_batch(init, tgt, None, seq_ind=1, num_iters=iters, with_mesh=False)
                 torch.cuda.synchronize(); t0 = time.perf_counter()
                 o = f.fit_batch(init, tgt, None, seq_ind=1, num_iters=iters, with_mesh=False)
@@ -39,7 +39,7 @@ if what == "time":
                 ev = float(o["evals"].float().mean())
                 print(f"{opt} B={B} iters={iters} evals/frame={ev:.1f} time={dt*1e3:.2f} ms  -> {dt/ (ev+1) * 1e6:.1f} us per eval-round, {B*(ev+1)/dt/1e6:.2f} M frame-evals/s")
 if what == "prof":
-    B = 148 * 128
+    B = 148 * 384
     opt = sys.argv[2] if len(sys.argv) > 2 else "adam"
     f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=opt == "lbfgs")
     mo = syn.make_motion(B, seed=3)
@@ -48,6 +48,6 @@ if what == "prof":
                 betas=torch.zeros(B, 10), transl=mo["transl"])
     init = {k: v.cuda() for k, v in init.items()}
     for _ in range(2):
-        o = f.fit_batch(init, tgt, None, seq_ind=1, num_iters=3, with_mesh=True)
+        o = f.fit_batch(init, tgt, None, seq_ind=1, num_iters=10, with_mesh=False)
     torch.cuda.synchronize()
     print("ok", float(o["loss"].mean()))
