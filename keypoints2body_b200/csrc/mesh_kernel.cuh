@@ -5,18 +5,23 @@
 //   v_posed = v_template + shapedirs.shape + (R[1:] - I).flatten() @ posedirs
 //   verts   = (sum_j W_vj A_j) (v_posed; 1) + transl,  joints = [chain positions ; verts[extra ids]]
 //
-// Round-1 implementation: FP32 CUDA-core contraction, register-tiled over 16 frames per thread
-// with the pose-feature / shape / skinning-matrix tiles of those frames in shared memory; the
-// blend output never touches HBM (the skinning is applied in the same kernel).  The tcgen05
-// version of the contraction replaces the inner loop in a later round.
+// Two paths:
+//  * tensor-core path (models whose blend depth 9(nj-1)+ns fits kTcKpadMax = 224, i.e. SMPL):
+//    mesh_pose_kernel -> blend_tc_kernel (tcgen05 TF32 GEMM, blend_tc.cuh) writes v_posed straight
+//    into the output vertex buffer -> skin_inplace_kernel applies LBS in place (HBM-bound).
+//  * CUDA-core path (SMPL-H / SMPL-X until the tensor-core kernel learns K-chunking): one fused
+//    FP32 kernel, register-tiled over 16 frames per thread; the blend output never touches HBM.
 #pragma once
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/k2b_b200.h"
+#include "blend_tc.cuh"
 #include "fit_core.cuh"
 
 namespace k2b {
@@ -38,11 +43,15 @@ struct MeshModel {
   int* ell_idx = nullptr;      // [ell][V]
   float* ell_w = nullptr;      // [ell][V]
   int* extra_ids = nullptr;    // [nextra]
+  // tensor-core blend (blend_tc.cuh)
+  bool tc = false;
+  int kpad = 0, n_tiles = 0;
+  float* b_tiles = nullptr;    // [n_tiles][tc_b_bytes/4] pre-tiled, TF32-rounded [posedirs ; shapedirs]
 };
 
 inline void mesh_model_free(MeshModel& m) {
   cudaFree(m.parents); cudaFree(m.rel); cudaFree(m.J0S); cudaFree(m.v_template); cudaFree(m.shapedirs);
-  cudaFree(m.posedirs); cudaFree(m.ell_idx); cudaFree(m.ell_w); cudaFree(m.extra_ids);
+  cudaFree(m.posedirs); cudaFree(m.ell_idx); cudaFree(m.ell_w); cudaFree(m.extra_ids); cudaFree(m.b_tiles);
   m = MeshModel();
 }
 
@@ -134,13 +143,50 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
             mesh_upload(vt, &m.v_template, err) && mesh_upload(sd, &m.shapedirs, err) &&
             mesh_upload(pd, &m.posedirs, err) && mesh_upload(eidx, &m.ell_idx, err) &&
             mesh_upload(ew, &m.ell_w, err) && mesh_upload(extra, &m.extra_ids, err);
+  // ---- tensor-core operand: dirs pre-tiled into the shared-memory image of every 48-column tile
+  const int kdepth = m.npose + 3 * ns;     // shape rows split hi/lo: [S_hi ; S_hi ; S_lo]
+  if (ok && kdepth <= kTcKpadMax) {
+    m.kpad = tc_kpad(kdepth);
+    const int ncols = nv * 3, kblocks = m.kpad / kTcBK;
+    m.n_tiles = (ncols + kTcN - 1) / kTcN;
+    const size_t blk_floats = (size_t)tc_b_bytes() / 4;
+    std::vector<float> bt((size_t)m.n_tiles * kblocks * blk_floats, 0.f);
+    auto tf32 = [](float v) {
+      uint32_t bits;
+      memcpy(&bits, &v, 4);
+      bits = (bits + 0x1000u) & ~0x1FFFu;        // cvt.rna.tf32: round to nearest, ties away
+      float r;
+      memcpy(&r, &bits, 4);
+      return r;
+    };
+    for (int nt = 0; nt < m.n_tiles; ++nt)
+      for (int n = 0; n < kTcN; ++n) {
+        const int col = nt * kTcN + n;
+        if (col >= ncols) continue;
+        for (int k = 0; k < kdepth; ++k) {
+          float r;
+          if (k < m.npose) {
+            r = tf32(d.posedirs[(size_t)k * ncols + col]);
+          } else {
+            const int part = (k - m.npose) / ns, s = (k - m.npose) - part * ns;
+            const float v = d.shapedirs[(size_t)col * ns + s];
+            const float hi = tf32(v);
+            r = part == 2 ? tf32(v - hi) : hi;         // [S_hi ; S_hi ; S_lo]
+          }
+          bt[((size_t)nt * kblocks + k / kTcBK) * blk_floats + tc_elem_off(n, k % kTcBK)] = r;
+        }
+      }
+    ok = mesh_upload(bt, &m.b_tiles, err);
+    m.tc = ok;
+  }
   m.ready = ok;
   return ok;
 }
 
-// workspace: pose features [B][npose] + skinning matrices [B][nj][12]
+// workspace: pose features [Bp][npose] + skinning matrices [Bp][nj][12], Bp = B padded to 128
+inline long mesh_padded_frames(long B) { return (B + kTcM - 1) / kTcM * kTcM; }
 inline size_t mesh_workspace_bytes(const MeshModel& m, long B) {
-  const long Bp = (B + kMeshFT - 1) / kMeshFT * kMeshFT;
+  const long Bp = mesh_padded_frames(B);
   return sizeof(float) * (size_t)Bp * (size_t)(m.npose + m.nj * 12);
 }
 
@@ -316,6 +362,69 @@ mesh_skin_kernel(int nj, int ns, int npose, int nv, int ell, const float* __rest
   }
 }
 
+// ---- in-place LBS on the tensor-core path: out[f][v] holds v_posed, becomes the skinned vertex ---
+__global__ void __launch_bounds__(kMeshVT)
+skin_inplace_kernel(int nj, int nv, int ell, const int* __restrict__ ell_idx, const float* __restrict__ ell_w,
+                    const float* __restrict__ skin, const float* __restrict__ transl, long B, float* __restrict__ verts) {
+  extern __shared__ __align__(16) float s_A[];     // [kMeshFT][nj*12]
+  const long f0 = (long)blockIdx.y * kMeshFT;
+  for (int i = threadIdx.x; i < nj * 12 * kMeshFT; i += kMeshVT) s_A[i] = skin[f0 * nj * 12 + i];
+  __syncthreads();
+  const int v = blockIdx.x * kMeshVT + threadIdx.x;
+  if (v >= nv) return;
+  int jk[8];
+  float wk[8];
+  const int ne = ell < 8 ? ell : 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    jk[k] = k < ne ? ell_idx[(long)k * nv + v] : 0;
+    wk[k] = k < ne ? ell_w[(long)k * nv + v] : 0.f;
+  }
+#pragma unroll 4
+  for (int ft = 0; ft < kMeshFT; ++ft) {
+    const long f = f0 + ft;
+    if (f >= B) break;
+    float* o = verts + (f * nv + v) * 3;
+    const float px = o[0], py = o[1], pz = o[2];
+    float T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < ne && wk[k] != 0.f) {
+        const float4* Aj = reinterpret_cast<const float4*>(s_A + (ft * nj + jk[k]) * 12);
+        const float4 a0 = Aj[0], a1 = Aj[1], a2 = Aj[2];
+        T[0] = fmaf(wk[k], a0.x, T[0]); T[1] = fmaf(wk[k], a0.y, T[1]); T[2] = fmaf(wk[k], a0.z, T[2]); T[3] = fmaf(wk[k], a0.w, T[3]);
+        T[4] = fmaf(wk[k], a1.x, T[4]); T[5] = fmaf(wk[k], a1.y, T[5]); T[6] = fmaf(wk[k], a1.z, T[6]); T[7] = fmaf(wk[k], a1.w, T[7]);
+        T[8] = fmaf(wk[k], a2.x, T[8]); T[9] = fmaf(wk[k], a2.y, T[9]); T[10] = fmaf(wk[k], a2.z, T[10]); T[11] = fmaf(wk[k], a2.w, T[11]);
+      }
+    }
+    for (int k = 8; k < ell; ++k) {
+      const float w = ell_w[(long)k * nv + v];
+      if (w == 0.f) continue;
+      const float* Aj = s_A + (ft * nj + ell_idx[(long)k * nv + v]) * 12;
+      for (int i = 0; i < 12; ++i) T[i] = fmaf(w, Aj[i], T[i]);
+    }
+    const float tx = transl ? transl[f * 3] : 0.f, ty = transl ? transl[f * 3 + 1] : 0.f,
+                tz = transl ? transl[f * 3 + 2] : 0.f;
+    o[0] = fmaf(T[0], px, fmaf(T[1], py, fmaf(T[2], pz, T[3]))) + tx;
+    o[1] = fmaf(T[4], px, fmaf(T[5], py, fmaf(T[6], pz, T[7]))) + ty;
+    o[2] = fmaf(T[8], px, fmaf(T[9], py, fmaf(T[10], pz, T[11]))) + tz;
+  }
+}
+
+// vertex-picked extra joints: joints[f][nj + e] = verts[f][extra_ids[e]]
+__global__ void gather_extra_kernel(const float* __restrict__ verts, const int* __restrict__ ids, int nextra, int nv,
+                                    int nj, long B, float* __restrict__ joints) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * nextra) return;
+  const long f = i / nextra;
+  const int e = (int)(i - f * nextra);
+  const float* s = verts + (f * nv + ids[e]) * 3;
+  float* o = joints + (f * (nj + nextra) + nj + e) * 3;
+  o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+}
+
 inline size_t mesh_skin_smem(const MeshModel& m) {
   return sizeof(float) * (size_t)((m.npose + m.ns) * kMeshFT + kMeshFT * m.nj * 12);
 }
@@ -323,7 +432,7 @@ inline size_t mesh_skin_smem(const MeshModel& m) {
 inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_t st, std::string& err,
                          int& launches) {
   const long B = a.num_frames;
-  const long Bp = (B + kMeshFT - 1) / kMeshFT * kMeshFT;
+  const long Bp = mesh_padded_frames(B);
   float* posefeat = (float*)a.workspace;
   float* skin = posefeat + Bp * m.npose;
   const int njout = m.nj + m.nextra;
@@ -331,6 +440,51 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
       m.nj, m.ns, m.parents, (const float4*)m.rel, (const float4*)m.J0S, a.full_pose, a.shape, a.transl, B, Bp,
       posefeat, skin, a.out_joints, njout);
   ++launches;
+  if (m.tc && a.out_vertices) {
+    // ---- tensor-core path: blend (tcgen05) -> in-place skinning -> extra-joint gather ----------
+    const size_t tsm = tc_smem_bytes();
+    static size_t tc_configured = 0;
+    if (tsm > tc_configured) {
+      cudaError_t e = cudaFuncSetAttribute(blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+      if (e != cudaSuccess) {
+        err = cudaGetErrorString(e);
+        return false;
+      }
+      tc_configured = tsm;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* dbg = getenv("K2B_TC_DEBUG");
+    BlendParams bp{posefeat, a.shape, m.b_tiles, m.v_template, a.out_vertices, B, m.npose, m.ns, m.kpad, m.nv * 3, m.n_tiles,
+                   dbg ? atoi(dbg) : 0};
+    const long mtiles = Bp / kTcM;
+    blend_tc_kernel<<<(unsigned)(mtiles < sms ? mtiles : sms), kTcThreads, tsm, st>>>(bp);
+    ++launches;
+    const size_t ssm = sizeof(float) * (size_t)kMeshFT * m.nj * 12;
+    const long ft_total = (B + kMeshFT - 1) / kMeshFT;
+    for (long y0 = 0; y0 < ft_total; y0 += 65535) {
+      const unsigned ny = (unsigned)(ft_total - y0 < 65535 ? ft_total - y0 : 65535);
+      const long fo = y0 * kMeshFT;
+      dim3 grid((m.nv + kMeshVT - 1) / kMeshVT, ny);
+      skin_inplace_kernel<<<grid, kMeshVT, ssm, st>>>(m.nj, m.nv, m.ell, m.ell_idx, m.ell_w, skin + fo * m.nj * 12,
+                                                       a.transl ? a.transl + fo * 3 : nullptr, B - fo,
+                                                       a.out_vertices + fo * m.nv * 3);
+      ++launches;
+    }
+    if (m.nextra > 0) {
+      const long n = B * m.nextra;
+      gather_extra_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.out_vertices, m.extra_ids, m.nextra, m.nv, m.nj, B,
+                                                                         a.out_joints);
+      ++launches;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      err = cudaGetErrorString(e);
+      return false;
+    }
+    return true;
+  }
   const size_t smem = mesh_skin_smem(m);
   static size_t configured = 0;
   if (smem > configured) {

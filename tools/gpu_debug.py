@@ -51,3 +51,40 @@ if what == "prof":
         o = f.fit_batch(init, tgt, None, seq_ind=1, num_iters=10, with_mesh=False)
     torch.cuda.synchronize()
     print("ok", float(o["loss"].mean()))
+if what == "mesh":
+    from oracle.smplx_shim import BodyModelShim
+    f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm)
+    shim = BodyModelShim(w)
+    for B in (37, 300, 128 * 5):
+        gg = torch.Generator().manual_seed(B)
+        params = dict(global_orient=0.3 * torch.randn(B, 3, generator=gg), body_pose=0.3 * torch.randn(B, 69, generator=gg),
+                      betas=torch.randn(B, 10, generator=gg), transl=torch.randn(B, 3, generator=gg))
+        out = f.forward_batch(params)
+        torch.cuda.synchronize()
+        ref = shim(**params)
+        dv = (out["vertices"].cpu() - ref.vertices).abs().max().item()
+        dj = (out["joints"].cpu() - ref.joints).abs().max().item()
+        print(f"mesh B={B}: max|verts-shim|={dv:.3e} max|joints-shim|={dj:.3e}", flush=True)
+    B = 1 << 18
+    gg = torch.Generator().manual_seed(1)
+    params = {k: v.cuda() for k, v in dict(global_orient=0.3 * torch.randn(B, 3, generator=gg), body_pose=0.3 * torch.randn(B, 69, generator=gg),
+                  betas=torch.randn(B, 10, generator=gg), transl=torch.randn(B, 3, generator=gg)).items()}
+    buf = torch.empty(B, 6890, 3, device="cuda")
+    for _ in range(2):
+        f.forward_batch(params, out_vertices=buf)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(3):
+        f.forward_batch(params, out_vertices=buf)
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
+    print(f"mesh B={B}: {dt*1e3:.2f} ms -> {B/dt/1e6:.2f} M frames/s, {B*6890*12/dt/1e9:.0f} GB/s of vertex output")
+if what == "meshprof":
+    f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm)
+    B = 148 * 128 * 2
+    gg = torch.Generator().manual_seed(1)
+    params = {k: v.cuda() for k, v in dict(global_orient=0.3 * torch.randn(B, 3, generator=gg), body_pose=0.3 * torch.randn(B, 69, generator=gg),
+                  betas=torch.randn(B, 10, generator=gg), transl=torch.randn(B, 3, generator=gg)).items()}
+    buf = torch.empty(B, 6890, 3, device="cuda")
+    for _ in range(2):
+        f.forward_batch(params, out_vertices=buf)
+    torch.cuda.synchronize()
+    print("ok")
