@@ -194,7 +194,7 @@ extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* st
   p.tab = DeviceTables{m->chol, m->mu, m->nlw, m->rel};
   p.num_frames = a->num_frames;
   const int grid = fit_grid(m, a->num_frames);
-  p.stride = (long)grid * fit_threads_rt(m->num_shape);
+  p.rows = scratch_rows(m->num_shape, a->optimizer == K2B_OPT_LBFGS ? kModeLbfgs : kModeAdam, lbfgs_history_capacity(a->num_iters));
   p.num_obs = a->num_obs;
   p.num_iters = a->num_iters;
   p.freeze_betas = a->freeze_betas;
@@ -231,7 +231,7 @@ extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, vo
   FitParams p{};
   p.tab = DeviceTables{m->chol, m->mu, m->nlw, m->rel};
   p.num_frames = a->num_frames;
-  p.stride = (long)grid * fit_threads_rt(m->num_shape);
+  p.rows = scratch_rows(m->num_shape, kModeEval, 0);
   p.num_obs = a->num_obs;
   p.conf_per_frame = a->conf_per_frame;
   p.preserve_all = a->preserve_all;

@@ -38,7 +38,7 @@ struct DeviceTables {      // global-memory copies owned by k2b_model
 struct FitParams {
   DeviceTables tab;
   long num_frames;
-  long stride;             // scratch column stride = gridDim.x * threads (scratch is per resident thread)
+  long rows;               // scratch rows per CTA; layout [CTA][row][thread] so the row stride is compile-time
   int num_obs;
   int num_iters;
   int freeze_betas;
@@ -117,8 +117,10 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
   tb.mu = s_mu;
   tb.nlw = s_nlw;
   tb.rel = reinterpret_cast<const float4*>(s_rel);
-  float* const scr = p.scratch + (long)blockIdx.x * kFitThreads + tid;   // this thread's scratch column
-  Cols c{s_x + tid, scr + kScrGrad * p.stride, kFitThreads, p.stride};
+  // this thread's scratch column: rows are kFitThreads floats apart (compile-time -> immediate offsets)
+  constexpr long kStride = kFitThreads;
+  float* const scr = p.scratch + (long)blockIdx.x * p.rows * kFitThreads + tid;
+  Cols c{s_x + tid, scr + kScrGrad * kStride, kFitThreads, kStride};
 
   const long num_tiles = (p.num_frames + kFitThreads - 1) / kFitThreads;
   for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -141,21 +143,21 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       }
       const float* tg = p.targets + fr * K * 3;
 #pragma unroll 2
-      for (int i = 0; i < K * 3; ++i) scr[(kScrTgt + i) * p.stride] = tg[i];
+      for (int i = 0; i < K * 3; ++i) scr[(kScrTgt + i) * kStride] = tg[i];
 #pragma unroll 2
       for (int j = 0; j < K; ++j) {
         const float cf = p.conf ? (p.conf_per_frame ? p.conf[fr * K + j] : p.conf[j]) : 1.f;
-        scr[(kScrWgt + j) * p.stride] = p.joint_w2 * cf * cf;
+        scr[(kScrWgt + j) * kStride] = p.joint_w2 * cf * cf;
       }
       const float* kp = p.preserve_pose ? p.preserve_pose + fr * kBodyDim : p.init_pose + fr * kPoseDim + 3;
 #pragma unroll 3
-      for (int i = 0; i < kBodyDim; ++i) scr[(kScrKeep + i) * p.stride] = kp[i];
+      for (int i = 0; i < kBodyDim; ++i) scr[(kScrKeep + i) * kStride] = kp[i];
     }
     FrameConsts fc;
-    fc.tgt = scr + kScrTgt * p.stride;
-    fc.wgt = scr + kScrWgt * p.stride;
-    fc.keep = scr + kScrKeep * p.stride;
-    fc.stride = p.stride;
+    fc.tgt = scr + kScrTgt * kStride;
+    fc.wgt = scr + kScrWgt * kStride;
+    fc.keep = scr + kScrKeep * kStride;
+    fc.stride = kStride;
     const bool keep_on = p.frame_preserve ? (p.frame_preserve[fr] != 0) : (p.preserve_all != 0);
     fc.keep_w2 = keep_on ? p.keep_w2 : 0.f;
     const bool freeze_betas = p.freeze_betas != 0;
@@ -185,12 +187,12 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
     }
 
     if (MODE == kModeAdam) {
-      float* m1 = scr + kScrOpt * p.stride;
-      float* m2 = m1 + (long)NX * p.stride;
+      float* m1 = scr + kScrOpt * kStride;
+      float* m2 = m1 + (long)NX * kStride;
 #pragma unroll 5
       for (int i = 0; i < NX; ++i) {
-        m1[i * p.stride] = 0.f;
-        m2[i * p.stride] = 0.f;
+        m1[i * kStride] = 0.f;
+        m2[i * kStride] = 0.f;
       }
       const int warp_iters = __reduce_max_sync(0xffffffffu, iters);
       // rounds 1..warp_iters: loss + gradient + Adam step; round warp_iters+1: joints-only
@@ -213,11 +215,11 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
 #pragma unroll 17
           for (int i = 0; i < NX; ++i) {
             if (freeze_betas && i >= kShapeOff && i < kShapeOff + 10) continue;
-            float mm = m1[i * p.stride], vv = m2[i * p.stride], x = c.X(i);
+            float mm = m1[i * kStride], vv = m2[i * kStride], x = c.X(i);
             adam_update(x, mm, vv, c.G(i), step_k, bc2_k);
             c.X(i) = x;
-            m1[i * p.stride] = mm;
-            m2[i * p.stride] = vv;
+            m1[i * kStride] = mm;
+            m2[i * kStride] = vv;
           }
         }
       }
@@ -225,8 +227,8 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
 
     if (MODE == kModeLbfgs) {
       Vecs v;
-      v.base = scr + kScrOpt * p.stride;
-      v.stride = p.stride;
+      v.base = scr + kScrOpt * kStride;
+      v.stride = kStride;
       v.n = NX;
       v.hmax = p.lbfgs_hmax;
       Lbfgs<NX> st;
@@ -246,8 +248,16 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         }
         if (freeze_betas)
           for (int i = 0; i < 10; ++i) ce.G(kShapeOff + i) = 0.f;
-        if (stage == 0 || !st.done) st.advance(c, v, loss, stage == 0, iters, p.lr);
+        if (stage == 0 || (!st.done && !st.need_outer)) st.advance(c, v, loss, stage == 0, iters, p.lr);
         stage = 1;
+        // Lanes reach their outer-iteration boundary on different rounds.  The direction update
+        // (two-loop recursion) is the expensive divergent part, so a lane that has finished its line
+        // search idles (its evaluations are discarded, its slots protected) until every live lane of
+        // the warp is at the boundary; then all of them run it together.  Per-frame arithmetic is
+        // unchanged -- only the round in which it happens.
+        if (__all_sync(0xffffffffu, st.done || st.need_outer)) {
+          if (st.need_outer && !st.done) st.start_outer(c, v);
+        }
         if (!__any_sync(0xffffffffu, !st.done)) {
           stage = 2;
 #pragma unroll 17

@@ -152,11 +152,26 @@ struct Lbfgs {
 
   // Drive one round after an evaluation: `first` selects begin() vs after_eval(); the outer-iteration
   // set-up (two-loop recursion etc.) is inlined at exactly one site.
+  // The caller runs start_outer() when `need_outer` is set (the kernel defers it until the whole warp
+  // is at the boundary; the serial harnesses run it at once via advance_now()).
   K2B_HD void advance(const Cols& c, const Vecs& v, float loss_f, bool first, int max_iter_, float lr_) {
     need_outer = false;
     if (first) begin(c, v, loss_f, max_iter_, lr_);
     else after_eval(c, v, loss_f);
-    if (need_outer) start_outer(c, v);
+    if (need_outer) park_cur();
+  }
+  K2B_HD void advance_now(const Cols& c, const Vecs& v, float loss_f, bool first, int max_iter_, float lr_) {
+    advance(c, v, loss_f, first, max_iter_, lr_);
+    if (need_outer && !done) start_outer(c, v);
+  }
+  // while waiting at the boundary, evaluations must not clobber flat_grad / prev_flat_grad
+  K2B_HD void park_cur() {
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      if (s != g0 && s != slot_prev_grad) {
+        cur = s;
+        return;
+      }
   }
   bool need_outer;
 
@@ -208,6 +223,7 @@ struct Lbfgs {
   // The two-loop's running vector q lives in the (idle between evaluations) x column.
   K2B_HD void start_outer(const Cols& c, const Vecs& v) {
     const int od = v.d(), og = v.gslot(g0);
+    need_outer = false;
     ++n_iter;
     if (n_iter == 1) {
 #pragma unroll 17

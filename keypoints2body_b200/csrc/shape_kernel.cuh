@@ -156,7 +156,7 @@ shape_pass_kernel(const __grid_constant__ ShapeParams p) {
       const Cols ce = st.eval_cols(c, v);
 #pragma unroll
       for (int s = 0; s < 10; ++s) ce.G(s) = fmaf(2.f * T * p.w2, betas[s], grad[s]);
-      st.advance(c, v, loss, stage == 0, p.num_iters, p.lr);
+      st.advance_now(c, v, loss, stage == 0, p.num_iters, p.lr);
       done = st.done;
       if (done) {
         for (int s = 0; s < 10; ++s) x[s] = v.at(s);

@@ -57,8 +57,8 @@ struct LbfgsAny {
   Lbfgs<95> b;
   explicit LbfgsAny(int n_) : n(n_) { a.init(); b.init(); }
   Cols eval_cols(const Cols& c, const Vecs& v) const { return n == 85 ? a.eval_cols(c, v) : b.eval_cols(c, v); }
-  void begin(const Cols& c, const Vecs& v, float l, int it, float lr) { n == 85 ? a.advance(c, v, l, true, it, lr) : b.advance(c, v, l, true, it, lr); }
-  void after_eval(const Cols& c, const Vecs& v, float l) { n == 85 ? a.advance(c, v, l, false, 0, 0.f) : b.advance(c, v, l, false, 0, 0.f); }
+  void begin(const Cols& c, const Vecs& v, float l, int it, float lr) { n == 85 ? a.advance_now(c, v, l, true, it, lr) : b.advance_now(c, v, l, true, it, lr); }
+  void after_eval(const Cols& c, const Vecs& v, float l) { n == 85 ? a.advance_now(c, v, l, false, 0, 0.f) : b.advance_now(c, v, l, false, 0, 0.f); }
   bool done_() const { return n == 85 ? a.done : b.done; }
   double t_() const { return n == 85 ? a.t : b.t; }
   int evals_() const { return n == 85 ? a.evals : b.evals; }
@@ -204,7 +204,7 @@ extern "C" int emu_shape_pass(void* model, const int* parents, int K, int T, int
     for (int s = 0; s < 10; ++s) bb += x[s] * x[s];
     loss += (float)T * w * w * bb;
     { const Cols ce = st.eval_cols(c, v); for (int s = 0; s < 10; ++s) ce.G(s) = grad[s] + 2.f * (float)T * w * w * x[s]; }
-    st.advance(c, v, loss, stage == 0, iters, lr);
+    st.advance_now(c, v, loss, stage == 0, iters, lr);
     stage = 1;
     if (st.done) break;
   }

@@ -48,7 +48,7 @@ if what == "prof":
                 betas=torch.zeros(B, 10), transl=mo["transl"])
     init = {k: v.cuda() for k, v in init.items()}
     for _ in range(2):
-        o = f.fit_batch(init, tgt, None, seq_ind=1, num_iters=10, with_mesh=False)
+        o = f.fit_batch(init, tgt, None, seq_ind=1, num_iters=int(os.environ.get("K2B_ITERS", "10")), with_mesh=False)
     torch.cuda.synchronize()
     print("ok", float(o["loss"].mean()))
 if what == "mesh":
