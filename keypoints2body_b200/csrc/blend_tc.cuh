@@ -10,21 +10,25 @@
 // smplx does this as `pose_feature @ posedirs` + `blend_shapes` [smplx-from-memory]; the reference
 // reaches it through the final forward (/root/reference/keypoints2body/core/fitters/world_space.py:258-278).
 //
-// Tiling: M = 128 frames per CTA pass.  The A operand (the frames' features, 128 x Kpad TF32)
-// lives in TENSOR MEMORY (Kpad <= 240 columns, written once per pass with tcgen05.st), so shared
-// memory is free for a 6-deep ring of B blocks.  An output tile is N = 128 columns (wide MMAs: a
-// chain of MMAs into one accumulator is latency-bound, ~130 cycles each, so N must be large
-// enough that the math time, N/2 cycles, is comparable); K is walked in blocks of 48 (6 MMAs of
-// K = 8).  The B operand (dirs) is pre-tiled on the host into the exact shared-memory image of each
-// (N tile, K block), so one elected thread streams a block with ONE 1-D TMA bulk copy
-// (cp.async.bulk -> mbarrier complete_tx).  One thread issues tcgen05.mma (A from TMEM, B from
-// smem descriptors, accumulators in TMEM: 2 stages x 128 columns); eight epilogue warps (row
-// quarter x column half) drain TMEM with tcgen05.ld, transpose 32x32 blocks through a padded
-// staging tile and write fp32 rows as full 128-byte segments (+ v_template).
+// Orientation: D[M = 128 output columns][N = 128 frames].  The M operand is a block of dirs^T
+// (pre-tiled on the host into the exact shared-memory image of each (column tile, K block), streamed
+// with ONE 1-D TMA bulk copy per block -- cp.async.bulk + mbarrier complete_tx -- into a 6-deep
+// ring); the N operand is the pass's 128 frames' features, resident in shared memory (128 KB).
+// Accumulators live in TENSOR MEMORY: 4 x 128 columns = all 512.  Two column tiles are processed
+// as a PAIR with their MMAs interleaved (a chain of MMAs into one accumulator is latency-bound,
+// ~200 cycles each against 64 cycles of math at N = 128; two independent chains fill the gaps), and
+// pairs alternate between accumulators {0,1} and {2,3} so the epilogue of one pair overlaps the
+// MMAs of the next.  One thread issues tcgen05.mma.kind::tf32 (M128 N128 K8).  Eight epilogue warps
+// (lane quarter x tile of the pair) read TMEM with tcgen05.ld: lane = output column, register i =
+// frame, so every store instruction writes 32 consecutive floats of one frame row (128 bytes,
+// no transpose needed) after adding v_template.  Warp roles synchronise only through mbarriers.
 //
-// B block layout (no swizzle, K-major "interleaved" canonical UMMA layout, cute mma_traits_sm100):
-//   byte address(row r, k) = (r / 8) * SBO + (k / 4) * 128 + (r % 8) * 16 + (k % 4) * 4
-// i.e. 8-row x 16-byte core matrices, contiguous along K (LBO = 128 B), SBO = (48 / 4) * 128 B.
+// Operand layout: K-major SWIZZLE_128B canonical UMMA layout (cute mma_traits_sm100: Swizzle<3,4,3>).
+// A K block of 32 TF32 is one 128-byte row per operand row; rows are 128 B apart, 8-row groups
+// 1024 B apart (SBO), and the 16-byte chunk index inside a row is XORed with (row % 8):
+//   byte address(row r, k) = (k / 32) * rows*128 + r * 128 + ((((k % 32) / 4) ^ (r % 8)) * 16) + (k % 4) * 4
+// The un-swizzled "interleaved" layout also works but is fetched one 16-byte row per cycle
+// (measured: 80 + 1.5 N cycles per MMA instead of ~N/2), which is why this layout is used.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -32,26 +36,24 @@
 
 namespace k2b {
 
-constexpr int kTcM = 128;          // frames per pass
-constexpr int kTcN = 128;          // output columns per tile
-constexpr int kTcBK = 48;          // K block streamed per TMA copy (6 MMAs of K = 8)
-constexpr int kTcKpadMax = 240;    // SMPL: 207 pose features + 3 x 10 split shape rows, padded to 5 x 48
+constexpr int kTcM = 128;          // frames per pass (the MMA's N)
+constexpr int kTcN = 128;          // output columns per tile (the MMA's M)
+constexpr int kTcBK = 32;          // K block streamed per TMA copy = one 128-byte swizzle atom (4 MMAs of K = 8)
+constexpr int kTcKpadMax = 256;    // SMPL: 207 pose features + 3 x 10 split shape rows, padded to 8 x 32
 constexpr int kTcThreads = 320;    // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
-constexpr int kTcStages = 6;       // B ring depth (K blocks)
-constexpr int kTcAccStages = 2;    // accumulator stages in TMEM
-constexpr int kTcTmemCols = 512;   // A: columns [0,240); accumulators at columns 256 and 384
-constexpr int kTcStageStride = 33; // padded row stride (floats) of the per-warp epilogue staging tile
+constexpr int kTcStages = 6;       // ring depth (K blocks of dirs, 16 KB each)
+constexpr int kTcAccStages = 4;    // accumulators in TMEM (two pairs)
+constexpr int kTcTmemCols = 512;
 
 __host__ __device__ constexpr int tc_kpad(int kdepth) { return (kdepth + kTcBK - 1) / kTcBK * kTcBK; }
-__host__ __device__ constexpr int tc_sbo_bytes() { return (kTcBK / 4) * 128; }
-__host__ __device__ constexpr int tc_b_bytes() { return (kTcN / 8) * tc_sbo_bytes(); }   // one (N tile, K block)
-__host__ __device__ constexpr int tc_stage_bytes() { return 8 * 32 * kTcStageStride * 4; }
-__host__ __device__ constexpr size_t tc_smem_bytes() {
-  return (size_t)kTcStages * (size_t)tc_b_bytes() + tc_stage_bytes() + 1024;
+__host__ __device__ constexpr int tc_b_bytes() { return kTcN * 128; }                    // one (column tile, K block)
+__host__ __device__ constexpr int tc_f_bytes(int kpad) { return (kpad / kTcBK) * kTcM * 128; }
+__host__ __device__ constexpr size_t tc_smem_bytes(int kpad) {
+  return (size_t)tc_f_bytes(kpad) + (size_t)kTcStages * (size_t)tc_b_bytes() + 1024;
 }
-// offset (in floats) of element (row, k) inside a B block image
+// offset (in floats) of element (row, k < 32) inside one 128-row swizzle-128B K block
 __host__ __device__ constexpr int tc_elem_off(int row, int k) {
-  return ((row / 8) * tc_sbo_bytes() + (k / 4) * 128 + (row % 8) * 16 + (k % 4) * 4) / 4;
+  return (row * 128 + (((k / 4) ^ (row % 8)) * 16) + (k % 4) * 4) / 4;
 }
 
 #if defined(__CUDACC__)
@@ -129,14 +131,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_NONE.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, bits [0,14)
-  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;         // leading byte offset (K direction), bits [16,30)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride byte offset (8-row groups), bits [32,46)
+  d |= (uint64_t)1 << 16;                              // leading byte offset: unused for swizzled K-major (1)
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;        // stride byte offset: 8 rows x 128 B, bits [32,46)
   d |= (uint64_t)1 << 46;                              // descriptor version 1 (sm_100)
-  return d;                                            // base offset 0, layout type 0 = SWIZZLE_NONE
+  d |= (uint64_t)2 << 61;                              // layout type 2 = SWIZZLE_128B
+  return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): TF32 x TF32 -> F32, K-major A and B.
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
@@ -153,7 +156,7 @@ __device__ __forceinline__ float to_tf32(float x) {
 struct BlendParams {
   const float* feat;        // [frames_padded][npose] pose features (frames padded to kTcM, zero rows)
   const float* shape;       // [B][ns]
-  const float* b_tiles;     // [n_tiles][kpad/48][tc_b_bytes/4] pre-tiled TF32 dirs
+  const float* b_tiles;     // [n_tiles (even)][kpad/48][tc_b_bytes/4] pre-tiled TF32 dirs^T blocks
   const float* v_template;  // [ncols]
   float* out;               // [B][ncols]  (ncols = 3V)
   long num_frames;
@@ -164,12 +167,13 @@ struct BlendParams {
 __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_constant__ BlendParams p) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   const int kpad = p.kpad;
-  constexpr int b_bytes = tc_b_bytes(), sbo = tc_sbo_bytes();
-  unsigned char* sB = tc_smem;
-  float* sStage = reinterpret_cast<float*>(tc_smem + (size_t)kTcStages * b_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + (size_t)kTcStages * b_bytes + tc_stage_bytes());
-  // bars: [0,6) b_full; [6,12) b_empty; [12,14) acc_full; [14,16) acc_empty; then the TMEM base word
-  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(bars + 16);
+  constexpr int b_bytes = tc_b_bytes();
+  const int f_bytes = tc_f_bytes(kpad);
+  float* sF = reinterpret_cast<float*>(tc_smem);                         // features of the pass
+  unsigned char* sR = tc_smem + f_bytes;                                 // dirs ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + f_bytes + (size_t)kTcStages * b_bytes);
+  // bars: [0,6) ring_full; [6,12) ring_empty; [12,16) acc_full; [16,20) acc_empty; then the TMEM base word
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = tc::smem_u32(bars);
@@ -177,12 +181,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
 
   if (tid == 0) {
     for (int i = 0; i < kTcStages; ++i) {
-      tc::mbar_init(BAR(i), 1);          // b_full: producer's expect_tx arrival
-      tc::mbar_init(BAR(6 + i), 1);      // b_empty: tcgen05.commit
+      tc::mbar_init(BAR(i), 1);          // ring_full: producer's expect_tx arrival
+      tc::mbar_init(BAR(6 + i), 1);      // ring_empty: tcgen05.commit
     }
     for (int i = 0; i < kTcAccStages; ++i) {
       tc::mbar_init(BAR(12 + i), 1);     // acc_full: tcgen05.commit
-      tc::mbar_init(BAR(14 + i), 256);   // acc_empty: all eight epilogue warps
+      tc::mbar_init(BAR(16 + i), 128);   // acc_empty: the four epilogue warps that drained it
     }
     tc::fence_barrier_init();
   }
@@ -191,146 +195,132 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_word;
-  const uint32_t tmem_acc = tmem_base + 256u;                 // accumulators: columns 256.. and 384..
 
-  const long num_mtiles = (p.num_frames + kTcM - 1) / kTcM;
-  const uint32_t idesc = tc::make_idesc(kTcM, kTcN);
+  const long num_passes = (p.num_frames + kTcM - 1) / kTcM;
+  const uint32_t idesc = tc::make_idesc(kTcN, kTcM);       // M = columns tile, N = frames
   const int kblocks = kpad / kTcBK;
-  uint32_t ph_bfull = 0, ph_bempty = 0, ph_afull = 0, ph_aempty = 0;   // one parity bit per stage
-  long tile_seq = 0;   // running N-tile counter across passes (accumulator ring position)
-  long blk_seq = 0;    // running K-block counter across passes (B ring position)
+  const int npairs = p.n_tiles / 2;                         // n_tiles is padded to an even count
+  uint32_t ph_rfull = 0, ph_rempty = 0, ph_afull = 0, ph_aempty = 0;   // one parity bit per stage
+  long pair_seq = 0;   // running pair counter across passes (accumulator ring position)
+  long blk_seq = 0;    // running K-block counter across passes (dirs ring position)
 
-  for (long mt = blockIdx.x; mt < num_mtiles; mt += gridDim.x) {
-    const long f0 = mt * kTcM;
-    // every MMA of the previous pass has retired (the epilogue saw its last acc_full) before A is rewritten
+  for (long ps = blockIdx.x; ps < num_passes; ps += gridDim.x) {
+    const long f0 = ps * kTcM;
+    // every MMA of the previous pass has retired (the epilogue saw its last acc_full) before the
+    // features are overwritten
     __syncthreads();
-    // ---- A operand -> tensor memory: warps 0-3, thread = frame row, Kpad columns ------------------
-    if (warp < 4) {
-      const long f = f0 + warp * 32 + lane;
-      const bool live = f < p.num_frames;
-      const float* fr = p.feat + f * p.npose;               // feat rows are padded to a multiple of kTcM
-      const float* sh = p.shape + (live ? f : 0) * p.ns;
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-      for (int k0 = 0; k0 < kpad; k0 += 8) {
-        uint32_t v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = k0 + i;
-          float x = 0.f;
-          if (k < p.npose) {
-            x = tc::to_tf32(fr[k]);
-          } else if (k < p.npose + 3 * p.ns && live) {
-            const int part = (k - p.npose) / p.ns, s = (k - p.npose) - part * p.ns;
-            const float b = sh[s];
-            const float hi = tc::to_tf32(b);
-            x = part == 1 ? tc::to_tf32(b - hi) : hi;       // [hi | lo | hi]
-          }
-          v[i] = __float_as_uint(x);
-        }
-        tc::tmem_st8(trow + (uint32_t)k0, v);
+    // ---- N operand: features of 128 frames -> shared memory (canonical K-major image) ----------
+    for (int i = tid; i < kTcM * kpad; i += kTcThreads) {
+      const int r = i / kpad, k = i - r * kpad;
+      const long f = f0 + r;
+      float x = 0.f;
+      if (k < p.npose) {
+        x = tc::to_tf32(p.feat[f * p.npose + k]);           // feat rows are padded to a multiple of kTcM
+      } else if (k < p.npose + 3 * p.ns && f < p.num_frames) {
+        const int part = (k - p.npose) / p.ns, s = (k - p.npose) - part * p.ns;
+        const float b = p.shape[f * p.ns + s];
+        const float hi = tc::to_tf32(b);
+        x = part == 1 ? tc::to_tf32(b - hi) : hi;           // [hi | lo | hi]
       }
-      tc::tmem_st_wait();
+      sF[(k >> 5) * (kTcM * 32) + tc_elem_off(r, k & 31)] = x;
     }
-    tc::tc_fence_before();
+    tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
-    tc::tc_fence_after();
 
     if (warp == 8) {
-      // ---- TMA producer: one bulk copy per (N tile, K block) into a 6-deep ring --------------------
+      // ---- TMA producer: blocks in the order the MMA warp consumes them: (2p,kb), (2p+1,kb) -------
       if (lane == 0) {
-        const int nblk = p.n_tiles * kblocks;
-        for (int i = 0; i < nblk; ++i) {
-          const long seq = blk_seq + i;
-          const int s = (int)(seq % kTcStages);
-          if (seq >= kTcStages) {
-            tc::mbar_wait(BAR(6 + s), (ph_bempty >> s) & 1u);
-            ph_bempty ^= 1u << s;
-          }
-          if (p.debug == 2 && seq >= kTcStages) {
-            tc::mbar_arrive(BAR(s));
-            continue;
-          }
-          tc::mbar_expect_tx(BAR(s), (uint32_t)b_bytes);
-          tc::bulk_g2s(tc::smem_u32(sB + (size_t)s * b_bytes), p.b_tiles + (size_t)i * (b_bytes / 4), (uint32_t)b_bytes,
-                       BAR(s));
-        }
+        long seq = blk_seq;
+        for (int pr = 0; pr < npairs; ++pr)
+          for (int kb = 0; kb < kblocks; ++kb)
+            for (int h = 0; h < 2; ++h, ++seq) {
+              const int s = (int)(seq % kTcStages);
+              if (seq >= kTcStages) {
+                tc::mbar_wait(BAR(6 + s), (ph_rempty >> s) & 1u);
+                ph_rempty ^= 1u << s;
+              }
+              const size_t blk = (size_t)(2 * pr + h) * kblocks + kb;
+              tc::mbar_expect_tx(BAR(s), (uint32_t)b_bytes);
+              tc::bulk_g2s(tc::smem_u32(sR + (size_t)s * b_bytes), p.b_tiles + blk * (b_bytes / 4), (uint32_t)b_bytes,
+                           BAR(s));
+            }
       }
     } else if (warp == 9) {
-      // ---- MMA issuer: one thread; per tile Kpad/8 x (M128 N128 K8), A from TMEM --------------------
+      // ---- MMA issuer: one thread; two interleaved accumulation chains per pair -------------------
       if (lane == 0) {
-        for (int nt = 0; nt < p.n_tiles; ++nt) {
-          const long tseq = tile_seq + nt;
-          const int sa = (int)(tseq % kTcAccStages);
-          if (tseq >= kTcAccStages) {
-            tc::mbar_wait(BAR(14 + sa), (ph_aempty >> sa) & 1u);   // epilogue drained this accumulator
-            ph_aempty ^= 1u << sa;
+        const uint32_t f_addr = tc::smem_u32(sF);
+        long seq = blk_seq;
+        for (int pr = 0; pr < npairs; ++pr) {
+          const long pseq = pair_seq + pr;
+          const int a0 = (int)(pseq & 1) * 2;
+          if (pseq >= 2) {
+            tc::mbar_wait(BAR(16 + a0), (ph_aempty >> a0) & 1u);
+            ph_aempty ^= 1u << a0;
+            tc::mbar_wait(BAR(16 + a0 + 1), (ph_aempty >> (a0 + 1)) & 1u);
+            ph_aempty ^= 1u << (a0 + 1);
           }
-          const uint32_t d_tmem = tmem_acc + (uint32_t)(sa * kTcN);
-          for (int kb = 0; kb < kblocks; ++kb) {
-            const long seq = blk_seq + (long)nt * kblocks + kb;
-            const int s = (int)(seq % kTcStages);
-            tc::mbar_wait(BAR(s), (ph_bfull >> s) & 1u);            // B block landed
-            ph_bfull ^= 1u << s;
+          const uint32_t d0 = tmem_base + (uint32_t)(a0 * kTcM), d1 = d0 + (uint32_t)kTcM;
+          for (int kb = 0; kb < kblocks; ++kb, seq += 2) {
+            const int s0 = (int)(seq % kTcStages), s1 = (int)((seq + 1) % kTcStages);
+            tc::mbar_wait(BAR(s0), (ph_rfull >> s0) & 1u);
+            ph_rfull ^= 1u << s0;
+            tc::mbar_wait(BAR(s1), (ph_rfull >> s1) & 1u);
+            ph_rfull ^= 1u << s1;
             tc::tc_fence_after();
-            const uint32_t b_addr = tc::smem_u32(sB + (size_t)s * b_bytes);
+            const uint32_t r0 = tc::smem_u32(sR + (size_t)s0 * b_bytes), r1 = tc::smem_u32(sR + (size_t)s1 * b_bytes);
 #pragma unroll
-            for (int j = 0; j < kTcBK / 8; ++j)
-              tc::mma_tf32_ts(d_tmem, tmem_base + (uint32_t)(kb * kTcBK + j * 8), tc::make_desc(b_addr + j * 256, sbo),
-                              idesc, (kb | j) ? 1u : 0u);
-            tc::mma_commit(BAR(6 + s));     // B stage free once these MMAs retire
+            for (int j = 0; j < kTcBK / 8; ++j) {
+              const uint64_t fdesc = tc::make_desc(f_addr + (uint32_t)(kb * (kTcM * 128) + j * 32));
+              const uint32_t acc = (kb | j) ? 1u : 0u;
+              tc::mma_tf32(d0, tc::make_desc(r0 + j * 32), fdesc, idesc, acc);
+              tc::mma_tf32(d1, tc::make_desc(r1 + j * 32), fdesc, idesc, acc);
+            }
+            tc::mma_commit(BAR(6 + s0));    // ring stages free once these MMAs retire
+            tc::mma_commit(BAR(6 + s1));
           }
-          tc::mma_commit(BAR(12 + sa));     // accumulator ready
+          tc::mma_commit(BAR(12 + a0));     // both accumulators of the pair ready
+          tc::mma_commit(BAR(12 + a0 + 1));
         }
       }
     } else {
-      // ---- epilogue warps 0-7: row quarter q = warp % 4, column half h = warp / 4 ------------------
-      const int q = warp & 3, hcol = warp >> 2;
-      float* stg = sStage + warp * 32 * kTcStageStride;      // this warp's 32 x 32 block (stride 33)
-      const int half = lane >> 4, cpair = (lane & 15) * 2;   // lane -> (row parity, column pair)
-      for (int nt = 0; nt < p.n_tiles; ++nt) {
-        const long tseq = tile_seq + nt;
-        const int sa = (int)(tseq % kTcAccStages);
-        tc::mbar_wait(BAR(12 + sa), (ph_afull >> sa) & 1u);
-        ph_afull ^= 1u << sa;
+      // ---- epilogue warps 0-7: lane quarter q = warp % 4, tile h = warp / 4 of every pair -----------
+      const int q = warp & 3, h = warp >> 2;
+      for (int pr = 0; pr < npairs; ++pr) {
+        const long pseq = pair_seq + pr;
+        const int a = (int)(pseq & 1) * 2 + h;
+        const int c = (2 * pr + h) * kTcN + q * 32 + lane;       // this lane's output column
+        const bool col_ok = c < p.ncols;
+        const float tv = col_ok ? __ldg(p.v_template + c) : 0.f; // issued before the wait
+        tc::mbar_wait(BAR(12 + a), (ph_afull >> a) & 1u);
+        ph_afull ^= 1u << a;
         tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kTcM);
+        float* o = p.out + f0 * (long)p.ncols + c;
+        if (p.debug == 3) {                                      // timing experiment: no TMEM reads / stores
+          tc::tc_fence_before();
+          tc::mbar_arrive(BAR(16 + a));
+          continue;
+        }
 #pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {                     // two 32-column chunks of this warp's half
-          const int cc = hcol * 64 + ch * 32;                // column offset inside the tile
-          const int c = nt * kTcN + cc + cpair;
-          const float t0 = c < p.ncols ? __ldg(p.v_template + c) : 0.f;
-          const float t1 = c + 1 < p.ncols ? __ldg(p.v_template + c + 1) : 0.f;
-          const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(sa * kTcN + cc);
-          uint32_t v[2][16];
-          tc::tmem_ld16(taddr, v[0]);
-          tc::tmem_ld16(taddr + 16, v[1]);
+        for (int ch = 0; ch < kTcM / 16; ++ch) {
+          uint32_t v[16];
+          tc::tmem_ld16(taddr + (uint32_t)(ch * 16), v);
           tc::tmem_ld_wait();
-          if (ch == 1) {
+          if (ch == kTcM / 16 - 1) {
             tc::tc_fence_before();
-            tc::mbar_arrive(BAR(14 + sa));                   // accumulator stage may be overwritten
+            tc::mbar_arrive(BAR(16 + a));                        // accumulator may be overwritten
           }
+          if (col_ok && p.debug != 1) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) stg[lane * kTcStageStride + h * 16 + i] = __uint_as_float(v[h][i]);
-          __syncwarp();
-#pragma unroll 4
-          for (int r2 = 0; r2 < 32; r2 += 2) {
-            const int r = r2 + half;
-            const long f = f0 + q * 32 + r;
-            if (f < p.num_frames && p.debug != 1) {
-              float2 w;
-              w.x = stg[r * kTcStageStride + cpair] + t0;
-              w.y = stg[r * kTcStageStride + cpair + 1] + t1;
-              float* o = p.out + f * (long)p.ncols + c;
-              if (c + 1 < p.ncols) *reinterpret_cast<float2*>(o) = w;
-              else if (c < p.ncols) o[0] = w.x;
+            for (int i = 0; i < 16; ++i) {
+              const long fr = ch * 16 + i;
+              if (f0 + fr < p.num_frames) o[fr * (long)p.ncols] = __uint_as_float(v[i]) + tv;
             }
           }
-          __syncwarp();
         }
       }
     }
-    tile_seq += p.n_tiles;
+    pair_seq += npairs;
     blk_seq += (long)p.n_tiles * kblocks;
   }
 

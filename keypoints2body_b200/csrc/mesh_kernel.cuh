@@ -148,7 +148,7 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
   if (ok && kdepth <= kTcKpadMax) {
     m.kpad = tc_kpad(kdepth);
     const int ncols = nv * 3, kblocks = m.kpad / kTcBK;
-    m.n_tiles = (ncols + kTcN - 1) / kTcN;
+    m.n_tiles = ((ncols + kTcN - 1) / kTcN + 1) / 2 * 2;   // tiles are consumed in pairs
     const size_t blk_floats = (size_t)tc_b_bytes() / 4;
     std::vector<float> bt((size_t)m.n_tiles * kblocks * blk_floats, 0.f);
     auto tf32 = [](float v) {
@@ -173,7 +173,7 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
             const float hi = tf32(v);
             r = part == 2 ? tf32(v - hi) : hi;         // [S_hi ; S_hi ; S_lo]
           }
-          bt[((size_t)nt * kblocks + k / kTcBK) * blk_floats + tc_elem_off(n, k % kTcBK)] = r;
+          bt[((size_t)nt * kblocks + k / kTcBK) * blk_floats + tc_elem_off(n, k % kTcBK)] = r;   // swizzle-128B image
         }
       }
     ok = mesh_upload(bt, &m.b_tiles, err);
@@ -442,7 +442,7 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
   ++launches;
   if (m.tc && a.out_vertices) {
     // ---- tensor-core path: blend (tcgen05) -> in-place skinning -> extra-joint gather ----------
-    const size_t tsm = tc_smem_bytes();
+    const size_t tsm = tc_smem_bytes(m.kpad);
     static size_t tc_configured = 0;
     if (tsm > tc_configured) {
       cudaError_t e = cudaFuncSetAttribute(blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
