@@ -115,6 +115,15 @@ typedef struct k2b_fit_args {
   /* scratch (device) */
   void* workspace;
   size_t workspace_bytes;    /* >= k2b_fit_workspace_bytes(...) */
+  /* camera-space fitter (core/fitters/camera_space.py:81-339); all zero / NULL for the world-space fitter.
+   * loss_kind 1 = stage 1: camera_fitting_loss_3d (core/losses.py:70-93) over RHip/LHip/RShoulder/LShoulder,
+   * only global_orient and the translation move, depth term depth_weight^2 |transl - depth_ref|^2 counted
+   * four times (the reference's (B,4,3)+(B,3) broadcast).  final_loss_mode 1 = stage 2: the returned loss is
+   * re-evaluated at the final parameters without the preserve term (camera_space.py:316-326). */
+  int32_t loss_kind;
+  int32_t final_loss_mode;
+  float depth_weight;        /* reference: 100 */
+  const float* depth_ref;    /* [B][3] initial camera translation, required for loss_kind 1 */
 } k2b_fit_args;
 
 size_t k2b_fit_workspace_bytes(const k2b_model* m, int64_t num_frames, int32_t optimizer,

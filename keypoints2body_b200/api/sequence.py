@@ -63,6 +63,24 @@ def fit_sequence_batched(fitter, xyz, conf, init: dict, seq_cfg: SequenceOptimiz
     seq_ind = torch.arange(first_seq_ind, first_seq_ind + T, device=xyz.device)
     kw = dict(joint_loss_weight=fc.joint_loss_weight, pose_preserve_weight=fc.pose_preserve_weight,
               freeze_betas=fc.freeze_betas)
+    camera = getattr(fitter, "num_iters", None) is not None and type(fitter).__name__ == "CameraSpaceFitter"
+    if camera:
+        # camera-space fits are B = 1 by construction in the reference (camera_space.py broadcasts (B,J,3)+(B,3));
+        # frames run as a serial loop (chained or from the fixed initialisation) and the mesh, which excludes
+        # the camera translation (camera_space.py:301-306), is produced by one batched pass at the end
+        if seq_cfg.schedule == "two_sweep":
+            raise NotImplementedError("schedule='two_sweep' is defined for the world-space fitter")
+        prev, rows = init, []
+        for t in range(T):
+            r = fitter.fit_batch(prev, xyz[t:t + 1], conf[t], seq_ind=first_seq_ind + t, with_mesh=False, **kw)
+            rows.append(r)
+            if seq_cfg.use_previous_frame_init:
+                prev = r["params"]
+        params = {k: torch.cat([r["params"][k] for r in rows], dim=0) for k in rows[0]["params"]}
+        out = {"params": params, "loss": torch.cat([r["loss"] for r in rows]),
+               "evals": torch.cat([r["evals"] for r in rows])}
+        out.update(fitter.forward_batch({k: v for k, v in params.items() if k != "transl"}))
+        return out
     if seq_cfg.schedule == "two_sweep":
         s0 = fitter.fit_batch(_expand(init, T), xyz, conf, seq_ind=torch.zeros_like(seq_ind), with_mesh=False, **kw)
         p0 = s0["params"]

@@ -14,6 +14,7 @@ import torch
 
 from ...models.smpl_data import BodyModelFitResult, BodyModelParams
 from ..config import FrameOptimizeConfig
+from ..fitters.camera_space import CameraSpaceFitter
 from ..fitters.world_space import WorldSpaceFitter
 
 
@@ -24,10 +25,15 @@ class OptimizationEstimator:
             raise NotImplementedError(
                 f"body_model='{model_type}' fitters are outside the accelerated path "
                 "(SURVEY.md section 8f row 4); use the reference implementation for them")
+        common = dict(model_type=model_type, prior_folder=getattr(frame_config, "prior_folder", "./data/models/"))
         if frame_config.coordinate_mode == "camera":
-            raise NotImplementedError(
-                "coordinate_mode='camera' (two-stage camera-space fitter) is not built yet "
-                "(SURVEY.md section 8f row 1)")
+            if model_type != "smpl":
+                raise NotImplementedError("the camera-space fitter handles SMPLData only (camera_space.py:83)")
+            self._fitter = CameraSpaceFitter(
+                smpl_model=model, step_size=frame_config.step_size, num_iters=frame_config.num_iters,
+                use_lbfgs=frame_config.use_lbfgs, joints_category=frame_config.joints_category, device=device,
+                pose_prior_num_gaussians=frame_config.pose_prior_num_gaussians, **common)
+            return
         self._fitter = WorldSpaceFitter(
             smpl_model=model, step_size=frame_config.step_size, num_iters_first=frame_config.num_iters_first,
             num_iters_followup=frame_config.num_iters_followup, use_lbfgs=frame_config.use_lbfgs,

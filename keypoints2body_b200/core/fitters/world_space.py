@@ -117,7 +117,7 @@ class WorldSpaceFitter:
     # ------------------------------------------------------------------ kernels
     def _run_fit(self, B, targets, conf, conf_per_frame, pose, betas, transl, expr, preserve, frame_iters,
                  frame_preserve, preserve_all, num_iters, optimizer, joint_loss_weight, pose_preserve_weight,
-                 freeze_betas, want_joints=True):
+                 freeze_betas, want_joints=True, loss_kind=0, final_loss_mode=0, depth_ref=None, depth_weight=100.0):
         dev = self.device
         out_pose = torch.empty(B, 72, device=dev)
         out_betas = torch.empty(B, 10, device=dev)
@@ -140,6 +140,8 @@ class WorldSpaceFitter:
             out_pose=nat.ptr(out_pose), out_betas=nat.ptr(out_betas), out_transl=nat.ptr(out_transl),
             out_expr=nat.ptr(out_expr), out_loss=nat.ptr(out_loss), out_joints=nat.ptr(out_joints),
             out_evals=nat.ptr(out_evals), workspace=nat.ptr(ws), workspace_bytes=ws.numel(),
+            loss_kind=int(loss_kind), final_loss_mode=int(final_loss_mode), depth_weight=float(depth_weight),
+            depth_ref=nat.ptr(depth_ref),
         )
         with torch.cuda.device(dev):
             nat.check(lib.k2b_fit_batch(self.native.handle, C.byref(a), nat.current_stream()))

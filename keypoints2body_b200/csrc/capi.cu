@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -211,6 +212,13 @@ extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* st
   p.out_loss = a->out_loss; p.out_joints = a->out_joints; p.out_evals = a->out_evals;
   p.scratch = (float*)a->workspace;
   p.lbfgs_hmax = lbfgs_history_capacity(a->num_iters);
+  p.debug_rounds = getenv("K2B_DEBUG_ROUNDS") != nullptr;
+  p.loss_kind = a->loss_kind;
+  p.final_mode = a->final_loss_mode;
+  p.depth_ref = a->depth_ref;
+  p.depth_w2 = 4.f * a->depth_weight * a->depth_weight;   // added to each of the 4 joint rows by the reference's broadcast
+  if (a->loss_kind == 1 && !a->depth_ref) return fail(K2B_EINVAL, "loss_kind 1 needs depth_ref");
+  if (a->loss_kind != 0 && a->loss_kind != 1) return fail(K2B_EINVAL, "unknown loss_kind");
   AdamTable at;
   fill_adam_table(at, (double)a->lr);
   cudaStream_t st = (cudaStream_t)stream;
@@ -274,7 +282,7 @@ extern "C" int k2b_fit_batch_host(k2b_model* m, const k2b_fit_args* h, void* str
   // staging size (upper bound incl. alignment slack)
   size_t need = 4096 + 256 * 24;
   need += sizeof(float) * B * (size_t)(K * 3 + K + 72 + 10 + 3 + 10 + 69);
-  need += sizeof(int32_t) * B + B;
+  need += sizeof(int32_t) * B + B + sizeof(float) * B * 3;
   need += sizeof(float) * B * (size_t)(72 + 10 + 3 + 10 + 1 + K * 3) + sizeof(int32_t) * B;
   if (m->stage_bytes < need) {
     cudaFree(m->stage);
@@ -306,6 +314,7 @@ extern "C" int k2b_fit_batch_host(k2b_model* m, const k2b_fit_args* h, void* str
   CUDA_TRY(h2d(d.preserve_pose, h->preserve_pose, (size_t)B * 69));
   CUDA_TRY(h2d(d.frame_iters, h->frame_iters, (size_t)B));
   CUDA_TRY(h2d(d.frame_preserve, h->frame_preserve, (size_t)B));
+  CUDA_TRY(h2d(d.depth_ref, h->depth_ref, (size_t)B * 3));
   d.out_pose = sg.take<float>((size_t)B * 72);
   d.out_betas = sg.take<float>((size_t)B * 10);
   d.out_transl = sg.take<float>((size_t)B * 3);

@@ -212,6 +212,11 @@ struct FrameConsts {
   const float* keep;     // preserve pose element i at keep[i*stride]
   long stride;
   float keep_w2;         // pose_preserve_weight^2 or 0
+  // camera-space stage 1 (camera_fitting_loss_3d, core/losses.py:70-93): plain squared joint error
+  // instead of GMoF, plus depth_w2 * |transl - depth_ref|^2
+  bool plain_sq;
+  float depth_w2;
+  float dref[3];
 };
 
 // Column accessor: element i of this frame's parameter vector x (shared memory on the device,
@@ -414,6 +419,10 @@ K2B_HD V3 residual(KinCtx<NS>& k, int j, V3 t) {
   const float ex = p.x - fc.tgt[(3 * j + 0) * fc.stride];
   const float ey = p.y - fc.tgt[(3 * j + 1) * fc.stride];
   const float ez = p.z - fc.tgt[(3 * j + 2) * fc.stride];
+  if (k.fc.plain_sq) {
+    k.loss = fmaf(w, fmaf(ex, ex, fmaf(ey, ey, ez * ez)), k.loss);
+    return v3(2.f * w * ex, 2.f * w * ey, 2.f * w * ez);
+  }
   const float ix = fdiv(1.f, kSigma2 + ex * ex), iy = fdiv(1.f, kSigma2 + ey * ey), iz = fdiv(1.f, kSigma2 + ez * ez);
   const float gx = kSigma2 * ex * ex * ix, gy = kSigma2 * ey * ey * iy, gz = kSigma2 * ez * ez * iz;
   k.loss = fmaf(w, (gx + gy) + gz, k.loss);
@@ -546,6 +555,12 @@ K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& f
   chain_bwd<NS>(k, kSpine, 0, 3, false, j9, a9);
   const V3 g0 = residual<NS>(k, 0, root.t);
   loss += k.loss;
+  V3 dgrad = v3(0.f, 0.f, 0.f);
+  if (fc.depth_w2 != 0.f) {   // camera-space stage 1: keep the translation near its initial estimate
+    const V3 d = v3(k.transl.x - fc.dref[0], k.transl.y - fc.dref[1], k.transl.z - fc.dref[2]);
+    loss = fmaf(fc.depth_w2, dot(d, d), loss);
+    dgrad = v3(2.f * fc.depth_w2 * d.x, 2.f * fc.depth_w2 * d.y, 2.f * fc.depth_w2 * d.z);
+  }
   if (with_grad) {
     acc_add(a0, a9);
     acc_point(a0, g0, root.t);
@@ -554,9 +569,9 @@ K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& f
     c.G(0) = rb.x;
     c.G(1) = rb.y;
     c.G(2) = rb.z;
-    c.G(kTranslOff) = a0.s.x;
-    c.G(kTranslOff + 1) = a0.s.y;
-    c.G(kTranslOff + 2) = a0.s.z;
+    c.G(kTranslOff) = a0.s.x + dgrad.x;
+    c.G(kTranslOff + 1) = a0.s.y + dgrad.y;
+    c.G(kTranslOff + 2) = a0.s.z + dgrad.z;
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       c.G(kShapeOff + s) = (with_priors && s < 10) ? fmaf(2.f * kShapePriorW2, k.shape[s], k.shape_bar[s]) : k.shape_bar[s];

@@ -56,6 +56,11 @@ struct FitParams {
   int* out_gmm_component;
   float* scratch;          // transposed per-frame scratch, see scratch_floats_per_frame
   int lbfgs_hmax;
+  int loss_kind;           // 0 body_fitting_loss_3d (world / camera stage 2), 1 camera_fitting_loss_3d (camera stage 1)
+  int final_mode;          // 1: returned loss = priors + joints at the final parameters, no preserve (camera_space.py:316-326)
+  const float* depth_ref;  // [B][3] initial camera translation (loss_kind 1)
+  float depth_w2;
+  int debug_rounds;        // K2B_DEBUG_ROUNDS: pack the warp's round count into out_evals (diagnostics)
 };
 
 struct AdamTable {
@@ -147,7 +152,10 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
 #pragma unroll 2
       for (int j = 0; j < K; ++j) {
         const float cf = p.conf ? (p.conf_per_frame ? p.conf[fr * K + j] : p.conf[j]) : 1.f;
-        scr[(kScrWgt + j) * kStride] = p.joint_w2 * cf * cf;
+        float wj = p.joint_w2 * cf * cf;
+        // camera stage 1 looks at RHip, LHip, RShoulder, LShoulder only, unweighted (losses.py:80-92)
+        if (p.loss_kind == 1) wj = (j == 1 || j == 2 || j == 16 || j == 17) ? 1.f : 0.f;
+        scr[(kScrWgt + j) * kStride] = wj;
       }
       const float* kp = p.preserve_pose ? p.preserve_pose + fr * kBodyDim : p.init_pose + fr * kPoseDim + 3;
 #pragma unroll 3
@@ -160,6 +168,14 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
     fc.stride = kStride;
     const bool keep_on = p.frame_preserve ? (p.frame_preserve[fr] != 0) : (p.preserve_all != 0);
     fc.keep_w2 = keep_on ? p.keep_w2 : 0.f;
+    const bool stage1 = p.loss_kind == 1;       // only global_orient and the translation are optimised
+    fc.plain_sq = stage1;
+    fc.depth_w2 = stage1 ? p.depth_w2 : 0.f;
+    fc.dref[0] = fc.dref[1] = fc.dref[2] = 0.f;
+    if (stage1) {
+      fc.dref[0] = p.depth_ref[fr * 3]; fc.dref[1] = p.depth_ref[fr * 3 + 1]; fc.dref[2] = p.depth_ref[fr * 3 + 2];
+    }
+    const bool priors = !stage1;
     const bool freeze_betas = p.freeze_betas != 0;
 
     float out_loss = 0.f;
@@ -173,7 +189,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
     // each round evaluates at the current x, then the mode-specific (cheap) update runs.
     if (MODE == kModeEval) {
       int comp = 0;
-      out_loss = eval_frame<NS, K>(c, tb, fc, true, true, jout, &comp);
+      out_loss = eval_frame<NS, K>(c, tb, fc, true, priors, jout, &comp);
       if (valid) {
         for (int i = 0; i < kPoseDim; ++i) p.out_grad_pose[f * kPoseDim + i] = c.G(i);
         for (int i = 0; i < 3; ++i) p.out_grad_transl[f * 3 + i] = c.G(kTranslOff + i);
@@ -197,10 +213,12 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       const int warp_iters = __reduce_max_sync(0xffffffffu, iters);
       // rounds 1..warp_iters: loss + gradient + Adam step; round warp_iters+1: joints-only
       // forward at the final parameters (world_space.py:258-278)
-      const int rounds = warp_iters + (p.out_joints ? 1 : 0);
+      const int rounds = warp_iters + ((p.out_joints || p.final_mode) ? 1 : 0);
       for (int k = 1; k <= rounds; ++k) {
         const bool last = k > warp_iters;
-        const float loss = eval_frame<NS, K>(c, tb, fc, !last, !last, last ? jout : nullptr, nullptr);
+        if (last) fc.keep_w2 = 0.f;
+        const float loss = eval_frame<NS, K>(c, tb, fc, !last, priors && (!last || p.final_mode), last ? jout : nullptr, nullptr);
+        if (last && p.final_mode) out_loss = loss;
         if (!last && k <= iters) {
           out_loss = loss;   // loss of the last iteration, before its step (world_space.py:250-256)
           ++evals;
@@ -215,6 +233,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
 #pragma unroll 17
           for (int i = 0; i < NX; ++i) {
             if (freeze_betas && i >= kShapeOff && i < kShapeOff + 10) continue;
+            if (stage1 && !(i < 3 || (i >= kTranslOff && i < kShapeOff))) continue;
             float mm = m1[i * kStride], vv = m2[i * kStride], x = c.X(i);
             adam_update(x, mm, vv, c.G(i), step_k, bc2_k);
             c.X(i) = x;
@@ -238,16 +257,24 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       // (world_space.py:246-247).  Each closure writes its gradient into the slot the machine
       // designates, so nothing is copied afterwards.
       int stage = 0;   // 0 first closure, 1 searching, 2 final loss
+      int rounds = 0;
       while (true) {
+        ++rounds;
         const bool fin = stage == 2;
         const Cols ce = st.eval_cols(c, v);
-        const float loss = eval_frame<NS, K>(ce, tb, fc, !fin, true, fin ? jout : nullptr, nullptr);
+        if (fin && p.final_mode) fc.keep_w2 = 0.f;
+        const float loss = eval_frame<NS, K>(ce, tb, fc, !fin, priors, fin ? jout : nullptr, nullptr);
         if (fin) {
           out_loss = loss;
           break;
         }
         if (freeze_betas)
           for (int i = 0; i < 10; ++i) ce.G(kShapeOff + i) = 0.f;
+        if (stage1) {
+#pragma unroll 3
+          for (int i = 3; i < kTranslOff; ++i) ce.G(i) = 0.f;
+          for (int i = kShapeOff; i < NX; ++i) ce.G(i) = 0.f;
+        }
         if (stage == 0 || (!st.done && !st.need_outer)) st.advance(c, v, loss, stage == 0, iters, p.lr);
         stage = 1;
         // Lanes reach their outer-iteration boundary on different rounds.  The direction update
@@ -265,6 +292,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         }
       }
       evals = st.evals;
+      if (p.debug_rounds) evals |= rounds << 16;
     }
 
     if (valid) {

@@ -176,6 +176,88 @@ def fit_frame(model, prior, init: dict, j3d, conf, *, seq_ind=0, num_obs=22, use
     }
 
 
+def camera_fitting_loss_3d(model_joints, camera_t, camera_t_est, j3d, depth_loss_weight=100.0):
+    """Stage-1 camera loss (core/losses.py:70-93); RHip, LHip, RShoulder, LShoulder = 2, 1, 17, 16 in both
+    joint maps.  Note the (B,4,3) + (B,3) broadcast: the depth term is added to each of the 4 joint rows."""
+    sel = [2, 1, 17, 16]
+    mj = model_joints + camera_t
+    err = (j3d[:, sel] - mj[:, sel]) ** 2
+    depth = (depth_loss_weight ** 2) * (camera_t - camera_t_est) ** 2
+    return (err + depth).sum()
+
+
+def fit_frame_camera(model, prior, init: dict, j3d, conf, *, seq_ind=0, num_obs=22, use_lbfgs=True, step_size=1e-2,
+                     num_iters=100, joint_loss_weight=600.0, pose_preserve_weight=5.0, freeze_betas=True,
+                     init_cam_t=None):
+    """``CameraSpaceFitter.fit_frame`` (core/fitters/camera_space.py:81-339), B = 1.
+
+    ``init_cam_t`` (camera_space.py:91,133) is both the start and the depth reference.  When it is left
+    to the stage-0 estimate the stage-1 translation gradient is analytically zero at the start, so Adam's
+    first step there is decided by rounding noise (g / (|g| + 1e-8)): only this restatement, which
+    issues the same torch ops in the same order, follows that trajectory; an independent implementation
+    is compared step for step from a caller-supplied ``init_cam_t`` instead."""
+    w_keep = pose_preserve_weight if seq_ind > 0 else 0.0
+    body_pose = init["body_pose"].detach().clone()
+    go = init["global_orient"].detach().clone()
+    betas = init["betas"].detach().clone()
+    idx = torch.arange(num_obs)
+    with torch.no_grad():
+        mj = model(global_orient=go, body_pose=body_pose, betas=betas).joints
+    sel = [2, 1, 17, 16]
+    if init_cam_t is None:
+        init_cam_t = ((j3d[:, sel] - mj[:, sel]).sum(dim=1) / 4.0).detach()      # guess_init_3d :16-41
+    else:
+        init_cam_t = init_cam_t.detach().clone()
+    cam_t = init_cam_t.clone()
+    preserve = body_pose.detach().clone()
+    go.requires_grad_(True)
+    cam_t.requires_grad_(True)
+
+    def make_opt(params):
+        if use_lbfgs:
+            return torch.optim.LBFGS(params, max_iter=num_iters, lr=step_size, line_search_fn="strong_wolfe")
+        return torch.optim.Adam(params, lr=step_size, betas=(0.9, 0.999))
+
+    def run(opt, loss_fn):
+        if use_lbfgs:
+            def closure():
+                opt.zero_grad()
+                loss = loss_fn()
+                loss.backward()
+                return loss
+            opt.step(closure)
+        else:
+            for _ in range(num_iters):
+                loss = loss_fn()
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+
+    def stage1():
+        j = model(global_orient=go, body_pose=body_pose, betas=betas).joints
+        return camera_fitting_loss_3d(j[:, idx], cam_t, init_cam_t, j3d[:, idx])
+
+    run(make_opt([go, cam_t]), stage1)
+    body_pose.requires_grad_(True)
+    move_betas = seq_ind == 0 or not freeze_betas
+    betas.requires_grad_(move_betas)
+    params = [body_pose, betas, go, cam_t] if move_betas else [body_pose, go, cam_t]
+    if conf is None:
+        conf = torch.ones(j3d.shape[1])
+
+    def stage2(jw=joint_loss_weight, wk=w_keep):
+        j = model(global_orient=go, body_pose=body_pose, betas=betas).joints
+        return body_fitting_loss_3d(body_pose, preserve, betas, j[:, idx] + cam_t, j3d[:, idx], prior, conf[idx], jw, wk)
+
+    run(make_opt(params), stage2)
+    with torch.no_grad():
+        out = model(global_orient=go, body_pose=body_pose, betas=betas)
+        final_loss = stage2(600.0, 0.0)                                           # :316-326
+    return {"params": {"global_orient": go.detach(), "body_pose": body_pose.detach(), "betas": betas.detach(),
+                       "transl": cam_t.detach()},
+            "joints": out.joints.detach(), "vertices": out.vertices.detach(), "loss": final_loss}
+
+
 def guess_transl(model, pose, betas, j3d):
     """``guess_init_transl_from_root`` (world_space.py:13-50): root-joint alignment."""
     with torch.no_grad():

@@ -243,6 +243,52 @@ def main():
             put(name + "_transl", r.params.transl)
             put(name + "_loss", r.loss)
 
+        # ---- F. camera-space two-stage fitter (reference CameraSpaceFitter, B = 1 per frame) -------
+        from keypoints2body.core.fitters.camera_space import CameraSpaceFitter
+
+        model = models["smpl"]
+        mo, tgtc = targets_for(model, 3, seed=41)
+        gcam = torch.Generator().manual_seed(42)
+        posec = mo["pose"] + 0.1 * torch.randn(3, 72, generator=gcam)
+        put("cam_in_target", tgtc)
+        put("cam_in_pose", posec)
+        for name, lb, iters, seq_ind, freeze in (("cam_adam", False, 15, 0, True), ("cam_adam_follow", False, 15, 2, True),
+                                                  ("cam_lbfgs", True, 20, 0, True)):
+            fit = CameraSpaceFitter(model, step_size=1e-2, num_iters=iters, use_lbfgs=lb, joints_category="AMASS")
+            outs = {k: [] for k in ("pose", "betas", "transl", "joints", "loss")}
+            for b in range(3):
+                init = SMPLData(betas=torch.zeros(1, 10), global_orient=posec[b:b + 1, :3], body_pose=posec[b:b + 1, 3:])
+                r = fit.fit_frame(init, tgtc[b:b + 1], torch.ones(22), seq_ind=seq_ind, freeze_betas=freeze)
+                outs["pose"].append(r.params.pose); outs["betas"].append(r.params.betas)
+                outs["transl"].append(r.params.transl); outs["joints"].append(r.joints)
+                outs["loss"].append(r.loss.reshape(1))
+            for k, v in outs.items():
+                put(f"{name}_{k}", torch.cat(v))
+        # caller-supplied init_cam_t (camera_space.py:91,133): start AND depth reference, away from the
+        # stage-0 stationary point, so Adam's first step is not decided by rounding noise
+        with torch.no_grad():
+            j0 = model(global_orient=posec[:, :3], body_pose=posec[:, 3:], betas=torch.zeros(3, 10)).joints
+        sel = [2, 1, 17, 16]
+        given = (tgtc[:, sel] - j0[:, sel]).sum(dim=1) / 4.0 + torch.tensor([[0.012, -0.02, 0.016]])
+        put("cam_given_init", given)
+        for name, seq_ind in (("cam_given_adam", 0), ("cam_given_adam_follow", 2)):
+            fit = CameraSpaceFitter(model, step_size=1e-2, num_iters=15, use_lbfgs=False, joints_category="AMASS")
+            outs = {k: [] for k in ("pose", "betas", "transl", "joints", "loss")}
+            for b in range(3):
+                init = SMPLData(betas=torch.zeros(1, 10), global_orient=posec[b:b + 1, :3], body_pose=posec[b:b + 1, 3:])
+                r = fit.fit_frame(init, tgtc[b:b + 1], torch.ones(22), seq_ind=seq_ind, freeze_betas=True,
+                                  init_cam_t=given[b:b + 1])
+                outs["pose"].append(r.params.pose); outs["betas"].append(r.params.betas)
+                outs["transl"].append(r.params.transl); outs["joints"].append(r.joints)
+                outs["loss"].append(r.loss.reshape(1))
+            for k, v in outs.items():
+                put(f"{name}_{k}", torch.cat(v))
+        r = ref.optimize_params_frame(tgtc[0].numpy(), body_model="smpl", joint_layout="AMASS", model=model,
+                                      config=dict(use_lbfgs=False, coordinate_mode="camera", num_iters=10))
+        put("frame_cam_adam_pose", r.params.pose)
+        put("frame_cam_adam_transl", r.params.transl)
+        put("frame_cam_adam_loss", r.loss)
+
         # ---- E. shape pass alone --------------------------------------------
         b = optimize_shape_multi_frame(model, init_betas=torch.zeros(1, 10),
                                        pose_init=torch.zeros(6, 72), j3d_world=tgt,

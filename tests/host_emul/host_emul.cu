@@ -79,19 +79,25 @@ static EvalFn pick(int ns, int K) {
 extern "C" int emu_fit(void* model, int mode, int B, int K, int iters, int freeze_betas, float lr, float joint_w,
                        float keep_w, const unsigned char* keep_on, const float* targets, const float* conf,
                        int conf_per_frame, const float* x0, const float* keep_pose, float* out_x, float* out_loss,
-                       float* out_joints, int* out_evals, int* out_comp, float* out_trace /* [B][64][3] or null */) {
+                       float* out_joints, int* out_evals, int* out_comp, float* out_trace /* [B][64][3] or null */,
+                       int loss_kind, int final_mode, float depth_weight, const float* depth_ref) {
   EmuModel* m = (EmuModel*)model;
   const int NS = m->ns, NX = 75 + NS;
   FitTables tb{m->chol.data(), m->mu.data(), m->nlw.data(), (const float4*)m->rel.data()};
   EvalFn ev = pick(NS, K);
   for (int f = 0; f < B; ++f) {
     std::vector<float> x(x0 + (size_t)f * NX, x0 + (size_t)(f + 1) * NX), g(NX, 0.f), w(K);
+    const bool stage1 = loss_kind == 1;
     for (int j = 0; j < K; ++j) {
       const float cf = conf ? (conf_per_frame ? conf[f * K + j] : conf[j]) : 1.f;
       w[j] = joint_w * joint_w * cf * cf;
+      if (stage1) w[j] = (j == 1 || j == 2 || j == 16 || j == 17) ? 1.f : 0.f;
     }
     FrameConsts fc{targets + (size_t)f * K * 3, w.data(), keep_pose + (size_t)f * kBodyDim, 1,
-                   (keep_on && keep_on[f]) ? keep_w * keep_w : 0.f};
+                   (keep_on && keep_on[f]) ? keep_w * keep_w : 0.f, stage1, stage1 ? 4.f * depth_weight * depth_weight : 0.f,
+                   {0.f, 0.f, 0.f}};
+    if (stage1) for (int i = 0; i < 3; ++i) fc.dref[i] = depth_ref[f * 3 + i];
+    const bool priors = !stage1;
     Cols c{x.data(), g.data(), 1, 1};
     float loss = 0.f;
     int evals = 0, comp = 0;
@@ -103,16 +109,21 @@ extern "C" int emu_fit(void* model, int mode, int B, int K, int iters, int freez
     } else if (mode == 1) {
       std::vector<float> m1(NX, 0.f), m2(NX, 0.f);
       for (int k = 1; k <= iters; ++k) {
-        loss = ev(c, tb, fc, true, true, nullptr, nullptr);
+        loss = ev(c, tb, fc, true, priors, nullptr, nullptr);
         ++evals;
         const float step_k = (float)((double)lr / (1.0 - std::pow(0.9, (double)k)));
         const float bc2_k = (float)std::sqrt(1.0 - std::pow(0.999, (double)k));
         for (int i = 0; i < NX; ++i) {
           if (freeze_betas && i >= kShapeOff && i < kShapeOff + 10) continue;
+          if (stage1 && !(i < 3 || (i >= kTranslOff && i < kShapeOff))) continue;
           adam_update(x[i], m1[i], m2[i], g[i], step_k, bc2_k);
         }
       }
-      (void)ev(c, tb, fc, false, false, jout, nullptr);
+      fc.keep_w2 = 0.f;
+      {
+        const float fl = ev(c, tb, fc, false, priors && final_mode, jout, nullptr);
+        if (final_mode) loss = fl;
+      }
       memcpy(out_x + (size_t)f * NX, x.data(), NX * sizeof(float));
     } else {
       const int hmax = lbfgs_history_capacity(iters);

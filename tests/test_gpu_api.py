@@ -105,6 +105,19 @@ def test_two_sweep_schedule_is_reference_fit_frame_calls(goldens, weights, asset
         assert (res[t].joints.cpu() - ref["joints"]).abs().max() < 2e-4
 
 
+def test_frame_api_camera_mode(goldens, weights, asset_cwd):
+    import keypoints2body_b200 as k2b
+
+    g = goldens
+    r = k2b.optimize_params_frame(g["cam_in_target"][0], body_model="smpl", joint_layout="AMASS", model=weights("smpl"),
+                                  config=dict(use_lbfgs=False, coordinate_mode="camera", num_iters=10))
+    # the API path starts from the stage-0 estimate (noise-seeded Adam first step): outcome-level comparison
+    assert np.abs(r.params.pose.cpu().numpy() - g["frame_cam_adam_pose"]).max() < 0.1
+    assert np.abs(r.params.transl.cpu().numpy() - g["frame_cam_adam_transl"]).max() < 0.05
+    assert abs(float(r.loss) - float(g["frame_cam_adam_loss"])) < 0.25 * float(g["frame_cam_adam_loss"])
+    assert r.vertices.shape == (1, 6890, 3) and r.joints.shape[0] == 1
+
+
 def test_error_behaviour(weights, asset_cwd):
     import keypoints2body_b200 as k2b
 

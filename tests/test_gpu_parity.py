@@ -267,3 +267,45 @@ def test_edge_cases(fitters, weights):
             torch.zeros(3, 24, 3), None, num_iters=1, with_mesh=False)
     with pytest.raises(ValueError):
         f.fit_batch({k: v for k, v in init.items() if k != "transl"}, tgt, None)
+
+
+@pytest.mark.parametrize("tag,iters,seq_ind", [("cam_given_adam", 15, 0), ("cam_given_adam_follow", 15, 2),
+                                               ("cam_adam", 15, 0), ("cam_adam_follow", 15, 2)])
+def test_camera_fitter_adam_vs_reference_goldens(goldens, weights, gmm, tag, iters, seq_ind):
+    """Camera-space two-stage fitter, Adam: reference CameraSpaceFitter goldens.  Strict from a
+    caller-supplied ``init_cam_t``; from the stage-0 estimate (zero translation gradient -> Adam's first
+    step is rounding noise in the reference too) only the outcome is compared."""
+    from keypoints2body_b200.core.fitters.camera_space import CameraSpaceFitter
+    from keypoints2body_b200.models.smpl_data import SMPLData
+
+    g = goldens
+    f = CameraSpaceFitter(weights("smpl"), num_iters=iters, use_lbfgs=False, joints_category="AMASS",
+                          model_type="smpl", gmm=gmm)
+    pose, tgt = T(g["cam_in_pose"]), T(g["cam_in_target"])
+    strict = "given" in tag
+    for b in range(3):
+        init = SMPLData(betas=torch.zeros(1, 10), global_orient=pose[b:b + 1, :3], body_pose=pose[b:b + 1, 3:])
+        r = f.fit_frame(init, tgt[b:b + 1], torch.ones(22), seq_ind=seq_ind, freeze_betas=True,
+                        init_cam_t=T(g["cam_given_init"][b:b + 1]) if strict else None)
+        ref_loss = float(g[tag + "_loss"][b])
+        if strict:
+            assert np.abs(cpu(r.params.pose) - g[tag + "_pose"][b:b + 1]).max() < 1e-4
+            assert np.abs(cpu(r.params.transl) - g[tag + "_transl"][b:b + 1]).max() < 1e-4
+            assert np.abs(cpu(r.params.betas) - g[tag + "_betas"][b:b + 1]).max() < 1e-4
+            assert np.abs(cpu(r.joints) - g[tag + "_joints"][b:b + 1]).max() < 1e-4   # no camera translation in joints
+            np.testing.assert_allclose(float(r.loss), ref_loss, rtol=1e-4)
+        else:
+            assert abs(float(r.loss) - ref_loss) < 0.25 * ref_loss
+            assert np.abs(cpu(r.params.pose) - g[tag + "_pose"][b:b + 1]).max() < 0.1
+
+
+def test_camera_fitter_lbfgs_statistics(goldens, weights, gmm):
+    from keypoints2body_b200.core.fitters.camera_space import CameraSpaceFitter
+
+    g = goldens
+    f = CameraSpaceFitter(weights("smpl"), num_iters=20, use_lbfgs=True, joints_category="AMASS", model_type="smpl", gmm=gmm)
+    pose, tgt = T(g["cam_in_pose"]), T(g["cam_in_target"])
+    out = f.fit_batch(dict(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=torch.zeros(3, 10)), tgt,
+                      torch.ones(22), seq_ind=0, freeze_betas=True)
+    assert np.median(cpu(out["loss"])) <= 1.5 * np.median(g["cam_lbfgs_loss"])
+    assert int(out["evals"].max()) <= 2 * (20 * 5 // 4 + 1)

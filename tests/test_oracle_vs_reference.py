@@ -122,3 +122,26 @@ def test_shape_pass_matches_reference(goldens, shims):
     b = rp.optimize_shape(shims("smpl"), torch.zeros(1, 10), torch.zeros(6, 72), T(g["seq_in_target"]),
                           torch.ones(22), frame_indices=list(range(5)), num_iters=40)
     np.testing.assert_allclose(b.numpy(), g["shape_pass_betas"], atol=1e-5)
+
+
+CAM_CASES = {"cam_adam": (False, 15, 0), "cam_adam_follow": (False, 15, 2), "cam_lbfgs": (True, 20, 0),
+             "cam_given_adam": (False, 15, 0), "cam_given_adam_follow": (False, 15, 2)}
+
+
+@pytest.mark.parametrize("tag", sorted(CAM_CASES))
+def test_camera_fitter_matches_reference(goldens, shims, oracle_prior, tag):
+    """Camera-space two-stage fitter (core/fitters/camera_space.py) restated in the oracle."""
+    lbfgs, iters, seq_ind = CAM_CASES[tag]
+    g = goldens
+    pose, tgt = T(g["cam_in_pose"]), T(g["cam_in_target"])
+    for b in range(3):
+        init = dict(global_orient=pose[b:b + 1, :3], body_pose=pose[b:b + 1, 3:], betas=torch.zeros(1, 10))
+        out = rp.fit_frame_camera(shims("smpl"), oracle_prior, init, tgt[b:b + 1], torch.ones(22), seq_ind=seq_ind,
+                                  use_lbfgs=lbfgs, num_iters=iters,
+                                  init_cam_t=T(g["cam_given_init"][b:b + 1]) if "given" in tag else None)
+        p = out["params"]
+        tol = 1e-4 if lbfgs else 2e-6
+        np.testing.assert_allclose(torch.cat([p["global_orient"], p["body_pose"]], 1).numpy(), g[tag + "_pose"][b:b + 1], atol=tol)
+        np.testing.assert_allclose(p["transl"].numpy(), g[tag + "_transl"][b:b + 1], atol=tol)
+        np.testing.assert_allclose(out["joints"].numpy(), g[tag + "_joints"][b:b + 1], atol=tol)
+        np.testing.assert_allclose(float(out["loss"]), float(g[tag + "_loss"][b]), rtol=1e-4)

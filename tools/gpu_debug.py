@@ -88,3 +88,17 @@ if what == "meshprof":
         f.forward_batch(params, out_vertices=buf)
     torch.cuda.synchronize()
     print("ok")
+if what == "rounds":
+    os.environ["K2B_DEBUG_ROUNDS"] = "1"
+    f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=True)
+    B = 148 * 384
+    mo = syn.make_motion(B, seed=3)
+    tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22).cuda()
+    for (iters, seq, scale) in ((30, 0, 0.0), (10, 1, 0.9)):
+        init = dict(global_orient=mo["pose"][:, :3].contiguous() * scale, body_pose=mo["pose"][:, 3:].contiguous() * scale,
+                    betas=torch.zeros(B, 10), transl=mo["transl"])
+        init = {k: v.cuda() for k, v in init.items()}
+        o = f.fit_batch(init, tgt, None, seq_ind=seq, num_iters=iters, with_mesh=False)
+        e = o["evals"].cpu().numpy()
+        ev, rd = e & 0xFFFF, e >> 16
+        print(f"iters={iters}: evals/frame mean {ev.mean():.2f} max {ev.max()}, rounds/warp mean {rd.mean():.2f} max {rd.max()} -> rounds/evals = {rd.mean()/ev.mean():.3f}")
