@@ -17,7 +17,7 @@ from .body_model import BodyModelWeights
 from .core.prior import GMMConstants
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libk2b_b200.so")
+LIB_PATH = os.environ.get("K2B_LIB", os.path.join(_HERE, "libk2b_b200.so"))
 
 OPT_ADAM, OPT_LBFGS = 0, 1
 

@@ -36,20 +36,23 @@
 
 namespace k2b {
 
-constexpr int kTcM = 128;          // frames per pass (the MMA's N)
+constexpr int kTcM = 128;          // frames per pass (the MMA's N) for blend depths up to 256 (SMPL)
+constexpr int kTcMDeep = 64;       // frames per pass for deeper blends (SMPL-H 512, SMPL-X 576): features must fit smem
 constexpr int kTcN = 128;          // output columns per tile (the MMA's M)
 constexpr int kTcBK = 32;          // K block streamed per TMA copy = one 128-byte swizzle atom (4 MMAs of K = 8)
-constexpr int kTcKpadMax = 256;    // SMPL: 207 pose features + 3 x 10 split shape rows, padded to 8 x 32
+constexpr int kTcKpadWide = 256;   // SMPL: 207 pose features + 3 x 10 split shape rows, padded to 8 x 32
+constexpr int kTcKpadMax = 576;    // SMPL-X: 486 pose features + 3 x 20 split shape/expression rows, 18 x 32
 constexpr int kTcThreads = 320;    // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
-constexpr int kTcStages = 6;       // ring depth (K blocks of dirs, 16 KB each)
+constexpr int kTcStages = 6;       // ring depth (K blocks of dirs, 16 KB each); 5 on the deep variant
+constexpr int kTcStagesDeep = 5;
 constexpr int kTcAccStages = 4;    // accumulators in TMEM (two pairs)
 constexpr int kTcTmemCols = 512;
 
 __host__ __device__ constexpr int tc_kpad(int kdepth) { return (kdepth + kTcBK - 1) / kTcBK * kTcBK; }
 __host__ __device__ constexpr int tc_b_bytes() { return kTcN * 128; }                    // one (column tile, K block)
-__host__ __device__ constexpr int tc_f_bytes(int kpad) { return (kpad / kTcBK) * kTcM * 128; }
-__host__ __device__ constexpr size_t tc_smem_bytes(int kpad) {
-  return (size_t)tc_f_bytes(kpad) + (size_t)kTcStages * (size_t)tc_b_bytes() + 1024;
+__host__ __device__ constexpr int tc_f_bytes(int kpad, int fr) { return (kpad / kTcBK) * fr * 128; }
+__host__ __device__ constexpr size_t tc_smem_bytes(int kpad, int fr, int stages) {
+  return (size_t)tc_f_bytes(kpad, fr) + (size_t)stages * (size_t)tc_b_bytes() + 1024;
 }
 // offset (in floats) of element (row, k < 32) inside one 128-row swizzle-128B K block
 __host__ __device__ constexpr int tc_elem_off(int row, int k) {
@@ -164,14 +167,17 @@ struct BlendParams {
   int debug;   // K2B_TC_DEBUG: 1 = skip output stores, 2 = skip B copies (timing experiments only)
 };
 
+// FR = frames per pass (MMA N), STAGES = dirs ring depth
+template <int FR, int STAGES>
 __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_constant__ BlendParams p) {
+  static_assert(FR % 16 == 0 && FR >= 16 && FR * kTcAccStages <= kTcTmemCols && STAGES <= 6, "tile shape");
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   const int kpad = p.kpad;
   constexpr int b_bytes = tc_b_bytes();
-  const int f_bytes = tc_f_bytes(kpad);
+  const int f_bytes = tc_f_bytes(kpad, FR);
   float* sF = reinterpret_cast<float*>(tc_smem);                         // features of the pass
   unsigned char* sR = tc_smem + f_bytes;                                 // dirs ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + f_bytes + (size_t)kTcStages * b_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + f_bytes + (size_t)STAGES * b_bytes);
   // bars: [0,6) ring_full; [6,12) ring_empty; [12,16) acc_full; [16,20) acc_empty; then the TMEM base word
   uint32_t* tmem_word = reinterpret_cast<uint32_t*>(bars + 20);
 
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
   if (tid == 0) {
-    for (int i = 0; i < kTcStages; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       tc::mbar_init(BAR(i), 1);          // ring_full: producer's expect_tx arrival
       tc::mbar_init(BAR(6 + i), 1);      // ring_empty: tcgen05.commit
     }
@@ -196,8 +202,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_word;
 
-  const long num_passes = (p.num_frames + kTcM - 1) / kTcM;
-  const uint32_t idesc = tc::make_idesc(kTcN, kTcM);       // M = columns tile, N = frames
+  const long num_passes = (p.num_frames + FR - 1) / FR;
+  const uint32_t idesc = tc::make_idesc(kTcN, FR);       // M = columns tile, N = frames
   const int kblocks = kpad / kTcBK;
   const int npairs = p.n_tiles / 2;                         // n_tiles is padded to an even count
   uint32_t ph_rfull = 0, ph_rempty = 0, ph_afull = 0, ph_aempty = 0;   // one parity bit per stage
@@ -205,24 +211,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
   long blk_seq = 0;    // running K-block counter across passes (dirs ring position)
 
   for (long ps = blockIdx.x; ps < num_passes; ps += gridDim.x) {
-    const long f0 = ps * kTcM;
+    const long f0 = ps * FR;
     // every MMA of the previous pass has retired (the epilogue saw its last acc_full) before the
     // features are overwritten
     __syncthreads();
     // ---- N operand: features of 128 frames -> shared memory (canonical K-major image) ----------
-    for (int i = tid; i < kTcM * kpad; i += kTcThreads) {
+    for (int i = tid; i < FR * kpad; i += kTcThreads) {
       const int r = i / kpad, k = i - r * kpad;
       const long f = f0 + r;
       float x = 0.f;
       if (k < p.npose) {
-        x = tc::to_tf32(p.feat[f * p.npose + k]);           // feat rows are padded to a multiple of kTcM
+        x = tc::to_tf32(p.feat[f * p.npose + k]);           // feat rows are padded to a multiple of 128
       } else if (k < p.npose + 3 * p.ns && f < p.num_frames) {
         const int part = (k - p.npose) / p.ns, s = (k - p.npose) - part * p.ns;
         const float b = p.shape[f * p.ns + s];
         const float hi = tc::to_tf32(b);
         x = part == 1 ? tc::to_tf32(b - hi) : hi;           // [hi | lo | hi]
       }
-      sF[(k >> 5) * (kTcM * 32) + tc_elem_off(r, k & 31)] = x;
+      sF[(k >> 5) * (FR * 32) + tc_elem_off(r, k & 31)] = x;
     }
     tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
@@ -234,8 +240,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
         for (int pr = 0; pr < npairs; ++pr)
           for (int kb = 0; kb < kblocks; ++kb)
             for (int h = 0; h < 2; ++h, ++seq) {
-              const int s = (int)(seq % kTcStages);
-              if (seq >= kTcStages) {
+              const int s = (int)(seq % STAGES);
+              if (seq >= STAGES) {
                 tc::mbar_wait(BAR(6 + s), (ph_rempty >> s) & 1u);
                 ph_rempty ^= 1u << s;
               }
@@ -259,9 +265,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
             tc::mbar_wait(BAR(16 + a0 + 1), (ph_aempty >> (a0 + 1)) & 1u);
             ph_aempty ^= 1u << (a0 + 1);
           }
-          const uint32_t d0 = tmem_base + (uint32_t)(a0 * kTcM), d1 = d0 + (uint32_t)kTcM;
+          const uint32_t d0 = tmem_base + (uint32_t)(a0 * FR), d1 = d0 + (uint32_t)FR;
           for (int kb = 0; kb < kblocks; ++kb, seq += 2) {
-            const int s0 = (int)(seq % kTcStages), s1 = (int)((seq + 1) % kTcStages);
+            const int s0 = (int)(seq % STAGES), s1 = (int)((seq + 1) % STAGES);
             tc::mbar_wait(BAR(s0), (ph_rfull >> s0) & 1u);
             ph_rfull ^= 1u << s0;
             tc::mbar_wait(BAR(s1), (ph_rfull >> s1) & 1u);
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
             const uint32_t r0 = tc::smem_u32(sR + (size_t)s0 * b_bytes), r1 = tc::smem_u32(sR + (size_t)s1 * b_bytes);
 #pragma unroll
             for (int j = 0; j < kTcBK / 8; ++j) {
-              const uint64_t fdesc = tc::make_desc(f_addr + (uint32_t)(kb * (kTcM * 128) + j * 32));
+              const uint64_t fdesc = tc::make_desc(f_addr + (uint32_t)(kb * (FR * 128) + j * 32));
               const uint32_t acc = (kb | j) ? 1u : 0u;
               tc::mma_tf32(d0, tc::make_desc(r0 + j * 32), fdesc, idesc, acc);
               tc::mma_tf32(d1, tc::make_desc(r1 + j * 32), fdesc, idesc, acc);
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
         tc::mbar_wait(BAR(12 + a), (ph_afull >> a) & 1u);
         ph_afull ^= 1u << a;
         tc::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kTcM);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * FR);
         float* o = p.out + f0 * (long)p.ncols + c;
         if (p.debug == 3) {                                      // timing experiment: no TMEM reads / stores
           tc::tc_fence_before();
@@ -302,11 +308,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
           continue;
         }
 #pragma unroll 1
-        for (int ch = 0; ch < kTcM / 16; ++ch) {
+        for (int ch = 0; ch < FR / 16; ++ch) {
           uint32_t v[16];
           tc::tmem_ld16(taddr + (uint32_t)(ch * 16), v);
           tc::tmem_ld_wait();
-          if (ch == kTcM / 16 - 1) {
+          if (ch == FR / 16 - 1) {
             tc::tc_fence_before();
             tc::mbar_arrive(BAR(16 + a));                        // accumulator may be overwritten
           }

@@ -6,11 +6,12 @@
 //   verts   = (sum_j W_vj A_j) (v_posed; 1) + transl,  joints = [chain positions ; verts[extra ids]]
 //
 // Two paths:
-//  * tensor-core path (models whose blend depth 9(nj-1)+ns fits kTcKpadMax = 224, i.e. SMPL):
-//    mesh_pose_kernel -> blend_tc_kernel (tcgen05 TF32 GEMM, blend_tc.cuh) writes v_posed straight
-//    into the output vertex buffer -> skin_inplace_kernel applies LBS in place (HBM-bound).
-//  * CUDA-core path (SMPL-H / SMPL-X until the tensor-core kernel learns K-chunking): one fused
-//    FP32 kernel, register-tiled over 16 frames per thread; the blend output never touches HBM.
+//  * tensor-core path (blend depth 9(nj-1)+3ns <= kTcKpadMax = 576: SMPL, SMPL-H, SMPL-X):
+//    mesh_pose_kernel -> blend_tc_kernel (tcgen05 TF32 GEMM, blend_tc.cuh; 128 frames per pass for
+//    SMPL, 64 for the deeper SMPL-H / SMPL-X blends) writes v_posed straight into the output
+//    vertex buffer -> skin_inplace_kernel applies LBS in place (HBM-bound).
+//  * CUDA-core path (any deeper model, or joints-only calls): one fused FP32 kernel, register-tiled
+//    over 16 frames per thread; the blend output never touches HBM.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -440,17 +441,21 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
       m.nj, m.ns, m.parents, (const float4*)m.rel, (const float4*)m.J0S, a.full_pose, a.shape, a.transl, B, Bp,
       posefeat, skin, a.out_joints, njout);
   ++launches;
-  if (m.tc && a.out_vertices) {
+  const char* force_fp32 = getenv("K2B_MESH_FP32");   // diagnostics / tests: take the CUDA-core path
+  if (m.tc && a.out_vertices && !(force_fp32 && atoi(force_fp32))) {
     // ---- tensor-core path: blend (tcgen05) -> in-place skinning -> extra-joint gather ----------
-    const size_t tsm = tc_smem_bytes(m.kpad);
-    static size_t tc_configured = 0;
-    if (tsm > tc_configured) {
-      cudaError_t e = cudaFuncSetAttribute(blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+    const bool wide = m.kpad <= kTcKpadWide;     // SMPL: 128 frames per pass; SMPL-H / SMPL-X: 64
+    const int fr = wide ? kTcM : kTcMDeep;
+    const size_t tsm = tc_smem_bytes(m.kpad, fr, wide ? kTcStages : kTcStagesDeep);
+    auto* kern = wide ? blend_tc_kernel<kTcM, kTcStages> : blend_tc_kernel<kTcMDeep, kTcStagesDeep>;
+    static size_t tc_configured[2] = {0, 0};
+    if (tsm > tc_configured[wide]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
       if (e != cudaSuccess) {
         err = cudaGetErrorString(e);
         return false;
       }
-      tc_configured = tsm;
+      tc_configured[wide] = tsm;
     }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -458,8 +463,8 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
     const char* dbg = getenv("K2B_TC_DEBUG");
     BlendParams bp{posefeat, a.shape, m.b_tiles, m.v_template, a.out_vertices, B, m.npose, m.ns, m.kpad, m.nv * 3, m.n_tiles,
                    dbg ? atoi(dbg) : 0};
-    const long mtiles = Bp / kTcM;
-    blend_tc_kernel<<<(unsigned)(mtiles < sms ? mtiles : sms), kTcThreads, tsm, st>>>(bp);
+    const long passes = Bp / fr;
+    kern<<<(unsigned)(passes < sms ? passes : sms), kTcThreads, tsm, st>>>(bp);
     ++launches;
     const size_t ssm = sizeof(float) * (size_t)kMeshFT * m.nj * 12;
     const long ft_total = (B + kMeshFT - 1) / kMeshFT;

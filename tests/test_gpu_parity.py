@@ -163,10 +163,13 @@ def test_lbfgs_fit_statistics_vs_oracle(fitters, shims, oracle_prior, weights):
     np.testing.assert_allclose(cpu(chk["loss"]), ours_loss, rtol=1e-5)
 
 
-@pytest.mark.parametrize("mt", ["smpl", "smplh", "smplx"])
-def test_mesh_vs_shim(fitters, shims, mt):
+@pytest.mark.parametrize("fp32_path", [False, True])
+@pytest.mark.parametrize("mt,B", [("smpl", 37), ("smplh", 37), ("smplx", 37), ("smpl", 300), ("smplx", 200)])
+def test_mesh_vs_shim(fitters, shims, mt, B, fp32_path, monkeypatch):
+    """Full mesh output against the smplx restatement: tcgen05 blend + in-place skinning (default) and the
+    fused CUDA-core kernel (K2B_MESH_FP32=1), at frame counts that leave partial passes / tiles."""
+    monkeypatch.setenv("K2B_MESH_FP32", "1" if fp32_path else "0")
     g = torch.Generator().manual_seed(7)
-    B = 37
     params = dict(global_orient=0.3 * torch.randn(B, 3, generator=g), body_pose=0.3 * torch.randn(B, 69, generator=g),
                   betas=torch.randn(B, 10, generator=g), transl=torch.randn(B, 3, generator=g))
     if mt in ("smplh", "smplx"):
