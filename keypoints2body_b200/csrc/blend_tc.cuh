@@ -45,14 +45,15 @@ constexpr int kTcKpadMax = 576;    // SMPL-X: 486 pose features + 3 x 20 split s
 constexpr int kTcThreads = 320;    // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
 constexpr int kTcStages = 6;       // ring depth (K blocks of dirs, 16 KB each); 5 on the deep variant
 constexpr int kTcStagesDeep = 5;
+constexpr int kTcFusedJoints = 24; // the fused blend + skinning kernel is instantiated for the SMPL skeleton
 constexpr int kTcAccStages = 4;    // accumulators in TMEM (two pairs)
 constexpr int kTcTmemCols = 512;
 
 __host__ __device__ constexpr int tc_kpad(int kdepth) { return (kdepth + kTcBK - 1) / kTcBK * kTcBK; }
 __host__ __device__ constexpr int tc_b_bytes() { return kTcN * 128; }                    // one (column tile, K block)
 __host__ __device__ constexpr int tc_f_bytes(int kpad, int fr) { return (kpad / kTcBK) * fr * 128; }
-__host__ __device__ constexpr size_t tc_smem_bytes(int kpad, int fr, int stages) {
-  return (size_t)tc_f_bytes(kpad, fr) + (size_t)stages * (size_t)tc_b_bytes() + 1024;
+__host__ __device__ constexpr size_t tc_smem_bytes(int kpad, int fr, int stages, int fused_joints) {
+  return (size_t)tc_f_bytes(kpad, fr) + (size_t)stages * (size_t)tc_b_bytes() + (size_t)fr * fused_joints * 48 + (fused_joints ? (size_t)fr * 16 : 0) + 1024;
 }
 // offset (in floats) of element (row, k < 32) inside one 128-row swizzle-128B K block
 __host__ __device__ constexpr int tc_elem_off(int row, int k) {
@@ -157,19 +158,35 @@ __device__ __forceinline__ float to_tf32(float x) {
 }  // namespace tc
 
 struct BlendParams {
-  const float* feat;        // [frames_padded][npose] pose features (frames padded to kTcM, zero rows)
+  const float* feat;        // [frames_padded][npose] pose features (frames padded to 128, zero rows)
   const float* shape;       // [B][ns]
-  const float* b_tiles;     // [n_tiles (even)][kpad/48][tc_b_bytes/4] pre-tiled TF32 dirs^T blocks
-  const float* v_template;  // [ncols]
-  float* out;               // [B][ncols]  (ncols = 3V)
+  const float* b_tiles;     // [n_tiles (even)][kpad/32][tc_b_bytes/4] pre-tiled TF32 dirs^T blocks
+  const float* v_template;  // [3V]
+  const float4* skin;       // [frames_padded][nj][3] rows of the 3x4 skinning matrices (mesh_pose_kernel)
+  const float* transl;      // [B][3] or null
+  const int* ell_idx;       // [ell][V] joints of each vertex's non-zero skinning weights
+  const float* ell_w;       // [ell][V]
+  float* out;               // [B][3V] skinned vertices
   long num_frames;
-  int npose, ns, kpad, ncols, n_tiles;
-  int debug;   // K2B_TC_DEBUG: 1 = skip output stores, 2 = skip B copies (timing experiments only)
+  int npose, ns, kpad, nv, nj, ell, n_tiles;
+  int debug;   // K2B_TC_DEBUG: 1 = skip output stores, 3 = skip the epilogue (timing experiments only)
 };
 
-// FR = frames per pass (MMA N), STAGES = dirs ring depth
-template <int FR, int STAGES>
-__global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_constant__ BlendParams p) {
+// Column tiles carry VERTICES, not raw columns: tile row n = 32 q + l holds coordinate l % 3 of vertex
+// tile * 40 + q * 10 + l / 3 (l < 30; rows 30, 31 of every quarter are zero padding), so the three
+// coordinates of a vertex sit in neighbouring TMEM lanes of the same epilogue warp.
+constexpr int kTcVertsPerQuarter = 10;
+constexpr int kTcVertsPerTile = 4 * kTcVertsPerQuarter;
+__host__ __device__ constexpr int tc_tile_vertex(int tile, int n) {
+  return (n % 32) < 30 ? tile * kTcVertsPerTile + (n / 32) * kTcVertsPerQuarter + (n % 32) / 3 : -1;
+}
+
+// FR = frames per pass (MMA N), STAGES = dirs ring depth; NE > 0 (ELL width) with NJ joints = LBS skinning in the epilogue (the pass's
+// skinning matrices are staged in shared memory; column tiles follow tc_tile_vertex) or plain v_posed output
+// (column tile t = columns [128 t, 128 t + 128), skinned afterwards by skin_inplace_kernel)
+template <int FR, int STAGES, int NE, int NJ>
+__global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __grid_constant__ BlendParams p) {
+  constexpr bool FUSED = NE > 0;   // NE = skinning weights per vertex (ELL width, 1..4); 0 = unfused
   static_assert(FR % 16 == 0 && FR >= 16 && FR * kTcAccStages <= kTcTmemCols && STAGES <= 6, "tile shape");
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   const int kpad = p.kpad;
@@ -177,7 +194,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
   const int f_bytes = tc_f_bytes(kpad, FR);
   float* sF = reinterpret_cast<float*>(tc_smem);                         // features of the pass
   unsigned char* sR = tc_smem + f_bytes;                                 // dirs ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + f_bytes + (size_t)STAGES * b_bytes);
+  float4* sA = reinterpret_cast<float4*>(tc_smem + f_bytes + (size_t)STAGES * b_bytes);   // FUSED: [FR][nj][3] rows
+  const size_t a_bytes = FUSED ? (size_t)FR * NJ * 48 + (size_t)FR * 16 : 0;
+  float4* sT = sA + FR * 3 * NJ;                                      // FUSED: [FR] translations
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + f_bytes + (size_t)STAGES * b_bytes + a_bytes);
   // bars: [0,6) ring_full; [6,12) ring_empty; [12,16) acc_full; [16,20) acc_empty; then the TMEM base word
   uint32_t* tmem_word = reinterpret_cast<uint32_t*>(bars + 20);
 
@@ -229,6 +249,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
         x = part == 1 ? tc::to_tf32(b - hi) : hi;           // [hi | lo | hi]
       }
       sF[(k >> 5) * (FR * 32) + tc_elem_off(r, k & 31)] = x;
+    }
+    if constexpr (FUSED) {     // this pass's skinning matrices (rows past the last frame are never read)
+      const float4* src = p.skin + f0 * (3L * NJ);
+      for (int i = tid; i < FR * 3 * NJ; i += kTcThreads) sA[i] = src[i];
+      if (tid < FR) {
+        const long f = f0 + tid;
+        const bool ok = p.transl && f < p.num_frames;
+        sT[tid] = ok ? make_float4(p.transl[f * 3], p.transl[f * 3 + 1], p.transl[f * 3 + 2], 0.f)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
@@ -289,38 +319,108 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_tc_kernel(const __grid_co
         }
       }
     } else {
-      // ---- epilogue warps 0-7: lane quarter q = warp % 4, tile h = warp / 4 of every pair -----------
-      const int q = warp & 3, h = warp >> 2;
-      for (int pr = 0; pr < npairs; ++pr) {
-        const long pseq = pair_seq + pr;
-        const int a = (int)(pseq & 1) * 2 + h;
-        const int c = (2 * pr + h) * kTcN + q * 32 + lane;       // this lane's output column
-        const bool col_ok = c < p.ncols;
-        const float tv = col_ok ? __ldg(p.v_template + c) : 0.f; // issued before the wait
-        tc::mbar_wait(BAR(12 + a), (ph_afull >> a) & 1u);
-        ph_afull ^= 1u << a;
-        tc::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * FR);
-        float* o = p.out + f0 * (long)p.ncols + c;
-        if (p.debug == 3) {                                      // timing experiment: no TMEM reads / stores
-          tc::tc_fence_before();
-          tc::mbar_arrive(BAR(16 + a));
-          continue;
-        }
-#pragma unroll 1
-        for (int ch = 0; ch < FR / 16; ++ch) {
-          uint32_t v[16];
-          tc::tmem_ld16(taddr + (uint32_t)(ch * 16), v);
-          tc::tmem_ld_wait();
-          if (ch == FR / 16 - 1) {
-            tc::tc_fence_before();
-            tc::mbar_arrive(BAR(16 + a));                        // accumulator may be overwritten
-          }
-          if (col_ok && p.debug != 1) {
+      if constexpr (FUSED) {
+        // ---- epilogue warps 0-7: lane quarter q = warp % 4, tile h = warp / 4 of every pair -----------
+        // Each lane owns ONE output coordinate c3 of one vertex: it fetches the vertex's blended position
+        // from its two neighbour lanes, builds row c3 of the vertex's skinning matrix
+        // sum_k w_k A[frame][joint_k] and writes verts[frame][vertex][c3] -- v_posed never leaves the SM.
+        // All per-frame strides are compile-time (NJ) or running pointers, so a frame costs ~25 instructions.
+        const int q = warp & 3, h = warp >> 2;
+        const int c3 = lane % 3, lbase = lane - c3;
+        const int sx = lbase, sy = lbase + 1 < 32 ? lbase + 1 : 31, sz = lbase + 2 < 32 ? lbase + 2 : 31;
+        const float* sTc = reinterpret_cast<const float*>(sT) + c3;
+        const long ncols = 3L * p.nv;
+        for (int pr = 0; pr < npairs; ++pr) {
+          const long pseq = pair_seq + pr;
+          const int a = (int)(pseq & 1) * 2 + h;
+          const int v = tc_tile_vertex(2 * pr + h, q * 32 + lane);
+          const bool v_ok = v >= 0 && v < p.nv;
+          const int col = v_ok ? 3 * v + c3 : 0;
+          const float tv = v_ok ? __ldg(p.v_template + col) : 0.f;   // issued before the wait
+          const float4* Ak[NE];
+          float wk[NE];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const long fr = ch * 16 + i;
-              if (f0 + fr < p.num_frames) o[fr * (long)p.ncols] = __uint_as_float(v[i]) + tv;
+          for (int k = 0; k < NE; ++k) {
+            Ak[k] = sA + 3 * (v_ok ? __ldg(p.ell_idx + (long)k * p.nv + v) : 0) + c3;
+            wk[k] = v_ok ? __ldg(p.ell_w + (long)k * p.nv + v) : 0.f;
+          }
+          tc::mbar_wait(BAR(12 + a), (ph_afull >> a) & 1u);
+          ph_afull ^= 1u << a;
+          tc::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * FR);
+          const bool st_ok = v_ok && p.debug != 1;
+          if (p.debug == 3) {                                      // timing experiment: no TMEM reads / stores
+            tc::tc_fence_before();
+            tc::mbar_arrive(BAR(16 + a));
+            continue;
+          }
+          float* o = p.out + f0 * ncols + col;
+          const long left = p.num_frames - f0;
+          int nvalid = (st_ok ? (left < FR ? (int)left : FR) : 0);   // frames of this pass this lane stores
+#pragma unroll 1
+          for (int ch = 0; ch < FR / 16; ++ch) {
+            uint32_t acc[16];
+            tc::tmem_ld16(taddr + (uint32_t)(ch * 16), acc);
+            tc::tmem_ld_wait();
+            if (ch == FR / 16 - 1) {
+              tc::tc_fence_before();
+              tc::mbar_arrive(BAR(16 + a));                        // accumulator may be overwritten
+            }
+            constexpr int FS = 3 * NJ;                             // float4 rows per frame
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {                         // fully unrolled, branch-free: 16 frames overlap
+              const float pc = __uint_as_float(acc[i]) + tv;
+              const float px = __shfl_sync(0xffffffffu, pc, sx), py = __shfl_sync(0xffffffffu, pc, sy),
+                          pz = __shfl_sync(0xffffffffu, pc, sz);
+              float4 T = make_float4(0.f, 0.f, 0.f, sTc[(ch * 16 + i) * 4]);
+#pragma unroll
+              for (int k = 0; k < NE; ++k) {
+                const float4 r = Ak[k][(ch * 16 + i) * FS];
+                T.x = fmaf(wk[k], r.x, T.x); T.y = fmaf(wk[k], r.y, T.y);
+                T.z = fmaf(wk[k], r.z, T.z); T.w = fmaf(wk[k], r.w, T.w);
+              }
+              const float ov = fmaf(T.x, px, fmaf(T.y, py, fmaf(T.z, pz, T.w)));
+              if (i < nvalid) o[0] = ov;
+              o += ncols;
+            }
+            nvalid -= 16;
+          }
+        }
+      } else {
+        // ---- epilogue warps 0-7: lane quarter q = warp % 4, tile h = warp / 4 of every pair -----------
+        const int q = warp & 3, h = warp >> 2;
+        for (int pr = 0; pr < npairs; ++pr) {
+          const long pseq = pair_seq + pr;
+          const int a = (int)(pseq & 1) * 2 + h;
+          const int c = (2 * pr + h) * kTcN + q * 32 + lane;       // this lane's output column
+          const bool col_ok = c < 3 * p.nv;
+          const float tv = col_ok ? __ldg(p.v_template + c) : 0.f; // issued before the wait
+          tc::mbar_wait(BAR(12 + a), (ph_afull >> a) & 1u);
+          ph_afull ^= 1u << a;
+          tc::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * FR);
+          const long ncols = 3L * p.nv;
+          float* o = p.out + f0 * ncols + c;
+          if (p.debug == 3) {                                      // timing experiment: no TMEM reads / stores
+            tc::tc_fence_before();
+            tc::mbar_arrive(BAR(16 + a));
+            continue;
+          }
+  #pragma unroll 1
+          for (int ch = 0; ch < FR / 16; ++ch) {
+            uint32_t v[16];
+            tc::tmem_ld16(taddr + (uint32_t)(ch * 16), v);
+            tc::tmem_ld_wait();
+            if (ch == FR / 16 - 1) {
+              tc::tc_fence_before();
+              tc::mbar_arrive(BAR(16 + a));                        // accumulator may be overwritten
+            }
+            if (col_ok && p.debug != 1) {
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const long fr = ch * 16 + i;
+                if (f0 + fr < p.num_frames) o[fr * ncols] = __uint_as_float(v[i]) + tv;
+              }
             }
           }
         }

@@ -7,9 +7,9 @@
 //
 // Two paths:
 //  * tensor-core path (blend depth 9(nj-1)+3ns <= kTcKpadMax = 576: SMPL, SMPL-H, SMPL-X):
-//    mesh_pose_kernel -> blend_tc_kernel (tcgen05 TF32 GEMM, blend_tc.cuh; 128 frames per pass for
-//    SMPL, 64 for the deeper SMPL-H / SMPL-X blends) writes v_posed straight into the output
-//    vertex buffer -> skin_inplace_kernel applies LBS in place (HBM-bound).
+//    mesh_pose_kernel -> blend_skin_tc_kernel (tcgen05 TF32 GEMM, blend_tc.cuh; 128 frames per pass
+//    for SMPL, 64 for the deeper SMPL-H / SMPL-X blends) whose epilogue applies LBS to the
+//    accumulators and writes the final vertices: v_posed never touches HBM.
 //  * CUDA-core path (any deeper model, or joints-only calls): one fused FP32 kernel, register-tiled
 //    over 16 frames per thread; the blend output never touches HBM.
 #pragma once
@@ -46,6 +46,7 @@ struct MeshModel {
   int* extra_ids = nullptr;    // [nextra]
   // tensor-core blend (blend_tc.cuh)
   bool tc = false;
+  bool fused = false;          // skinning fused into the blend epilogue (needs features + skinning rows in smem)
   int kpad = 0, n_tiles = 0;
   float* b_tiles = nullptr;    // [n_tiles][tc_b_bytes/4] pre-tiled, TF32-rounded [posedirs ; shapedirs]
 };
@@ -149,7 +150,10 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
   if (ok && kdepth <= kTcKpadMax) {
     m.kpad = tc_kpad(kdepth);
     const int ncols = nv * 3, kblocks = m.kpad / kTcBK;
-    m.n_tiles = ((ncols + kTcN - 1) / kTcN + 1) / 2 * 2;   // tiles are consumed in pairs
+    // SMPL: 64 frames of features (64 KB) + their skinning rows (72 KB) + the ring fit one SM -> fused epilogue
+    m.fused = nj == kTcFusedJoints && ell <= 4 && m.kpad <= kTcKpadWide && tc_smem_bytes(m.kpad, kTcMDeep, kTcStagesDeep, nj) <= 227 * 1024;
+    const int per_tile = m.fused ? kTcVertsPerTile * 3 : kTcN;
+    m.n_tiles = ((ncols + per_tile - 1) / per_tile + 1) / 2 * 2;   // tiles are consumed in pairs
     const size_t blk_floats = (size_t)tc_b_bytes() / 4;
     std::vector<float> bt((size_t)m.n_tiles * kblocks * blk_floats, 0.f);
     auto tf32 = [](float v) {
@@ -162,7 +166,11 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
     };
     for (int nt = 0; nt < m.n_tiles; ++nt)
       for (int n = 0; n < kTcN; ++n) {
-        const int col = nt * kTcN + n;
+        int col = nt * kTcN + n;
+        if (m.fused) {
+          const int vert = tc_tile_vertex(nt, n);
+          col = vert < 0 ? ncols : 3 * vert + (n % 32) % 3;
+        }
         if (col >= ncols) continue;
         for (int k = 0; k < kdepth; ++k) {
           float r;
@@ -444,38 +452,47 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
   const char* force_fp32 = getenv("K2B_MESH_FP32");   // diagnostics / tests: take the CUDA-core path
   if (m.tc && a.out_vertices && !(force_fp32 && atoi(force_fp32))) {
     // ---- tensor-core path: blend (tcgen05) -> in-place skinning -> extra-joint gather ----------
-    const bool wide = m.kpad <= kTcKpadWide;     // SMPL: 128 frames per pass; SMPL-H / SMPL-X: 64
-    const int fr = wide ? kTcM : kTcMDeep;
-    const size_t tsm = tc_smem_bytes(m.kpad, fr, wide ? kTcStages : kTcStagesDeep);
-    auto* kern = wide ? blend_tc_kernel<kTcM, kTcStages> : blend_tc_kernel<kTcMDeep, kTcStagesDeep>;
-    static size_t tc_configured[2] = {0, 0};
-    if (tsm > tc_configured[wide]) {
+    // SMPL: fused blend + skinning, 64 frames per pass.  SMPL-H / SMPL-X: 64-frame blend, then in-place skinning.
+    const int fr = kTcMDeep;
+    const size_t tsm = tc_smem_bytes(m.kpad, fr, kTcStagesDeep, m.fused ? m.nj : 0);
+    auto* kern = blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 0, 0>;
+    if (m.fused) {
+      kern = m.ell == 1 ? blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 1, kTcFusedJoints>
+           : m.ell == 2 ? blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 2, kTcFusedJoints>
+           : m.ell == 3 ? blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 3, kTcFusedJoints>
+                        : blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 4, kTcFusedJoints>;
+    }
+    static size_t tc_configured[5] = {0, 0, 0, 0, 0};
+    const int variant = m.fused ? m.ell : 0;
+    if (tsm > tc_configured[variant]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
       if (e != cudaSuccess) {
         err = cudaGetErrorString(e);
         return false;
       }
-      tc_configured[wide] = tsm;
+      tc_configured[variant] = tsm;
     }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char* dbg = getenv("K2B_TC_DEBUG");
-    BlendParams bp{posefeat, a.shape, m.b_tiles, m.v_template, a.out_vertices, B, m.npose, m.ns, m.kpad, m.nv * 3, m.n_tiles,
-                   dbg ? atoi(dbg) : 0};
+    BlendParams bp{posefeat, a.shape, m.b_tiles, m.v_template, (const float4*)skin, a.transl, m.ell_idx, m.ell_w,
+                   a.out_vertices, B, m.npose, m.ns, m.kpad, m.nv, m.nj, m.ell, m.n_tiles, dbg ? atoi(dbg) : 0};
     const long passes = Bp / fr;
     kern<<<(unsigned)(passes < sms ? passes : sms), kTcThreads, tsm, st>>>(bp);
     ++launches;
-    const size_t ssm = sizeof(float) * (size_t)kMeshFT * m.nj * 12;
-    const long ft_total = (B + kMeshFT - 1) / kMeshFT;
-    for (long y0 = 0; y0 < ft_total; y0 += 65535) {
-      const unsigned ny = (unsigned)(ft_total - y0 < 65535 ? ft_total - y0 : 65535);
-      const long fo = y0 * kMeshFT;
-      dim3 grid((m.nv + kMeshVT - 1) / kMeshVT, ny);
-      skin_inplace_kernel<<<grid, kMeshVT, ssm, st>>>(m.nj, m.nv, m.ell, m.ell_idx, m.ell_w, skin + fo * m.nj * 12,
-                                                       a.transl ? a.transl + fo * 3 : nullptr, B - fo,
-                                                       a.out_vertices + fo * m.nv * 3);
-      ++launches;
+    if (!m.fused) {
+      const size_t ssm = sizeof(float) * (size_t)kMeshFT * m.nj * 12;
+      const long ft_total = (B + kMeshFT - 1) / kMeshFT;
+      for (long y0 = 0; y0 < ft_total; y0 += 65535) {
+        const unsigned ny = (unsigned)(ft_total - y0 < 65535 ? ft_total - y0 : 65535);
+        const long fo = y0 * kMeshFT;
+        dim3 grid((m.nv + kMeshVT - 1) / kMeshVT, ny);
+        skin_inplace_kernel<<<grid, kMeshVT, ssm, st>>>(m.nj, m.nv, m.ell, m.ell_idx, m.ell_w, skin + fo * m.nj * 12,
+                                                         a.transl ? a.transl + fo * 3 : nullptr, B - fo,
+                                                         a.out_vertices + fo * m.nv * 3);
+        ++launches;
+      }
     }
     if (m.nextra > 0) {
       const long n = B * m.nextra;
