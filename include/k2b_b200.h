@@ -15,6 +15,7 @@
  *   k2b_evaluate_batch    <- one compute_loss()+backward(), world_space.py:173-212,239-243
  *   k2b_mesh_batch        <- the final body-model forward, world_space.py:258-278
  *   k2b_shape_pass        <- optimize_shape_multi_frame, core/shape.py:10-115
+ *   k2b_mpjae             <- evaluate_pose_pair / compute_angular_error_deg, cli/eval.py:88-157
  *
  * Conventions
  *   - all arrays are dense row-major float32 unless stated; "dev" pointers live
@@ -204,6 +205,15 @@ typedef struct k2b_shape_args {
 
 size_t k2b_shape_workspace_bytes(const k2b_model* m, int32_t num_sequences, int32_t num_iters);
 int k2b_shape_pass(const k2b_model* m, const k2b_shape_args* args, void* cuda_stream);
+
+/* Mean per-joint angular error between two pose arrays (cli/eval.py:129-157).
+ * pred_pose [num_frames][pred_dims] and gt_pose [num_frames][gt_dims] are device arrays of axis-angle
+ * triples; the first min(pred_dims, gt_dims) / 3 joints of every frame are compared.  *out_sum_deg
+ * (device, float64) receives the sum of the angles in degrees (the caller divides by
+ * num_frames * joints); out_angles_deg (device, [num_frames][joints], may be null) the angles.
+ * Enqueues a memset of *out_sum_deg and one kernel on the stream; does not synchronise. */
+int k2b_mpjae(const float* pred_pose, int32_t pred_dims, const float* gt_pose, int32_t gt_dims, int64_t num_frames,
+              float* out_angles_deg, double* out_sum_deg, void* cuda_stream);
 
 /* FP32-FMA micro-benchmark used as the roofline denominator of the fit kernel:
  * returns achieved TFLOP/s (2 flop per FMA) over `iters` dependent-chain rounds. */

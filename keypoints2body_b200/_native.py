@@ -88,7 +88,7 @@ class ShapeArgs(C.Structure):
 EXPORTS = (
     "k2b_model_create", "k2b_model_destroy", "k2b_fit_workspace_bytes", "k2b_fit_batch",
     "k2b_fit_batch_host", "k2b_evaluate_batch", "k2b_mesh_workspace_bytes", "k2b_mesh_batch",
-    "k2b_shape_workspace_bytes", "k2b_shape_pass", "k2b_fma_peak", "k2b_launch_count", "k2b_last_error", "k2b_version",
+    "k2b_shape_workspace_bytes", "k2b_shape_pass", "k2b_mpjae", "k2b_fma_peak", "k2b_launch_count", "k2b_last_error", "k2b_version",
 )
 
 _lib = None
@@ -121,6 +121,8 @@ def load_library():
     lib.k2b_shape_workspace_bytes.restype = C.c_size_t
     lib.k2b_mesh_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
     lib.k2b_mesh_workspace_bytes.restype = C.c_size_t
+    lib.k2b_mpjae.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.k2b_mpjae.restype = C.c_int
     lib.k2b_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
     lib.k2b_fma_peak.restype = C.c_int
     lib.k2b_launch_count.restype = C.c_int64

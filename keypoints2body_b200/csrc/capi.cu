@@ -12,6 +12,7 @@
 #include "../../include/k2b_b200.h"
 #include "fit_kernel.cuh"
 #include "fit_launch.h"
+#include "eval_kernel.cuh"
 #include "mesh_kernel.cuh"
 #include "shape_kernel.cuh"
 
@@ -213,6 +214,10 @@ extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* st
   p.scratch = (float*)a->workspace;
   p.lbfgs_hmax = lbfgs_history_capacity(a->num_iters);
   p.debug_rounds = getenv("K2B_DEBUG_ROUNDS") != nullptr;
+  {
+    const char* q = getenv("K2B_LBFGS_QUORUM");   // tuning knob; results do not depend on it
+    p.outer_quorum = q ? atoi(q) : 32;
+  }
   p.loss_kind = a->loss_kind;
   p.final_mode = a->final_loss_mode;
   p.depth_ref = a->depth_ref;
@@ -417,6 +422,26 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters) {
   if (s == 12345.678f) out[0] = s;  // never true; keeps the chain alive
 }
 }  // namespace
+
+extern "C" int k2b_mpjae(const float* pred_pose, int32_t pred_dims, const float* gt_pose, int32_t gt_dims,
+                         int64_t num_frames, float* out_angles_deg, double* out_sum_deg, void* stream) {
+  if (!pred_pose || !gt_pose || !out_sum_deg) return fail(K2B_EINVAL, "null argument");
+  const int joints = (pred_dims < gt_dims ? pred_dims : gt_dims) / 3;
+  if (joints <= 0 || num_frames <= 0) return fail(K2B_EINVAL, "need at least one frame and one joint");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(out_sum_deg, 0, sizeof(double), st));
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long total = (long)num_frames * joints;
+  long blocks = (total + kEvalThreads - 1) / kEvalThreads;
+  if (blocks > (long)sms * 8) blocks = (long)sms * 8;
+  mpjae_kernel<<<(unsigned)blocks, kEvalThreads, 0, st>>>(pred_pose, pred_dims, gt_pose, gt_dims, (long)num_frames, joints,
+                                                           out_angles_deg, out_sum_deg);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return K2B_OK;
+}
 
 extern "C" int k2b_fma_peak(int iters, double* out_tflops, double* out_ms, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

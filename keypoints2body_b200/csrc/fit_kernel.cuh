@@ -61,6 +61,7 @@ struct FitParams {
   const float* depth_ref;  // [B][3] initial camera translation (loss_kind 1)
   float depth_w2;
   int debug_rounds;        // K2B_DEBUG_ROUNDS: pack the warp's round count into out_evals (diagnostics)
+  int outer_quorum;        // lanes waiting at an outer-iteration boundary that trigger the direction update
 };
 
 struct AdamTable {
@@ -282,8 +283,13 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         // search idles (its evaluations are discarded, its slots protected) until every live lane of
         // the warp is at the boundary; then all of them run it together.  Per-frame arithmetic is
         // unchanged -- only the round in which it happens.
-        if (__all_sync(0xffffffffu, st.done || st.need_outer)) {
-          if (st.need_outer && !st.done) st.start_outer(c, v);
+        {
+          const bool waiting = st.need_outer && !st.done;
+          const int n_wait = __popc(__ballot_sync(0xffffffffu, waiting));
+          const int n_live = __popc(__ballot_sync(0xffffffffu, !st.done));
+          if (n_wait > 0 && (n_wait == n_live || n_wait >= p.outer_quorum)) {
+            if (waiting) st.start_outer(c, v);
+          }
         }
         if (!__any_sync(0xffffffffu, !st.done)) {
           stage = 2;

@@ -293,3 +293,44 @@ def flatten(params: dict, freeze_betas=False) -> torch.Tensor:
     """Concatenate the optimised blocks in PARAM_ORDER (the L-BFGS flat layout)."""
     keys = [k for k in PARAM_ORDER if params.get(k) is not None and (k != "betas" or not freeze_betas)]
     return torch.cat([params[k] for k in keys], dim=1)
+
+
+# ---- MPJAE evaluation (cli/eval.py:88-157), numpy float32 like the reference ------------------------
+def eval_rotmat(rotvec, eps=1e-8):
+    """``rotvec_to_rotmat`` (cli/eval.py:88-127): closed-form Rodrigues with a Taylor branch at theta <= eps."""
+    import numpy as np
+    rv = np.asarray(rotvec, dtype=np.float32)
+    x, y, z = rv[..., 0], rv[..., 1], rv[..., 2]
+    t2 = x * x + y * y + z * z
+    th = np.sqrt(t2)
+    big = th > eps
+    ths = np.where(big, th, 1.0).astype(np.float32)
+    a = np.sin(ths) / ths
+    b = (1.0 - np.cos(ths)) / (ths * ths)
+    a = np.where(big, a, 1.0 - t2 / 6.0 + t2 * t2 / 120.0).astype(np.float32)
+    b = np.where(big, b, 0.5 - t2 / 24.0 + t2 * t2 / 720.0).astype(np.float32)
+    # products are formed first, then scaled (b * (x*y), not (b*x) * y), as cli/eval.py:106-126 does
+    xy, xz, yz, xx, yy, zz = x * y, x * z, y * z, x * x, y * y, z * z
+    r = np.empty(rv.shape[:-1] + (3, 3), dtype=np.float32)
+    r[..., 0, 0] = 1.0 - b * (yy + zz); r[..., 0, 1] = b * xy - a * z; r[..., 0, 2] = b * xz + a * y
+    r[..., 1, 0] = b * xy + a * z; r[..., 1, 1] = 1.0 - b * (xx + zz); r[..., 1, 2] = b * yz - a * x
+    r[..., 2, 0] = b * xz - a * y; r[..., 2, 1] = b * yz + a * x; r[..., 2, 2] = 1.0 - b * (xx + yy)
+    return r
+
+
+def angular_error_deg(pred_rotvec, gt_rotvec):
+    """``compute_angular_error_deg`` (cli/eval.py:130-139)."""
+    import numpy as np
+    tr = np.sum(eval_rotmat(pred_rotvec) * eval_rotmat(gt_rotvec), axis=(-1, -2))
+    c = np.clip((tr - 1.0) * 0.5, -1.0 + 1e-6, 1.0 - 1e-6)
+    return np.degrees(np.arccos(c))
+
+
+def evaluate_pose_pair(pred_pose, gt_pose):
+    """``evaluate_pose_pair`` (cli/eval.py:142-157) -> (mean_deg, sum_deg, count)."""
+    import numpy as np
+    n = min(gt_pose.shape[0], pred_pose.shape[0])
+    d = min(gt_pose.shape[1], pred_pose.shape[1]) // 3 * 3
+    ang = angular_error_deg(pred_pose[:n, :d].reshape(n, d // 3, 3), gt_pose[:n, :d].reshape(n, d // 3, 3))
+    s = float(np.sum(ang, dtype=np.float64))
+    return s / ang.size, s, int(ang.size)

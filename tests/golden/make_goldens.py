@@ -297,6 +297,48 @@ def main():
                                        joints3d_conf=torch.ones(22), shape_prior_weight=5.0)
         put("shape_pass_betas", b)
 
+        # ---- G. MPJAE evaluation (cli/eval.py) and the on-disk formats (io/motion.py) -----------------
+        from keypoints2body.cli.eval import compute_angular_error_deg, evaluate_pose_pair
+        from keypoints2body.io.motion import load_motion_data, write_smplx_zip
+
+        ge = np.random.default_rng(11)
+        gt_pose = (0.6 * ge.standard_normal((17, 72))).astype(np.float32)
+        pred_pose = (gt_pose[:, :66] + 0.05 * ge.standard_normal((17, 66))).astype(np.float32)
+        pred_pose[0, :6] = gt_pose[0, :6]            # identical rotations -> clipped cosine
+        pred_pose[1, :3] = 0.0                       # zero rotation vector (Taylor branch)
+        gt_pose[1, 3:6] = 0.0
+        pred_pose[1, 3:6] = 0.0
+        gt_pose[2, :3] = np.array([3.1, 0.0, 0.0])   # near pi
+        pred_pose[2, :3] = np.array([-3.1, 0.05, 0.0])
+        pred_pose = pred_pose[:15]                   # fewer predicted frames than ground truth
+        put("mpjae_in_pred", pred_pose)
+        put("mpjae_in_gt", gt_pose)
+        put("mpjae_angles", compute_angular_error_deg(pred_pose.reshape(15, 22, 3), gt_pose[:15, :66].reshape(15, 22, 3)))
+        mean, total, count = evaluate_pose_pair(pred_pose, gt_pose)
+        put("mpjae_summary", np.array([mean, total, count], np.float64))
+
+        io_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "io")
+        os.makedirs(io_dir, exist_ok=True)
+        seq22 = (0.3 * ge.standard_normal((4, 22, 3))).astype(np.float32)
+        seq25 = (0.3 * ge.standard_normal((3, 25, 3))).astype(np.float64)
+        np.save(os.path.join(io_dir, "seq22.npy"), seq22)
+        np.savez(os.path.join(io_dir, "seq25.npz"), joints=seq25)
+        with open(os.path.join(io_dir, "seq22.csv"), "w") as fh:
+            for h in range(5):
+                fh.write(f"header line {h},,\n")
+            for t in range(4):
+                fh.write(",".join([str(t), f"{t / 120.0:.6f}"] + [repr(float(v)) for v in seq22[t].reshape(-1)]) + "\n")
+        import warnings as _w
+        with _w.catch_warnings():
+            _w.simplefilter("ignore")
+            for name, layout in (("seq22.npy", None), ("seq22.csv", "AMASS"), ("seq25.npz", None)):
+                j, lay, k = load_motion_data(__import__("pathlib").Path(io_dir) / name, layout)
+                put("io_" + name.replace(".", "_") + "_joints", np.asarray(j, np.float64))
+                G["io_" + name.replace(".", "_") + "_layout"] = np.array([lay, str(k)])
+        zp = write_smplx_zip(__import__("pathlib").Path(io_dir), gt_pose[:3].astype(np.float64), np.linspace(-1, 1, 10),
+                             (0.1 * ge.standard_normal((3, 3))), zip_name="ref_params.zip", person_idx=1)
+        print("reference zip:", zp, os.path.getsize(zp), "bytes")
+
     np.savez_compressed(OUT, **G)
     print("wrote", OUT, os.path.getsize(OUT) / 1e3, "KB,", len(G), "arrays")
 

@@ -143,3 +143,28 @@ def test_error_behaviour(weights, asset_cwd):
     os.remove("data/models/gmm_08.pkl")
     with pytest.raises(FileNotFoundError):
         k2b.optimize_params_frame(j, model=weights("smplh"), body_model="smplh")
+
+
+def test_mpjae_matches_reference(goldens):
+    """k2b_mpjae (eval_kernel.cuh) against the reference's evaluate_pose_pair goldens and the oracle."""
+    from keypoints2body_b200.evaluation import angular_error_deg, evaluate_pose_pair
+    from oracle import reference_port as rp
+
+    pred, gt = goldens["mpjae_in_pred"], goldens["mpjae_in_gt"]
+    angles, _ = angular_error_deg(pred, gt)
+    # the clipped cosine makes acos ill-conditioned below ~0.1 deg: 0.02 deg absolute covers sin/cos ulps there
+    assert np.abs(angles.cpu().numpy() - goldens["mpjae_angles"]).max() < 0.02
+    mean, total, count = evaluate_pose_pair(pred, gt)
+    ref_mean, ref_total, ref_count = goldens["mpjae_summary"]
+    assert count == int(ref_count)
+    assert abs(mean - ref_mean) < 1e-3
+    # full-size property check: 1M x 24 joints against the oracle on a slice, and sum == sum of the angle array
+    g = torch.Generator().manual_seed(5)
+    big_gt = 0.7 * torch.randn(1 << 20, 72, generator=g)
+    big_pred = big_gt + 0.02 * torch.randn(1 << 20, 72, generator=g)
+    a, s = angular_error_deg(big_pred, big_gt)
+    assert abs(float(s.item()) - float(a.double().sum().item())) < 1e-6 * float(s.item())
+    o_mean, _, _ = rp.evaluate_pose_pair(big_pred[:4096].numpy(), big_gt[:4096].numpy())
+    assert abs(float(a[:4096].double().mean().item()) - o_mean) < 1e-3
+    with pytest.raises(ValueError):
+        evaluate_pose_pair(np.zeros((0, 72), np.float32), np.zeros((0, 72), np.float32))
