@@ -315,7 +315,7 @@ def run_ours(args):
             "ms_per_launch_pair": fit_ms_step, "share_of_step": fit_ms_step / ms_step, "traffic": None,
         },
         "roofline_mesh": {
-            "kernel": "mesh_pose_kernel + mesh_skin_kernel", "bound": "hbm",
+            "kernel": "mesh_pose_kernel + blend_skin_tc_kernel (tcgen05 blend, LBS in the epilogue) + gather_extra_kernel", "bound": "hbm",
             "achieved": mesh_bytes / (mesh_ms * 1e-3) / 1e9 if mesh_ms > 0 else None,
             "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
