@@ -31,20 +31,21 @@
 // (measured: 80 + 1.5 N cycles per MMA instead of ~N/2), which is why this layout is used.
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace k2b {
 
-constexpr int kTcM = 128;          // frames per pass (the MMA's N) for blend depths up to 256 (SMPL)
-constexpr int kTcMDeep = 64;       // frames per pass for deeper blends (SMPL-H 512, SMPL-X 576): features must fit smem
+constexpr int kTcM = 128;          // frames per pass (the MMA's N) of the plain blend (SMPL-H, SMPL-X; features <= 144 KB)
+constexpr int kTcMFused = 64;      // frames per pass when the skinning rows share shared memory with the features (SMPL)
 constexpr int kTcN = 128;          // output columns per tile (the MMA's M)
-constexpr int kTcBK = 32;          // K block streamed per TMA copy = one 128-byte swizzle atom (4 MMAs of K = 8)
+constexpr int kTcBK = 64;          // K block streamed per TMA copy = one 128-byte swizzle atom of FP16 (4 MMAs of K = 16)
 constexpr int kTcKpadWide = 256;   // SMPL: 207 pose features + 3 x 10 split shape rows, padded to 8 x 32
 constexpr int kTcKpadMax = 576;    // SMPL-X: 486 pose features + 3 x 20 split shape/expression rows, 18 x 32
 constexpr int kTcThreads = 320;    // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
-constexpr int kTcStages = 6;       // ring depth (K blocks of dirs, 16 KB each); 5 on the deep variant
-constexpr int kTcStagesDeep = 5;
+constexpr int kTcStages = 4;       // ring depth (K blocks of dirs, 16 KB each) of the plain blend
+constexpr int kTcStagesFused = 6;
 constexpr int kTcFusedJoints = 24; // the fused blend + skinning kernel is instantiated for the SMPL skeleton
 constexpr int kTcAccStages = 4;    // accumulators in TMEM (two pairs)
 constexpr int kTcTmemCols = 512;
@@ -55,9 +56,9 @@ __host__ __device__ constexpr int tc_f_bytes(int kpad, int fr) { return (kpad / 
 __host__ __device__ constexpr size_t tc_smem_bytes(int kpad, int fr, int stages, int fused_joints) {
   return (size_t)tc_f_bytes(kpad, fr) + (size_t)stages * (size_t)tc_b_bytes() + (size_t)fr * fused_joints * 48 + (fused_joints ? (size_t)fr * 16 : 0) + 1024;
 }
-// offset (in floats) of element (row, k < 32) inside one 128-row swizzle-128B K block
+// offset (in FP16 elements) of element (row, k < 64) inside one swizzle-128B K block
 __host__ __device__ constexpr int tc_elem_off(int row, int k) {
-  return (row * 128 + (((k / 4) ^ (row % 8)) * 16) + (k % 4) * 4) / 4;
+  return (row * 128 + (((k / 8) ^ (row % 8)) * 16) + (k % 8) * 2) / 2;
 }
 
 #if defined(__CUDACC__)
@@ -101,10 +102,10 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], TF32 inputs, FP32 accumulate
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -145,9 +146,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                              // layout type 2 = SWIZZLE_128B
   return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): TF32 x TF32 -> F32, K-major A and B.
+// Instruction descriptor (cute::UMMA::InstrDescriptor): F16 x F16 -> F32 (A/B format 0), K-major A and B.
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -160,7 +161,8 @@ __device__ __forceinline__ float to_tf32(float x) {
 struct BlendParams {
   const float* feat;        // [frames_padded][npose] pose features (frames padded to 128, zero rows)
   const float* shape;       // [B][ns]
-  const float* b_tiles;     // [n_tiles (even)][kpad/32][tc_b_bytes/4] pre-tiled TF32 dirs^T blocks
+  const __half* b_tiles;    // [n_tiles (even)][kpad/64][tc_b_bytes/2] pre-tiled FP16 (dirs * dir_scale)^T blocks
+  float inv_scale;          // 1 / dir_scale (a power of two)
   const float* v_template;  // [3V]
   const float4* skin;       // [frames_padded][nj][3] rows of the 3x4 skinning matrices (mesh_pose_kernel)
   const float* transl;      // [B][3] or null
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
   const int kpad = p.kpad;
   constexpr int b_bytes = tc_b_bytes();
   const int f_bytes = tc_f_bytes(kpad, FR);
-  float* sF = reinterpret_cast<float*>(tc_smem);                         // features of the pass
+  __half* sF = reinterpret_cast<__half*>(tc_smem);                       // features of the pass
   unsigned char* sR = tc_smem + f_bytes;                                 // dirs ring
   float4* sA = reinterpret_cast<float4*>(tc_smem + f_bytes + (size_t)STAGES * b_bytes);   // FUSED: [FR][nj][3] rows
   const size_t a_bytes = FUSED ? (size_t)FR * NJ * 48 + (size_t)FR * 16 : 0;
@@ -239,16 +241,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
     for (int i = tid; i < FR * kpad; i += kTcThreads) {
       const int r = i / kpad, k = i - r * kpad;
       const long f = f0 + r;
-      float x = 0.f;
+      __half x = __float2half_rn(0.f);
       if (k < p.npose) {
-        x = tc::to_tf32(p.feat[f * p.npose + k]);           // feat rows are padded to a multiple of 128
+        x = __float2half_rn(p.feat[f * p.npose + k]);       // feat rows are padded to a multiple of 128
       } else if (k < p.npose + 3 * p.ns && f < p.num_frames) {
         const int part = (k - p.npose) / p.ns, s = (k - p.npose) - part * p.ns;
         const float b = p.shape[f * p.ns + s];
-        const float hi = tc::to_tf32(b);
-        x = part == 1 ? tc::to_tf32(b - hi) : hi;           // [hi | lo | hi]
+        const __half hi = __float2half_rn(b);
+        x = part == 1 ? __float2half_rn(b - __half2float(hi)) : hi;   // [hi | lo | hi]
       }
-      sF[(k >> 5) * (FR * 32) + tc_elem_off(r, k & 31)] = x;
+      sF[(k >> 6) * (FR * 64) + tc_elem_off(r, k & 63)] = x;
     }
     if constexpr (FUSED) {     // this pass's skinning matrices (rows past the last frame are never read)
       const float4* src = p.skin + f0 * (3L * NJ);
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
               }
               const size_t blk = (size_t)(2 * pr + h) * kblocks + kb;
               tc::mbar_expect_tx(BAR(s), (uint32_t)b_bytes);
-              tc::bulk_g2s(tc::smem_u32(sR + (size_t)s * b_bytes), p.b_tiles + blk * (b_bytes / 4), (uint32_t)b_bytes,
+              tc::bulk_g2s(tc::smem_u32(sR + (size_t)s * b_bytes), p.b_tiles + blk * (b_bytes / 2), (uint32_t)b_bytes,
                            BAR(s));
             }
       }
@@ -305,11 +307,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
             tc::tc_fence_after();
             const uint32_t r0 = tc::smem_u32(sR + (size_t)s0 * b_bytes), r1 = tc::smem_u32(sR + (size_t)s1 * b_bytes);
 #pragma unroll
-            for (int j = 0; j < kTcBK / 8; ++j) {
+            for (int j = 0; j < kTcBK / 16; ++j) {
               const uint64_t fdesc = tc::make_desc(f_addr + (uint32_t)(kb * (FR * 128) + j * 32));
               const uint32_t acc = (kb | j) ? 1u : 0u;
-              tc::mma_tf32(d0, tc::make_desc(r0 + j * 32), fdesc, idesc, acc);
-              tc::mma_tf32(d1, tc::make_desc(r1 + j * 32), fdesc, idesc, acc);
+              tc::mma_f16(d0, tc::make_desc(r0 + j * 32), fdesc, idesc, acc);
+              tc::mma_f16(d1, tc::make_desc(r1 + j * 32), fdesc, idesc, acc);
             }
             tc::mma_commit(BAR(6 + s0));    // ring stages free once these MMAs retire
             tc::mma_commit(BAR(6 + s1));
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
             constexpr int FS = 3 * NJ;                             // float4 rows per frame
 #pragma unroll
             for (int i = 0; i < 16; ++i) {                         // fully unrolled, branch-free: 16 frames overlap
-              const float pc = __uint_as_float(acc[i]) + tv;
+              const float pc = fmaf(__uint_as_float(acc[i]), p.inv_scale, tv);
               const float px = __shfl_sync(0xffffffffu, pc, sx), py = __shfl_sync(0xffffffffu, pc, sy),
                           pz = __shfl_sync(0xffffffffu, pc, sz);
               float4 T = make_float4(0.f, 0.f, 0.f, sTc[(ch * 16 + i) * 4]);
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
   #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const long fr = ch * 16 + i;
-                if (f0 + fr < p.num_frames) o[fr * ncols] = __uint_as_float(v[i]) + tv;
+                if (f0 + fr < p.num_frames) o[fr * ncols] = fmaf(__uint_as_float(v[i]), p.inv_scale, tv);
               }
             }
           }

@@ -48,7 +48,8 @@ struct MeshModel {
   bool tc = false;
   bool fused = false;          // skinning fused into the blend epilogue (needs features + skinning rows in smem)
   int kpad = 0, n_tiles = 0;
-  float* b_tiles = nullptr;    // [n_tiles][tc_b_bytes/4] pre-tiled, TF32-rounded [posedirs ; shapedirs]
+  __half* b_tiles = nullptr;   // [n_tiles][kpad/64][tc_b_bytes/2] pre-tiled FP16 image of dir_scale * [posedirs ; shapedirs]
+  float dir_scale = 1.f;       // power of two that lifts the dirs into FP16's normal range
 };
 
 inline void mesh_model_free(MeshModel& m) {
@@ -151,19 +152,21 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
     m.kpad = tc_kpad(kdepth);
     const int ncols = nv * 3, kblocks = m.kpad / kTcBK;
     // SMPL: 64 frames of features (64 KB) + their skinning rows (72 KB) + the ring fit one SM -> fused epilogue
-    m.fused = nj == kTcFusedJoints && ell <= 4 && m.kpad <= kTcKpadWide && tc_smem_bytes(m.kpad, kTcMDeep, kTcStagesDeep, nj) <= 227 * 1024;
+    m.fused = nj == kTcFusedJoints && ell <= 4 && m.kpad <= kTcKpadWide &&
+              tc_smem_bytes(m.kpad, kTcMFused, kTcStagesFused, nj) <= 227 * 1024;
     const int per_tile = m.fused ? kTcVertsPerTile * 3 : kTcN;
     m.n_tiles = ((ncols + per_tile - 1) / per_tile + 1) / 2 * 2;   // tiles are consumed in pairs
-    const size_t blk_floats = (size_t)tc_b_bytes() / 4;
-    std::vector<float> bt((size_t)m.n_tiles * kblocks * blk_floats, 0.f);
-    auto tf32 = [](float v) {
-      uint32_t bits;
-      memcpy(&bits, &v, 4);
-      bits = (bits + 0x1000u) & ~0x1FFFu;        // cvt.rna.tf32: round to nearest, ties away
-      float r;
-      memcpy(&r, &bits, 4);
-      return r;
-    };
+    const size_t blk_halfs = (size_t)tc_b_bytes() / 2;
+    // FP16 keeps TF32's 10 mantissa bits only in its normal range (>= 6.1e-5): scale the dirs by a power of two
+    // so their largest entry sits near 2^10; the epilogue multiplies the accumulator by 1 / scale (exact).
+    float dmax = 0.f;
+    for (size_t i = 0; i < (size_t)m.npose * ncols; ++i) dmax = fmaxf(dmax, fabsf(d.posedirs[i]));
+    for (size_t i = 0; i < (size_t)ncols * ns; ++i) dmax = fmaxf(dmax, fabsf(d.shapedirs[i]));
+    int e = 0;
+    if (dmax > 0.f) frexpf(dmax, &e);                 // dmax = f * 2^e, f in [0.5, 1)
+    m.dir_scale = ldexpf(1.f, 10 - e);
+    const float S = m.dir_scale;
+    std::vector<__half> bt((size_t)m.n_tiles * kblocks * blk_halfs, __float2half_rn(0.f));
     for (int nt = 0; nt < m.n_tiles; ++nt)
       for (int n = 0; n < kTcN; ++n) {
         int col = nt * kTcN + n;
@@ -173,16 +176,16 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
         }
         if (col >= ncols) continue;
         for (int k = 0; k < kdepth; ++k) {
-          float r;
+          __half r;
           if (k < m.npose) {
-            r = tf32(d.posedirs[(size_t)k * ncols + col]);
+            r = __float2half_rn(S * d.posedirs[(size_t)k * ncols + col]);
           } else {
             const int part = (k - m.npose) / ns, s = (k - m.npose) - part * ns;
-            const float v = d.shapedirs[(size_t)col * ns + s];
-            const float hi = tf32(v);
-            r = part == 2 ? tf32(v - hi) : hi;         // [S_hi ; S_hi ; S_lo]
+            const float v = S * d.shapedirs[(size_t)col * ns + s];
+            const __half hi = __float2half_rn(v);
+            r = part == 2 ? __float2half_rn(v - __half2float(hi)) : hi;         // [S_hi ; S_hi ; S_lo]
           }
-          bt[((size_t)nt * kblocks + k / kTcBK) * blk_floats + tc_elem_off(n, k % kTcBK)] = r;   // swizzle-128B image
+          bt[((size_t)nt * kblocks + k / kTcBK) * blk_halfs + tc_elem_off(n, k % kTcBK)] = r;   // swizzle-128B image
         }
       }
     ok = mesh_upload(bt, &m.b_tiles, err);
@@ -452,15 +455,15 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
   const char* force_fp32 = getenv("K2B_MESH_FP32");   // diagnostics / tests: take the CUDA-core path
   if (m.tc && a.out_vertices && !(force_fp32 && atoi(force_fp32))) {
     // ---- tensor-core path: blend (tcgen05) -> in-place skinning -> extra-joint gather ----------
-    // SMPL: fused blend + skinning, 64 frames per pass.  SMPL-H / SMPL-X: 64-frame blend, then in-place skinning.
-    const int fr = kTcMDeep;
-    const size_t tsm = tc_smem_bytes(m.kpad, fr, kTcStagesDeep, m.fused ? m.nj : 0);
-    auto* kern = blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 0, 0>;
+    // SMPL: fused blend + skinning, 64 frames per pass.  SMPL-H / SMPL-X: 128-frame blend, then in-place skinning.
+    const int fr = m.fused ? kTcMFused : kTcM;
+    const size_t tsm = tc_smem_bytes(m.kpad, fr, m.fused ? kTcStagesFused : kTcStages, m.fused ? m.nj : 0);
+    auto* kern = blend_skin_tc_kernel<kTcM, kTcStages, 0, 0>;
     if (m.fused) {
-      kern = m.ell == 1 ? blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 1, kTcFusedJoints>
-           : m.ell == 2 ? blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 2, kTcFusedJoints>
-           : m.ell == 3 ? blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 3, kTcFusedJoints>
-                        : blend_skin_tc_kernel<kTcMDeep, kTcStagesDeep, 4, kTcFusedJoints>;
+      kern = m.ell == 1 ? blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 1, kTcFusedJoints>
+           : m.ell == 2 ? blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 2, kTcFusedJoints>
+           : m.ell == 3 ? blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 3, kTcFusedJoints>
+                        : blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 4, kTcFusedJoints>;
     }
     static size_t tc_configured[5] = {0, 0, 0, 0, 0};
     const int variant = m.fused ? m.ell : 0;
@@ -476,7 +479,7 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char* dbg = getenv("K2B_TC_DEBUG");
-    BlendParams bp{posefeat, a.shape, m.b_tiles, m.v_template, (const float4*)skin, a.transl, m.ell_idx, m.ell_w,
+    BlendParams bp{posefeat, a.shape, m.b_tiles, 1.f / m.dir_scale, m.v_template, (const float4*)skin, a.transl, m.ell_idx, m.ell_w,
                    a.out_vertices, B, m.npose, m.ns, m.kpad, m.nv, m.nj, m.ell, m.n_tiles, dbg ? atoi(dbg) : 0};
     const long passes = Bp / fr;
     kern<<<(unsigned)(passes < sms ? passes : sms), kTcThreads, tsm, st>>>(bp);
