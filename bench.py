@@ -256,14 +256,20 @@ def run_ours(args):
     h_loss = torch.empty(F, pin_memory=True)
     h_joints = torch.empty(F, n_j, 3, pin_memory=True)
 
+    side = torch.cuda.Stream(device=dev)
+    fitted = torch.cuda.Event()
+
     def step_host():
         d_targets.copy_(h_targets, non_blocking=True)
-        o = sf.run(d_targets, seq_ind)
-        h_pose.copy_(o["pose"], non_blocking=True)
-        h_betas.copy_(o["params"]["betas"], non_blocking=True)
-        h_transl.copy_(o["params"]["transl"], non_blocking=True)
-        h_loss.copy_(o["loss"], non_blocking=True)
+        o = sf.run(d_targets, seq_ind, params_ready=fitted)
+        with torch.cuda.stream(side):          # parameters and losses go home while the mesh pass runs
+            side.wait_event(fitted)
+            h_pose.copy_(o["pose"], non_blocking=True)
+            h_betas.copy_(o["params"]["betas"], non_blocking=True)
+            h_transl.copy_(o["params"]["transl"], non_blocking=True)
+            h_loss.copy_(o["loss"], non_blocking=True)
         h_joints.copy_(o["joints"], non_blocking=True)
+        torch.cuda.current_stream().wait_stream(side)
 
     for _ in range(max(1, args.warmup // 2)):
         step_host()

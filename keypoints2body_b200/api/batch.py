@@ -81,12 +81,15 @@ class SequenceBatchFitter:
 
     def run(self, targets: torch.Tensor, seq_ind: torch.Tensor, conf: Optional[torch.Tensor] = None,
             init_pose: Optional[torch.Tensor] = None, init_betas: Optional[torch.Tensor] = None,
-            use_lbfgs: Optional[bool] = None, with_mesh: bool = True, group=None) -> dict:
+            use_lbfgs: Optional[bool] = None, with_mesh: bool = True, group=None,
+            params_ready: Optional[torch.cuda.Event] = None) -> dict:
         """Fit ``targets`` (F,K,3) whose frame f is frame ``seq_ind[f]`` of its sequence.
 
         Sweep-0 initialisation = ``init_pose`` (1,72)|(F,72) (default zeros = the synthetic mean pose),
         ``init_betas`` likewise, and a per-frame root-aligned translation (what
         ``optimize_params_frame`` does for a lone frame, engine.py:89-128).
+        ``params_ready`` (optional event) is recorded once the fitted parameters and losses are final, i.e.
+        before the mesh pass, so a caller can copy them to the host on another stream while the mesh runs.
         """
         f, F, cfg = self.f, self.F, self.cfg
         dev = f.device
@@ -145,6 +148,8 @@ class SequenceBatchFitter:
             params["expression"] = self.s1["expr"]
         out = {"params": params, "pose": self.s1["pose"], "loss": self.loss1,
                "evals": self.evals0 + self.evals1}
+        if params_ready is not None:
+            params_ready.record()
         if with_mesh:
             mesh = f.forward_batch(params, with_vertices=self.vertices is not None, out_vertices=self.vertices)
             out["joints"], out["vertices"] = mesh["joints"], mesh["vertices"]

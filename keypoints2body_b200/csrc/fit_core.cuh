@@ -405,9 +405,19 @@ K2B_HD void rel_offset_bwd(const FitTables& tb, int j, V3 rb, float (&shape_bar)
 
 K2B_HD V3 load_rot(const Cols& c, int j) { return v3(c.X(3 * j), c.X(3 * j + 1), c.X(3 * j + 2)); }
 
+// Observation of one joint (weight, target), read from global scratch: requested one joint ahead of its
+// use so the L2 latency overlaps the previous joint's arithmetic.
+struct Obs {
+  float w, x, y, z;
+};
+K2B_HD Obs load_obs(const FrameConsts& fc, int j) {
+  return Obs{fc.wgt[j * fc.stride], fc.tgt[(3 * j + 0) * fc.stride], fc.tgt[(3 * j + 1) * fc.stride],
+             fc.tgt[(3 * j + 2) * fc.stride]};
+}
+
 // Residual of joint j at position t: accumulates the loss, returns d loss / d position.
 template <int NS>
-K2B_HD V3 residual(KinCtx<NS>& k, int j, V3 t) {
+K2B_HD V3 residual(KinCtx<NS>& k, int j, V3 t, const Obs& ob) {
   const V3 p = t + k.transl;
   if (k.joints_out) {
     k.joints_out[3 * j + 0] = p.x;
@@ -415,10 +425,10 @@ K2B_HD V3 residual(KinCtx<NS>& k, int j, V3 t) {
     k.joints_out[3 * j + 2] = p.z;
   }
   const FrameConsts& fc = k.fc;
-  const float w = fc.wgt[j * fc.stride];
-  const float ex = p.x - fc.tgt[(3 * j + 0) * fc.stride];
-  const float ey = p.y - fc.tgt[(3 * j + 1) * fc.stride];
-  const float ez = p.z - fc.tgt[(3 * j + 2) * fc.stride];
+  const float w = ob.w;
+  const float ex = p.x - ob.x;
+  const float ey = p.y - ob.y;
+  const float ez = p.z - ob.z;
   if (k.fc.plain_sq) {
     k.loss = fmaf(w, fmaf(ex, ex, fmaf(ey, ey, ez * ez)), k.loss);
     return v3(2.f * w * ex, 2.f * w * ey, 2.f * w * ez);
@@ -468,9 +478,11 @@ K2B_HD void chain_fwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail
 // leaf).  Walks back to the base, emitting losses / gradients; returns with `a` = chain sums.
 template <int NS>
 K2B_HD void chain_bwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail, KinState& s, Acc& a) {
+  Obs ob = load_obs(k.fc, chain_joint(type, side, len - 1));
 #pragma unroll 1
   for (int i = len - 1; i >= 0; --i) {
     const int j = chain_joint(type, side, i);
+    const Obs ob_next = load_obs(k.fc, chain_joint(type, side, i > 0 ? i - 1 : 0));   // next joint's, in flight
     const bool has_rot = !(leaf_tail && i == len - 1);
     M3 Rp = s.R;
     V3 r = v3(0.f, 0.f, 0.f);
@@ -479,7 +491,8 @@ K2B_HD void chain_bwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail
       r = load_rot(k.c, j);
       Rp = matmul_nt(s.R, rodrigues(r, o));    // Rw_p = Rw_j R_j^T
     }
-    const V3 g = residual<NS>(k, j, s.t);
+    const V3 g = residual<NS>(k, j, s.t, ob);
+    ob = ob_next;
     if (k.with_grad) {
       acc_point(a, g, s.t);
       rel_offset_bwd<NS>(k.tb, j, matvec_t(Rp, a.s), k.shape_bar);
@@ -552,8 +565,9 @@ K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& f
     }
   }
   // ---- spine backward 9 -> 6 -> 3, then the root -------------------------------------------
+  const Obs ob0 = load_obs(fc, 0);          // in flight during the spine's backward walk
   chain_bwd<NS>(k, kSpine, 0, 3, false, j9, a9);
-  const V3 g0 = residual<NS>(k, 0, root.t);
+  const V3 g0 = residual<NS>(k, 0, root.t, ob0);
   loss += k.loss;
   V3 dgrad = v3(0.f, 0.f, 0.f);
   if (fc.depth_w2 != 0.f) {   // camera-space stage 1: keep the translation near its initial estimate
