@@ -312,3 +312,34 @@ def test_camera_fitter_lbfgs_statistics(goldens, weights, gmm):
                       torch.ones(22), seq_ind=0, freeze_betas=True)
     assert np.median(cpu(out["loss"])) <= 1.5 * np.median(g["cam_lbfgs_loss"])
     assert int(out["evals"].max()) <= 2 * (20 * 5 // 4 + 1)
+
+
+def test_extreme_inputs_terminate_and_match_oracle(fitters, shims, oracle_prior, weights):
+    """Rotations beyond pi, all-zero targets (the reference's smoke input) and non-finite observations:
+    evaluation parity where the oracle is finite, and guaranteed termination (bounded budgets) where it is not."""
+    g = torch.Generator().manual_seed(99)
+    B = 4
+    pose = torch.zeros(B, 72)
+    pose[0, :3] = torch.tensor([3.1, 0.2, -0.1])              # near pi
+    pose[1, 3:6] = torch.tensor([0.0, 4.6, 0.0])               # beyond pi
+    pose[2] = 1.5 * torch.randn(72, generator=g)               # large everywhere
+    params = dict(global_orient=pose[:, :3].contiguous(), body_pose=pose[:, 3:].contiguous(),
+                  betas=2.0 * torch.randn(B, 10, generator=g), transl=torch.randn(B, 3, generator=g))
+    tgt = torch.zeros(B, 22, 3)                                  # tests/test_integration_smoke.py:17-20 feeds zeros
+    f = fitters("smpl", use_lbfgs=False)
+    keep = params["body_pose"] * 0.5
+    ours = f.evaluate_batch(params, tgt, torch.ones(22), preserve_pose=keep, preserve_on=True, pose_preserve_weight=5.0)
+    ref_loss, ref_grads, _ = rp.evaluate(shims("smpl"), oracle_prior, params, keep, tgt, torch.ones(22),
+                                         pose_preserve_weight=5.0)
+    np.testing.assert_allclose(cpu(ours["loss"]), ref_loss.numpy().reshape(-1), rtol=2e-5)
+    gref = ref_grads["body_pose"].numpy()
+    assert np.abs(cpu(ours["grad_pose"])[:, 3:] - gref).max() <= 2e-4 * np.abs(gref).max()
+    # non-finite observations: both optimisers return (NaN results are fine, hanging is not)
+    bad = tgt.clone()
+    bad[0, 3, 1] = float("nan")
+    bad[1, 7, 0] = float("inf")
+    for lb in (False, True):
+        out = fitters("smpl", use_lbfgs=lb).fit_batch(params, bad, None, seq_ind=0, num_iters=10, with_mesh=False)
+        ev = cpu(out["evals"])
+        assert ev.max() <= 10 * 5 // 4 + 2 and ev.min() >= 1
+        assert np.isfinite(cpu(out["loss"])[2:]).all()           # finite frames are unaffected by their neighbours
