@@ -1,34 +1,34 @@
-// blend_tc.cuh -- K2: pose / shape blend as a TF32 GEMM on the 5th-gen tensor cores (tcgen05).
+// blend_tc.cuh -- K2 (+K3): pose / shape blend as an FP16 GEMM on the 5th-gen tensor cores (tcgen05), with the
+// LBS skinning optionally fused into its epilogue.
 //
 //   v_posed[f][c] = v_template[c] + sum_k feat[f][k] * dirs[k][c],   c in [0, 3V)
 //   feat[f] = [ (R_1..R_{nj-1} - I).flatten() (9(nj-1)) | shape_hi | shape_lo | shape_hi | 0-pad ]
-//   dirs    = [ posedirs ; S_hi ; S_hi ; S_lo ]
-// The shape blend carries decimetre-scale offsets, so its 10 rows are split into TF32 hi/lo parts on
-// both sides (x = x_hi + x_lo, x_hi*S_hi + x_lo*S_hi + x_hi*S_lo; only the lo*lo term is dropped):
-// that keeps the blend within ~1e-6 m of FP32 instead of ~7e-5 m for plain TF32.
+//   dirs    = [ posedirs ; S_hi ; S_hi ; S_lo ] * dir_scale
+// The shape blend carries decimetre-scale offsets, so its rows are split into FP16 hi/lo parts on both
+// sides (x = x_hi + x_lo, x_hi*S_hi + x_lo*S_hi + x_hi*S_lo; only the lo*lo term is dropped): that keeps the
+// blend within ~1e-6 m of FP32.  FP16 has TF32's 10 mantissa bits but K = 16 per MMA instruction instead of
+// 8, and the kernel is bound by MMA issue (~80 + 1.5 N cycles per instruction), so FP16 halves its time;
+// dirs are scaled by a power of two into FP16's normal range and the epilogue multiplies by the inverse.
 //
 // smplx does this as `pose_feature @ posedirs` + `blend_shapes` [smplx-from-memory]; the reference
 // reaches it through the final forward (/root/reference/keypoints2body/core/fitters/world_space.py:258-278).
 //
-// Orientation: D[M = 128 output columns][N = 128 frames].  The M operand is a block of dirs^T
-// (pre-tiled on the host into the exact shared-memory image of each (column tile, K block), streamed
-// with ONE 1-D TMA bulk copy per block -- cp.async.bulk + mbarrier complete_tx -- into a 6-deep
-// ring); the N operand is the pass's 128 frames' features, resident in shared memory (128 KB).
-// Accumulators live in TENSOR MEMORY: 4 x 128 columns = all 512.  Two column tiles are processed
-// as a PAIR with their MMAs interleaved (a chain of MMAs into one accumulator is latency-bound,
-// ~200 cycles each against 64 cycles of math at N = 128; two independent chains fill the gaps), and
-// pairs alternate between accumulators {0,1} and {2,3} so the epilogue of one pair overlaps the
-// MMAs of the next.  One thread issues tcgen05.mma.kind::tf32 (M128 N128 K8).  Eight epilogue warps
-// (lane quarter x tile of the pair) read TMEM with tcgen05.ld: lane = output column, register i =
-// frame, so every store instruction writes 32 consecutive floats of one frame row (128 bytes,
-// no transpose needed) after adding v_template.  Warp roles synchronise only through mbarriers.
+// Orientation: D[M = 128 output coordinates][N = FR frames].  The M operand is a block of dirs^T
+// (pre-tiled on the host into the exact shared-memory image of each (tile, 64-deep K block), streamed
+// with ONE 1-D TMA bulk copy per block -- cp.async.bulk + mbarrier complete_tx -- into a ring); the N
+// operand is the pass's frames' features, resident in shared memory.  Accumulators live in TENSOR MEMORY
+// (4 x FR columns).  Two tiles are processed as a PAIR with their MMAs interleaved, and pairs alternate
+// between accumulators {0,1} and {2,3} so the epilogue of one pair overlaps the MMAs of the next.  One thread
+// issues tcgen05.mma.kind::f16 (M128 N<FR> K16).  Eight epilogue warps (lane quarter x tile of the pair)
+// read TMEM with tcgen05.ld: lane = output coordinate, register i = frame.  Unfused (SMPL-H / SMPL-X,
+// FR = 128): every store instruction writes 32 consecutive floats of one frame row of v_posed.  Fused
+// (SMPL, FR = 64): see the epilogue -- tiles carry vertices, each lane skins its own coordinate.
+// Warp roles synchronise only through mbarriers.
 //
 // Operand layout: K-major SWIZZLE_128B canonical UMMA layout (cute mma_traits_sm100: Swizzle<3,4,3>).
-// A K block of 32 TF32 is one 128-byte row per operand row; rows are 128 B apart, 8-row groups
+// A K block of 64 FP16 is one 128-byte row per operand row; rows are 128 B apart, 8-row groups
 // 1024 B apart (SBO), and the 16-byte chunk index inside a row is XORed with (row % 8):
-//   byte address(row r, k) = (k / 32) * rows*128 + r * 128 + ((((k % 32) / 4) ^ (r % 8)) * 16) + (k % 4) * 4
-// The un-swizzled "interleaved" layout also works but is fetched one 16-byte row per cycle
-// (measured: 80 + 1.5 N cycles per MMA instead of ~N/2), which is why this layout is used.
+//   byte address(row r, k) = (k / 64) * rows*128 + r * 128 + ((((k % 64) / 8) ^ (r % 8)) * 16) + (k % 8) * 2
 #pragma once
 
 #include <cuda_fp16.h>
