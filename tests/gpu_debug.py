@@ -1,4 +1,7 @@
-"""Scratch GPU diagnostics (not part of the product or the tests)."""
+"""Scratch GPU diagnostics (test infrastructure: it may use the oracle; the product and tools/ do not).
+
+    python tests/gpu_debug.py eval|time|prof|mesh|meshx|meshprof|rounds
+"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
