@@ -262,11 +262,28 @@ K2B_HD void gmm_zpanel(const Cols& c, const float* __restrict__ Lm, const float*
 // Rows of panel P of g = L z.  Adds, in the same pass, the other body-pose terms so the
 // gradient column is touched once: G(3+i) = kinematic part (already there) + pose-prior part
 // + temporal pose-preserve part (losses.py:57-59) + angle-prior part (losses.py:13-21).
+// Ask for the kinematic gradients (and preserve poses) of panel P ahead of their use: they sit in global
+// scratch (L2), and nothing else is in flight to hide that latency.  No registers are held.
 template <int P>
+K2B_HD void gmm_gprefetch(const Cols& c, const FrameConsts& fc) {
+#if defined(__CUDA_ARCH__)
+  if (P <= 8) {
+    constexpr int ROWS = P < 8 ? 8 : 5;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(&c.G(3 + 8 * P + r)));
+      if (fc.keep_w2 != 0.f) asm volatile("prefetch.global.L1 [%0];" ::"l"(fc.keep + (8 * P + r) * fc.stride));
+    }
+  }
+#endif
+}
+
+template <int P, bool HINTS>
 K2B_HD void gmm_gpanel(const Cols& c, const FrameConsts& fc, const float* __restrict__ Lb, const float2 (&z)[36],
                        float& extra_loss) {
   constexpr int W = 8 * (P + 1);
   constexpr int ROWS = P < 8 ? 8 : 5;
+  if (HINTS) gmm_gprefetch<P + 2>(c, fc);
   const float* row = Lb + chol_panel_off(P);
 #pragma unroll (P <= 1 ? 4 : (P <= 4 ? 2 : 1))
   for (int r = 0; r < ROWS; ++r, row += W) {
@@ -298,6 +315,7 @@ K2B_HD void gmm_gpanel(const Cols& c, const FrameConsts& fc, const float* __rest
 
 // with_grad: also folds the preserve / angle terms in (see gmm_gpanel) and returns their loss in
 // `extra_loss`; without it the caller adds those terms itself.
+template <bool HINTS>
 K2B_HD float gmm_prior(const Cols& c, const FitTables& tb, const FrameConsts& fc, bool with_grad, int* best_m_out,
                        float& extra_loss) {
   float best = INFINITY;
@@ -332,11 +350,15 @@ K2B_HD float gmm_prior(const Cols& c, const FitTables& tb, const FrameConsts& fc
   if (best_m_out) *best_m_out = best_m;
   if (with_grad) {
     const float* __restrict__ Lb = tb.chol + best_m * kCholStride;
-    gmm_gpanel<0>(c, fc, Lb, z, extra_loss); gmm_gpanel<1>(c, fc, Lb, z, extra_loss);
-    gmm_gpanel<2>(c, fc, Lb, z, extra_loss); gmm_gpanel<3>(c, fc, Lb, z, extra_loss);
-    gmm_gpanel<4>(c, fc, Lb, z, extra_loss); gmm_gpanel<5>(c, fc, Lb, z, extra_loss);
-    gmm_gpanel<6>(c, fc, Lb, z, extra_loss); gmm_gpanel<7>(c, fc, Lb, z, extra_loss);
-    gmm_gpanel<8>(c, fc, Lb, z, extra_loss);
+    if (HINTS) {
+      gmm_gprefetch<0>(c, fc);
+      gmm_gprefetch<1>(c, fc);
+    }
+    gmm_gpanel<0, HINTS>(c, fc, Lb, z, extra_loss); gmm_gpanel<1, HINTS>(c, fc, Lb, z, extra_loss);
+    gmm_gpanel<2, HINTS>(c, fc, Lb, z, extra_loss); gmm_gpanel<3, HINTS>(c, fc, Lb, z, extra_loss);
+    gmm_gpanel<4, HINTS>(c, fc, Lb, z, extra_loss); gmm_gpanel<5, HINTS>(c, fc, Lb, z, extra_loss);
+    gmm_gpanel<6, HINTS>(c, fc, Lb, z, extra_loss); gmm_gpanel<7, HINTS>(c, fc, Lb, z, extra_loss);
+    gmm_gpanel<8, HINTS>(c, fc, Lb, z, extra_loss);
   }
   return kPosePriorW2 * best;
 }
@@ -476,13 +498,14 @@ K2B_HD void chain_fwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail
 
 // Backward: `s` stands on the tail; `a` holds the subtree sums of the tail's children (zero for a
 // leaf).  Walks back to the base, emitting losses / gradients; returns with `a` = chain sums.
-template <int NS>
+template <int NS, bool HINTS>
 K2B_HD void chain_bwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail, KinState& s, Acc& a) {
   Obs ob = load_obs(k.fc, chain_joint(type, side, len - 1));
 #pragma unroll 1
   for (int i = len - 1; i >= 0; --i) {
     const int j = chain_joint(type, side, i);
-    const Obs ob_next = load_obs(k.fc, chain_joint(type, side, i > 0 ? i - 1 : 0));   // next joint's, in flight
+    // HINTS: the next joint's observation is requested now; otherwise each one is loaded where it is used
+    const Obs ob_next = HINTS ? load_obs(k.fc, chain_joint(type, side, i > 0 ? i - 1 : 0)) : Obs{};
     const bool has_rot = !(leaf_tail && i == len - 1);
     M3 Rp = s.R;
     V3 r = v3(0.f, 0.f, 0.f);
@@ -491,7 +514,7 @@ K2B_HD void chain_bwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail
       r = load_rot(k.c, j);
       Rp = matmul_nt(s.R, rodrigues(r, o));    // Rw_p = Rw_j R_j^T
     }
-    const V3 g = residual<NS>(k, j, s.t, ob);
+    const V3 g = residual<NS>(k, j, s.t, HINTS || i == len - 1 ? ob : load_obs(k.fc, j));
     ob = ob_next;
     if (k.with_grad) {
       acc_point(a, g, s.t);
@@ -512,7 +535,9 @@ K2B_HD void chain_bwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail
 // with_grad fills G(0 .. 75+NS) completely; with_priors = false skips every prior term
 // (joints-only final forward).  Returns the total loss (losses.py:41-67).
 // ---------------------------------------------------------------------------------
-template <int NS, int K>
+// HINTS: software latency hints (observations one joint ahead, L1 prefetch of the gradient rows).  They pay
+// in the Adam kernel (+3 %) and cost in the L-BFGS kernel (-2 %), so the kernel picks per optimiser.
+template <int NS, int K, bool HINTS = false>
 K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& fc, bool with_grad,
                         bool with_priors, float* joints_out, int* gmm_component) {
   constexpr int ARM_LEN = (K == 24) ? 5 : 4;
@@ -559,14 +584,14 @@ K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& f
     s.t = from9 ? j9.t : root.t;
     chain_fwd<NS>(k, type, side, len, true, s);
     Acc a{zero3(), v3(0.f, 0.f, 0.f)};
-    chain_bwd<NS>(k, type, side, len, true, s, a);
+    chain_bwd<NS, HINTS>(k, type, side, len, true, s, a);
     if (with_grad) {
       if (from9) acc_add(a9, a); else acc_add(a0, a);
     }
   }
   // ---- spine backward 9 -> 6 -> 3, then the root -------------------------------------------
   const Obs ob0 = load_obs(fc, 0);          // in flight during the spine's backward walk
-  chain_bwd<NS>(k, kSpine, 0, 3, false, j9, a9);
+  chain_bwd<NS, HINTS>(k, kSpine, 0, 3, false, j9, a9);
   const V3 g0 = residual<NS>(k, 0, root.t, ob0);
   loss += k.loss;
   V3 dgrad = v3(0.f, 0.f, 0.f);
@@ -598,7 +623,7 @@ K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& f
   // ---- priors on the body pose (after the kinematic part of the gradient is in place) -------
   if (with_priors) {
     float extra = 0.f;
-    loss += gmm_prior(c, tb, fc, with_grad, gmm_component, extra);
+    loss += gmm_prior<HINTS>(c, tb, fc, with_grad, gmm_component, extra);
     if (!with_grad) {
       // angle prior (losses.py:13-21) on body-pose entries 52, 55, 9, 12 with signs +,-,-,-
 #pragma unroll

@@ -17,6 +17,10 @@
 #include "fit_core.cuh"
 #include "lbfgs_core.cuh"
 
+#ifndef K2B_LBFGS_HINTS
+#define K2B_LBFGS_HINTS false
+#endif
+
 namespace k2b {
 
 template <int NS>
@@ -218,7 +222,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       for (int k = 1; k <= rounds; ++k) {
         const bool last = k > warp_iters;
         if (last) fc.keep_w2 = 0.f;
-        const float loss = eval_frame<NS, K>(c, tb, fc, !last, priors && (!last || p.final_mode), last ? jout : nullptr, nullptr);
+        const float loss = eval_frame<NS, K, true>(c, tb, fc, !last, priors && (!last || p.final_mode), last ? jout : nullptr, nullptr);
         if (last && p.final_mode) out_loss = loss;
         if (!last && k <= iters) {
           out_loss = loss;   // loss of the last iteration, before its step (world_space.py:250-256)
@@ -264,7 +268,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         const bool fin = stage == 2;
         const Cols ce = st.eval_cols(c, v);
         if (fin && p.final_mode) fc.keep_w2 = 0.f;
-        const float loss = eval_frame<NS, K>(ce, tb, fc, !fin, priors, fin ? jout : nullptr, nullptr);
+        const float loss = eval_frame<NS, K, K2B_LBFGS_HINTS>(ce, tb, fc, !fin, priors, fin ? jout : nullptr, nullptr);
         if (fin) {
           out_loss = loss;
           break;
