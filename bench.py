@@ -145,6 +145,34 @@ def cpu_reference_rate(frames: int, threads: int, optimizer: str, seed: int = 77
     return one_pass
 
 
+def cpu_reference_batched_adam(frames: int, threads: int, seed: int = 78) -> dict:
+    """SURVEY 8(d) "reference, batched by hand": the reference's Adam path is batch-separable, so B frames can go
+    through ONE fit_frame call per sweep (its L-BFGS path cannot: the line search couples the batch).  Times the
+    oracle port that way, schedule S2, all host threads; reported next to the B = 1 number, never as the target."""
+    from keypoints2body_b200 import synthetic as syn
+    from oracle import reference_port as rp
+    from oracle.smplx_shim import BodyModelShim
+
+    torch.set_num_threads(threads)
+    weights = syn.make_body_model("smpl", seed=0)
+    model, prior = BodyModelShim(weights), rp.GMMPrior(syn.make_gmm(seed=0))
+    mo = syn.make_motion(frames, seed=seed)
+    tgt = syn.kinematic_joints(weights, mo["pose"][:, :66], mo["betas"], mo["transl"], 22)
+    conf = torch.ones(22)
+    root0 = model(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10)).joints[:, 0]
+    init = {k: None for k in rp.PARAM_ORDER}
+    init.update(global_orient=torch.zeros(frames, 3), body_pose=torch.zeros(frames, 69), betas=torch.zeros(frames, 10),
+                transl=tgt[:, 0] - root0)
+    t0 = time.perf_counter()
+    s0 = rp.fit_frame(model, prior, init, tgt, conf, seq_ind=0, use_lbfgs=False)
+    prev = {k: (v[:-1] if v is not None else None) for k, v in s0["params"].items()}
+    rp.fit_frame(model, prior, prev, tgt[1:], conf, seq_ind=1, use_lbfgs=False)
+    dt = time.perf_counter() - t0
+    return {"value": frames / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{frames} frames in one batched call per sweep (S2, 30 + 10 iterations), adam, torch CPU, "
+                      "full-mesh forward per evaluation"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -172,6 +200,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "bounded sample of the ours-arm workload: " + sample, "optimizer": args.optimizer},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline_batched_adam": cpu_reference_batched_adam(1024, threads),
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -318,7 +347,11 @@ def run_ours(args):
             "peak_source": "in-run FFMA micro-benchmark (k2b_fma_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f" % nominal,
             "frac_of_nominal": achieved / nominal if achieved else None,
             "flop_per_eval": EVAL_FLOP["smpl"], "evals_per_launch": [evals0 + F, evals1 + F],
-            "ms_per_launch_pair": fit_ms_step, "share_of_step": fit_ms_step / ms_step, "traffic": None,
+            "ms_per_launch_pair": fit_ms_step, "share_of_step": fit_ms_step / ms_step,
+            "traffic": ncu_fit_traffic(args.optimizer, F),
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the sweep-0 launch from the committed ncu "
+                            "--set full capture (profiles/r01_fit_lbfgs_ncu_metrics.txt, same frame count); the "
+                            "algorithmic HBM bytes are ~1.5 KB/frame, the rest is L-BFGS (s, y) history that does not fit L2",
         },
         "roofline_mesh": {
             "kernel": "mesh_pose_kernel + blend_skin_tc_kernel (tcgen05 blend, LBS in the epilogue) + gather_extra_kernel", "bound": "hbm",
@@ -345,9 +378,29 @@ def run_ours(args):
             "value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n} frames, schedule S2 (30 + 10 budgets), {args.optimizer}, B=1 per frame, torch CPU, "
                       "full-mesh forward per evaluation like the reference"}
+        line["cpu_baseline_batched_adam"] = cpu_reference_batched_adam(1024, threads)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_fit_traffic(optimizer: str, frames: int):
+    """DRAM bytes of the dominant launch (sweep 0 of the L-BFGS fit kernel) from the committed ncu capture; null
+    when there is no capture for this optimiser / frame count."""
+    if optimizer != "lbfgs" or frames != 256 * SEQ_LEN:
+        return None
+    try:
+        total, seen = 0.0, 0
+        for ln in open(os.path.join(ROOT, "profiles", "r01_fit_lbfgs_ncu_metrics.txt")):
+            if ln.startswith("## launch 1"):
+                break
+            if ln.startswith("dram__bytes_read.sum") or ln.startswith("dram__bytes_write.sum"):
+                val, unit = ln.split("=")[1].split()
+                total += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+                seen += 1
+        return total if seen == 2 else None
+    except Exception:
+        return None
 
 
 def ctypes_double():
