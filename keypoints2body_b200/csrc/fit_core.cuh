@@ -206,6 +206,18 @@ struct FitTables {
 
 // Per-frame observations (targets, weights, preserve pose) -- device: transposed global
 // scratch (coalesced across the warp); host emulation: plain arrays with stride 1.
+// ---------------------------------------------------------------------------------
+// Adam, torch single-tensor semantics (torch/optim/adam.py:346-548, non-capturable CPU path):
+//   m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g g; p -= step_k * m / (sqrt(v)/bc2_k + eps)
+// step_k = lr / (1 - b1^k) and bc2_k = sqrt(1 - b2^k) are computed in double on the host.
+// ---------------------------------------------------------------------------------
+K2B_HD void adam_update(float& p, float& m, float& v, float g, float step_k, float bc2_k) {
+  m = fmaf(0.1f, g - m, m);                 // 1 - 0.9 as float32
+  v = fmaf(0.001f, g * g, v * 0.999f);      // float32(1 - 0.999) == 0.001f
+  const float denom = fdiv(sqrtf(v), bc2_k) + 1e-8f;
+  p = p - fdiv(step_k * m, denom);
+}
+
 struct FrameConsts {
   const float* tgt;      // element (j*3+c) at tgt[(j*3+c)*stride]
   const float* wgt;      // joint weight joint_w^2 * conf_j^2 at wgt[j*stride]
@@ -217,6 +229,12 @@ struct FrameConsts {
   bool plain_sq;
   float depth_w2;
   float dref[3];
+  // Adam fused into the gradient pass (Adam kernel only): when adam_m is set, the 69 body-pose entries are
+  // updated where their gradient is produced (moments at adam_m / adam_v [(3 + i) * stride]) and their
+  // gradient is not written back; the caller updates the remaining entries.
+  float* adam_m;
+  float* adam_v;
+  float adam_step, adam_bc2;
 };
 
 // Column accessor: element i of this frame's parameter vector x (shared memory on the device,
@@ -273,6 +291,10 @@ K2B_HD void gmm_gprefetch(const Cols& c, const FrameConsts& fc) {
     for (int r = 0; r < ROWS; ++r) {
       asm volatile("prefetch.global.L1 [%0];" ::"l"(&c.G(3 + 8 * P + r)));
       if (fc.keep_w2 != 0.f) asm volatile("prefetch.global.L1 [%0];" ::"l"(fc.keep + (8 * P + r) * fc.stride));
+      if (fc.adam_m) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(fc.adam_m + (3 + 8 * P + r) * fc.stride));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(fc.adam_v + (3 + 8 * P + r) * fc.stride));
+      }
     }
   }
 #endif
@@ -289,6 +311,12 @@ K2B_HD void gmm_gpanel(const Cols& c, const FrameConsts& fc, const float* __rest
   for (int r = 0; r < ROWS; ++r, row += W) {
     const int i = 8 * P + r;
     const float gk = c.G(3 + i);                      // issued early, consumed after the dot product
+    const bool fuse = HINTS && fc.adam_m != nullptr;
+    float am = 0.f, av = 0.f;
+    if (fuse) {
+      am = fc.adam_m[(3 + i) * fc.stride];
+      av = fc.adam_v[(3 + i) * fc.stride];
+    }
     const float xi = c.X(3 + i);
     const float keep = fc.keep_w2 != 0.f ? fc.keep[i * fc.stride] : xi;
     const float4* r4 = reinterpret_cast<const float4*>(row);
@@ -309,7 +337,15 @@ K2B_HD void gmm_gpanel(const Cols& c, const FrameConsts& fc, const float* __rest
       extra_loss = fmaf(kAnglePriorW2, e * e, extra_loss);
       g = fmaf(2.f * kAnglePriorW2 * sgn, e * e, g);
     }
-    c.G(3 + i) = g;
+    if (fuse) {   // Adam step of this entry, right where its gradient exists
+      float xn = xi;
+      adam_update(xn, am, av, g, fc.adam_step, fc.adam_bc2);
+      c.X(3 + i) = xn;
+      fc.adam_m[(3 + i) * fc.stride] = am;
+      fc.adam_v[(3 + i) * fc.stride] = av;
+    } else {
+      c.G(3 + i) = g;
+    }
   }
 }
 
@@ -535,8 +571,9 @@ K2B_HD void chain_bwd(KinCtx<NS>& k, int type, int side, int len, bool leaf_tail
 // with_grad fills G(0 .. 75+NS) completely; with_priors = false skips every prior term
 // (joints-only final forward).  Returns the total loss (losses.py:41-67).
 // ---------------------------------------------------------------------------------
-// HINTS: software latency hints (observations one joint ahead, L1 prefetch of the gradient rows).  They pay
-// in the Adam kernel (+3 %) and cost in the L-BFGS kernel (-2 %), so the kernel picks per optimiser.
+// HINTS (the Adam kernel's build): software latency hints (observations one joint ahead, L1 prefetch of the
+// gradient rows; +3 % there, -2 % in the L-BFGS kernel) and the option of fusing the Adam step of the
+// body-pose entries into the gradient pass (FrameConsts::adam_m).
 template <int NS, int K, bool HINTS = false>
 K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& fc, bool with_grad,
                         bool with_priors, float* joints_out, int* gmm_component) {
@@ -646,18 +683,6 @@ K2B_HD float eval_frame(const Cols& c, const FitTables& tb, const FrameConsts& f
     loss += extra;
   }
   return loss;
-}
-
-// ---------------------------------------------------------------------------------
-// Adam, torch single-tensor semantics (torch/optim/adam.py:346-548, non-capturable CPU path):
-//   m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g g; p -= step_k * m / (sqrt(v)/bc2_k + eps)
-// step_k = lr / (1 - b1^k) and bc2_k = sqrt(1 - b2^k) are computed in double on the host.
-// ---------------------------------------------------------------------------------
-K2B_HD void adam_update(float& p, float& m, float& v, float g, float step_k, float bc2_k) {
-  m = fmaf(0.1f, g - m, m);                 // 1 - 0.9 as float32
-  v = fmaf(0.001f, g * g, v * 0.999f);      // float32(1 - 0.999) == 0.001f
-  const float denom = fdiv(sqrtf(v), bc2_k) + 1e-8f;
-  p = p - fdiv(step_k * m, denom);
 }
 
 }  // namespace k2b

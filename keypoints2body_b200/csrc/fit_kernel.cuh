@@ -222,12 +222,9 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       for (int k = 1; k <= rounds; ++k) {
         const bool last = k > warp_iters;
         if (last) fc.keep_w2 = 0.f;
-        const float loss = eval_frame<NS, K, true>(c, tb, fc, !last, priors && (!last || p.final_mode), last ? jout : nullptr, nullptr);
-        if (last && p.final_mode) out_loss = loss;
-        if (!last && k <= iters) {
-          out_loss = loss;   // loss of the last iteration, before its step (world_space.py:250-256)
-          ++evals;
-          float step_k, bc2_k;
+        const bool stepping = !last && k <= iters;
+        float step_k = 0.f, bc2_k = 1.f;
+        if (stepping) {
           if (k <= kAdamTable) {
             step_k = at.step[k - 1];
             bc2_k = at.bc2[k - 1];
@@ -235,8 +232,21 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
             step_k = (float)((double)p.lr / (1.0 - pow(0.9, (double)k)));
             bc2_k = (float)sqrt(1.0 - pow(0.999, (double)k));
           }
-#pragma unroll 17
+        }
+        // with the priors on, the body-pose entries take their Adam step inside the gradient pass
+        const bool fused = stepping && priors;
+        fc.adam_m = fused ? m1 : nullptr;
+        fc.adam_v = m2;
+        fc.adam_step = step_k;
+        fc.adam_bc2 = bc2_k;
+        const float loss = eval_frame<NS, K, true>(c, tb, fc, !last, priors && (!last || p.final_mode), last ? jout : nullptr, nullptr);
+        if (last && p.final_mode) out_loss = loss;
+        if (stepping) {
+          out_loss = loss;   // loss of the last iteration, before its step (world_space.py:250-256)
+          ++evals;
+#pragma unroll 4
           for (int i = 0; i < NX; ++i) {
+            if (fused && i >= 3 && i < kTranslOff) continue;
             if (freeze_betas && i >= kShapeOff && i < kShapeOff + 10) continue;
             if (stage1 && !(i < 3 || (i >= kTranslOff && i < kShapeOff))) continue;
             float mm = m1[i * kStride], vv = m2[i * kStride], x = c.X(i);

@@ -65,14 +65,19 @@ struct LbfgsAny {
   float dot_cur_d(const Vecs& v) const { return n == 85 ? a.dot_cur_d(v) : b.dot_cur_d(v); }
 };
 
-template <int NS, int K>
+template <int NS, int K, bool ADAM>
 static float run_eval(const Cols& c, const FitTables& tb, const FrameConsts& fc, bool g, bool pr, float* j, int* comp) {
-  return eval_frame<NS, K>(c, tb, fc, g, pr, j, comp);
+  return eval_frame<NS, K, ADAM>(c, tb, fc, g, pr, j, comp);
 }
 typedef float (*EvalFn)(const Cols&, const FitTables&, const FrameConsts&, bool, bool, float*, int*);
-static EvalFn pick(int ns, int K) {
-  if (K == 24) return run_eval<10, 24>;
-  return ns == 20 ? run_eval<20, 22> : run_eval<10, 22>;
+// adam_build = the instantiation the Adam kernel uses (fused body-pose step inside the gradient pass)
+static EvalFn pick(int ns, int K, bool adam_build = false) {
+  if (adam_build) {
+    if (K == 24) return run_eval<10, 24, true>;
+    return ns == 20 ? run_eval<20, 22, true> : run_eval<10, 22, true>;
+  }
+  if (K == 24) return run_eval<10, 24, false>;
+  return ns == 20 ? run_eval<20, 22, false> : run_eval<10, 22, false>;
 }
 
 // mode 0: evaluate (out_x = gradient), 1: Adam, 2: L-BFGS.  x layout [go3|body69|transl3|betas10|expr10?]
@@ -108,18 +113,27 @@ extern "C" int emu_fit(void* model, int mode, int B, int K, int iters, int freez
       memcpy(out_x + (size_t)f * NX, g.data(), NX * sizeof(float));
     } else if (mode == 1) {
       std::vector<float> m1(NX, 0.f), m2(NX, 0.f);
+      EvalFn eva = pick(NS, K, true);
       for (int k = 1; k <= iters; ++k) {
-        loss = ev(c, tb, fc, true, priors, nullptr, nullptr);
-        ++evals;
         const float step_k = (float)((double)lr / (1.0 - std::pow(0.9, (double)k)));
         const float bc2_k = (float)std::sqrt(1.0 - std::pow(0.999, (double)k));
+        // same split as fit_kernel: with the priors on, body-pose entries step inside the gradient pass
+        const bool fused = priors;
+        fc.adam_m = fused ? m1.data() : nullptr;
+        fc.adam_v = m2.data();
+        fc.adam_step = step_k;
+        fc.adam_bc2 = bc2_k;
+        loss = eva(c, tb, fc, true, priors, nullptr, nullptr);
+        ++evals;
         for (int i = 0; i < NX; ++i) {
+          if (fused && i >= 3 && i < kTranslOff) continue;
           if (freeze_betas && i >= kShapeOff && i < kShapeOff + 10) continue;
           if (stage1 && !(i < 3 || (i >= kTranslOff && i < kShapeOff))) continue;
           adam_update(x[i], m1[i], m2[i], g[i], step_k, bc2_k);
         }
       }
       fc.keep_w2 = 0.f;
+      fc.adam_m = nullptr;
       {
         const float fl = ev(c, tb, fc, false, priors && final_mode, jout, nullptr);
         if (final_mode) loss = fl;
