@@ -218,6 +218,8 @@ extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* st
     // Lanes waiting at an outer-iteration boundary that trigger the (warp-wide) direction update.  Measured on
     // B200 at 227 k frames: a 30-iteration budget runs 2.4 % faster at 28 than at 32 (fewer idle rounds), a
     // 10-iteration budget 7 % slower (more divergent updates).  Results do not depend on it.
+    const char* fz = getenv("K2B_ADAM_FUSE");
+    p.adam_fuse = fz ? atoi(fz) : 1;
     const char* q = getenv("K2B_LBFGS_QUORUM");
     p.outer_quorum = q ? atoi(q) : (a->num_iters >= 20 ? 28 : 32);
   }

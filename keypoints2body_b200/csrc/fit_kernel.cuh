@@ -66,6 +66,7 @@ struct FitParams {
   float depth_w2;
   int debug_rounds;        // K2B_DEBUG_ROUNDS: pack the warp's round count into out_evals (diagnostics)
   int outer_quorum;        // lanes waiting at an outer-iteration boundary that trigger the direction update
+  int adam_fuse;           // 1: body-pose Adam steps inside the gradient pass (K2B_ADAM_FUSE=0 turns it off; same results)
 };
 
 struct AdamTable {
@@ -234,7 +235,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
           }
         }
         // with the priors on, the body-pose entries take their Adam step inside the gradient pass
-        const bool fused = stepping && priors;
+        const bool fused = stepping && priors && p.adam_fuse;
         fc.adam_m = fused ? m1 : nullptr;
         fc.adam_v = m2;
         fc.adam_step = step_k;

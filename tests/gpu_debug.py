@@ -35,9 +35,9 @@ if what == "time":
                         betas=torch.zeros(B, 10), transl=mo["transl"])
             init = {k: v.cuda() for k, v in init.items()}
             for iters in (10, 30):
-                f.fit_batch(init, tgt, None, seq_ind=1, num_iters=iters, with_mesh=False)
+                f.fit_batch(init, tgt, None, seq_ind=int(os.environ.get("K2B_SEQ", "1")), num_iters=iters, with_mesh=False)
                 torch.cuda.synchronize(); t0 = time.perf_counter()
-                o = f.fit_batch(init, tgt, None, seq_ind=1, num_iters=iters, with_mesh=False)
+                o = f.fit_batch(init, tgt, None, seq_ind=int(os.environ.get("K2B_SEQ", "1")), num_iters=iters, with_mesh=False)
                 torch.cuda.synchronize(); dt = time.perf_counter() - t0
                 ev = float(o["evals"].float().mean())
                 print(f"{opt} B={B} iters={iters} evals/frame={ev:.1f} time={dt*1e3:.2f} ms  -> {dt/ (ev+1) * 1e6:.1f} us per eval-round, {B*(ev+1)/dt/1e6:.2f} M frame-evals/s")
