@@ -176,11 +176,13 @@ def optimize_params_sequence(
                                              seq_cfg.frame.coordinate_mode).transl
 
     out = fit_sequence_batched(fitter, xyz, conf, init, seq_cfg)
+    # per-frame views in one C++ pass per field (split / unbind), not 8 Python slicing calls per frame
+    rows = {k: v.split(1) for k, v in out["params"].items() if v is not None}
+    verts, joints, losses = out["vertices"].split(1), out["joints"].split(1), out["loss"].unbind(0)
     results = []
     for t in range(xyz.shape[0]):
-        results.append(BodyModelFitResult(params=dict_to_params(body_model, out["params"], t),
-                                          vertices=out["vertices"][t:t + 1], joints=out["joints"][t:t + 1],
-                                          loss=out["loss"][t]))
+        results.append(BodyModelFitResult(params=dict_to_params(body_model, {k: r[t] for k, r in rows.items()}),
+                                          vertices=verts[t], joints=joints[t], loss=losses[t]))
     return results
 
 
