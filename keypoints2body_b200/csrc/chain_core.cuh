@@ -1,0 +1,672 @@
+// chain_core.cuh -- warp-cooperative evaluation and optimiser steps: one WARP owns one frame.
+//
+// The fused fitting kernel (fit_kernel.cuh) maps one thread to one frame: best throughput for
+// thousands of independent frames, but a lone frame takes ~1.3 ms, and the reference's default
+// sequence schedule (api/sequence.py:214-281: frame t starts from frame t-1's result) is serial in
+// t.  Here the 32 lanes of a warp share ONE frame, so an evaluation takes microseconds and a whole
+// sequence can be walked serially inside one launch (chain_kernel.cuh).
+//
+// Same maths as fit_core.cuh (paths into /root/reference/keypoints2body):
+//   core/fitters/world_space.py:173-212  compute_loss        core/losses.py:6-67  gmof, angle_prior, loss
+//   core/prior.py:182-195                MaxMixturePrior     smplx lbs (joint branch) [smplx-from-memory]
+// and the same L-BFGS machine (lbfgs_core.cuh) through a lane-distributed vector policy (WarpOps).
+//
+// Ownership: element e of the parameter vector [go 3 | body 69 | transl 3 | shape NS] belongs to lane
+// e / 3, register e % 3 -- lane j < 24 owns the rotation of joint j, lane 24 the translation, lanes
+// 25.. the shape coefficients.
+//   kinematic tree   lane = joint; world transforms level by level (parent state fetched with
+//                    shuffles), subtree sums of the world-frame backward gathered child -> parent the
+//                    same way;
+//   GMM prior        y = P_m d with the symmetric precision P_m = L_m L_m^T in shared memory: 27 lanes
+//                    as 3 row groups x 9 column chunks of 8; q_m = d.y needs no cross-group exchange,
+//                    only the arg-min component's y is combined (its gradient is P d itself).
+// Host build (tests/host_emul/warp_emul.cu, a debugging harness): the lanes run as 32 coroutines and
+// the shuffle / sync hooks below switch between them.
+#pragma once
+
+#include "fit_core.cuh"
+#include "lbfgs_core.cuh"
+
+#if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
+int k2b_emul_lane();
+float k2b_emul_shfl(float v, int src);
+void k2b_emul_sync();
+#endif
+
+namespace k2b {
+namespace wc {
+
+constexpr int kPStride = 72;                       // row stride of a precision matrix (69 + 3 zero columns)
+constexpr int kPFloats = kBodyDim * kPStride;      // per component
+constexpr int kWarpVec = 96;                       // 32 lanes x 3 elements
+constexpr int kWarpMemFloats = 96 + 80 + 72 + 4 * kWarpVec;   // xs, dbuf, ybuf, 4 gradient slots
+
+K2B_HD int lane_id() {
+#if defined(__CUDA_ARCH__)
+  return threadIdx.x & 31;
+#elif defined(K2B_WARP_EMUL)
+  return k2b_emul_lane();
+#else
+  return 0;
+#endif
+}
+K2B_HD float shfl(float v, int src) {
+#if defined(__CUDA_ARCH__)
+  return __shfl_sync(0xffffffffu, v, src);
+#elif defined(K2B_WARP_EMUL)
+  return k2b_emul_shfl(v, src & 31);
+#else
+  return v;
+#endif
+}
+K2B_HD void wsync() {
+#if defined(__CUDA_ARCH__)
+  __syncwarp();
+#elif defined(K2B_WARP_EMUL)
+  k2b_emul_sync();
+#endif
+}
+K2B_HD float wsum(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += shfl(v, lane_id() ^ m);
+  return v;
+}
+K2B_HD float wmax(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, shfl(v, lane_id() ^ m));
+  return v;
+}
+
+// SMPL body tree (identical in SMPL / SMPL-H / SMPL-X for the first 22 joints; 22, 23 = SMPL hands)
+K2B_HD int tree_parent(int j) {
+  if (j <= 3) return 0;
+  if (j <= 12) return j - 3;
+  if (j <= 14) return 9;
+  if (j <= 17) return j - 3;
+  return j - 2;
+}
+K2B_HD int tree_depth(int j) {
+  // 0 | 1 1 1 | 2 2 2 | 3 3 3 | 4 4 4 4 4 | 5 5 5 | 6 6 | 7 7 | 8 8
+  const unsigned long long lo = 0x5444443332221110ull, hi = 0x88776655ull;
+  return (int)(((j < 16 ? lo >> (4 * j) : hi >> (4 * (j - 16)))) & 15ull);
+}
+template <int NJ>
+K2B_HD int tree_first_child(int j) {
+  int c = -1;
+  if (j == 0) c = 1;
+  else if (j <= 9) c = j + 3;
+  else if (j >= 12 && j <= 14) c = j + 3;
+  else if (j >= 16 && j <= 21) c = j + 2;
+  return c < NJ ? c : -1;
+}
+
+struct WarpTables {    // shared by every warp of a CTA (shared memory on the device)
+  const float* P;      // [8][69][kPStride] symmetric precisions
+  const float* mu;     // [8][kMuStride]
+  const float* nlw;    // [8]
+  const float4* rel;   // [24][1 + NS]
+};
+struct WarpMem {       // per-warp shared memory, kWarpMemFloats floats
+  float* xs;           // [96] evaluation point, readable by every lane
+  float* dbuf;         // [72 (+8)] x_body - mu_m
+  float* ybuf;         // [72] P d of the arg-min component
+  float* gs;           // [4][96] gradient slots (slot 0 only for Adam)
+};
+struct FrameObs {      // this lane's share of the frame's observations
+  float tx, ty, tz, w; // lane j < K: target and weight joint_w^2 conf_j^2 of joint j
+  float keep[3];       // preserve pose of the owned body-pose entries
+  float keep_w2;       // pose_preserve_weight^2 or 0
+};
+
+K2B_HD Acc shfl_acc(const Acc& a, int src) {
+  Acc r;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.S.m[i] = shfl(a.S.m[i], src);
+  r.s = v3(shfl(a.s.x, src), shfl(a.s.y, src), shfl(a.s.z, src));
+  return r;
+}
+
+// One function evaluation of one frame by the whole warp.  xr: owned elements of the evaluation point
+// (zero where 3*lane + c >= 75 + NS).  Returns the total loss in every lane; with_grad fills gr with the
+// gradient of the owned elements (zero for unowned ones).  joints_out: global [K][3] or null.
+template <int NS, int K>
+K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& ob, const float (&xr)[3],
+                       bool with_grad, bool with_priors, float (&gr)[3], float* joints_out, int* gmm_component) {
+  constexpr int NJ = (K == 24) ? 24 : 22;
+  constexpr int MAXD = (K == 24) ? 8 : 7;
+  const int lane = lane_id();
+#pragma unroll
+  for (int c = 0; c < 3; ++c) wm.xs[3 * lane + c] = xr[c];
+  if (lane == 0) { wm.dbuf[69] = 0.f; wm.dbuf[70] = 0.f; wm.dbuf[71] = 0.f; }
+  wsync();
+  float shape[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) shape[s] = wm.xs[kShapeOff + s];
+  const V3 transl = v3(wm.xs[kTranslOff], wm.xs[kTranslOff + 1], wm.xs[kTranslOff + 2]);
+  float lsum = 0.f;    // this lane's share of the loss
+  float uni = 0.f;     // terms every lane computes identically
+  if (with_priors) {   // shape prior on betas only (losses.py:56)
+    float acc = 0.f;
+#pragma unroll
+    for (int s = 0; s < 10; ++s) acc = fmaf(shape[s], shape[s], acc);
+    uni = kShapePriorW2 * acc;
+  }
+
+  // ---- kinematic tree, lane = joint ------------------------------------------------------------
+  const bool isj = lane < NJ;
+  const int j = isj ? lane : 0;
+  const int par = tree_parent(j);
+  const int dep = isj ? tree_depth(j) : 99;
+  const int c0 = isj ? tree_first_child<NJ>(j) : -1;
+  const int c1 = (lane == 0) ? 2 : (lane == 9 ? 13 : -1);
+  const int c2 = (lane == 0) ? 3 : (lane == 9 ? 14 : -1);
+  V3 rel;
+  {
+    const float4* e = tb.rel + j * (1 + NS);
+    const float4 r0 = e[0];
+    float x = r0.x, y = r0.y, z = r0.z;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float4 d = e[1 + s];
+      x = fmaf(d.x, shape[s], x);
+      y = fmaf(d.y, shape[s], y);
+      z = fmaf(d.z, shape[s], z);
+    }
+    rel = v3(x, y, z);
+  }
+  Rod o;
+  const V3 r = v3(xr[0], xr[1], xr[2]);
+  const M3 R = rodrigues(r, o);
+  M3 Rw = R, Rp = eye3();
+  V3 t = rel;
+#pragma unroll 1
+  for (int lev = 1; lev <= MAXD; ++lev) {
+    M3 Rq;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rq.m[i] = shfl(Rw.m[i], par);
+    const V3 tq = v3(shfl(t.x, par), shfl(t.y, par), shfl(t.z, par));
+    if (dep == lev) {
+      Rp = Rq;
+      t = matvec(Rq, rel) + tq;
+      Rw = matmul(Rq, R);
+    }
+  }
+
+  // ---- residuals (gmof, losses.py:6-10) ----------------------------------------------------------
+  V3 g = v3(0.f, 0.f, 0.f);
+  if (lane < K) {
+    const V3 p = t + transl;
+    if (joints_out) {
+      joints_out[3 * lane + 0] = p.x;
+      joints_out[3 * lane + 1] = p.y;
+      joints_out[3 * lane + 2] = p.z;
+    }
+    const float ex = p.x - ob.tx, ey = p.y - ob.ty, ez = p.z - ob.tz;
+    const float ix = fdiv(1.f, kSigma2 + ex * ex), iy = fdiv(1.f, kSigma2 + ey * ey), iz = fdiv(1.f, kSigma2 + ez * ez);
+    const float gx = kSigma2 * ex * ex * ix, gy = kSigma2 * ey * ey * iy, gz = kSigma2 * ez * ez * iz;
+    lsum = ob.w * ((gx + gy) + gz);
+    const float c2w = 2.f * kSigma2 * kSigma2 * ob.w;
+    g = v3(c2w * ex * ix * ix, c2w * ey * iy * iy, c2w * ez * iz * iz);
+  }
+  gr[0] = gr[1] = gr[2] = 0.f;
+
+  // ---- world-frame backward: subtree sums child -> parent, then per-joint gradients ---------------
+  if (with_grad) {
+    Acc a{zero3(), v3(0.f, 0.f, 0.f)};
+    if (lane < K) acc_point(a, g, t);
+#pragma unroll 1
+    for (int lev = MAXD; lev >= 1; --lev) {
+      const bool mine = dep == lev - 1;
+      Acc v = shfl_acc(a, c0 >= 0 ? c0 : lane);
+      if (mine && c0 >= 0) acc_add(a, v);
+      if (lev == 1 || lev == 4) {       // joints 0 and 9 have three children
+        v = shfl_acc(a, c1 >= 0 ? c1 : lane);
+        if (mine && c1 >= 0) acc_add(a, v);
+        v = shfl_acc(a, c2 >= 0 ? c2 : lane);
+        if (mine && c2 >= 0) acc_add(a, v);
+      }
+    }
+    V3 rb = v3(0.f, 0.f, 0.f);           // a leaf's own rotation moves nothing observed
+    V3 drel = v3(0.f, 0.f, 0.f);
+    if (isj) {
+      if (c0 >= 0) rb = rodrigues_bwd(rot_grad(a, Rp, Rw, t), r, o);
+      drel = matvec_t(Rp, a.s);         // d loss / d rel_j
+    }
+    float shape_bar[NS];
+    {
+      const float4* e = tb.rel + j * (1 + NS);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float4 d = e[1 + s];
+        shape_bar[s] = wsum(fmaf(d.x, drel.x, fmaf(d.y, drel.y, d.z * drel.z)));
+      }
+    }
+    const V3 s0 = v3(shfl(a.s.x, 0), shfl(a.s.y, 0), shfl(a.s.z, 0));
+    if (lane < 24) {
+      gr[0] = rb.x; gr[1] = rb.y; gr[2] = rb.z;
+    } else if (lane == 24) {
+      gr[0] = s0.x; gr[1] = s0.y; gr[2] = s0.z;
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float v = (with_priors && s < 10) ? fmaf(2.f * kShapePriorW2, shape[s], shape_bar[s]) : shape_bar[s];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (3 * lane + c == kShapeOff + s) gr[c] = v;
+      }
+    }
+  }
+
+  // ---- priors on the body pose -----------------------------------------------------------------
+  if (with_priors) {
+    const bool body_owner = lane >= 1 && lane < 24;     // elements 3 .. 71
+    const int i0 = body_owner ? 3 * lane - 3 : 0;       // body-pose index of xr[0]
+    const int rg = lane / 9, cc = lane - 9 * rg;
+    const bool act = lane < 27;
+    float best = INFINITY;
+    int bm = 0;
+    float2 yb[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll 1
+    for (int m = 0; m < kGmmM; ++m) {
+      if (body_owner) {
+        const float* mum = tb.mu + m * kMuStride + i0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) wm.dbuf[i0 + c] = xr[c] - mum[c];
+      }
+      wsync();
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      float part = 0.f;
+      if (act) {
+        const float* row = tb.P + (size_t)m * kPFloats + rg * kPStride + 8 * cc;
+        const float* dj = wm.dbuf + rg;
+#pragma unroll 23
+        for (int it = 0; it < 23; ++it, row += 3 * kPStride, dj += 3) {
+          const float d1 = *dj;
+          const float2 d2 = make_float2(d1, d1);
+          const float4 l0 = reinterpret_cast<const float4*>(row)[0];
+          const float4 l1 = reinterpret_cast<const float4*>(row)[1];
+          acc[0] = fma2(make_float2(l0.x, l0.y), d2, acc[0]);
+          acc[1] = fma2(make_float2(l0.z, l0.w), d2, acc[1]);
+          acc[2] = fma2(make_float2(l1.x, l1.y), d2, acc[2]);
+          acc[3] = fma2(make_float2(l1.z, l1.w), d2, acc[3]);
+        }
+        const float4 e0 = reinterpret_cast<const float4*>(wm.dbuf + 8 * cc)[0];
+        const float4 e1 = reinterpret_cast<const float4*>(wm.dbuf + 8 * cc)[1];
+        part = fmaf(acc[0].x, e0.x, fmaf(acc[0].y, e0.y, fmaf(acc[1].x, e0.z, acc[1].y * e0.w))) +
+               fmaf(acc[2].x, e1.x, fmaf(acc[2].y, e1.y, fmaf(acc[3].x, e1.z, acc[3].y * e1.w)));
+      }
+      const float q = wsum(part);
+      const float ll = fmaf(0.5f, q, tb.nlw[m]);
+      if (ll < best) {   // strict: first minimum wins, like torch.min
+        best = ll;
+        bm = m;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) yb[k] = acc[k];
+      }
+      wsync();           // dbuf is rewritten for the next component
+    }
+    if (gmm_component) *gmm_component = bm;
+    uni = fmaf(kPosePriorW2, best, uni);
+    if (with_grad) {
+      // y = sum over the three row groups; lanes 0..8 then hold columns 8 lane .. 8 lane + 7
+      float y[8] = {yb[0].x, yb[0].y, yb[1].x, yb[1].y, yb[2].x, yb[2].y, yb[3].x, yb[3].y};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] = (y[k] + shfl(y[k], lane + 9)) + shfl(y[k], lane + 18);
+      if (lane < 9) {
+        reinterpret_cast<float4*>(wm.ybuf + 8 * lane)[0] = make_float4(y[0], y[1], y[2], y[3]);
+        reinterpret_cast<float4*>(wm.ybuf + 8 * lane)[1] = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      wsync();
+    }
+    if (body_owner) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int i = i0 + c;
+        const float xi = xr[c];
+        float gi = gr[c];
+        if (with_grad) gi = fmaf(kPosePriorW2, wm.ybuf[i], gi);
+        if (ob.keep_w2 != 0.f) {      // temporal pose-preserve term (losses.py:57-59)
+          const float d = xi - ob.keep[c];
+          lsum = fmaf(ob.keep_w2 * d, d, lsum);
+          gi = fmaf(2.f * ob.keep_w2, d, gi);
+        }
+        if (i == 9 || i == 12 || i == 52 || i == 55) {   // angle prior (losses.py:13-21)
+          const float sgn = i == 52 ? 1.f : -1.f;
+          const float e = expf(xi * sgn);
+          lsum = fmaf(kAnglePriorW2, e * e, lsum);
+          gi = fmaf(2.f * kAnglePriorW2 * sgn, e * e, gi);
+        }
+        gr[c] = gi;
+      }
+    }
+  }
+  return wsum(lsum) + uni;
+}
+
+// ---------------------------------------------------------------------------------------------
+// L-BFGS over lane-distributed vectors.  Every lane carries the same scalar state (all reductions
+// are butterfly all-reduces, so the lanes agree bit for bit) and runs the same control flow.
+// ---------------------------------------------------------------------------------------------
+struct WVec {
+  mutable float x[3];    // trial point; the two-loop's running vector between evaluations
+  mutable float xk[3];   // iterate
+  mutable float d[3];    // search direction
+  float* gs;             // [4][96] gradient slots (shared memory)
+  float* hist;           // this warp's (y, s) history in global memory: vector v of pair h at
+                         // hist[((2 h + v) * 3 + c) * 32 + lane]
+  float* ro;             // [hmax] (shared memory)
+  float* al;             // [hmax]
+  int hmax;
+  K2B_HD float& G(int slot, int c) const { return gs[slot * kWarpVec + 3 * lane_id() + c]; }
+  K2B_HD float& H(int h, int v, int c) const { return hist[((2 * h + v) * 3 + c) * 32 + lane_id()]; }
+};
+
+struct WarpOps {
+  typedef WVec C;
+  typedef WVec V;
+  static K2B_HD float dot3(const float (&a)[3], const float (&b)[3]) {
+    return wsum(fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])));
+  }
+  static K2B_HD float dot_cur_d(const V& v, int cur) {
+    const float g[3] = {v.G(cur, 0), v.G(cur, 1), v.G(cur, 2)};
+    return dot3(g, v.d);
+  }
+  static K2B_HD void set_trial(const C&, const V& v, float tf) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.x[c] = fmaf(tf, v.d[c], v.xk[c]);
+  }
+  static K2B_HD float begin_copy(const C&, const V& v) {
+    float gm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v.xk[c] = v.x[c];
+      gm = fmaxf(gm, fabsf(v.G(0, c)));
+    }
+    return wmax(gm);
+  }
+  static K2B_HD void neg_grad(const C&, const V& v, int g0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.x[c] = -v.G(g0, c);
+  }
+  static K2B_HD void update_direction(const C&, const V& v, int g0, int slot_prev_grad, float tf, int& num_old,
+                                      int& head, float& H_diag) {
+    int h = (head + num_old) % v.hmax;
+    if (num_old == v.hmax) h = head;
+    float y[3], s[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float gi = v.G(g0, c);
+      y[c] = gi - v.G(slot_prev_grad, c);
+      s[c] = v.d[c] * tf;
+      v.x[c] = -gi;
+      v.H(h, 0, c) = y[c];
+      v.H(h, 1, c) = s[c];
+    }
+    const float ys = dot3(y, s), yy = dot3(y, y);
+    if (ys > 1e-10f) {
+      if (num_old == v.hmax) head = (head + 1) % v.hmax;
+      else ++num_old;
+      v.ro[h] = 1.f / ys;           // every lane stores the same value
+      H_diag = ys / yy;
+    }
+    wsync();
+    // two-loop recursion (lbfgs.py:430-442); the next pair is requested before this one is used
+    float yn[3], sn[3];
+    if (num_old > 0) {
+      const int hk = (head + num_old - 1) % v.hmax;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { yn[c] = v.H(hk, 0, c); sn[c] = v.H(hk, 1, c); }
+    }
+#pragma unroll 1
+    for (int k = num_old - 1; k >= 0; --k) {
+      const int hk = (head + k) % v.hmax;
+      float yk[3], sk[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { yk[c] = yn[c]; sk[c] = sn[c]; }
+      if (k > 0) {
+        const int hn = (head + k - 1) % v.hmax;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { yn[c] = v.H(hn, 0, c); sn[c] = v.H(hn, 1, c); }
+      }
+      const float a = dot3(sk, v.x) * v.ro[hk];
+      v.al[hk] = a;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v.x[c] = fmaf(-a, yk[c], v.x[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.x[c] *= H_diag;
+    wsync();
+    if (num_old > 0) {
+      const int hk = head % v.hmax;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { yn[c] = v.H(hk, 0, c); sn[c] = v.H(hk, 1, c); }
+    }
+#pragma unroll 1
+    for (int k = 0; k < num_old; ++k) {
+      const int hk = (head + k) % v.hmax;
+      float yk[3], sk[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { yk[c] = yn[c]; sk[c] = sn[c]; }
+      if (k + 1 < num_old) {
+        const int hn = (head + k + 1) % v.hmax;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { yn[c] = v.H(hn, 0, c); sn[c] = v.H(hn, 1, c); }
+      }
+      const float coef = v.al[hk] - dot3(yk, v.x) * v.ro[hk];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v.x[c] = fmaf(coef, sk[c], v.x[c]);
+    }
+  }
+  static K2B_HD void commit_direction(const C&, const V& v, int g0, float& gsum, float& gtd, float& dmax) {
+    float g[3], ga = 0.f, dm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      g[c] = v.G(g0, c);
+      v.d[c] = v.x[c];
+      ga += fabsf(g[c]);
+      dm = fmaxf(dm, fabsf(v.d[c]));
+    }
+    gsum = wsum(ga);
+    gtd = dot3(g, v.d);
+    dmax = wmax(dm);
+  }
+  static K2B_HD void first_trial(const C&, const V& v, float tf) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.x[c] = fmaf(tf, v.x[c], v.xk[c]);
+  }
+  static K2B_HD float move_iterate(const C&, const V& v, float tf) {
+    float dm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v.xk[c] = fmaf(tf, v.d[c], v.xk[c]);
+      dm = fmaxf(dm, fabsf(v.d[c] * tf));
+    }
+    return wmax(dm);
+  }
+  static K2B_HD float grad_max(const V& v, int slot) {
+    float gm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gm = fmaxf(gm, fabsf(v.G(slot, c)));
+    return wmax(gm);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// One WorldSpaceFitter.fit_frame (world_space.py:93-257) by the warp.  xr: in = initial parameters,
+// out = fitted parameters (owned elements).  Returns the reported loss; *evals = closure evaluations
+// that count (Adam: iterations; L-BFGS: func_evals).
+// ---------------------------------------------------------------------------------------------
+struct FitOpts {
+  int iters;
+  bool lbfgs;
+  bool freeze_betas;
+  float lr;
+  const float* adam_step;   // [kAdamTableW] lr / (1 - 0.9^k)
+  const float* adam_bc2;    // sqrt(1 - 0.999^k)
+  int adam_table;
+};
+
+template <int NS, int K>
+K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& ob, float (&xr)[3], const FitOpts& fo,
+                      float* hist, float* ro, float* al, int hmax, float* joints_out, int* evals_out) {
+  const int lane = lane_id();
+  bool frozen[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int e = 3 * lane + c;
+    frozen[c] = e >= 75 + NS || (fo.freeze_betas && e >= kShapeOff && e < kShapeOff + 10);
+  }
+  float gr[3];
+  float out_loss = 0.f;
+  int evals = 0;
+  if (!fo.lbfgs) {
+    float m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int k = 1; k <= fo.iters; ++k) {
+      float step_k, bc2_k;
+      if (k <= fo.adam_table) {
+        step_k = fo.adam_step[k - 1];
+        bc2_k = fo.adam_bc2[k - 1];
+      } else {
+        step_k = (float)((double)fo.lr / (1.0 - pow(0.9, (double)k)));
+        bc2_k = (float)sqrt(1.0 - pow(0.999, (double)k));
+      }
+      out_loss = eval_warp<NS, K>(tb, wm, ob, xr, true, true, gr, nullptr, nullptr);   // loss before the step
+      ++evals;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (!frozen[c]) adam_update(xr[c], m1[c], m2[c], gr[c], step_k, bc2_k);
+    }
+    // joints at the final parameters (world_space.py:258-278)
+    if (joints_out) eval_warp<NS, K>(tb, wm, ob, xr, false, false, gr, joints_out, nullptr);
+  } else {
+    WVec v;
+    v.gs = wm.gs;
+    v.hist = hist;
+    v.ro = ro;
+    v.al = al;
+    v.hmax = hmax;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { v.x[c] = xr[c]; v.xk[c] = xr[c]; v.d[c] = 0.f; }
+    Lbfgs<75 + NS, WarpOps> st;
+    st.init();
+    bool first = true;
+#pragma unroll 1
+    while (true) {
+      const float loss = eval_warp<NS, K>(tb, wm, ob, v.x, true, true, gr, nullptr, nullptr);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
+      wsync();
+      st.advance_now(v, v, loss, first, fo.iters, fo.lr);
+      first = false;
+      if (st.done) break;
+    }
+    evals = st.evals;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xr[c] = v.xk[c];
+    // loss (and joints) re-evaluated at the returned parameters (world_space.py:246-247)
+    out_loss = eval_warp<NS, K>(tb, wm, ob, xr, false, true, gr, joints_out, nullptr);
+  }
+  if (evals_out) *evals_out = evals;
+  return out_loss;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A whole sequence by one warp: the reference's frame loop (api/sequence.py:214-281).
+// ---------------------------------------------------------------------------------------------
+constexpr int kAdamTableW = 64;
+
+struct ChainParams {
+  long num_seq;            // S sequences, one warp each
+  int frames;              // T frames per sequence, walked serially
+  long first_seq_ind;      // seq_ind of frame 0 (0: first-frame budget, no temporal term; world_space.py:211,214)
+  int chain;               // 1: frame t starts from frame t-1's result (use_previous_frame_init); 0: from the init
+  int iters_first, iters_follow;
+  int lbfgs, freeze_betas;
+  int conf_mode;           // 0 none, 1 shared [K], 2 per frame [S][T][K]
+  float lr, joint_w2, keep_w2;
+  const float* targets;    // [S][T][K][3]
+  const float* conf;
+  const float* init_pose;  // [S][72]
+  const float* init_betas; // [S][10]
+  const float* init_transl;// [S][3]
+  const float* init_expr;  // [S][10] (NS == 20)
+  const float* preserve_pose;   // [S][T][69] or null = the frame's initial body pose (world_space.py:159)
+  float* out_pose; float* out_betas; float* out_transl; float* out_expr;   // [S][T][..]
+  float* out_loss; float* out_joints; int* out_evals;
+  float* hist;             // L-BFGS (y, s) history, hist_floats(hmax) per resident warp
+  int hmax;
+  float adam_step[kAdamTableW], adam_bc2[kAdamTableW];
+};
+K2B_HD constexpr long hist_floats(int hmax) { return (long)hmax * 2 * kWarpVec; }
+K2B_HD constexpr int warp_mem_floats(int hmax) { return kWarpMemFloats + ((2 * hmax + 3) & ~3); }
+
+template <int NS>
+K2B_HD float load_elem(const ChainParams& p, long s, int e) {
+  if (e < kPoseDim) return p.init_pose[s * kPoseDim + e];
+  if (e < kShapeOff) return p.init_transl[s * 3 + (e - kTranslOff)];
+  if (e < kShapeOff + 10) return p.init_betas[s * 10 + (e - kShapeOff)];
+  if (NS == 20 && e < kShapeOff + 20) return p.init_expr[s * 10 + (e - kShapeOff - 10)];
+  return 0.f;
+}
+template <int NS>
+K2B_HD void store_elem(const ChainParams& p, long f, int e, float v) {
+  if (e < kPoseDim) p.out_pose[f * kPoseDim + e] = v;
+  else if (e < kShapeOff) p.out_transl[f * 3 + (e - kTranslOff)] = v;
+  else if (e < kShapeOff + 10) p.out_betas[f * 10 + (e - kShapeOff)] = v;
+  else if (NS == 20 && e < kShapeOff + 20 && p.out_expr) p.out_expr[f * 10 + (e - kShapeOff - 10)] = v;
+}
+
+template <int NS, int K>
+K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb, const WarpMem& wm, float* hist,
+                           float* ro, float* al) {
+  const int lane = lane_id();
+  float x0[3], xr[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    x0[c] = load_elem<NS>(p, seq, 3 * lane + c);
+    xr[c] = x0[c];
+  }
+  FitOpts fo;
+  fo.lbfgs = p.lbfgs != 0;
+  fo.freeze_betas = p.freeze_betas != 0;
+  fo.lr = p.lr;
+  fo.adam_step = p.adam_step;
+  fo.adam_bc2 = p.adam_bc2;
+  fo.adam_table = kAdamTableW;
+  const bool body_owner = lane >= 1 && lane < 24;
+#pragma unroll 1
+  for (int t = 0; t < p.frames; ++t) {
+    const long f = seq * p.frames + t;
+    if (!p.chain) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) xr[c] = x0[c];
+    }
+    FrameObs ob;
+    ob.tx = ob.ty = ob.tz = ob.w = 0.f;
+    if (lane < K) {
+      const float* tg = p.targets + (f * K + lane) * 3;
+      ob.tx = tg[0]; ob.ty = tg[1]; ob.tz = tg[2];
+      const float cf = p.conf_mode == 0 ? 1.f : (p.conf_mode == 1 ? p.conf[lane] : p.conf[f * K + lane]);
+      ob.w = p.joint_w2 * cf * cf;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[f * kBodyDim + 3 * lane - 3 + c] : xr[c];
+    const bool first = p.first_seq_ind + t == 0;
+    ob.keep_w2 = first ? 0.f : p.keep_w2;
+    fo.iters = first ? p.iters_first : p.iters_follow;
+    int evals = 0;
+    const float loss = fit_warp<NS, K>(tb, wm, ob, xr, fo, hist, ro, al, p.hmax,
+                                       p.out_joints ? p.out_joints + f * K * 3 : nullptr, &evals);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) store_elem<NS>(p, f, 3 * lane + c, xr[c]);
+    if (lane == 0) {
+      p.out_loss[f] = loss;
+      if (p.out_evals) p.out_evals[f] = evals;
+    }
+  }
+}
+
+}  // namespace wc
+}  // namespace k2b

@@ -86,8 +86,153 @@ K2B_HD double cubic_interpolate(double x1, double f1, float g1, double x2, doubl
 // slot `cur` (the caller points Cols::g at it), so keeping a gradient -- as flat_grad, g_prev or a
 // bracket end -- is a matter of remembering the slot index, never a copy.  After each evaluation
 // `cur` moves to a slot that holds nothing still needed (g0 + at most two others are ever kept).
+
+// Vector passes of the machine, one thread per frame: vectors in per-frame scratch columns (Vecs), the
+// trial point in the x column (Cols).  The warp-cooperative kernel (chain_core.cuh) supplies its own
+// policy with the same entry points over lane-distributed vectors; the scalar logic below is shared.
 template <int N>
+struct ThreadOps {
+  typedef Cols C;
+  typedef Vecs V;
+  static K2B_HD float dot_cur_d(const V& v, int cur) {
+    const int og = v.gslot(cur), od = v.d();
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) {
+      if (i & 1) a1 = fmaf(v.at(og + i), v.at(od + i), a1);
+      else a0 = fmaf(v.at(og + i), v.at(od + i), a0);
+    }
+    return a0 + a1;
+  }
+  static K2B_HD void set_trial(const C& c, const V& v, float tf) {
+    const int od = v.d();
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, v.at(od + i), v.at(i));
+  }
+  // xk = x; returns max |flat_grad| (slot 0)
+  static K2B_HD float begin_copy(const C& c, const V& v) {
+    float gmax = 0.f;
+    const int og = v.gslot(0);
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) {
+      v.at(i) = c.X(i);
+      gmax = fmaxf(gmax, fabsf(v.at(og + i)));
+    }
+    return gmax;
+  }
+  // first outer iteration: q = -flat_grad (q lives in the x column)
+  static K2B_HD void neg_grad(const C& c, const V& v, int g0) {
+    const int og = v.gslot(g0);
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) c.X(i) = -v.at(og + i);
+  }
+  // later outer iterations: history update + two-loop recursion (lbfgs.py:399-442); leaves q in the x column
+  static K2B_HD void update_direction(const C& c, const V& v, int g0, int slot_prev_grad, float tf, int& num_old,
+                                      int& head, float& H_diag) {
+    const int od = v.d(), og = v.gslot(g0);
+    // y = flat_grad - prev_flat_grad (slot slot_prev_grad), s = d * t
+    const int op = v.gslot(slot_prev_grad);
+    int h = (head + num_old) % v.hmax;          // where the pair goes if it is accepted
+    if (num_old == v.hmax) h = head;
+    const int oy = v.y(h), os = v.s(h);
+    float ys0 = 0.f, ys1 = 0.f, yy0 = 0.f, yy1 = 0.f;
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) {
+      const float gi = v.at(og + i);
+      const float yi = gi - v.at(op + i);
+      const float si = v.at(od + i) * tf;
+      c.X(i) = -gi;
+      v.at(oy + i) = yi;                        // written speculatively; committed by num_old / head
+      v.at(os + i) = si;
+      if (i & 1) { ys1 = fmaf(yi, si, ys1); yy1 = fmaf(yi, yi, yy1); }
+      else       { ys0 = fmaf(yi, si, ys0); yy0 = fmaf(yi, yi, yy0); }
+    }
+    const float ys = ys0 + ys1, yy = yy0 + yy1;
+    if (ys > 1e-10f) {
+      if (num_old == v.hmax) head = (head + 1) % v.hmax;   // drop the oldest pair (ring buffer)
+      else ++num_old;
+      v.at(v.ro(h)) = 1.f / ys;
+      H_diag = ys / yy;
+    }
+    // two-loop recursion (lbfgs.py:430-442)
+#pragma unroll 1
+    for (int k = num_old - 1; k >= 0; --k) {
+      const int hk = (head + k) % v.hmax;
+      const int oyk = v.y(hk), osk = v.s(hk);
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 17
+      for (int i = 0; i < N; ++i) {
+        if (i & 1) a1 = fmaf(v.at(osk + i), c.X(i), a1);
+        else a0 = fmaf(v.at(osk + i), c.X(i), a0);
+      }
+      const float a = (a0 + a1) * v.at(v.ro(hk));
+      v.at(v.al(hk)) = a;
+#pragma unroll 17
+      for (int i = 0; i < N; ++i) c.X(i) = fmaf(-a, v.at(oyk + i), c.X(i));
+    }
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) c.X(i) *= H_diag;
+#pragma unroll 1
+    for (int k = 0; k < num_old; ++k) {
+      const int hk = (head + k) % v.hmax;
+      const int oyk = v.y(hk), osk = v.s(hk);
+      float b0 = 0.f, b1 = 0.f;
+#pragma unroll 17
+      for (int i = 0; i < N; ++i) {
+        if (i & 1) b1 = fmaf(v.at(oyk + i), c.X(i), b1);
+        else b0 = fmaf(v.at(oyk + i), c.X(i), b0);
+      }
+      const float coef = v.at(v.al(hk)) - (b0 + b1) * v.at(v.ro(hk));
+#pragma unroll 17
+      for (int i = 0; i < N; ++i) c.X(i) = fmaf(coef, v.at(osk + i), c.X(i));
+    }
+  }
+  // d = q; sum |g|, g.d, max |d|
+  static K2B_HD void commit_direction(const C& c, const V& v, int g0, float& gsum, float& gtd, float& dmax) {
+    const int od = v.d(), og = v.gslot(g0);
+    float gtd0a = 0.f, gtd1a = 0.f;
+    gsum = 0.f;
+    dmax = 0.f;
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) {
+      const float gi = v.at(og + i), di = c.X(i);
+      v.at(od + i) = di;
+      gsum += fabsf(gi);
+      if (i & 1) gtd1a = fmaf(gi, di, gtd1a); else gtd0a = fmaf(gi, di, gtd0a);
+      dmax = fmaxf(dmax, fabsf(di));
+    }
+    gtd = gtd0a + gtd1a;
+  }
+  // first trial point: x = xk + t d with d still in the x column
+  static K2B_HD void first_trial(const C& c, const V& v, float tf) {
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, c.X(i), v.at(i));
+  }
+  // xk += t d (_add_grad); returns max |t d|
+  static K2B_HD float move_iterate(const C& c, const V& v, float tf) {
+    const int od = v.d();
+    float dtmax = 0.f;
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) {
+      const float di = v.at(od + i);
+      v.at(i) = fmaf(tf, di, v.at(i));
+      dtmax = fmaxf(dtmax, fabsf(di * tf));
+    }
+    return dtmax;
+  }
+  static K2B_HD float grad_max(const V& v, int slot) {
+    float gmax = 0.f;
+    const int og = v.gslot(slot);
+#pragma unroll 17
+    for (int i = 0; i < N; ++i) gmax = fmaxf(gmax, fabsf(v.at(og + i)));
+    return gmax;
+  }
+};
+
+template <int N, class Ops = ThreadOps<N>>
 struct Lbfgs {
+  typedef typename Ops::C C;
+  typedef typename Ops::V V;
   // configuration
   int max_iter, max_eval;
   float lr;
@@ -133,34 +278,20 @@ struct Lbfgs {
     }
   }
 
-  K2B_HD float dot_cur_d(const Vecs& v) const {
-    const int og = v.gslot(cur), od = v.d();
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll 17
-    for (int i = 0; i < N; ++i) {
-      if (i & 1) a1 = fmaf(v.at(og + i), v.at(od + i), a1);
-      else a0 = fmaf(v.at(og + i), v.at(od + i), a0);
-    }
-    return a0 + a1;
-  }
-  K2B_HD void set_trial(const Cols& c, const Vecs& v) const {
-    const float tf = (float)t;
-    const int od = v.d();
-#pragma unroll 17
-    for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, v.at(od + i), v.at(i));
-  }
+  K2B_HD float dot_cur_d(const V& v) const { return Ops::dot_cur_d(v, cur); }
+  K2B_HD void set_trial(const C& c, const V& v) const { Ops::set_trial(c, v, (float)t); }
 
   // Drive one round after an evaluation: `first` selects begin() vs after_eval(); the outer-iteration
   // set-up (two-loop recursion etc.) is inlined at exactly one site.
   // The caller runs start_outer() when `need_outer` is set (the kernel defers it until the whole warp
   // is at the boundary; the serial harnesses run it at once via advance_now()).
-  K2B_HD void advance(const Cols& c, const Vecs& v, float loss_f, bool first, int max_iter_, float lr_) {
+  K2B_HD void advance(const C& c, const V& v, float loss_f, bool first, int max_iter_, float lr_) {
     need_outer = false;
     if (first) begin(c, v, loss_f, max_iter_, lr_);
     else after_eval(c, v, loss_f);
     if (need_outer) park_cur();
   }
-  K2B_HD void advance_now(const Cols& c, const Vecs& v, float loss_f, bool first, int max_iter_, float lr_) {
+  K2B_HD void advance_now(const C& c, const V& v, float loss_f, bool first, int max_iter_, float lr_) {
     advance(c, v, loss_f, first, max_iter_, lr_);
     if (need_outer && !done) start_outer(c, v);
   }
@@ -190,7 +321,7 @@ struct Lbfgs {
   }
 
   // Called once after the first evaluation at the initial parameters (loss; gradient in slot 0).
-  K2B_HD void begin(const Cols& c, const Vecs& v, float loss0, int max_iter_, float lr_) {
+  K2B_HD void begin(const C& c, const V& v, float loss0, int max_iter_, float lr_) {
     max_iter = max_iter_;
     max_eval = max_iter_ * 5 / 4;
     lr = lr_;
@@ -205,13 +336,7 @@ struct Lbfgs {
     H_diag = 1.f;
     g0 = 0;
     slot_prev_grad = 0;
-    float gmax = 0.f;
-    const int og = v.gslot(0);
-#pragma unroll 17
-    for (int i = 0; i < N; ++i) {
-      v.at(i) = c.X(i);
-      gmax = fmaxf(gmax, fabsf(v.at(og + i)));
-    }
+    const float gmax = Ops::begin_copy(c, v);
     if (max_iter_ <= 0 || (double)gmax <= kTolGrad) {
       done = true;
       return;
@@ -221,88 +346,22 @@ struct Lbfgs {
 
   // lbfgs.py:388-476: direction update, initial step, line-search setup, first trial point.
   // The two-loop's running vector q lives in the (idle between evaluations) x column.
-  K2B_HD void start_outer(const Cols& c, const Vecs& v) {
-    const int od = v.d(), og = v.gslot(g0);
+  K2B_HD void start_outer(const C& c, const V& v) {
     need_outer = false;
     ++n_iter;
     if (n_iter == 1) {
-#pragma unroll 17
-      for (int i = 0; i < N; ++i) c.X(i) = -v.at(og + i);
+      Ops::neg_grad(c, v, g0);
       H_diag = 1.f;
       num_old = 0;
       head = 0;
     } else {
-      // y = flat_grad - prev_flat_grad (slot slot_prev_grad), s = d * t
-      const int op = v.gslot(slot_prev_grad);
-      const float tf = (float)t;
-      int h = (head + num_old) % v.hmax;          // where the pair goes if it is accepted
-      if (num_old == v.hmax) h = head;
-      const int oy = v.y(h), os = v.s(h);
-      float ys0 = 0.f, ys1 = 0.f, yy0 = 0.f, yy1 = 0.f;
-#pragma unroll 17
-      for (int i = 0; i < N; ++i) {
-        const float gi = v.at(og + i);
-        const float yi = gi - v.at(op + i);
-        const float si = v.at(od + i) * tf;
-        c.X(i) = -gi;
-        v.at(oy + i) = yi;                        // written speculatively; committed by num_old / head
-        v.at(os + i) = si;
-        if (i & 1) { ys1 = fmaf(yi, si, ys1); yy1 = fmaf(yi, yi, yy1); }
-        else       { ys0 = fmaf(yi, si, ys0); yy0 = fmaf(yi, yi, yy0); }
-      }
-      const float ys = ys0 + ys1, yy = yy0 + yy1;
-      if (ys > 1e-10f) {
-        if (num_old == v.hmax) head = (head + 1) % v.hmax;   // drop the oldest pair (ring buffer)
-        else ++num_old;
-        v.at(v.ro(h)) = 1.f / ys;
-        H_diag = ys / yy;
-      }
-      // two-loop recursion (lbfgs.py:430-442)
-#pragma unroll 1
-      for (int k = num_old - 1; k >= 0; --k) {
-        const int hk = (head + k) % v.hmax;
-        const int oyk = v.y(hk), osk = v.s(hk);
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 17
-        for (int i = 0; i < N; ++i) {
-          if (i & 1) a1 = fmaf(v.at(osk + i), c.X(i), a1);
-          else a0 = fmaf(v.at(osk + i), c.X(i), a0);
-        }
-        const float a = (a0 + a1) * v.at(v.ro(hk));
-        v.at(v.al(hk)) = a;
-#pragma unroll 17
-        for (int i = 0; i < N; ++i) c.X(i) = fmaf(-a, v.at(oyk + i), c.X(i));
-      }
-#pragma unroll 17
-      for (int i = 0; i < N; ++i) c.X(i) *= H_diag;
-#pragma unroll 1
-      for (int k = 0; k < num_old; ++k) {
-        const int hk = (head + k) % v.hmax;
-        const int oyk = v.y(hk), osk = v.s(hk);
-        float b0 = 0.f, b1 = 0.f;
-#pragma unroll 17
-        for (int i = 0; i < N; ++i) {
-          if (i & 1) b1 = fmaf(v.at(oyk + i), c.X(i), b1);
-          else b0 = fmaf(v.at(oyk + i), c.X(i), b0);
-        }
-        const float coef = v.at(v.al(hk)) - (b0 + b1) * v.at(v.ro(hk));
-#pragma unroll 17
-        for (int i = 0; i < N; ++i) c.X(i) = fmaf(coef, v.at(osk + i), c.X(i));
-      }
+      Ops::update_direction(c, v, g0, slot_prev_grad, (float)t, num_old, head, H_diag);
     }
     slot_prev_grad = g0;  // prev_flat_grad.copy_(flat_grad)
     prev_loss = loss;
 
-    float gsum = 0.f, gtd0a = 0.f, gtd1a = 0.f, dmax = 0.f;
-#pragma unroll 17
-    for (int i = 0; i < N; ++i) {
-      const float gi = v.at(og + i), di = c.X(i);
-      v.at(od + i) = di;
-      gsum += fabsf(gi);
-      if (i & 1) gtd1a = fmaf(gi, di, gtd1a); else gtd0a = fmaf(gi, di, gtd0a);
-      dmax = fmaxf(dmax, fabsf(di));
-    }
-    const float gtd = gtd0a + gtd1a;
+    float gsum, gtd, dmax;
+    Ops::commit_direction(c, v, g0, gsum, gtd, dmax);
     if (n_iter == 1) {
       const float inv = 1.f / gsum;
       t_f32 = inv < 1.f;   // Python min(1.0, tensor) keeps the tensor only when it is smaller
@@ -332,15 +391,12 @@ struct Lbfgs {
     insuf = false;
     br_n = 0;
     pick_cur();
-    // first trial point: x = xk + t d with d still in the x column
-    const float tf = (float)t;
-#pragma unroll 17
-    for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, c.X(i), v.at(i));
+    Ops::first_trial(c, v, (float)t);
   }
 
   // Process the evaluation at the current trial point (loss f_new, gradient in G).
   // Afterwards either `done` is set (parameters are in v.xk) or X holds the next trial point.
-  K2B_HD void after_eval(const Cols& c, const Vecs& v, float f_new_f) {
+  K2B_HD void after_eval(const C& c, const V& v, float f_new_f) {
     const double f_new = (double)f_new_f;
     const float gtd_new = dot_cur_d(v);      // the evaluation wrote its gradient to slot `cur`
     ++ls_evals;
@@ -485,23 +541,12 @@ struct Lbfgs {
 
   // Line search returned: move the iterate, account evaluations, test termination,
   // and either stop or start the next outer iteration.
-  K2B_HD void g0_next(const Cols& c, const Vecs& v, int new_g_slot) {
-    const int od = v.d();
-    const float tf = (float)t;
-    float dtmax = 0.f;
-#pragma unroll 17
-    for (int i = 0; i < N; ++i) {
-      const float di = v.at(od + i);
-      v.at(i) = fmaf(tf, di, v.at(i));      // _add_grad(t, d)
-      dtmax = fmaxf(dtmax, fabsf(di * tf));
-    }
+  K2B_HD void g0_next(const C& c, const V& v, int new_g_slot) {
+    const float dtmax = Ops::move_iterate(c, v, (float)t);      // _add_grad(t, d)
     evals += ls_evals;
     // keep prev_flat_grad readable for the next y = g - prev_g: it stays in slot_prev_grad
     g0 = new_g_slot;
-    float gmax = 0.f;
-    const int og = v.gslot(g0);
-#pragma unroll 17
-    for (int i = 0; i < N; ++i) gmax = fmaxf(gmax, fabsf(v.at(og + i)));
+    const float gmax = Ops::grad_max(v, g0);
     if (n_iter == max_iter || evals >= max_eval || (double)gmax <= kTolGrad ||
         (double)dtmax <= kTolChange || fabs(loss - prev_loss) < kTolChange) {
       done = true;

@@ -1,0 +1,220 @@
+// warp_emul.cu -- DEBUGGING HARNESS, NOT PART OF THE PRODUCT.
+//
+// Runs the warp-cooperative fitting code (keypoints2body_b200/csrc/chain_core.cuh) on the CPU: the 32
+// lanes of a warp are 32 coroutines (ucontext), scheduled round-robin; a shuffle publishes the lane's
+// value, yields once around the ring and reads the source lane's value; a warp sync is one trip around
+// the ring.  This is valid for warp-uniform control flow, which is what the device code has.  Built into
+// tests/host_emul/libk2b_warp_emul.so by build.sh, loaded only by tests/test_warp_emul.py.
+#define K2B_WARP_EMUL 1
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../keypoints2body_b200/csrc/chain_core.cuh"
+
+using namespace k2b;
+
+namespace {
+constexpr int kLanes = 32;
+constexpr size_t kStack = 1 << 20;
+ucontext_t g_ctx[kLanes], g_main;
+char* g_stacks = nullptr;
+int g_lane = 0, g_done = 0;
+float g_buf[2][kLanes];
+int g_par[kLanes];
+void (*g_job)() = nullptr;
+
+void yield_next() {
+  const int cur = g_lane, nxt = (cur + 1) & 31;
+  g_lane = nxt;
+  swapcontext(&g_ctx[cur], &g_ctx[nxt]);
+  g_lane = cur;
+}
+void lane_entry() {
+  g_job();
+  const int me = g_lane;
+  ++g_done;
+  while (true) {
+    if (g_done == kLanes) swapcontext(&g_ctx[me], &g_main);
+    yield_next();
+  }
+}
+void run_warp(void (*job)()) {
+  if (!g_stacks) g_stacks = (char*)malloc(kStack * kLanes);
+  g_job = job;
+  g_done = 0;
+  for (int l = 0; l < kLanes; ++l) {
+    g_par[l] = 0;
+    getcontext(&g_ctx[l]);
+    g_ctx[l].uc_stack.ss_sp = g_stacks + kStack * l;
+    g_ctx[l].uc_stack.ss_size = kStack;
+    g_ctx[l].uc_link = nullptr;
+    makecontext(&g_ctx[l], lane_entry, 0);
+  }
+  g_lane = 0;
+  swapcontext(&g_main, &g_ctx[0]);
+}
+}  // namespace
+
+int k2b_emul_lane() { return g_lane; }
+float k2b_emul_shfl(float v, int src) {
+  const int me = g_lane, p = g_par[me];
+  g_buf[p][me] = v;
+  g_par[me] = p ^ 1;
+  yield_next();
+  return g_buf[p][src];
+}
+void k2b_emul_sync() { yield_next(); }
+
+struct WEmuModel {
+  int ns;
+  std::vector<float> P, mu, nlw, rel;
+};
+
+// chol69: [8][69][69] lower-triangular L; the precision tables are rebuilt as L L^T in double, like
+// k2b_model_create does for the device tables.
+extern "C" void* wemu_model_create(int ns, const float* chol69, const float* means, const float* nlw,
+                                   const double* J0, const double* JS, const int* parents, int nj) {
+  WEmuModel* m = new WEmuModel();
+  m->ns = ns;
+  m->P.assign((size_t)kGmmM * wc::kPFloats, 0.f);
+  m->mu.assign((size_t)kGmmM * kMuStride, 0.f);
+  m->nlw.assign(nlw, nlw + kGmmM);
+  for (int c = 0; c < kGmmM; ++c) {
+    const float* L = chol69 + (size_t)c * kBodyDim * kBodyDim;
+    for (int i = 0; i < kBodyDim; ++i) {
+      for (int j = 0; j < kBodyDim; ++j) {
+        double acc = 0.0;
+        const int kmax = i < j ? i : j;
+        for (int k = 0; k <= kmax; ++k) acc += (double)L[i * kBodyDim + k] * (double)L[j * kBodyDim + k];
+        m->P[(size_t)c * wc::kPFloats + i * wc::kPStride + j] = (float)acc;
+      }
+      m->mu[(size_t)c * kMuStride + i] = means[(size_t)c * kBodyDim + i];
+    }
+  }
+  m->rel.assign((size_t)kMaxFitJoints * (1 + ns) * 4, 0.f);
+  const int nfit = nj < kMaxFitJoints ? nj : kMaxFitJoints;
+  for (int j = 0; j < nfit; ++j) {
+    const int pj = parents[j];
+    for (int k = 0; k < 3; ++k) {
+      m->rel[((size_t)j * (1 + ns)) * 4 + k] = (float)(J0[j * 3 + k] - (pj >= 0 ? J0[pj * 3 + k] : 0.0));
+      for (int s = 0; s < ns; ++s)
+        m->rel[((size_t)j * (1 + ns) + 1 + s) * 4 + k] =
+            (float)(JS[((size_t)j * 3 + k) * ns + s] - (pj >= 0 ? JS[((size_t)pj * 3 + k) * ns + s] : 0.0));
+    }
+  }
+  return m;
+}
+extern "C" void wemu_model_destroy(void* m) { delete (WEmuModel*)m; }
+
+namespace {
+struct Job {
+  const WEmuModel* m;
+  wc::ChainParams p;
+  int K;
+  long seq;
+  // evaluate-only
+  bool eval_only;
+  const float* x;      // [NX]
+  float* grad;         // [NX]
+  float* loss;
+  float* joints;
+  int* comp;
+  std::vector<float> wmem, hist;
+} g;
+
+template <int NS, int K>
+void lane_job() {
+  wc::WarpTables tb{g.m->P.data(), g.m->mu.data(), g.m->nlw.data(), (const float4*)g.m->rel.data()};
+  float* w = g.wmem.data();
+  wc::WarpMem wm{w, w + 96, w + 176, w + 248};
+  if (g.eval_only) {
+    const int lane = wc::lane_id();
+    float xr[3], gr[3];
+    for (int c = 0; c < 3; ++c) xr[c] = 3 * lane + c < 75 + NS ? g.x[3 * lane + c] : 0.f;
+    wc::FrameObs ob;
+    ob.tx = ob.ty = ob.tz = ob.w = 0.f;
+    if (lane < K) {
+      ob.tx = g.p.targets[lane * 3]; ob.ty = g.p.targets[lane * 3 + 1]; ob.tz = g.p.targets[lane * 3 + 2];
+      const float cf = g.p.conf ? g.p.conf[lane] : 1.f;
+      ob.w = g.p.joint_w2 * cf * cf;
+    }
+    for (int c = 0; c < 3; ++c)
+      ob.keep[c] = (lane >= 1 && lane < 24) ? g.p.preserve_pose[3 * lane - 3 + c] : 0.f;
+    ob.keep_w2 = g.p.keep_w2;
+    int comp = 0;
+    const float loss = wc::eval_warp<NS, K>(tb, wm, ob, xr, true, true, gr, g.joints, &comp);
+    for (int c = 0; c < 3; ++c)
+      if (3 * lane + c < 75 + NS) g.grad[3 * lane + c] = gr[c];
+    if (lane == 0) { *g.loss = loss; *g.comp = comp; }
+    return;
+  }
+  float* ro = w + wc::kWarpMemFloats;
+  wc::run_chain_warp<NS, K>(g.p, g.seq, tb, wm, g.hist.data(), ro, ro + g.p.hmax);
+}
+
+void (*pick_job(int ns, int K))() {
+  if (K == 24) return lane_job<10, 24>;
+  return ns == 20 ? lane_job<20, 22> : lane_job<10, 22>;
+}
+}  // namespace
+
+// One evaluation (loss, gradient, joints, arg-min component) of one frame; x layout [go3|body69|transl3|shape NS].
+extern "C" int wemu_eval(void* model, int K, float joint_w, float keep_w, const float* targets, const float* conf,
+                         const float* x, const float* keep_pose, float* out_grad, float* out_loss, float* out_joints,
+                         int* out_comp) {
+  g.m = (WEmuModel*)model;
+  g.K = K;
+  g.eval_only = true;
+  g.p = wc::ChainParams{};
+  g.p.targets = targets;
+  g.p.conf = conf;
+  g.p.joint_w2 = joint_w * joint_w;
+  g.p.keep_w2 = keep_w * keep_w;
+  g.p.preserve_pose = keep_pose;
+  g.x = x; g.grad = out_grad; g.loss = out_loss; g.joints = out_joints; g.comp = out_comp;
+  g.wmem.assign(wc::warp_mem_floats(1), 0.f);
+  run_warp(pick_job(g.m->ns, K));
+  return 0;
+}
+
+// S sequences of T frames each, walked by one (emulated) warp per sequence.
+extern "C" int wemu_chain(void* model, int K, int S, int T, long first_seq_ind, int chain, int lbfgs, int iters_first,
+                          int iters_follow, int freeze_betas, float lr, float joint_w, float keep_w, const float* targets,
+                          const float* conf, int conf_mode, const float* init_pose, const float* init_betas,
+                          const float* init_transl, const float* init_expr, const float* preserve_pose, float* out_pose,
+                          float* out_betas, float* out_transl, float* out_expr, float* out_loss, float* out_joints,
+                          int* out_evals) {
+  g.m = (WEmuModel*)model;
+  g.K = K;
+  g.eval_only = false;
+  wc::ChainParams& p = g.p;
+  p = wc::ChainParams{};
+  p.num_seq = S; p.frames = T; p.first_seq_ind = first_seq_ind; p.chain = chain;
+  p.iters_first = iters_first; p.iters_follow = iters_follow; p.lbfgs = lbfgs; p.freeze_betas = freeze_betas;
+  p.conf_mode = conf ? conf_mode : 0;
+  p.lr = lr; p.joint_w2 = joint_w * joint_w; p.keep_w2 = keep_w * keep_w;
+  p.targets = targets; p.conf = conf;
+  p.init_pose = init_pose; p.init_betas = init_betas; p.init_transl = init_transl; p.init_expr = init_expr;
+  p.preserve_pose = preserve_pose;
+  p.out_pose = out_pose; p.out_betas = out_betas; p.out_transl = out_transl; p.out_expr = out_expr;
+  p.out_loss = out_loss; p.out_joints = out_joints; p.out_evals = out_evals;
+  const int max_it = iters_first > iters_follow ? iters_first : iters_follow;
+  p.hmax = lbfgs_history_capacity(max_it);
+  for (int k = 1; k <= wc::kAdamTableW; ++k) {
+    p.adam_step[k - 1] = (float)((double)lr / (1.0 - std::pow(0.9, (double)k)));
+    p.adam_bc2[k - 1] = (float)std::sqrt(1.0 - std::pow(0.999, (double)k));
+  }
+  g.wmem.assign(wc::warp_mem_floats(p.hmax), 0.f);
+  g.hist.assign(wc::hist_floats(p.hmax), 0.f);
+  p.hist = g.hist.data();
+  for (long s = 0; s < S; ++s) {
+    g.seq = s;
+    run_warp(pick_job(g.m->ns, K));
+  }
+  return 0;
+}

@@ -1,0 +1,197 @@
+"""Checks the warp-cooperative fitting code (csrc/chain_core.cuh) on the CPU.
+
+tests/host_emul/libk2b_warp_emul.so runs the device code's warp-level routines with the 32 lanes as
+coroutines (see warp_emul.cu): the same evaluation / Adam / L-BFGS / sequence-chain code the chain
+kernel runs, compared here with the goldens made from the unmodified reference.  The `-m gpu` tests then
+check the real kernel through the C ABI.
+"""
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from keypoints2body_b200.core.prior import prepare_gmm
+
+from test_host_emul import ADAM_CASES, LBFGS_CASES, f32, pack_x
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "host_emul")
+EMU_LIB = os.path.join(EMU_DIR, "libk2b_warp_emul.so")
+CSRC = os.path.join(HERE, "..", "keypoints2body_b200", "csrc")
+
+pytestmark = pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc needed to build the harness")
+
+fp = C.POINTER(C.c_float)
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+
+
+def _stale():
+    if not os.path.exists(EMU_LIB):
+        return True
+    t = os.path.getmtime(EMU_LIB)
+    srcs = [os.path.join(EMU_DIR, "warp_emul.cu")] + [os.path.join(CSRC, f) for f in
+                                                      ("fit_core.cuh", "lbfgs_core.cuh", "chain_core.cuh")]
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+@pytest.fixture(scope="module")
+def wemu():
+    if _stale():
+        subprocess.run(["sh", os.path.join(EMU_DIR, "build.sh")], check=True, capture_output=True)
+    lib = C.CDLL(EMU_LIB)
+    lib.wemu_model_create.restype = C.c_void_p
+    lib.wemu_model_create.argtypes = [C.c_int, fp, fp, fp, dp, dp, ip, C.c_int]
+    lib.wemu_eval.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, fp, fp, fp, fp, fp, fp, fp, ip]
+    lib.wemu_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_float, C.c_float, C.c_float, fp, fp, C.c_int, fp, fp, fp, fp, fp,
+                               fp, fp, fp, fp, fp, fp, ip]
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(fp)
+
+
+class WModel:
+    def __init__(self, lib, weights, gmm, ns):
+        self.lib, self.ns = lib, ns
+        g = prepare_gmm(gmm)
+        Jr = weights.J_regressor.double().numpy()
+        J0 = np.ascontiguousarray(Jr @ weights.v_template.double().numpy())
+        JS = np.ascontiguousarray(np.einsum("jv,vkl->jkl", Jr, weights.shapedirs.double().numpy()[..., :ns]))
+        par = np.ascontiguousarray(weights.parents.numpy().astype(np.int32))
+        self.h = lib.wemu_model_create(ns, _p(f32(g.chol)), _p(f32(g.means)), _p(f32(g.neg_log_w)),
+                                       J0.ctypes.data_as(dp), JS.ctypes.data_as(dp), par.ctypes.data_as(ip), len(par))
+
+    def evaluate(self, x, target, conf, keep, keep_w, joint_w=600.0):
+        K, NX = target.shape[0], 75 + self.ns
+        x, target, conf, keep = f32(x), f32(target), f32(conf), f32(keep)
+        grad, loss, joints = np.zeros(NX, np.float32), np.zeros(1, np.float32), np.zeros((K, 3), np.float32)
+        comp = np.zeros(1, np.int32)
+        self.lib.wemu_eval(self.h, K, joint_w, keep_w, _p(target), _p(conf), _p(x), _p(keep), _p(grad), _p(loss),
+                           _p(joints), comp.ctypes.data_as(ip))
+        return dict(grad=grad, loss=float(loss[0]), joints=joints, comp=int(comp[0]))
+
+    def chain(self, x0, targets, conf=None, first_seq_ind=0, chain=True, lbfgs=False, iters_first=30,
+              iters_follow=10, freeze=False, lr=1e-2, joint_w=600.0, keep_w=5.0, keep=None):
+        """x0 (S,NX); targets (S,T,K,3); returns arrays shaped (S,T,..)."""
+        S, T, K = targets.shape[:3]
+        x0, targets = f32(x0), f32(targets)
+        pose, transl, betas = f32(x0[:, :72]), f32(x0[:, 72:75]), f32(x0[:, 75:85])
+        expr = f32(x0[:, 85:95]) if self.ns == 20 else None
+        conf = None if conf is None else f32(conf)
+        keep = None if keep is None else f32(keep)
+        o = dict(pose=np.zeros((S, T, 72), np.float32), betas=np.zeros((S, T, 10), np.float32),
+                 transl=np.zeros((S, T, 3), np.float32), expr=np.zeros((S, T, 10), np.float32),
+                 loss=np.zeros((S, T), np.float32), joints=np.zeros((S, T, K, 3), np.float32),
+                 evals=np.zeros((S, T), np.int32))
+        self.lib.wemu_chain(self.h, K, S, T, first_seq_ind, int(chain), int(lbfgs), iters_first, iters_follow,
+                            int(freeze), lr, joint_w, keep_w, _p(targets), _p(conf),
+                            0 if conf is None else (1 if conf.ndim == 1 else 2), _p(pose), _p(betas), _p(transl),
+                            _p(expr), _p(keep), _p(o["pose"]), _p(o["betas"]), _p(o["transl"]), _p(o["expr"]),
+                            _p(o["loss"]), _p(o["joints"]), o["evals"].ctypes.data_as(ip))
+        return o
+
+
+@pytest.fixture(scope="module")
+def wmodels(wemu, weights, gmm):
+    cache = {}
+
+    def get(mt):
+        if mt not in cache:
+            cache[mt] = WModel(wemu, weights(mt), gmm, 20 if mt == "smplx" else 10)
+        return cache[mt]
+
+    return get
+
+
+@pytest.mark.parametrize("tag", ["eval_smpl_22_w0", "eval_smpl_22_w5", "eval_smpl_24_w5",
+                                 "eval_smplh_22_w5", "eval_smplx_22_w0", "eval_smplx_22_w5"])
+def test_warp_evaluation_matches_reference(goldens, wmodels, tag):
+    """G1 for the warp-cooperative evaluation: loss rel <= 1e-5, gradient <= 1e-4 of its max, joints <= 1e-5 m."""
+    _, mt, nobs, w = tag.split("_")
+    g = goldens
+    pose = np.concatenate([g[tag + "_in_global_orient"], g[tag + "_in_body_pose"]], axis=1)
+    expr = g.get(tag + "_in_expression")
+    x0 = pack_x(pose, g[tag + "_in_transl"], g[tag + "_in_betas"], expr)
+    keep_w = float(w[1:])
+    ref_pose = np.concatenate([g[tag + "_grad_global_orient"], g[tag + "_grad_body_pose"]], axis=1)
+    for b in range(x0.shape[0]):
+        out = wmodels(mt).evaluate(x0[b], g[tag + "_in_target"][b], g[tag + "_in_conf"], g[tag + "_in_keep"][b], keep_w)
+        np.testing.assert_allclose(out["loss"], g[tag + "_loss"].reshape(-1)[b], rtol=1e-5)
+        np.testing.assert_allclose(out["joints"], g[tag + "_joints"][b, : int(nobs)], atol=1e-5)
+        gx = out["grad"]
+        assert (np.abs(gx[:72] - ref_pose[b]) / np.abs(ref_pose[b]).max()).max() < 1e-4
+        for name, sl in (("transl", slice(72, 75)), ("betas", slice(75, 85))):
+            ref = g[f"{tag}_grad_{name}"][b]
+            assert (np.abs(gx[sl] - ref) / np.abs(ref).max()).max() < 1e-4
+        if expr is not None:
+            ref = g[tag + "_grad_expression"][b]
+            assert (np.abs(gx[85:95] - ref) / np.abs(ref).max()).max() < 1e-4
+
+
+@pytest.mark.parametrize("tag", sorted(ADAM_CASES))
+def test_warp_adam_fit_matches_reference(goldens, wmodels, tag):
+    """G2 for the warp-cooperative path: each frame is a one-frame chain starting at seq_ind."""
+    mt, iters, seq_ind, freeze, nobs = ADAM_CASES[tag]
+    g = goldens
+    B = g[tag + "_in_pose"].shape[0]
+    expr = np.zeros((B, 10), np.float32) if mt == "smplx" else None
+    x0 = pack_x(g[tag + "_in_pose"], g[tag + "_in_transl"], g[tag + "_in_betas"], expr)
+    out = wmodels(mt).chain(x0, g[tag + "_in_target"][:, None], np.ones(nobs), first_seq_ind=seq_ind,
+                            iters_first=iters, iters_follow=iters, freeze=freeze)
+    assert np.abs(out["pose"][:, 0] - g[tag + "_pose"]).max() < 1e-4
+    assert np.abs(out["transl"][:, 0] - g[tag + "_transl"]).max() < 1e-5
+    assert np.abs(out["betas"][:, 0] - g[tag + "_betas"]).max() < 1e-4
+    assert np.abs(out["joints"][:, 0] - g[tag + "_joints"][:, :nobs]).max() < 1e-4
+    np.testing.assert_allclose(out["loss"].sum(), float(g[tag + "_loss"]), rtol=1e-4)
+    if mt == "smplx":
+        assert np.abs(out["expr"][:, 0] - g[tag + "_expression"]).max() < 1e-4
+    assert (out["evals"] == iters).all()
+
+
+@pytest.mark.parametrize("tag", sorted(LBFGS_CASES))
+def test_warp_lbfgs_statistics(goldens, wmodels, tag):
+    """G4 for the warp-cooperative L-BFGS (same machine as the per-thread kernel, lane-distributed vectors):
+    evaluation budgets like torch's, final losses not worse than the reference's in distribution."""
+    mt, iters, seq_ind = LBFGS_CASES[tag]
+    g = goldens
+    B = g[tag + "_in_pose"].shape[0]
+    expr = np.zeros((B, 10), np.float32) if mt == "smplx" else None
+    x0 = pack_x(g[tag + "_in_pose"], g[tag + "_in_transl"], g[tag + "_in_betas"], expr)
+    out = wmodels(mt).chain(x0, g[tag + "_in_target"][:, None], np.ones(22), first_seq_ind=seq_ind, lbfgs=True,
+                            iters_first=iters, iters_follow=iters)
+    ev, ref_ev = out["evals"][:, 0], g[tag + "_nevals"].reshape(-1)
+    assert (ev <= iters * 5 // 4 + 1).all()
+    assert (np.abs(ev - ref_ev) <= 2).all(), (ev, ref_ev)
+    ref_loss = g[tag + "_loss"].reshape(-1)
+    assert np.median(out["loss"]) <= 1.5 * np.median(ref_loss)
+    print(tag, "evals", ev, "ref", ref_ev, "loss", out["loss"].ravel(), "ref", ref_loss)
+
+
+def _sequence_init(g, shims):
+    tgt = g["seq_in_target"]
+    with torch.no_grad():
+        root = shims("smpl")(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69),
+                             betas=torch.zeros(1, 10)).joints[0, 0].numpy()
+    return pack_x(np.zeros((1, 72), np.float32), (tgt[0, 0] - root)[None], np.zeros((1, 10), np.float32)), tgt
+
+
+@pytest.mark.parametrize("name,chain", [("seq_adam_chain", True), ("seq_adam_indep", False)])
+def test_warp_sequence_chain_matches_reference(goldens, wmodels, shims, name, chain):
+    """The reference's sequence loop (api/sequence.py:214-281) inside one warp: frame t starts from frame t-1's
+    result (or from the fixed initialisation), 30 / 10 Adam iterations, temporal term from frame 1 on."""
+    g = goldens
+    x0, tgt = _sequence_init(g, shims)
+    out = wmodels("smpl").chain(x0, tgt[None], np.ones(22), chain=chain)
+    assert np.abs(out["pose"][0] - g[name + "_pose"]).max() < 1e-4
+    assert np.abs(out["betas"][0] - g[name + "_betas"]).max() < 1e-4
+    assert np.abs(out["transl"][0] - g[name + "_transl"]).max() < 1e-5
+    assert np.abs(out["joints"][0] - g[name + "_joints"][:, :22]).max() < 1e-4
+    np.testing.assert_allclose(out["loss"][0], g[name + "_loss"], rtol=1e-4)
