@@ -12,6 +12,9 @@
  *   k2b_fit_batch         <- WorldSpaceFitter.fit_frame, core/fitters/world_space.py:93-257
  *                            (compute_loss :173-212, L-BFGS :231-247, Adam :248-256),
  *                            called per frame from api/sequence.py:214-281
+ *   k2b_fit_chain         <- the frame loop of optimize_params_sequence, api/sequence.py:214-281
+ *                            (frame t starts from frame t-1's result), one warp per sequence;
+ *                            also WorldSpaceFitter.fit_frame for small batches (low latency)
  *   k2b_evaluate_batch    <- one compute_loss()+backward(), world_space.py:173-212,239-243
  *   k2b_mesh_batch        <- the final body-model forward, world_space.py:258-278
  *   k2b_shape_pass        <- optimize_shape_multi_frame, core/shape.py:10-115
@@ -135,6 +138,50 @@ int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* args, void* cuda_strea
  * NULL (allocated internally and cached on the model).  Performs H2D copies, the fit,
  * D2H copies, then synchronises. */
 int k2b_fit_batch_host(k2b_model* m, const k2b_fit_args* host_args, void* cuda_stream);
+
+/* Sequences walked serially in t inside ONE launch, one warp per sequence: the reference's default
+ * schedule (api/sequence.py:214-281, use_previous_frame_init=True).  Frame t of sequence s is one
+ * WorldSpaceFitter.fit_frame(init, j3d[s][t], conf, seq_ind = first_seq_ind + t): seq_ind 0 gets
+ * num_iters_first and no temporal term, later frames num_iters_followup and the pose-preserve term
+ * against their own initial body pose (world_space.py:159,211,214).  chain_init 1: init = result of
+ * frame t-1 (frame 0: the sequence's init); 0: every frame starts from the sequence's init
+ * (use_previous_frame_init=False).  With frames_per_sequence = 1 this is a low-latency k2b_fit_batch
+ * (world loss only).  Outputs are [S][T][..] (loss / evals semantics as k2b_fit_batch). */
+typedef struct k2b_chain_args {
+  int64_t num_sequences;        /* S */
+  int32_t frames_per_sequence;  /* T */
+  int32_t num_obs;              /* K: 22 or 24 */
+  int32_t optimizer;            /* K2B_OPT_* */
+  int32_t num_iters_first;      /* reference default 30 */
+  int32_t num_iters_followup;   /* reference default 10 */
+  int64_t first_seq_ind;        /* seq_ind of every sequence's frame 0 */
+  int32_t chain_init;           /* 1 = use_previous_frame_init */
+  int32_t freeze_betas;
+  int32_t conf_mode;            /* 0 none, 1 conf is [K], 2 conf is [S][T][K] */
+  float lr;
+  float joint_loss_weight;
+  float pose_preserve_weight;
+  const float* targets;         /* [S][T][K][3] (device) */
+  const float* conf;
+  const float* init_pose;       /* [S][72] */
+  const float* init_betas;      /* [S][10] */
+  const float* init_transl;     /* [S][3] */
+  const float* init_expr;       /* [S][10] or NULL (required iff model num_shape == 20) */
+  const float* preserve_pose;   /* [S][T][69] or NULL = each frame's initial body pose */
+  float* out_pose;              /* [S][T][72] */
+  float* out_betas;             /* [S][T][10] */
+  float* out_transl;            /* [S][T][3] */
+  float* out_expr;              /* [S][T][10] or NULL */
+  float* out_loss;              /* [S][T] */
+  float* out_joints;            /* [S][T][K][3] or NULL */
+  int32_t* out_evals;           /* [S][T] or NULL */
+  void* workspace;              /* L-BFGS history; may be NULL for Adam */
+  size_t workspace_bytes;       /* >= k2b_chain_workspace_bytes(m, S, optimizer, max(num_iters_*)) */
+} k2b_chain_args;
+
+size_t k2b_chain_workspace_bytes(const k2b_model* m, int64_t num_sequences, int32_t optimizer,
+                                 int32_t max_iters);
+int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* args, void* cuda_stream);
 
 /* One evaluation of loss and gradient at given parameters (parity / debugging). */
 typedef struct k2b_eval_args {

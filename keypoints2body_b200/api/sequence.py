@@ -6,8 +6,8 @@ batched onto the GPU according to the schedule:
 
 S1  ``schedule="reference"`` and ``use_previous_frame_init=True`` (the reference default): a
     Gauss-Seidel chain -- frame t starts from frame t-1's result, so it is serial in t by
-    construction; each frame is one B=1 launch of the fused kernel, the mesh of all frames is
-    produced by one batched pass at the end.
+    construction; ONE launch of the warp-per-sequence kernel (``k2b_fit_chain``) walks the whole
+    sequence, the mesh of all frames is produced by one batched pass at the end.
 S0  ``schedule="reference"`` and ``use_previous_frame_init=False``: every frame starts from the
     frame-0 initialisation; ONE launch fits all T frames (frame 0: first-frame budget without the
     temporal term; frames t>0: follow-up budget with it) -- exactly the reference's semantics.
@@ -20,6 +20,7 @@ S2  ``schedule="two_sweep"``: frame-parallel Jacobi variant of the chain: sweep 
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -103,7 +104,12 @@ def fit_sequence_batched(fitter, xyz, conf, init: dict, seq_cfg: SequenceOptimiz
         return out
     if not seq_cfg.use_previous_frame_init:
         return fitter.fit_batch(_expand(init, T), xyz, conf, seq_ind=seq_ind, **kw)
-    # S1: serial chain, one B=1 launch per frame; mesh once at the end
+    # S1: the serial chain runs inside ONE launch -- a warp walks the sequence frame by frame
+    # (k2b_fit_chain); the mesh of all frames is one batched pass at the end
+    if os.environ.get("K2B_S1_LAUNCH_PER_FRAME", "0") != "1":
+        return fitter.fit_chain({k: v for k, v in init.items() if v is not None}, xyz[None], conf[None],
+                                first_seq_ind=first_seq_ind, chain=True, **kw)
+    # diagnostic path: one B=1 launch per frame
     prev, rows = init, []
     for t in range(T):
         r = fitter.fit_batch(prev, xyz[t:t + 1], conf[t], seq_ind=first_seq_ind + t, with_mesh=False, **kw)

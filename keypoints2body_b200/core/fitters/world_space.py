@@ -18,6 +18,7 @@ its first row, world_space.py:163-164).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -95,6 +96,7 @@ class WorldSpaceFitter:
         self.device = device
         self.joints_category = joints_category
         self.num_obs = 24 if joints_category == "SMPL24" else 22
+        self.warp_kernel_max_frames = int(os.environ.get("K2B_WARP_MAX_FRAMES", "1024"))
 
         if isinstance(smpl_model, nat.NativeModel):
             self.native = smpl_model
@@ -145,6 +147,39 @@ class WorldSpaceFitter:
         )
         with torch.cuda.device(dev):
             nat.check(lib.k2b_fit_batch(self.native.handle, C.byref(a), nat.current_stream()))
+        return dict(pose=out_pose, betas=out_betas, transl=out_transl, expression=out_expr, loss=out_loss,
+                    fit_joints=out_joints, evals=out_evals)
+
+    def _run_chain(self, S, T, targets, conf, conf_mode, pose, betas, transl, expr, preserve, first_seq_ind, chain,
+                   iters_first, iters_follow, optimizer, joint_loss_weight, pose_preserve_weight, freeze_betas,
+                   want_joints=True):
+        """One launch of the warp-per-sequence kernel (``k2b_fit_chain``): S sequences x T frames, serial in t."""
+        dev = self.device
+        F = S * T
+        out_pose = torch.empty(F, 72, device=dev)
+        out_betas = torch.empty(F, 10, device=dev)
+        out_transl = torch.empty(F, 3, device=dev)
+        out_expr = torch.empty(F, 10, device=dev) if self.has_expr else None
+        out_loss = torch.empty(F, device=dev)
+        out_joints = torch.empty(F, self.num_obs, 3, device=dev) if want_joints else None
+        out_evals = torch.empty(F, dtype=torch.int32, device=dev)
+        lib = self.native.lib
+        ws_bytes = lib.k2b_chain_workspace_bytes(self.native.handle, S, optimizer, int(max(iters_first, iters_follow)))
+        ws = self.native.workspace("chain", ws_bytes)
+        a = nat.ChainArgs(
+            num_sequences=S, frames_per_sequence=T, num_obs=self.num_obs, optimizer=optimizer,
+            num_iters_first=int(iters_first), num_iters_followup=int(iters_follow), first_seq_ind=int(first_seq_ind),
+            chain_init=int(bool(chain)), freeze_betas=int(bool(freeze_betas)), conf_mode=int(conf_mode),
+            lr=self.step_size, joint_loss_weight=float(joint_loss_weight),
+            pose_preserve_weight=float(pose_preserve_weight),
+            targets=nat.ptr(targets), conf=nat.ptr(conf), init_pose=nat.ptr(pose), init_betas=nat.ptr(betas),
+            init_transl=nat.ptr(transl), init_expr=nat.ptr(expr), preserve_pose=nat.ptr(preserve),
+            out_pose=nat.ptr(out_pose), out_betas=nat.ptr(out_betas), out_transl=nat.ptr(out_transl),
+            out_expr=nat.ptr(out_expr), out_loss=nat.ptr(out_loss), out_joints=nat.ptr(out_joints),
+            out_evals=nat.ptr(out_evals), workspace=nat.ptr(ws), workspace_bytes=ws.numel(),
+        )
+        with torch.cuda.device(dev):
+            nat.check(lib.k2b_fit_chain(self.native.handle, C.byref(a), nat.current_stream()))
         return dict(pose=out_pose, betas=out_betas, transl=out_transl, expression=out_expr, loss=out_loss,
                     fit_joints=out_joints, evals=out_evals)
 
@@ -258,8 +293,11 @@ class WorldSpaceFitter:
     # ------------------------------------------------------------------ public
     def fit_batch(self, init: dict, j3d, conf=None, *, seq_ind=0, preserve_pose=None, num_iters=None,
                   joint_loss_weight=600.0, pose_preserve_weight=5.0, freeze_betas=False, use_lbfgs=None,
-                  with_mesh=True, out_vertices=None):
+                  with_mesh=True, out_vertices=None, kernel="auto"):
         """Fit B independent frames in one launch.
+
+        ``kernel``: "frame" = one thread per frame (``k2b_fit_batch``, throughput), "warp" = one warp per frame
+        (``k2b_fit_chain``, latency), "auto" = warp for small batches.
 
         ``init``: dict of (B,dim) arrays with keys global_orient, body_pose, betas, transl
         (+ SMPL-H / SMPL-X blocks).  ``seq_ind``: int or (B,) integer tensor; 0 selects the
@@ -306,15 +344,80 @@ class WorldSpaceFitter:
             preserve_all = int(seq_ind > 0)
         lbfgs = self.use_lbfgs if use_lbfgs is None else use_lbfgs
         keep_pose = _f32(preserve_pose, dev)
-        res = self._run_fit(B, targets, conf, conf_pf, pose, betas, transl, expr if self.has_expr else None,
-                            keep_pose, frame_iters, frame_preserve, preserve_all, budget,
-                            nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight, pose_preserve_weight,
-                            freeze_betas)
+        if kernel == "auto":
+            # few frames: one thread per frame leaves the GPU idle and a frame takes ~1.3 ms; a warp per frame
+            # (k2b_fit_chain with one-frame sequences) finishes in a fraction of that
+            kernel = "warp" if (frame_iters is None and B <= self.warp_kernel_max_frames) else "frame"
+        if kernel == "warp":
+            if frame_iters is not None:
+                raise ValueError("kernel='warp' needs a scalar seq_ind")
+            if conf is not None and conf_pf:
+                conf = conf.reshape(B, 1, self.num_obs)
+            res = self._run_chain(B, 1, targets.reshape(B, 1, self.num_obs, 3), conf,
+                                  0 if conf is None else (2 if conf_pf else 1), pose, betas, transl,
+                                  expr if self.has_expr else None, keep_pose, 0 if not preserve_all else 1, True,
+                                  budget, budget, nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight,
+                                  pose_preserve_weight, freeze_betas)
+        else:
+            res = self._run_fit(B, targets, conf, conf_pf, pose, betas, transl, expr if self.has_expr else None,
+                                keep_pose, frame_iters, frame_preserve, preserve_all, budget,
+                                nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight, pose_preserve_weight,
+                                freeze_betas)
         params = {"global_orient": res["pose"][:, :3], "body_pose": res["pose"][:, 3:], "betas": res["betas"],
                   "transl": res["transl"]}
         for k in _EXTRA_BLOCKS:
             if extras[k] is not None:
                 params[k] = extras[k]      # receive no gradient from body keypoints: passed through
+        if self.has_expr:
+            params["expression"] = res["expression"]
+        out = {"params": params, "loss": res["loss"], "evals": res["evals"], "fit_joints": res["fit_joints"]}
+        if with_mesh:
+            out.update(self.forward_batch(params, with_vertices=True, out_vertices=out_vertices))
+        return out
+
+    def fit_chain(self, init: dict, j3d, conf=None, *, first_seq_ind=0, chain=True, joint_loss_weight=600.0,
+                  pose_preserve_weight=5.0, freeze_betas=False, use_lbfgs=None, with_mesh=True, out_vertices=None):
+        """Fit S sequences of T frames each the way the reference's sequence loop does (api/sequence.py:214-281):
+        serially in t, frame t starting from frame t-1's result (``chain=True``) or from the sequence's
+        initialisation (``chain=False``), all inside ONE launch -- one warp per sequence.
+
+        ``init``: dict of (S,dim) arrays = initialisation of every sequence's frame 0.  ``j3d``: (S,T,K,3).
+        ``conf``: None, (K,) or (S,T,K).  Returns the same dict as ``fit_batch`` with S*T leading rows
+        (sequence-major).
+        """
+        dev = self.device
+        targets = _f32(j3d, dev)
+        if targets.dim() != 4 or targets.shape[2] < self.num_obs:
+            raise ValueError(f"j3d must be (S, T, K>={self.num_obs}, 3), got {tuple(targets.shape)}")
+        S, T = targets.shape[0], targets.shape[1]
+        targets = targets[:, :, : self.num_obs].contiguous()
+        go, bp = _f32(init["global_orient"], dev), _f32(init["body_pose"], dev)
+        if init.get("transl") is None:
+            raise ValueError("init_params.transl must be provided")
+        pose = torch.cat([go, bp], dim=1).expand(S, -1).contiguous()
+        betas = _f32(init["betas"], dev).expand(S, -1).contiguous()
+        transl = _f32(init["transl"], dev).expand(S, -1).contiguous()
+        conf = _f32(conf, dev)
+        conf_mode = 0
+        if conf is not None:
+            conf = conf[..., : self.num_obs].contiguous()
+            conf_mode = 1 if conf.dim() == 1 else 2
+            if conf_mode == 2 and conf.numel() != S * T * self.num_obs:
+                raise ValueError("per-frame confidences must be (S, T, K)")
+        extras = {k: _f32(init.get(k), dev) for k in _EXTRA_BLOCKS}
+        expr = extras["expression"]
+        if self.has_expr:
+            expr = (expr if expr is not None else torch.zeros(S, 10, device=dev)).expand(S, -1).contiguous()
+        lbfgs = self.use_lbfgs if use_lbfgs is None else use_lbfgs
+        res = self._run_chain(S, T, targets, conf, conf_mode, pose, betas, transl, expr if self.has_expr else None,
+                              None, first_seq_ind, chain, self.num_iters_first, self.num_iters_followup,
+                              nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight, pose_preserve_weight,
+                              freeze_betas)
+        params = {"global_orient": res["pose"][:, :3], "body_pose": res["pose"][:, 3:], "betas": res["betas"],
+                  "transl": res["transl"]}
+        for k in _EXTRA_BLOCKS:
+            if extras[k] is not None:    # receive no gradient from body keypoints: passed through to every frame
+                params[k] = extras[k].expand(S, -1).repeat_interleave(T, dim=0)
         if self.has_expr:
             params["expression"] = res["expression"]
         out = {"params": params, "loss": res["loss"], "evals": res["evals"], "fit_joints": res["fit_joints"]}

@@ -12,6 +12,7 @@
 #include "../../include/k2b_b200.h"
 #include "fit_kernel.cuh"
 #include "fit_launch.h"
+#include "chain_kernel.cuh"
 #include "eval_kernel.cuh"
 #include "mesh_kernel.cuh"
 #include "shape_kernel.cuh"
@@ -46,6 +47,7 @@ struct k2b_model {
   bool smpl24_ok = false;
   int device = 0, num_sms = 0;
   float *chol = nullptr, *mu = nullptr, *nlw = nullptr, *rel = nullptr;
+  float* prec = nullptr;   // [8][69][72] symmetric precisions L L^T (warp-per-sequence kernel)
   MeshModel mesh;
   // cached device staging for the *_host entry points
   void* stage = nullptr;
@@ -60,7 +62,7 @@ extern "C" int64_t k2b_launch_count(void) { return g_launches.load(); }
 
 extern "C" void k2b_model_destroy(k2b_model* m) {
   if (!m) return;
-  cudaFree(m->chol); cudaFree(m->mu); cudaFree(m->nlw); cudaFree(m->rel);
+  cudaFree(m->chol); cudaFree(m->mu); cudaFree(m->nlw); cudaFree(m->rel); cudaFree(m->prec);
   mesh_model_free(m->mesh);
   cudaFree(m->stage); cudaFree(m->ws);
   delete m;
@@ -93,6 +95,18 @@ extern "C" int k2b_model_create(const k2b_model_desc* d, k2b_model** out) {
     }
     nlw[c] = d->gmm_neg_log_w[c];
   }
+  // the same precisions as dense symmetric matrices P = L L^T (float64 product), rows padded to 72
+  std::vector<float> prec((size_t)kGmmM * wc::kPFloats, 0.f);
+  for (int c = 0; c < kGmmM; ++c) {
+    const float* L = d->gmm_chol + (size_t)c * kBodyDim * kBodyDim;
+    for (int i = 0; i < kBodyDim; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k <= j; ++k) acc += (double)L[i * kBodyDim + k] * (double)L[j * kBodyDim + k];
+        prec[(size_t)c * wc::kPFloats + i * wc::kPStride + j] = (float)acc;
+        prec[(size_t)c * wc::kPFloats + j * wc::kPStride + i] = (float)acc;
+      }
+  }
   // rest-pose offsets relative to the parent, and their shape derivatives (float64 contraction)
   if (!d->v_template || !d->shapedirs || !d->J_regressor || !d->posedirs || !d->lbs_weights) {
     delete m;
@@ -117,7 +131,8 @@ extern "C" int k2b_model_create(const k2b_model_desc* d, k2b_model** out) {
   }
   cudaError_t e;
   if ((e = upload(chol, &m->chol)) != cudaSuccess || (e = upload(mu, &m->mu)) != cudaSuccess ||
-      (e = upload(nlw, &m->nlw)) != cudaSuccess || (e = upload(rel, &m->rel)) != cudaSuccess) {
+      (e = upload(nlw, &m->nlw)) != cudaSuccess || (e = upload(rel, &m->rel)) != cudaSuccess ||
+      (e = upload(prec, &m->prec)) != cudaSuccess) {
     k2b_model_destroy(m);
     return fail(K2B_ECUDA, std::string("table upload: ") + cudaGetErrorString(e));
   }
@@ -265,6 +280,86 @@ extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, vo
   p.scratch = (float*)a->workspace;
   AdamTable at{};
   return launch_fit_ns<kModeEval>(m->num_shape, p, at, grid, (cudaStream_t)stream);
+}
+
+// ---- warp-per-sequence fit (serial chains, small batches) ------------------------------------
+namespace {
+void chain_geometry(const k2b_model* m, long S, int& grid, int& warps) {
+  long w = (S + m->num_sms - 1) / m->num_sms;
+  if (const char* e = getenv("K2B_CHAIN_WARPS")) w = atoi(e);
+  warps = (int)(w < 1 ? 1 : (w > kChainMaxWarps ? kChainMaxWarps : w));
+  const long ctas = (S + warps - 1) / warps;
+  grid = (int)(ctas < m->num_sms ? ctas : m->num_sms);
+}
+int chain_hmax(const k2b_chain_args* a) {
+  const int it = a->num_iters_first > a->num_iters_followup ? a->num_iters_first : a->num_iters_followup;
+  return lbfgs_history_capacity(it);
+}
+}  // namespace
+
+extern "C" size_t k2b_chain_workspace_bytes(const k2b_model* m, int64_t num_sequences, int32_t optimizer,
+                                            int32_t max_iters) {
+  if (!m || num_sequences <= 0) return 0;
+  if (optimizer != K2B_OPT_LBFGS) return 256;
+  int grid, warps;
+  chain_geometry(m, num_sequences, grid, warps);
+  return sizeof(float) * (size_t)grid * warps * (size_t)wc::hist_floats(lbfgs_history_capacity(max_iters));
+}
+
+extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* stream) {
+  if (!a) return fail(K2B_EINVAL, "null args");
+  int rc = check_common(m, a->num_sequences, a->num_obs, a->init_expr);
+  if (rc) return rc;
+  if (a->frames_per_sequence <= 0) return fail(K2B_EINVAL, "frames_per_sequence must be positive");
+  if (a->optimizer != K2B_OPT_ADAM && a->optimizer != K2B_OPT_LBFGS) return fail(K2B_EINVAL, "unknown optimizer");
+  if (!a->targets || !a->init_pose || !a->init_betas || !a->init_transl || !a->out_pose || !a->out_betas ||
+      !a->out_transl || !a->out_loss)
+    return fail(K2B_EINVAL, "missing required array");
+  if (a->num_iters_first < 0 || a->num_iters_followup < 0) return fail(K2B_EINVAL, "iteration budgets must be >= 0");
+  if (a->conf_mode < 0 || a->conf_mode > 2) return fail(K2B_EINVAL, "conf_mode must be 0, 1 or 2");
+  const int hmax = chain_hmax(a);
+  int grid, warps;
+  chain_geometry(m, a->num_sequences, grid, warps);
+  while (warps > 1 && chain_smem_bytes(m->num_shape, warps, hmax) > 227 * 1024) --warps;   // very long budgets
+  if (chain_smem_bytes(m->num_shape, warps, hmax) > 227 * 1024) return fail(K2B_EUNSUPPORTED, "iteration budget too large");
+  wc::ChainParams p{};
+  p.num_seq = a->num_sequences;
+  p.frames = a->frames_per_sequence;
+  p.first_seq_ind = a->first_seq_ind;
+  p.chain = a->chain_init;
+  p.iters_first = a->num_iters_first;
+  p.iters_follow = a->num_iters_followup;
+  p.lbfgs = a->optimizer == K2B_OPT_LBFGS;
+  p.freeze_betas = a->freeze_betas;
+  p.conf_mode = a->conf ? a->conf_mode : 0;
+  p.lr = a->lr;
+  p.joint_w2 = a->joint_loss_weight * a->joint_loss_weight;
+  p.keep_w2 = a->pose_preserve_weight * a->pose_preserve_weight;
+  p.targets = a->targets; p.conf = a->conf;
+  p.init_pose = a->init_pose; p.init_betas = a->init_betas; p.init_transl = a->init_transl; p.init_expr = a->init_expr;
+  p.preserve_pose = a->preserve_pose;
+  p.out_pose = a->out_pose; p.out_betas = a->out_betas; p.out_transl = a->out_transl; p.out_expr = a->out_expr;
+  p.out_loss = a->out_loss; p.out_joints = a->out_joints; p.out_evals = a->out_evals;
+  p.hmax = hmax;
+  p.hist = nullptr;
+  if (p.lbfgs) {
+    const size_t need = sizeof(float) * (size_t)grid * warps * (size_t)wc::hist_floats(hmax);
+    if (!a->workspace || a->workspace_bytes < need) return fail(K2B_ENOMEM, "workspace too small");
+    p.hist = (float*)a->workspace;
+  }
+  for (int k = 1; k <= wc::kAdamTableW; ++k) {
+    p.adam_step[k - 1] = (float)((double)a->lr / (1.0 - std::pow(0.9, (double)k)));
+    p.adam_bc2[k - 1] = (float)std::sqrt(1.0 - std::pow(0.999, (double)k));
+  }
+  const ChainTables tab{m->prec, m->mu, m->nlw, m->rel};
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (a->num_obs == 24) e = launch_chain<10, 24>(p, tab, grid, warps, st);
+  else if (m->num_shape == 20) e = launch_chain<20, 22>(p, tab, grid, warps, st);
+  else e = launch_chain<10, 22>(p, tab, grid, warps, st);
+  g_launches.fetch_add(1);
+  if (e != cudaSuccess) return fail(K2B_ECUDA, std::string("chain kernel launch: ") + cudaGetErrorString(e));
+  return K2B_OK;
 }
 
 // ---- host-buffer variant: H2D, fit, D2H, synchronise ---------------------------------------

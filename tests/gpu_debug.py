@@ -133,3 +133,38 @@ if what == "meshx":
             print(f"{mt} mesh B={B} {'cuda-core' if fp32 == '1' else 'tcgen05  '}: {dt*1e3:.2f} ms -> {B/dt/1e6:.3f} M frames/s, "
                   f"{B*nv*12/dt/1e9:.0f} GB/s of vertex output", flush=True)
         print(f"  max |tc - fp32| = {(res['0'] - res['1']).abs().max().item():.3e} m")
+if what == "chain":
+    # warp-per-sequence kernel: time S sequences x T frames (schedule S1) and the lone-frame latency
+    cfgs = [(1, 1), (1, 64), (148, 64), (256, 64), (1024, 32), (2368, 16), (8192, 8)]
+    if len(sys.argv) > 2:
+        cfgs = [tuple(int(v) for v in a.split("x")) for a in sys.argv[2:]]
+    for opt in ("adam", "lbfgs"):
+        f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=opt == "lbfgs")
+        for S, Tn in cfgs:
+            mo = syn.make_motion(S * Tn, seed=3)
+            tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22).reshape(S, Tn, 22, 3).cuda()
+            init = dict(global_orient=torch.zeros(S, 3), body_pose=torch.zeros(S, 69), betas=torch.zeros(S, 10),
+                        transl=mo["transl"].reshape(S, Tn, 3)[:, 0].contiguous())
+            init = {k: v.cuda() for k, v in init.items()}
+            f.fit_chain(init, tgt, None, with_mesh=False)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            o = f.fit_chain(init, tgt, None, with_mesh=False)
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            ev = o["evals"].float().reshape(S, Tn)
+            err = float((o["fit_joints"].reshape(S, Tn, 22, 3) - tgt).norm(dim=-1).mean())
+            print(f"chain {opt} S={S} T={Tn}: {dt*1e3:.2f} ms, {S*Tn/dt/1e3:.1f} k frames/s, "
+                  f"{dt/Tn*1e6:.1f} us per frame-step, evals first/follow {float(ev[:, 0].mean()):.1f}/"
+                  f"{float(ev[:, 1:].mean()) if Tn > 1 else 0:.1f}, mean joint err {err*1e3:.2f} mm", flush=True)
+    import keypoints2body_b200 as k2b, tempfile
+    d = tempfile.mkdtemp(); syn.write_assets(d + "/data/models", seed=0); os.chdir(d)
+    frame = g["seq_in_target"][0]
+    for cfg in (None, dict(use_lbfgs=False)):
+        for kern in ("1024", "0"):
+            os.environ["K2B_WARP_MAX_FRAMES"] = kern
+            r = k2b.optimize_params_frame(frame, body_model="smpl", joint_layout="AMASS", model=w, config=cfg)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(10):
+                r = k2b.optimize_params_frame(frame, body_model="smpl", joint_layout="AMASS", model=w, config=cfg)
+            torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 10
+            print(f"optimize_params_frame {'lbfgs' if cfg is None else 'adam'} kernel={'warp' if kern != '0' else 'frame'}: "
+                  f"{dt*1e3:.2f} ms per call, loss {float(r.loss):.1f}", flush=True)

@@ -29,9 +29,13 @@ def fitters(weights, gmm):
         key = (mt, cat, tuple(sorted(kw.items())))
         if key not in cache:
             cache[key] = WorldSpaceFitter(weights(mt), joints_category=cat, model_type=mt, gmm=gmm, **kw)
+        cache[key].warp_kernel_max_frames = 0      # one thread per frame unless a test asks for the warp kernel
         return cache[key]
 
     return get
+
+
+KERNELS = ("frame", "warp")      # k2b_fit_batch (one thread per frame) / k2b_fit_chain (one warp per frame)
 
 
 def cpu(x):
@@ -82,13 +86,14 @@ def golden_init(g, tag, mt):
     return init
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("tag", sorted(ADAM_CASES))
-def test_adam_fit_vs_reference_goldens(goldens, fitters, tag):
+def test_adam_fit_vs_reference_goldens(goldens, fitters, tag, kernel):
     mt, iters, seq_ind, freeze, nobs = ADAM_CASES[tag]
     g = goldens
     f = fitters(mt, "SMPL24" if nobs == 24 else "AMASS", use_lbfgs=False)
     out = f.fit_batch(golden_init(g, tag, mt), T(g[tag + "_in_target"]), torch.ones(nobs), seq_ind=seq_ind,
-                      num_iters=iters, freeze_betas=freeze)
+                      num_iters=iters, freeze_betas=freeze, kernel=kernel)
     p = out["params"]
     pose = np.concatenate([cpu(p["global_orient"]), cpu(p["body_pose"])], axis=1)
     assert np.abs(pose - g[tag + "_pose"]).max() < 1e-4
@@ -117,11 +122,12 @@ def make_problem(weights, n, seed, noise=0.005, init_noise=0.1):
     return tgt, init
 
 
-def test_adam_fit_vs_oracle_batch(fitters, shims, oracle_prior, weights):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_adam_fit_vs_oracle_batch(fitters, shims, oracle_prior, weights, kernel):
     """Fresh seeded inputs, B = 96 (ragged vs the 128-frame tile), per-frame confidences."""
     tgt, init = make_problem(weights, 96, seed=101)
     f = fitters("smpl", use_lbfgs=False)
-    out = f.fit_batch(init, tgt, torch.ones(22), seq_ind=4, num_iters=10)
+    out = f.fit_batch(init, tgt, torch.ones(22), seq_ind=4, num_iters=10, kernel=kernel)
     full = {k: None for k in rp.PARAM_ORDER}
     full.update(init)
     ref = rp.fit_frame(shims("smpl"), oracle_prior, full, tgt, torch.ones(22), seq_ind=4, use_lbfgs=False,
@@ -133,13 +139,14 @@ def test_adam_fit_vs_oracle_batch(fitters, shims, oracle_prior, weights):
     assert (cpu(out["vertices"]) - ref["vertices"].numpy()).__abs__().max() < 1e-4
 
 
-def test_lbfgs_fit_statistics_vs_oracle(fitters, shims, oracle_prior, weights):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_lbfgs_fit_statistics_vs_oracle(fitters, shims, oracle_prior, weights, kernel):
     """G4: budgets honoured like torch (max_eval = 5/4 max_iter, one-evaluation overshoot) and the
     distribution of final losses / joint errors is not worse than the reference's."""
     n = 12
     tgt, init = make_problem(weights, n, seed=202)
     f = fitters("smpl", use_lbfgs=True)
-    out = f.fit_batch(init, tgt, torch.ones(22), seq_ind=0)
+    out = f.fit_batch(init, tgt, torch.ones(22), seq_ind=0, kernel=kernel)
     ev = cpu(out["evals"])
     assert ev.max() <= 30 * 5 // 4 + 1 and ev.min() >= 30
     ref_loss, ref_err = [], []
@@ -343,3 +350,78 @@ def test_extreme_inputs_terminate_and_match_oracle(fitters, shims, oracle_prior,
         ev = cpu(out["evals"])
         assert ev.max() <= 10 * 5 // 4 + 2 and ev.min() >= 1
         assert np.isfinite(cpu(out["loss"])[2:]).all()           # finite frames are unaffected by their neighbours
+
+
+# ---- warp-per-sequence kernel (k2b_fit_chain): the reference's serial frame loop in one launch ----------
+def _chain_init(g, shims, S):
+    tgt = T(g["seq_in_target"])
+    with torch.no_grad():
+        root = shims("smpl")(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69),
+                             betas=torch.zeros(1, 10)).joints[0, 0]
+    init = dict(global_orient=torch.zeros(S, 3), body_pose=torch.zeros(S, 69), betas=torch.zeros(S, 10),
+                transl=(tgt[0, 0] - root).expand(S, 3).contiguous())
+    return init, tgt
+
+
+@pytest.mark.parametrize("name,chain", [("seq_adam_chain", True), ("seq_adam_indep", False)])
+def test_chain_kernel_vs_reference_sequence_goldens(goldens, fitters, shims, name, chain):
+    """Five copies of the golden sequence, one warp each, per-frame confidences: every copy must reproduce the
+    reference's optimize_params_sequence (api/sequence.py:214-281) result, mesh included."""
+    g, S = goldens, 5
+    init, tgt = _chain_init(g, shims, S)
+    f = fitters("smpl", use_lbfgs=False)
+    out = f.fit_chain(init, tgt[None].expand(S, -1, -1, -1), torch.ones(S, tgt.shape[0], 22), chain=chain)
+    Tn = tgt.shape[0]
+    p = out["params"]
+    pose = np.concatenate([cpu(p["global_orient"]), cpu(p["body_pose"])], axis=1).reshape(S, Tn, 72)
+    for s in range(S):
+        assert np.abs(pose[s] - g[name + "_pose"]).max() < 1e-4
+        assert np.abs(cpu(p["betas"]).reshape(S, Tn, 10)[s] - g[name + "_betas"]).max() < 1e-4
+        assert np.abs(cpu(p["transl"]).reshape(S, Tn, 3)[s] - g[name + "_transl"]).max() < 1e-5
+        assert np.abs(cpu(out["joints"]).reshape(S, Tn, -1, 3)[s] - g[name + "_joints"]).max() < 1e-4
+        np.testing.assert_allclose(cpu(out["loss"]).reshape(S, Tn)[s], g[name + "_loss"], rtol=1e-4)
+    assert (cpu(out["evals"]).reshape(S, Tn) == np.array([30] + [10] * (Tn - 1))).all()
+
+
+def test_chain_kernel_many_sequences_vs_frame_kernel(fitters, weights):
+    """3 000 two-frame chains (more warps than one wave holds; 16 warps per CTA) against the same chains run as
+    two launches of the one-thread-per-frame kernel.  Both are within 1e-4 of the oracle, so within 2e-4 of each other."""
+    S = 3000
+    tgt, init = make_problem(weights, 2 * S, seed=303)
+    tgt = tgt.reshape(S, 2, 22, 3)
+    init = {k: v[:S].contiguous() for k, v in init.items()}
+    f = fitters("smpl", use_lbfgs=False)
+    out = f.fit_chain(init, tgt, None, with_mesh=False)
+    a = f.fit_batch(init, tgt[:, 0], None, seq_ind=0, with_mesh=False, kernel="frame")
+    b = f.fit_batch(a["params"], tgt[:, 1], None, seq_ind=1, with_mesh=False, kernel="frame")
+    for k in ("global_orient", "body_pose", "betas", "transl"):
+        got = cpu(out["params"][k]).reshape(S, 2, -1)
+        assert np.abs(got[:, 0] - cpu(a["params"][k])).max() < 2e-4, k
+        assert np.abs(got[:, 1] - cpu(b["params"][k])).max() < 2e-4, k
+    np.testing.assert_allclose(cpu(out["loss"]).reshape(S, 2)[:, 1], cpu(b["loss"]), rtol=1e-3)
+
+
+def test_chain_kernel_lbfgs_sequence_statistics(fitters, weights):
+    """L-BFGS chains (reference default): budgets like torch's and final losses in distribution equal to the
+    same chain run frame by frame through the one-thread-per-frame kernel (same machine, different rounding)."""
+    from keypoints2body_b200 import synthetic as syn
+
+    S, Tn = 24, 6
+    w = weights("smpl")
+    mo = syn.make_motion(S * Tn, seed=404)
+    tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22).reshape(S, Tn, 22, 3)
+    init = dict(global_orient=torch.zeros(S, 3), body_pose=torch.zeros(S, 69), betas=torch.zeros(S, 10),
+                transl=mo["transl"].reshape(S, Tn, 3)[:, 0].contiguous())
+    f = fitters("smpl", use_lbfgs=True)
+    out = f.fit_chain(init, tgt, None, with_mesh=False)
+    ev = cpu(out["evals"]).reshape(S, Tn)
+    assert ev[:, 0].max() <= 38 and ev[:, 1:].max() <= 13
+    prev, losses = init, []
+    for t in range(Tn):
+        r = f.fit_batch(prev, tgt[:, t], None, seq_ind=t, with_mesh=False, kernel="frame")
+        prev = r["params"]
+        losses.append(cpu(r["loss"]))
+    ours, ref = cpu(out["loss"]).reshape(S, Tn), np.stack(losses, axis=1)
+    print("chain lbfgs median loss per frame", np.median(ours, axis=0), "frame kernel", np.median(ref, axis=0))
+    assert np.median(ours[:, -1]) <= 1.25 * np.median(ref[:, -1])
+    assert np.median(ours) <= 1.25 * np.median(ref)
