@@ -39,7 +39,8 @@ namespace wc {
 constexpr int kPStride = 72;                       // row stride of a precision matrix (69 + 3 zero columns)
 constexpr int kPFloats = kBodyDim * kPStride;      // per component
 constexpr int kWarpVec = 96;                       // 32 lanes x 3 elements
-constexpr int kWarpMemFloats = 96 + 80 + 72 + 4 * kWarpVec;   // xs, dbuf, ybuf, 4 gradient slots
+constexpr int kDbufStride = 80;                    // one staged difference vector (72 used)
+constexpr int kWarpMemFloats = 96 + 2 * kDbufStride + 80 + 256 + 4 * kWarpVec;   // xs, dbuf x2, ybuf, qbuf, 4 gradient slots
 
 K2B_HD int lane_id() {
 #if defined(__CUDA_ARCH__)
@@ -108,10 +109,44 @@ struct WarpTables {    // shared by every warp of a CTA (shared memory on the de
 };
 struct WarpMem {       // per-warp shared memory, kWarpMemFloats floats
   float* xs;           // [96] evaluation point, readable by every lane
-  float* dbuf;         // [72 (+8)] x_body - mu_m
+  float* dbuf;         // [2][kDbufStride] x_body - mu_m, double-buffered over the components
   float* ybuf;         // [72] P d of the arg-min component
-  float* gs;           // [4][96] gradient slots (slot 0 only for Adam)
+  float* qbuf;         // [8][32] per-lane partial sums of d.P_m d
+  float* gs;           // [4][96] gradient slots (L-BFGS)
 };
+K2B_HD WarpMem make_warp_mem(float* w) {
+  return WarpMem{w, w + 96, w + 96 + 2 * kDbufStride, w + 96 + 2 * kDbufStride + 80, w + 96 + 2 * kDbufStride + 80 + 256};
+}
+
+// ---- GMM prior pieces ----------------------------------------------------------------------------
+// Lane -> (row group rg, column chunk cc): lanes 0-7 / 8-15 / 16-23 are row groups 0 / 1 / 2 with chunks 0..7,
+// lanes 24-26 are chunk 8 of the three groups.  Chunk cc covers columns 4cc..4cc+3 and 36+4cc..36+4cc+3, row
+// group rg the rows 3 it + rg: every quarter-warp of an LDS.128 then touches 32 distinct banks.
+K2B_HD void gmm_stage(const WarpTables& tb, float* dbuf, const float (&xr)[3], bool body_owner, int i0, int m) {
+  if (body_owner) {
+    const float* mum = tb.mu + m * kMuStride + i0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dbuf[i0 + c] = xr[c] - mum[c];
+  }
+}
+K2B_HD void gmm_rows(const WarpTables& tb, const float* dbuf, int m, int rg, int cc, float2 (&acc)[4]) {
+  const float* row = tb.P + (size_t)m * kPFloats + rg * kPStride + 4 * cc;
+  const float* dj = dbuf + rg;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll 23
+  for (int it = 0; it < 23; ++it, row += 3 * kPStride, dj += 3) {
+    const float d1 = *dj;
+    const float2 d2 = make_float2(d1, d1);
+    const float4 l0 = *reinterpret_cast<const float4*>(row);
+    const float4 l1 = *reinterpret_cast<const float4*>(row + 36);
+    acc[0] = fma2(make_float2(l0.x, l0.y), d2, acc[0]);
+    acc[1] = fma2(make_float2(l0.z, l0.w), d2, acc[1]);
+    acc[2] = fma2(make_float2(l1.x, l1.y), d2, acc[2]);
+    acc[3] = fma2(make_float2(l1.z, l1.w), d2, acc[3]);
+  }
+}
+
 struct FrameObs {      // this lane's share of the frame's observations
   float tx, ty, tz, w; // lane j < K: target and weight joint_w^2 conf_j^2 of joint j
   float keep[3];       // preserve pose of the owned body-pose entries
@@ -137,7 +172,7 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
   const int lane = lane_id();
 #pragma unroll
   for (int c = 0; c < 3; ++c) wm.xs[3 * lane + c] = xr[c];
-  if (lane == 0) { wm.dbuf[69] = 0.f; wm.dbuf[70] = 0.f; wm.dbuf[71] = 0.f; }
+  if (lane < 6) wm.dbuf[(lane / 3) * kDbufStride + 69 + lane % 3] = 0.f;   // padding columns of both buffers
   wsync();
   float shape[NS];
 #pragma unroll
@@ -261,60 +296,68 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
   if (with_priors) {
     const bool body_owner = lane >= 1 && lane < 24;     // elements 3 .. 71
     const int i0 = body_owner ? 3 * lane - 3 : 0;       // body-pose index of xr[0]
-    const int rg = lane / 9, cc = lane - 9 * rg;
+    const int rg = lane < 24 ? lane >> 3 : lane - 24;
+    const int cc = lane < 24 ? lane & 7 : 8;
     const bool act = lane < 27;
-    float best = INFINITY;
-    int bm = 0;
-    float2 yb[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float2 acc[4];
+    gmm_stage(tb, wm.dbuf, xr, body_owner, i0, 0);
 #pragma unroll 1
     for (int m = 0; m < kGmmM; ++m) {
-      if (body_owner) {
-        const float* mum = tb.mu + m * kMuStride + i0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) wm.dbuf[i0 + c] = xr[c] - mum[c];
-      }
-      wsync();
-      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      wsync();           // d_m is staged; every lane is done with the buffer d_{m+1} goes to
+      float* dm = wm.dbuf + (m & 1) * kDbufStride;
+      if (m + 1 < kGmmM) gmm_stage(tb, wm.dbuf + ((m + 1) & 1) * kDbufStride, xr, body_owner, i0, m + 1);
       float part = 0.f;
       if (act) {
-        const float* row = tb.P + (size_t)m * kPFloats + rg * kPStride + 8 * cc;
-        const float* dj = wm.dbuf + rg;
-#pragma unroll 23
-        for (int it = 0; it < 23; ++it, row += 3 * kPStride, dj += 3) {
-          const float d1 = *dj;
-          const float2 d2 = make_float2(d1, d1);
-          const float4 l0 = reinterpret_cast<const float4*>(row)[0];
-          const float4 l1 = reinterpret_cast<const float4*>(row)[1];
-          acc[0] = fma2(make_float2(l0.x, l0.y), d2, acc[0]);
-          acc[1] = fma2(make_float2(l0.z, l0.w), d2, acc[1]);
-          acc[2] = fma2(make_float2(l1.x, l1.y), d2, acc[2]);
-          acc[3] = fma2(make_float2(l1.z, l1.w), d2, acc[3]);
-        }
-        const float4 e0 = reinterpret_cast<const float4*>(wm.dbuf + 8 * cc)[0];
-        const float4 e1 = reinterpret_cast<const float4*>(wm.dbuf + 8 * cc)[1];
+        gmm_rows(tb, dm, m, rg, cc, acc);
+        const float4 e0 = *reinterpret_cast<const float4*>(dm + 4 * cc);
+        const float4 e1 = *reinterpret_cast<const float4*>(dm + 36 + 4 * cc);
         part = fmaf(acc[0].x, e0.x, fmaf(acc[0].y, e0.y, fmaf(acc[1].x, e0.z, acc[1].y * e0.w))) +
                fmaf(acc[2].x, e1.x, fmaf(acc[2].y, e1.y, fmaf(acc[3].x, e1.z, acc[3].y * e1.w)));
       }
-      const float q = wsum(part);
-      const float ll = fmaf(0.5f, q, tb.nlw[m]);
-      if (ll < best) {   // strict: first minimum wins, like torch.min
-        best = ll;
-        bm = m;
+      wm.qbuf[m * 32 + lane] = part;
+    }
+    wsync();
+    // q_m = sum of the 32 partials of component m: lanes 4m..4m+3 add 8 each, two butterfly steps finish;
+    // then the arg-min over the components (first minimum wins, like torch.min) by three more steps
+    float best;
+    int bm = lane >> 2;
+    {
+      const float4 a = *reinterpret_cast<const float4*>(wm.qbuf + 8 * lane);
+      const float4 b = *reinterpret_cast<const float4*>(wm.qbuf + 8 * lane + 4);
+      float q = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+      q += shfl(q, lane ^ 1);
+      q += shfl(q, lane ^ 2);
+      best = fmaf(0.5f, q, tb.nlw[bm]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) yb[k] = acc[k];
+      for (int msk = 4; msk <= 16; msk <<= 1) {
+        const float ol = shfl(best, lane ^ msk);
+        const int om = (int)shfl((float)bm, lane ^ msk);
+        if (ol < best || (ol == best && om < bm)) {
+          best = ol;
+          bm = om;
+        }
       }
-      wsync();           // dbuf is rewritten for the next component
     }
     if (gmm_component) *gmm_component = bm;
     uni = fmaf(kPosePriorW2, best, uni);
     if (with_grad) {
-      // y = sum over the three row groups; lanes 0..8 then hold columns 8 lane .. 8 lane + 7
-      float y[8] = {yb[0].x, yb[0].y, yb[1].x, yb[1].y, yb[2].x, yb[2].y, yb[3].x, yb[3].y};
+      // y = P d of the arg-min component, recomputed (cheaper than keeping eight results alive), then summed
+      // over the three row groups: lanes 0..7 and 24 hold the totals of their chunk
+      gmm_stage(tb, wm.dbuf, xr, body_owner, i0, bm);
+      wsync();
+      if (act) gmm_rows(tb, wm.dbuf, bm, rg, cc, acc);
+      else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) y[k] = (y[k] + shfl(y[k], lane + 9)) + shfl(y[k], lane + 18);
-      if (lane < 9) {
-        reinterpret_cast<float4*>(wm.ybuf + 8 * lane)[0] = make_float4(y[0], y[1], y[2], y[3]);
-        reinterpret_cast<float4*>(wm.ybuf + 8 * lane)[1] = make_float4(y[4], y[5], y[6], y[7]);
+        for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+      }
+      float y[8] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, acc[3].x, acc[3].y};
+      const int p1 = lane < 24 ? (lane + 8) % 24 : 24 + (lane - 23) % 3;
+      const int p2 = lane < 24 ? (lane + 16) % 24 : 24 + (lane - 22) % 3;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] = (y[k] + shfl(y[k], p1)) + shfl(y[k], p2);
+      if (act && rg == 0) {
+        *reinterpret_cast<float4*>(wm.ybuf + 4 * cc) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(wm.ybuf + 36 + 4 * cc) = make_float4(y[4], y[5], y[6], y[7]);
       }
       wsync();
     }

@@ -15,7 +15,7 @@
 
 namespace k2b {
 
-constexpr int kChainMaxWarps = 16;
+constexpr int kChainMaxWarps = 12;
 
 struct ChainTables {       // global-memory copies owned by k2b_model
   const float* P;          // [8][69][72]
@@ -60,7 +60,7 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
   const int warp = tid >> 5, nwarps = nthr >> 5;
   const wc::WarpTables tb{s_P, s_mu, s_nlw, reinterpret_cast<const float4*>(s_rel)};
   float* w = s_warp + (size_t)warp * wc::warp_mem_floats(p.hmax);
-  const wc::WarpMem wm{w, w + 96, w + 176, w + 248};
+  const wc::WarpMem wm = wc::make_warp_mem(w);
   float* ro = w + wc::kWarpMemFloats;
   float* al = ro + p.hmax;
   const long slot = (long)blockIdx.x * nwarps + warp;

@@ -168,3 +168,16 @@ if what == "chain":
             torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 10
             print(f"optimize_params_frame {'lbfgs' if cfg is None else 'adam'} kernel={'warp' if kern != '0' else 'frame'}: "
                   f"{dt*1e3:.2f} ms per call, loss {float(r.loss):.1f}", flush=True)
+if what == "chainprof":
+    opt = sys.argv[2] if len(sys.argv) > 2 else "adam"
+    S, Tn = (int(v) for v in (sys.argv[3] if len(sys.argv) > 3 else "256x16").split("x"))
+    f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=opt == "lbfgs")
+    mo = syn.make_motion(S * Tn, seed=3)
+    tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22).reshape(S, Tn, 22, 3).cuda()
+    init = dict(global_orient=torch.zeros(S, 3), body_pose=torch.zeros(S, 69), betas=torch.zeros(S, 10),
+                transl=mo["transl"].reshape(S, Tn, 3)[:, 0].contiguous())
+    init = {k: v.cuda() for k, v in init.items()}
+    for _ in range(2):
+        o = f.fit_chain(init, tgt, None, with_mesh=False)
+    torch.cuda.synchronize()
+    print("ok", float(o["loss"].mean()))

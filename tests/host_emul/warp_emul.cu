@@ -131,7 +131,7 @@ template <int NS, int K>
 void lane_job() {
   wc::WarpTables tb{g.m->P.data(), g.m->mu.data(), g.m->nlw.data(), (const float4*)g.m->rel.data()};
   float* w = g.wmem.data();
-  wc::WarpMem wm{w, w + 96, w + 176, w + 248};
+  const wc::WarpMem wm = wc::make_warp_mem(w);
   if (g.eval_only) {
     const int lane = wc::lane_id();
     float xr[3], gr[3];
