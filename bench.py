@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=256 * SEQ_LEN)
     ap.add_argument("--optimizer", default="lbfgs", choices=["lbfgs", "adam"])
+    ap.add_argument("--schedule", default="two_sweep", choices=["two_sweep", "reference"],
+                    help="two_sweep = S2 (frame-parallel, halo exchange); reference = S1, the reference's own serial "
+                         "chain (frame t starts from frame t-1), one warp per sequence, whole sequences per GPU")
     ap.add_argument("--no-vertices", action="store_true", help="skip the vertex output (joints only)")
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="0 = choose for ~20 s of CPU work")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -116,9 +119,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(frames: int, threads: int, optimizer: str, seed: int = 77):
+def cpu_reference_rate(frames: int, threads: int, optimizer: str, seed: int = 77, schedule: str = "two_sweep"):
     """Times the oracle port (the reference's algorithm on torch CPU, B = 1 per frame like the API,
-    full-mesh forward per evaluation like smplx) on `frames` frames with schedule S2."""
+    full-mesh forward per evaluation like smplx) on `frames` frames with schedule S2 or S1."""
     from keypoints2body_b200 import synthetic as syn
     from oracle import reference_port as rp
     from oracle.smplx_shim import BodyModelShim
@@ -131,6 +134,16 @@ def cpu_reference_rate(frames: int, threads: int, optimizer: str, seed: int = 77
     lbfgs = optimizer == "lbfgs"
     conf = torch.ones(22)
     root0 = model(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10)).joints[:, 0]
+
+    def chain_pass():      # S1: api/sequence.py:214-281
+        prev = {k: None for k in rp.PARAM_ORDER}
+        prev.update(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10),
+                    transl=tgt[0:1, 0] - root0)
+        for t in range(frames):
+            prev = rp.fit_frame(model, prior, prev, tgt[t:t + 1], conf, seq_ind=t, use_lbfgs=lbfgs)["params"]
+
+    if schedule == "reference":
+        return chain_pass
 
     def one_pass():
         s0 = []
@@ -178,13 +191,13 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    probe = cpu_reference_rate(2, threads, args.optimizer)
+    probe = cpu_reference_rate(2, threads, args.optimizer, schedule=args.schedule)
     t0 = time.perf_counter()
     probe()
     per_frame = (time.perf_counter() - t0) / 2
     budget = 150.0 / max(1, args.steps + args.warmup)
     n = args.cpu_sample_frames or int(max(2, min(64, budget / per_frame)))
-    one_pass = cpu_reference_rate(n, threads, args.optimizer)
+    one_pass = cpu_reference_rate(n, threads, args.optimizer, schedule=args.schedule)
     for _ in range(args.warmup):
         one_pass()
     t0 = time.perf_counter()
@@ -192,17 +205,57 @@ def run_reference(args):
         one_pass()
     dt = (time.perf_counter() - t0) / args.steps
     val = n / dt
-    sample = (f"{n} frames/step, schedule S2 (30 + 10 iteration budgets), {args.optimizer}, B=1 per frame, "
+    sched = "S2 (30 + 10 iteration budgets)" if args.schedule == "two_sweep" else "S1 (serial chain, 30 then 10 iterations)"
+    sample = (f"{n} frames/step, schedule {sched}, {args.optimizer}, B=1 per frame, "
               f"torch {torch.__version__} CPU, full-mesh forward per evaluation")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "bounded sample of the ours-arm workload: " + sample, "optimizer": args.optimizer},
+        "config": {"workload": "bounded sample of the ours-arm workload: " + sample, "optimizer": args.optimizer,
+                   "schedule": args.schedule},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "cpu_baseline_batched_adam": cpu_reference_batched_adam(1024, threads),
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+class ChainRunner:
+    """Schedule S1 for the benchmark: every sequence is walked serially by one warp (k2b_fit_chain), then one
+    batched mesh pass.  Same interface as SequenceBatchFitter as far as run_ours uses it."""
+
+    def __init__(self, fitter, num_frames, with_vertices=True):
+        self.f, self.F, self.S = fitter, num_frames, num_frames // SEQ_LEN
+        dev = fitter.device
+        self.vertices = torch.empty(num_frames, fitter.native.num_vertices, 3, device=dev) if with_vertices else None
+        z = {"global_orient": torch.zeros(1, 3, device=dev), "body_pose": torch.zeros(1, 69, device=dev),
+             "betas": torch.zeros(1, 10, device=dev)}
+        self.root0 = fitter.forward_batch(z, with_vertices=False)["joints"][:, 0, :]
+        self.init = {"global_orient": torch.zeros(self.S, 3, device=dev), "body_pose": torch.zeros(self.S, 69, device=dev),
+                     "betas": torch.zeros(self.S, 10, device=dev)}
+        self.kernel_events = None
+        self.evals0 = self.evals1 = torch.zeros(1, device=dev)
+
+    def run(self, targets, seq_ind=None, params_ready=None):
+        f = self.f
+        tg = targets.view(self.S, SEQ_LEN, 22, 3)
+        init = dict(self.init, transl=tg[:, 0, 0] - self.root0)     # root alignment of frame 0 (engine.py:89-128)
+        ev = self.kernel_events
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        out = f.fit_chain(init, tg, None, with_mesh=False)
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
+        if params_ready is not None:
+            params_ready.record()
+        p = out["params"]
+        out["pose"] = torch.cat([p["global_orient"], p["body_pose"]], dim=1)
+        mesh = f.forward_batch(p, with_vertices=self.vertices is not None, out_vertices=self.vertices)
+        out["joints"], out["vertices"] = mesh["joints"], mesh["vertices"]
+        self.evals0 = out["evals"]
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -229,9 +282,13 @@ def run_ours(args):
     fitter = WorldSpaceFitter(weights, joints_category="AMASS", use_lbfgs=args.optimizer == "lbfgs",
                               model_type="smpl", gmm=syn.make_gmm(seed=0), device=dev)
     cfg = FrameOptimizeConfig()
-    sf = SequenceBatchFitter(fitter, F, cfg, with_vertices=not args.no_vertices)
+    chain = args.schedule == "reference"
+    if chain and F % SEQ_LEN:
+        raise SystemExit("--schedule reference needs whole sequences per GPU")
+    sf = ChainRunner(fitter, F, not args.no_vertices) if chain else SequenceBatchFitter(
+        fitter, F, cfg, with_vertices=not args.no_vertices)
     targets = make_targets(weights, lo, hi, dev)
-    seq_ind = seq_index(lo, hi, dev)
+    seq_ind = seq_index(lo, hi, dev)       # S2 only; S1 takes [lo, hi) as F / 4096 whole sequences
     lib = fitter.native.lib
 
     def barrier():
@@ -268,7 +325,7 @@ def run_ours(args):
     launches = (lib.k2b_launch_count() - launches0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
     torch.cuda.synchronize()
-    fit_ms = [a.elapsed_time(b) for a, b in sf.kernel_events]          # two fit launches per step
+    fit_ms = [a.elapsed_time(b) for a, b in sf.kernel_events]          # S2: two fit launches per step; S1: one
     sf.kernel_events = None
     out = step_device()
     evals_total = float(out["evals"].sum())
@@ -328,10 +385,14 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": (f"SMPL AMASS-22 sequence fit, {F} frames/GPU ({F // SEQ_LEN} sequences x {SEQ_LEN}; "
-                         "BASELINE configs[3] shard, each sequence = configs[1]), schedule S2: sweep0 30-iteration "
-                         f"budget + sweep1 10-iteration budget with pose-preserve, {args.optimizer}, "
+                         "BASELINE configs[3] shard, each sequence = configs[1]), "
+                         + ("schedule S1 = the reference's own serial chain (frame t starts from frame t-1's result; 30 "
+                            "iterations for frame 0, 10 + pose-preserve after), one warp per sequence, whole sequences "
+                            "per GPU, " if chain else
+                            "schedule S2: sweep0 30-iteration budget + sweep1 10-iteration budget with pose-preserve, ")
+                         + f"{args.optimizer}, "
                          + ("full mesh (6890 verts + 45 joints) per frame" if not args.no_vertices else "joints only")),
-            "optimizer": args.optimizer, "frames_per_gpu": F, "seq_len": SEQ_LEN,
+            "optimizer": args.optimizer, "schedule": args.schedule, "frames_per_gpu": F, "seq_len": SEQ_LEN,
             "l2_policy": "inputs larger than L2 (targets %.0f MB/GPU, outputs %.1f GB/GPU)" % (h2d / 1e6, mesh_bytes / 1e9),
             "evals_per_frame": evals_total / F, "mean_joint_error_m": mean_err,
         },
@@ -341,14 +402,15 @@ def run_ours(args):
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
         "roofline": {
-            "kernel": "fit_kernel<10,22,%s> (sweep 0 + sweep 1)" % ("lbfgs" if args.optimizer == "lbfgs" else "adam"),
+            "kernel": ("chain_kernel<10,22> (%s; one launch, latency-bound: F/4096 warps)" if chain else
+                       "fit_kernel<10,22,%s> (sweep 0 + sweep 1)") % ("lbfgs" if args.optimizer == "lbfgs" else "adam"),
             "bound": "fp32_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops if achieved and peak_tflops else None,
             "peak_source": "in-run FFMA micro-benchmark (k2b_fma_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f" % nominal,
             "frac_of_nominal": achieved / nominal if achieved else None,
-            "flop_per_eval": EVAL_FLOP["smpl"], "evals_per_launch": [evals0 + F, evals1 + F],
+            "flop_per_eval": EVAL_FLOP["smpl"], "evals_per_launch": [evals0 + F] if chain else [evals0 + F, evals1 + F],
             "ms_per_launch_pair": fit_ms_step, "share_of_step": fit_ms_step / ms_step,
-            "traffic": ncu_fit_traffic(args.optimizer, F),
+            "traffic": None if chain else ncu_fit_traffic(args.optimizer, F),
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the sweep-0 launch from the committed ncu "
                             "--set full capture (profiles/r01_fit_lbfgs_ncu_metrics.txt, same frame count); the "
                             "algorithmic HBM bytes are ~1.5 KB/frame, the rest is L-BFGS (s, y) history that does not fit L2",
@@ -365,18 +427,18 @@ def run_ours(args):
     del tf
     if world == 1 and not args.skip_cpu_baseline:
         threads = os.cpu_count() or 1
-        probe = cpu_reference_rate(2, threads, args.optimizer)
+        probe = cpu_reference_rate(2, threads, args.optimizer, schedule=args.schedule)
         t0 = time.perf_counter()
         probe()
         per_frame = (time.perf_counter() - t0) / 2
         n = args.cpu_sample_frames or int(max(2, min(64, 20.0 / per_frame)))
-        one_pass = cpu_reference_rate(n, threads, args.optimizer)
+        one_pass = cpu_reference_rate(n, threads, args.optimizer, schedule=args.schedule)
         t0 = time.perf_counter()
         one_pass()
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {
             "value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} frames, schedule S2 (30 + 10 budgets), {args.optimizer}, B=1 per frame, torch CPU, "
+            "sample": f"{n} frames, schedule {'S1 (serial chain)' if chain else 'S2 (30 + 10 budgets)'}, {args.optimizer}, B=1 per frame, torch CPU, "
                       "full-mesh forward per evaluation like the reference"}
         line["cpu_baseline_batched_adam"] = cpu_reference_batched_adam(1024, threads)
     print(json.dumps(line))

@@ -284,11 +284,20 @@ extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, vo
 
 // ---- warp-per-sequence fit (serial chains, small batches) ------------------------------------
 namespace {
-void chain_geometry(const k2b_model* m, long S, int& grid, int& warps) {
-  long w = (S + m->num_sms - 1) / m->num_sms;
-  if (const char* e = getenv("K2B_CHAIN_WARPS")) w = atoi(e);
-  warps = (int)(w < 1 ? 1 : (w > kChainMaxWarps ? kChainMaxWarps : w));
-  const long ctas = (S + warps - 1) / warps;
+// groups = sequences walked concurrently by one CTA; a group is 1 + helpers warps
+void chain_geometry(const k2b_model* m, long S, int& grid, int& groups, int& helpers) {
+  // few sequences: the launch is latency-bound and most schedulers idle, so a second warp per sequence takes
+  // the mixture prior; with enough sequences to fill the SMs one warp per sequence has the best throughput
+  helpers = S <= (long)m->num_sms * 6 ? 1 : 0;
+  if (const char* e = getenv("K2B_CHAIN_HELPERS")) helpers = atoi(e);
+  if (helpers < 0) helpers = 0;
+  if (helpers > 3) helpers = 3;
+  int cap = kChainMaxWarps / (1 + helpers);
+  if (helpers > 0 && cap > 7) cap = 7;            // two named barriers per group, ids 1..15
+  long g = (S + m->num_sms - 1) / m->num_sms;
+  if (const char* e = getenv("K2B_CHAIN_WARPS")) g = atoi(e);
+  groups = (int)(g < 1 ? 1 : (g > cap ? cap : g));
+  const long ctas = (S + groups - 1) / groups;
   grid = (int)(ctas < m->num_sms ? ctas : m->num_sms);
 }
 int chain_hmax(const k2b_chain_args* a) {
@@ -301,9 +310,9 @@ extern "C" size_t k2b_chain_workspace_bytes(const k2b_model* m, int64_t num_sequ
                                             int32_t max_iters) {
   if (!m || num_sequences <= 0) return 0;
   if (optimizer != K2B_OPT_LBFGS) return 256;
-  int grid, warps;
-  chain_geometry(m, num_sequences, grid, warps);
-  return sizeof(float) * (size_t)grid * warps * (size_t)wc::hist_floats(lbfgs_history_capacity(max_iters));
+  int grid, groups, helpers;
+  chain_geometry(m, num_sequences, grid, groups, helpers);
+  return sizeof(float) * (size_t)grid * groups * (size_t)wc::hist_floats(lbfgs_history_capacity(max_iters));
 }
 
 extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* stream) {
@@ -318,10 +327,12 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   if (a->num_iters_first < 0 || a->num_iters_followup < 0) return fail(K2B_EINVAL, "iteration budgets must be >= 0");
   if (a->conf_mode < 0 || a->conf_mode > 2) return fail(K2B_EINVAL, "conf_mode must be 0, 1 or 2");
   const int hmax = chain_hmax(a);
-  int grid, warps;
-  chain_geometry(m, a->num_sequences, grid, warps);
-  while (warps > 1 && chain_smem_bytes(m->num_shape, warps, hmax) > 227 * 1024) --warps;   // very long budgets
-  if (chain_smem_bytes(m->num_shape, warps, hmax) > 227 * 1024) return fail(K2B_EUNSUPPORTED, "iteration budget too large");
+  int grid, groups, helpers;
+  chain_geometry(m, a->num_sequences, grid, groups, helpers);
+  while (groups > 1 && chain_smem_bytes(m->num_shape, groups * (1 + helpers), hmax) > 227 * 1024) --groups;   // very long budgets
+  if (chain_smem_bytes(m->num_shape, groups * (1 + helpers), hmax) > 227 * 1024)
+    return fail(K2B_EUNSUPPORTED, "iteration budget too large");
+  const int warps = groups * (1 + helpers);
   wc::ChainParams p{};
   p.num_seq = a->num_sequences;
   p.frames = a->frames_per_sequence;
@@ -341,9 +352,10 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   p.out_pose = a->out_pose; p.out_betas = a->out_betas; p.out_transl = a->out_transl; p.out_expr = a->out_expr;
   p.out_loss = a->out_loss; p.out_joints = a->out_joints; p.out_evals = a->out_evals;
   p.hmax = hmax;
+  p.helpers = helpers;
   p.hist = nullptr;
   if (p.lbfgs) {
-    const size_t need = sizeof(float) * (size_t)grid * warps * (size_t)wc::hist_floats(hmax);
+    const size_t need = sizeof(float) * (size_t)grid * groups * (size_t)wc::hist_floats(hmax);
     if (!a->workspace || a->workspace_bytes < need) return fail(K2B_ENOMEM, "workspace too small");
     p.hist = (float*)a->workspace;
   }

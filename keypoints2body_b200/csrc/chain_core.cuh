@@ -113,9 +113,28 @@ struct WarpMem {       // per-warp shared memory, kWarpMemFloats floats
   float* ybuf;         // [72] P d of the arg-min component
   float* qbuf;         // [8][32] per-lane partial sums of d.P_m d
   float* gs;           // [4][96] gradient slots (L-BFGS)
+  // GMM delegation (chain_kernel.cuh, device only): `helpers` > 0 means this warp leads a group whose other
+  // warps scan the mixture components while it walks the kinematic tree.  Named barriers bar_id (work posted)
+  // and bar_id + 1 (results ready); helper h's shared-memory block starts at helper_mem + h * helper_stride.
+  int helpers;
+  int bar_id;
+  float* helper_mem;
+  int helper_stride;
 };
+constexpr int kYbufOff = 96 + 2 * kDbufStride;
 K2B_HD WarpMem make_warp_mem(float* w) {
-  return WarpMem{w, w + 96, w + 96 + 2 * kDbufStride, w + 96 + 2 * kDbufStride + 80, w + 96 + 2 * kDbufStride + 80 + 256};
+  return WarpMem{w, w + 96, w + kYbufOff, w + kYbufOff + 80, w + kYbufOff + 80 + 256, 0, 0, nullptr, 0};
+}
+K2B_HD void bar_arrive(int id, int threads) {
+#if defined(__CUDA_ARCH__)
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+#endif
+}
+K2B_HD void bar_sync(int id, int threads) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+#endif
 }
 
 // ---- GMM prior pieces ----------------------------------------------------------------------------
@@ -147,6 +166,84 @@ K2B_HD void gmm_rows(const WarpTables& tb, const float* dbuf, int m, int rg, int
   }
 }
 
+// Scans the components m0, m0 + step, ... of the max-mixture prior at the point whose owned elements are xr:
+// best = min(0.5 d.P_m d + nlw_m) (first minimum wins, like torch.min), bm its component; with want_y the
+// product P d of that component (its gradient) is left in wm.ybuf.  Uses wm.dbuf / qbuf / ybuf.
+K2B_HD void gmm_scan(const WarpTables& tb, const WarpMem& wm, const float (&xr)[3], int m0, int step, bool want_y,
+                     float& best, int& bm) {
+  const int lane = lane_id();
+  const bool body_owner = lane >= 1 && lane < 24;     // elements 3 .. 71
+  const int i0 = body_owner ? 3 * lane - 3 : 0;       // body-pose index of xr[0]
+  const int rg = lane < 24 ? lane >> 3 : lane - 24;
+  const int cc = lane < 24 ? lane & 7 : 8;
+  const bool act = lane < 27;
+  float2 acc[4];
+  if (lane < 6) wm.dbuf[(lane / 3) * kDbufStride + 69 + lane % 3] = 0.f;   // padding columns of both buffers
+  if (step > 1) {
+#pragma unroll
+    for (int m = 0; m < kGmmM; ++m) wm.qbuf[m * 32 + lane] = 0.f;
+  }
+  gmm_stage(tb, wm.dbuf, xr, body_owner, i0, m0);
+  int par = 0;
+#pragma unroll 1
+  for (int m = m0; m < kGmmM; m += step, par ^= 1) {
+    wsync();           // d_m is staged; every lane is done with the buffer the next d goes to
+    float* dm = wm.dbuf + par * kDbufStride;
+    if (m + step < kGmmM) gmm_stage(tb, wm.dbuf + (par ^ 1) * kDbufStride, xr, body_owner, i0, m + step);
+    float part = 0.f;
+    if (act) {
+      gmm_rows(tb, dm, m, rg, cc, acc);
+      const float4 e0 = *reinterpret_cast<const float4*>(dm + 4 * cc);
+      const float4 e1 = *reinterpret_cast<const float4*>(dm + 36 + 4 * cc);
+      part = fmaf(acc[0].x, e0.x, fmaf(acc[0].y, e0.y, fmaf(acc[1].x, e0.z, acc[1].y * e0.w))) +
+             fmaf(acc[2].x, e1.x, fmaf(acc[2].y, e1.y, fmaf(acc[3].x, e1.z, acc[3].y * e1.w)));
+    }
+    wm.qbuf[m * 32 + lane] = part;
+  }
+  wsync();
+  // q_m = sum of the 32 partials of component m: lanes 4m..4m+3 add 8 each, two butterfly steps finish;
+  // then the arg-min over the components by three more steps
+  bm = lane >> 2;
+  {
+    const float4 a = *reinterpret_cast<const float4*>(wm.qbuf + 8 * lane);
+    const float4 b = *reinterpret_cast<const float4*>(wm.qbuf + 8 * lane + 4);
+    float q = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+    q += shfl(q, lane ^ 1);
+    q += shfl(q, lane ^ 2);
+    best = (bm - m0) % step == 0 && bm >= m0 ? fmaf(0.5f, q, tb.nlw[bm]) : INFINITY;
+#pragma unroll
+    for (int msk = 4; msk <= 16; msk <<= 1) {
+      const float ol = shfl(best, lane ^ msk);
+      const int om = (int)shfl((float)bm, lane ^ msk);
+      if (ol < best || (ol == best && om < bm)) {
+        best = ol;
+        bm = om;
+      }
+    }
+  }
+  if (want_y) {
+    // y = P d of the arg-min component, recomputed (cheaper than keeping eight results alive), then summed
+    // over the three row groups: lanes 0..7 and 24 hold the totals of their chunk
+    gmm_stage(tb, wm.dbuf, xr, body_owner, i0, bm);
+    wsync();
+    if (act) gmm_rows(tb, wm.dbuf, bm, rg, cc, acc);
+    else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+    }
+    float y[8] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, acc[3].x, acc[3].y};
+    const int p1 = lane < 24 ? (lane + 8) % 24 : 24 + (lane - 23) % 3;
+    const int p2 = lane < 24 ? (lane + 16) % 24 : 24 + (lane - 22) % 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y[k] = (y[k] + shfl(y[k], p1)) + shfl(y[k], p2);
+    if (act && rg == 0) {
+      *reinterpret_cast<float4*>(wm.ybuf + 4 * cc) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(wm.ybuf + 36 + 4 * cc) = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    wsync();
+  }
+}
+
 struct FrameObs {      // this lane's share of the frame's observations
   float tx, ty, tz, w; // lane j < K: target and weight joint_w^2 conf_j^2 of joint j
   float keep[3];       // preserve pose of the owned body-pose entries
@@ -172,7 +269,10 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
   const int lane = lane_id();
 #pragma unroll
   for (int c = 0; c < 3; ++c) wm.xs[3 * lane + c] = xr[c];
-  if (lane < 6) wm.dbuf[(lane / 3) * kDbufStride + 69 + lane % 3] = 0.f;   // padding columns of both buffers
+  if (with_priors && wm.helpers > 0) {   // hand the point to the helper warps (they read xs and dbuf[0])
+    if (lane == 0) wm.dbuf[0] = with_grad ? 2.f : 1.f;
+    bar_arrive(wm.bar_id, 32 * (1 + wm.helpers));
+  }
   wsync();
   float shape[NS];
 #pragma unroll
@@ -296,78 +396,34 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
   if (with_priors) {
     const bool body_owner = lane >= 1 && lane < 24;     // elements 3 .. 71
     const int i0 = body_owner ? 3 * lane - 3 : 0;       // body-pose index of xr[0]
-    const int rg = lane < 24 ? lane >> 3 : lane - 24;
-    const int cc = lane < 24 ? lane & 7 : 8;
-    const bool act = lane < 27;
-    float2 acc[4];
-    gmm_stage(tb, wm.dbuf, xr, body_owner, i0, 0);
-#pragma unroll 1
-    for (int m = 0; m < kGmmM; ++m) {
-      wsync();           // d_m is staged; every lane is done with the buffer d_{m+1} goes to
-      float* dm = wm.dbuf + (m & 1) * kDbufStride;
-      if (m + 1 < kGmmM) gmm_stage(tb, wm.dbuf + ((m + 1) & 1) * kDbufStride, xr, body_owner, i0, m + 1);
-      float part = 0.f;
-      if (act) {
-        gmm_rows(tb, dm, m, rg, cc, acc);
-        const float4 e0 = *reinterpret_cast<const float4*>(dm + 4 * cc);
-        const float4 e1 = *reinterpret_cast<const float4*>(dm + 36 + 4 * cc);
-        part = fmaf(acc[0].x, e0.x, fmaf(acc[0].y, e0.y, fmaf(acc[1].x, e0.z, acc[1].y * e0.w))) +
-               fmaf(acc[2].x, e1.x, fmaf(acc[2].y, e1.y, fmaf(acc[3].x, e1.z, acc[3].y * e1.w)));
-      }
-      wm.qbuf[m * 32 + lane] = part;
-    }
-    wsync();
-    // q_m = sum of the 32 partials of component m: lanes 4m..4m+3 add 8 each, two butterfly steps finish;
-    // then the arg-min over the components (first minimum wins, like torch.min) by three more steps
-    float best;
-    int bm = lane >> 2;
-    {
-      const float4 a = *reinterpret_cast<const float4*>(wm.qbuf + 8 * lane);
-      const float4 b = *reinterpret_cast<const float4*>(wm.qbuf + 8 * lane + 4);
-      float q = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
-      q += shfl(q, lane ^ 1);
-      q += shfl(q, lane ^ 2);
-      best = fmaf(0.5f, q, tb.nlw[bm]);
-#pragma unroll
-      for (int msk = 4; msk <= 16; msk <<= 1) {
-        const float ol = shfl(best, lane ^ msk);
-        const int om = (int)shfl((float)bm, lane ^ msk);
-        if (ol < best || (ol == best && om < bm)) {
-          best = ol;
-          bm = om;
+    float best = INFINITY;
+    int bm = 0;
+    const float* ysrc = wm.ybuf;
+    if (wm.helpers > 0) {
+      // the helper warps were handed this point at the top of the evaluation; collect their results
+      bar_sync(wm.bar_id + 1, 32 * (1 + wm.helpers));
+      for (int h = 0; h < wm.helpers; ++h) {
+        const float* hm = wm.helper_mem + h * wm.helper_stride;
+        const float ll = hm[0];
+        const int m = (int)hm[1];
+        if (ll < best || (ll == best && m < bm)) {
+          best = ll;
+          bm = m;
+          ysrc = hm + kYbufOff;
         }
       }
+    } else {
+      gmm_scan(tb, wm, xr, 0, 1, with_grad, best, bm);
     }
     if (gmm_component) *gmm_component = bm;
     uni = fmaf(kPosePriorW2, best, uni);
-    if (with_grad) {
-      // y = P d of the arg-min component, recomputed (cheaper than keeping eight results alive), then summed
-      // over the three row groups: lanes 0..7 and 24 hold the totals of their chunk
-      gmm_stage(tb, wm.dbuf, xr, body_owner, i0, bm);
-      wsync();
-      if (act) gmm_rows(tb, wm.dbuf, bm, rg, cc, acc);
-      else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
-      }
-      float y[8] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, acc[3].x, acc[3].y};
-      const int p1 = lane < 24 ? (lane + 8) % 24 : 24 + (lane - 23) % 3;
-      const int p2 = lane < 24 ? (lane + 16) % 24 : 24 + (lane - 22) % 3;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) y[k] = (y[k] + shfl(y[k], p1)) + shfl(y[k], p2);
-      if (act && rg == 0) {
-        *reinterpret_cast<float4*>(wm.ybuf + 4 * cc) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(wm.ybuf + 36 + 4 * cc) = make_float4(y[4], y[5], y[6], y[7]);
-      }
-      wsync();
-    }
     if (body_owner) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int i = i0 + c;
         const float xi = xr[c];
         float gi = gr[c];
-        if (with_grad) gi = fmaf(kPosePriorW2, wm.ybuf[i], gi);
+        if (with_grad) gi = fmaf(kPosePriorW2, ysrc[i], gi);
         if (ob.keep_w2 != 0.f) {      // temporal pose-preserve term (losses.py:57-59)
           const float d = xi - ob.keep[c];
           lsum = fmaf(ob.keep_w2 * d, d, lsum);
@@ -639,6 +695,7 @@ struct ChainParams {
   float* out_loss; float* out_joints; int* out_evals;
   float* hist;             // L-BFGS (y, s) history, hist_floats(hmax) per resident warp
   int hmax;
+  int helpers;             // helper warps per sequence that scan the mixture components (0 = the walking warp does it)
   float adam_step[kAdamTableW], adam_bc2[kAdamTableW];
 };
 K2B_HD constexpr long hist_floats(int hmax) { return (long)hmax * 2 * kWarpVec; }

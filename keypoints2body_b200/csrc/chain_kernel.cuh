@@ -5,6 +5,8 @@
 // the rest-offset table.  Per-warp shared memory: the evaluation point, the GMM difference / gradient
 // staging vectors, four gradient slots and the L-BFGS rho / alpha arrays (~2.7 KB).  The L-BFGS (y, s)
 // history lives in global scratch (one block per resident warp, L2-resident), read one pair ahead.
+// With few sequences a second warp per sequence scans the mixture prior (FMA-bound, a third of an evaluation)
+// while the first walks the kinematic tree; the two meet through named barriers.
 // Used for the reference's default sequence schedule (serial in t) and for small batches, where the
 // one-thread-per-frame kernel is latency-bound.
 #pragma once
@@ -59,14 +61,48 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
 
   const int warp = tid >> 5, nwarps = nthr >> 5;
   const wc::WarpTables tb{s_P, s_mu, s_nlw, reinterpret_cast<const float4*>(s_rel)};
-  float* w = s_warp + (size_t)warp * wc::warp_mem_floats(p.hmax);
-  const wc::WarpMem wm = wc::make_warp_mem(w);
-  float* ro = w + wc::kWarpMemFloats;
-  float* al = ro + p.hmax;
-  const long slot = (long)blockIdx.x * nwarps + warp;
-  float* hist = p.hist ? p.hist + slot * wc::hist_floats(p.hmax) : nullptr;
-  for (long seq = slot; seq < p.num_seq; seq += (long)gridDim.x * nwarps)
-    wc::run_chain_warp<NS, K>(p, seq, tb, wm, hist, ro, al);
+  const int wmf = wc::warp_mem_floats(p.hmax);
+  // a group = the warp that walks the sequence + p.helpers warps that scan the mixture components for it
+  const int G = 1 + p.helpers, ngroups = nwarps / G;
+  const int group = warp / G, role = warp - group * G;
+  float* w = s_warp + (size_t)warp * wmf;
+  wc::WarpMem wm = wc::make_warp_mem(w);
+  const int bar = 1 + 2 * group;          // named barriers bar (work posted) and bar + 1 (results ready)
+  if (role == 0) {
+    wm.helpers = p.helpers;
+    wm.bar_id = bar;
+    wm.helper_mem = w + wmf;
+    wm.helper_stride = wmf;
+    float* ro = w + wc::kWarpMemFloats;
+    float* al = ro + p.hmax;
+    const long slot = (long)blockIdx.x * ngroups + group;
+    float* hist = p.hist ? p.hist + slot * wc::hist_floats(p.hmax) : nullptr;
+    for (long seq = slot; seq < p.num_seq; seq += (long)gridDim.x * ngroups)
+      wc::run_chain_warp<NS, K>(p, seq, tb, wm, hist, ro, al);
+    if (p.helpers > 0) {                  // release the helpers
+      if ((tid & 31) == 0) wm.dbuf[0] = 0.f;
+      wc::bar_arrive(bar, 32 * G);
+    }
+  } else {
+    const float* lead = w - (size_t)role * wmf;       // the leader's block: xs at 0, command word at dbuf[0]
+    const int lane = tid & 31;
+    while (true) {
+      wc::bar_sync(bar, 32 * G);
+      const float cmd = *reinterpret_cast<const volatile float*>(lead + 96);
+      if (cmd == 0.f) break;
+      float xr[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) xr[c] = *reinterpret_cast<const volatile float*>(lead + 3 * lane + c);
+      float best;
+      int bm;
+      wc::gmm_scan(tb, wm, xr, role - 1, p.helpers, cmd == 2.f, best, bm);
+      if (lane == 0) {
+        w[0] = best;
+        w[1] = (float)bm;
+      }
+      wc::bar_arrive(bar + 1, 32 * G);
+    }
+  }
 }
 
 // NS: shape coefficients (10 | 20); K: observed joints (22 | 24).  Specialised in chain_inst.cu.
