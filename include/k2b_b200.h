@@ -157,18 +157,22 @@ typedef struct k2b_chain_args {
   int64_t first_seq_ind;        /* seq_ind of every sequence's frame 0 */
   int32_t chain_init;           /* 1 = use_previous_frame_init */
   int32_t freeze_betas;
-  int32_t conf_mode;            /* 0 none, 1 conf is [K], 2 conf is [S][T][K] */
+  int32_t conf_mode;            /* 0 none, 1 conf is [K], 2 conf is [S][stride][K] */
+  int32_t out_time_major;       /* 0: outputs are [S][T][..]; 1: [T][S][..] (a time chunk of every sequence is contiguous) */
+  int64_t in_sequence_stride;   /* frames between consecutive sequences in targets / conf / preserve_pose; 0 = T.
+                                   A launch can cover a time window of longer sequences: pass pointers to the
+                                   window's first frame, the full length here and the window start as first_seq_ind */
   float lr;
   float joint_loss_weight;
   float pose_preserve_weight;
-  const float* targets;         /* [S][T][K][3] (device) */
+  const float* targets;         /* [S][stride][K][3] (device) */
   const float* conf;
   const float* init_pose;       /* [S][72] */
   const float* init_betas;      /* [S][10] */
   const float* init_transl;     /* [S][3] */
   const float* init_expr;       /* [S][10] or NULL (required iff model num_shape == 20) */
-  const float* preserve_pose;   /* [S][T][69] or NULL = each frame's initial body pose */
-  float* out_pose;              /* [S][T][72] */
+  const float* preserve_pose;   /* [S][stride][69] or NULL = each frame's initial body pose */
+  float* out_pose;              /* [S][T][72] ([T][S][72] if out_time_major; likewise below) */
   float* out_betas;             /* [S][T][10] */
   float* out_transl;            /* [S][T][3] */
   float* out_expr;              /* [S][T][10] or NULL */
@@ -181,6 +185,9 @@ typedef struct k2b_chain_args {
 
 size_t k2b_chain_workspace_bytes(const k2b_model* m, int64_t num_sequences, int32_t optimizer,
                                  int32_t max_iters);
+/* Launch geometry k2b_fit_chain uses for S sequences: CTAs (one per SM, at most the SM count) and warps per CTA;
+ * returns the number of SMs of the device (so a caller can size concurrent work for the SMs left free). */
+int k2b_chain_geometry(const k2b_model* m, int64_t num_sequences, int32_t* out_ctas, int32_t* out_warps);
 int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* args, void* cuda_stream);
 
 /* One evaluation of loss and gradient at given parameters (parity / debugging). */
@@ -222,6 +229,8 @@ typedef struct k2b_mesh_args {
   float* out_joints;         /* [B][n_j + num_extra][3] */
   void* workspace;
   size_t workspace_bytes;
+  int32_t max_ctas;          /* 0 = one CTA per SM; otherwise the persistent blend / skinning kernel uses at most
+                                this many CTAs (so it fits beside another resident kernel, e.g. k2b_fit_chain) */
 } k2b_mesh_args;
 
 size_t k2b_mesh_workspace_bytes(const k2b_model* m, int64_t num_frames);

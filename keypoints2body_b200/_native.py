@@ -58,8 +58,8 @@ class ChainArgs(C.Structure):
         ("num_sequences", C.c_int64), ("frames_per_sequence", C.c_int32), ("num_obs", C.c_int32),
         ("optimizer", C.c_int32), ("num_iters_first", C.c_int32), ("num_iters_followup", C.c_int32),
         ("first_seq_ind", C.c_int64), ("chain_init", C.c_int32), ("freeze_betas", C.c_int32),
-        ("conf_mode", C.c_int32), ("lr", C.c_float), ("joint_loss_weight", C.c_float),
-        ("pose_preserve_weight", C.c_float),
+        ("conf_mode", C.c_int32), ("out_time_major", C.c_int32), ("in_sequence_stride", C.c_int64),
+        ("lr", C.c_float), ("joint_loss_weight", C.c_float), ("pose_preserve_weight", C.c_float),
         ("targets", C.c_void_p), ("conf", C.c_void_p), ("init_pose", C.c_void_p), ("init_betas", C.c_void_p),
         ("init_transl", C.c_void_p), ("init_expr", C.c_void_p), ("preserve_pose", C.c_void_p),
         ("out_pose", C.c_void_p), ("out_betas", C.c_void_p), ("out_transl", C.c_void_p), ("out_expr", C.c_void_p),
@@ -85,7 +85,7 @@ class MeshArgs(C.Structure):
     _fields_ = [
         ("num_frames", C.c_int64), ("full_pose", C.c_void_p), ("shape", C.c_void_p),
         ("transl", C.c_void_p), ("out_vertices", C.c_void_p), ("out_joints", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("max_ctas", C.c_int32),
     ]
 
 
@@ -102,7 +102,7 @@ class ShapeArgs(C.Structure):
 
 EXPORTS = (
     "k2b_model_create", "k2b_model_destroy", "k2b_fit_workspace_bytes", "k2b_fit_batch",
-    "k2b_fit_batch_host", "k2b_chain_workspace_bytes", "k2b_fit_chain", "k2b_evaluate_batch", "k2b_mesh_workspace_bytes", "k2b_mesh_batch",
+    "k2b_fit_batch_host", "k2b_chain_workspace_bytes", "k2b_chain_geometry", "k2b_fit_chain", "k2b_evaluate_batch", "k2b_mesh_workspace_bytes", "k2b_mesh_batch",
     "k2b_shape_workspace_bytes", "k2b_shape_pass", "k2b_mpjae", "k2b_fma_peak", "k2b_launch_count", "k2b_last_error", "k2b_version",
 )
 
@@ -128,6 +128,8 @@ def load_library():
     lib.k2b_fit_workspace_bytes.restype = C.c_size_t
     lib.k2b_chain_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
     lib.k2b_chain_workspace_bytes.restype = C.c_size_t
+    lib.k2b_chain_geometry.argtypes = [C.c_void_p, C.c_int64, _c_int_p, _c_int_p]
+    lib.k2b_chain_geometry.restype = C.c_int
     for name, st in (("k2b_fit_batch", FitArgs), ("k2b_fit_batch_host", FitArgs), ("k2b_fit_chain", ChainArgs),
                      ("k2b_evaluate_batch", EvalArgs), ("k2b_mesh_batch", MeshArgs),
                      ("k2b_shape_pass", ShapeArgs)):

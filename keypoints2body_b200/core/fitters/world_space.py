@@ -152,36 +152,47 @@ class WorldSpaceFitter:
 
     def _run_chain(self, S, T, targets, conf, conf_mode, pose, betas, transl, expr, preserve, first_seq_ind, chain,
                    iters_first, iters_follow, optimizer, joint_loss_weight, pose_preserve_weight, freeze_betas,
-                   want_joints=True):
-        """One launch of the warp-per-sequence kernel (``k2b_fit_chain``): S sequences x T frames, serial in t."""
+                   want_joints=True, outs=None, window=None, time_major=False):
+        """One launch of the warp-per-sequence kernel (``k2b_fit_chain``): S sequences x T frames, serial in t.
+
+        ``outs``: preallocated output dict (rows of this launch), else allocated here.  ``window = (a, b, T_total)``:
+        the launch covers frames [a, b) of sequences that are T_total frames long in ``targets`` / ``conf``.
+        """
         dev = self.device
-        F = S * T
-        out_pose = torch.empty(F, 72, device=dev)
-        out_betas = torch.empty(F, 10, device=dev)
-        out_transl = torch.empty(F, 3, device=dev)
-        out_expr = torch.empty(F, 10, device=dev) if self.has_expr else None
-        out_loss = torch.empty(F, device=dev)
-        out_joints = torch.empty(F, self.num_obs, 3, device=dev) if want_joints else None
-        out_evals = torch.empty(F, dtype=torch.int32, device=dev)
+        a0, b0, t_total = window if window is not None else (0, T, T)
+        Tw = b0 - a0
+        F = S * Tw
+        if outs is None:
+            outs = dict(pose=torch.empty(F, 72, device=dev), betas=torch.empty(F, 10, device=dev),
+                        transl=torch.empty(F, 3, device=dev),
+                        expression=torch.empty(F, 10, device=dev) if self.has_expr else None,
+                        loss=torch.empty(F, device=dev),
+                        fit_joints=torch.empty(F, self.num_obs, 3, device=dev) if want_joints else None,
+                        evals=torch.empty(F, dtype=torch.int32, device=dev))
         lib = self.native.lib
         ws_bytes = lib.k2b_chain_workspace_bytes(self.native.handle, S, optimizer, int(max(iters_first, iters_follow)))
         ws = self.native.workspace("chain", ws_bytes)
+        K = self.num_obs
+        tgt_ptr = targets.data_ptr() + 4 * a0 * K * 3
+        conf_ptr = None if conf is None else conf.data_ptr() + (4 * a0 * K if conf_mode == 2 else 0)
+        keep_ptr = None if preserve is None else preserve.data_ptr() + 4 * a0 * 69
         a = nat.ChainArgs(
-            num_sequences=S, frames_per_sequence=T, num_obs=self.num_obs, optimizer=optimizer,
-            num_iters_first=int(iters_first), num_iters_followup=int(iters_follow), first_seq_ind=int(first_seq_ind),
-            chain_init=int(bool(chain)), freeze_betas=int(bool(freeze_betas)), conf_mode=int(conf_mode),
+            num_sequences=S, frames_per_sequence=Tw, num_obs=K, optimizer=optimizer,
+            num_iters_first=int(iters_first), num_iters_followup=int(iters_follow),
+            first_seq_ind=int(first_seq_ind) + a0, chain_init=int(bool(chain)), freeze_betas=int(bool(freeze_betas)),
+            conf_mode=int(conf_mode), out_time_major=int(bool(time_major)), in_sequence_stride=int(t_total),
             lr=self.step_size, joint_loss_weight=float(joint_loss_weight),
             pose_preserve_weight=float(pose_preserve_weight),
-            targets=nat.ptr(targets), conf=nat.ptr(conf), init_pose=nat.ptr(pose), init_betas=nat.ptr(betas),
-            init_transl=nat.ptr(transl), init_expr=nat.ptr(expr), preserve_pose=nat.ptr(preserve),
-            out_pose=nat.ptr(out_pose), out_betas=nat.ptr(out_betas), out_transl=nat.ptr(out_transl),
-            out_expr=nat.ptr(out_expr), out_loss=nat.ptr(out_loss), out_joints=nat.ptr(out_joints),
-            out_evals=nat.ptr(out_evals), workspace=nat.ptr(ws), workspace_bytes=ws.numel(),
+            targets=tgt_ptr, conf=conf_ptr, init_pose=nat.ptr(pose), init_betas=nat.ptr(betas),
+            init_transl=nat.ptr(transl), init_expr=nat.ptr(expr), preserve_pose=keep_ptr,
+            out_pose=nat.ptr(outs["pose"]), out_betas=nat.ptr(outs["betas"]), out_transl=nat.ptr(outs["transl"]),
+            out_expr=nat.ptr(outs["expression"]), out_loss=nat.ptr(outs["loss"]),
+            out_joints=nat.ptr(outs["fit_joints"]), out_evals=nat.ptr(outs["evals"]), workspace=nat.ptr(ws),
+            workspace_bytes=ws.numel(),
         )
         with torch.cuda.device(dev):
             nat.check(lib.k2b_fit_chain(self.native.handle, C.byref(a), nat.current_stream()))
-        return dict(pose=out_pose, betas=out_betas, transl=out_transl, expression=out_expr, loss=out_loss,
-                    fit_joints=out_joints, evals=out_evals)
+        return outs
 
     def evaluate_batch(self, params: dict, j3d, conf=None, preserve_pose=None, preserve_on=False,
                        joint_loss_weight=600.0, pose_preserve_weight=5.0):
@@ -220,7 +231,7 @@ class WorldSpaceFitter:
             nat.check(lib.k2b_evaluate_batch(self.native.handle, C.byref(a), nat.current_stream()))
         return outs
 
-    def forward_batch(self, params: dict, with_vertices=True, out_vertices=None):
+    def forward_batch(self, params: dict, with_vertices=True, out_vertices=None, out_joints=None, max_ctas=0):
         """Body-model forward (mesh kernels): joints ``(B, n_j + extras, 3)`` and vertices ``(B,V,3)``."""
         dev = self.device
         go = _f32(params["global_orient"], dev)
@@ -237,7 +248,7 @@ class WorldSpaceFitter:
         shape = shape.contiguous()
         transl = _f32(params.get("transl"), dev)
         n_out = self.native.num_joints + self.native.num_extra
-        joints = torch.empty(B, n_out, 3, device=dev)
+        joints = out_joints if out_joints is not None else torch.empty(B, n_out, 3, device=dev)
         verts = None
         if with_vertices:
             verts = out_vertices if out_vertices is not None else torch.empty(B, self.native.num_vertices, 3, device=dev)
@@ -245,7 +256,7 @@ class WorldSpaceFitter:
         ws = self.native.workspace("mesh", lib.k2b_mesh_workspace_bytes(self.native.handle, B))
         a = nat.MeshArgs(num_frames=B, full_pose=nat.ptr(full_pose), shape=nat.ptr(shape), transl=nat.ptr(transl),
                          out_vertices=nat.ptr(verts), out_joints=nat.ptr(joints), workspace=nat.ptr(ws),
-                         workspace_bytes=ws.numel())
+                         workspace_bytes=ws.numel(), max_ctas=int(max_ctas))
         with torch.cuda.device(dev):
             nat.check(lib.k2b_mesh_batch(self.native.handle, C.byref(a), nat.current_stream()))
         return {"joints": joints, "vertices": verts}
@@ -376,14 +387,21 @@ class WorldSpaceFitter:
         return out
 
     def fit_chain(self, init: dict, j3d, conf=None, *, first_seq_ind=0, chain=True, joint_loss_weight=600.0,
-                  pose_preserve_weight=5.0, freeze_betas=False, use_lbfgs=None, with_mesh=True, out_vertices=None):
+                  pose_preserve_weight=5.0, freeze_betas=False, use_lbfgs=None, with_mesh=True, out_vertices=None,
+                  time_major=False, chunks=1, params_ready=None):
         """Fit S sequences of T frames each the way the reference's sequence loop does (api/sequence.py:214-281):
         serially in t, frame t starting from frame t-1's result (``chain=True``) or from the sequence's
-        initialisation (``chain=False``), all inside ONE launch -- one warp per sequence.
+        initialisation (``chain=False``) -- one warp per sequence, all frames inside one launch.
 
         ``init``: dict of (S,dim) arrays = initialisation of every sequence's frame 0.  ``j3d``: (S,T,K,3).
-        ``conf``: None, (K,) or (S,T,K).  Returns the same dict as ``fit_batch`` with S*T leading rows
-        (sequence-major).
+        ``conf``: None, (K,) or (S,T,K).  Returns the same dict as ``fit_batch`` with S*T leading rows, sequence-major
+        (row s*T + t) or, with ``time_major``, time-major (row t*S + s).
+
+        ``chunks`` > 1 (needs ``time_major`` or S == 1, and ``chain``): the time axis is cut into that many windows;
+        each window is one launch on a high-priority stream that continues from the previous window's last frame
+        (same arithmetic, same results), and the mesh pass of a finished window runs on the caller's stream
+        while the next window is being fitted -- the fit leaves most of every SM idle when there are few
+        sequences.  ``params_ready``: optional event recorded when the fitted parameters are final.
         """
         dev = self.device
         targets = _f32(j3d, dev)
@@ -409,20 +427,91 @@ class WorldSpaceFitter:
         if self.has_expr:
             expr = (expr if expr is not None else torch.zeros(S, 10, device=dev)).expand(S, -1).contiguous()
         lbfgs = self.use_lbfgs if use_lbfgs is None else use_lbfgs
-        res = self._run_chain(S, T, targets, conf, conf_mode, pose, betas, transl, expr if self.has_expr else None,
-                              None, first_seq_ind, chain, self.num_iters_first, self.num_iters_followup,
-                              nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight, pose_preserve_weight,
-                              freeze_betas)
-        params = {"global_orient": res["pose"][:, :3], "body_pose": res["pose"][:, 3:], "betas": res["betas"],
-                  "transl": res["transl"]}
-        for k in _EXTRA_BLOCKS:
-            if extras[k] is not None:    # receive no gradient from body keypoints: passed through to every frame
-                params[k] = extras[k].expand(S, -1).repeat_interleave(T, dim=0)
-        if self.has_expr:
-            params["expression"] = res["expression"]
-        out = {"params": params, "loss": res["loss"], "evals": res["evals"], "fit_joints": res["fit_joints"]}
+        optimizer = nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM
+        chunks = max(1, min(int(chunks), T))
+        if chunks > 1 and not (chain and (time_major or S == 1)):
+            raise ValueError("chunks > 1 needs chain=True and time_major=True (or a single sequence)")
+        tm = bool(time_major) and S > 1
+        F = S * T
+        outs = dict(pose=torch.empty(F, 72, device=dev), betas=torch.empty(F, 10, device=dev),
+                    transl=torch.empty(F, 3, device=dev),
+                    expression=torch.empty(F, 10, device=dev) if self.has_expr else None,
+                    loss=torch.empty(F, device=dev), fit_joints=torch.empty(F, self.num_obs, 3, device=dev),
+                    evals=torch.empty(F, dtype=torch.int32, device=dev))
+        common = (self.num_iters_first, self.num_iters_followup, optimizer, joint_loss_weight, pose_preserve_weight,
+                  freeze_betas)
+
+        def params_of(rows):
+            p = {"global_orient": outs["pose"][rows, :3], "body_pose": outs["pose"][rows, 3:],
+                 "betas": outs["betas"][rows], "transl": outs["transl"][rows]}
+            n = outs["pose"][rows].shape[0]
+            for k in _EXTRA_BLOCKS:
+                if extras[k] is not None:    # receive no gradient from body keypoints: passed through to every frame
+                    e = extras[k].expand(S, -1)
+                    p[k] = e.repeat(n // S, 1) if tm else e.repeat_interleave(n // S, dim=0)
+            if self.has_expr:
+                p["expression"] = outs["expression"][rows]
+            return p
+
+        out = {"loss": outs["loss"], "evals": outs["evals"], "fit_joints": outs["fit_joints"]}
+        if chunks == 1:
+            self._run_chain(S, T, targets, conf, conf_mode, pose, betas, transl, expr if self.has_expr else None, None,
+                            first_seq_ind, chain, *common, outs=outs, time_major=tm)
+            if params_ready is not None:
+                params_ready.record()
+            out["params"] = params_of(slice(0, F))
+            if with_mesh:
+                out.update(self.forward_batch(out["params"], with_vertices=True, out_vertices=out_vertices))
+            return out
+
+        # ---- windows of the time axis: fit on a high-priority stream, mesh of finished windows behind it --------
+        n_out = self.native.num_joints + self.native.num_extra
+        joints = torch.empty(F, n_out, 3, device=dev) if with_mesh else None
+        verts = None
         if with_mesh:
-            out.update(self.forward_batch(params, with_vertices=True, out_vertices=out_vertices))
+            verts = out_vertices if out_vertices is not None else torch.empty(F, self.native.num_vertices, 3, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        if getattr(self, "_chain_stream", None) is None:
+            self._chain_stream = torch.cuda.Stream(device=dev, priority=-1)
+        hp = self._chain_stream
+        hp.wait_stream(cur)
+        timing = getattr(self, "chain_events", None)
+        if timing is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(hp)
+        # while windows are still being fitted, the mesh kernel is held to the SMs the fit leaves free (its CTAs are
+        # long-lived and would otherwise keep the next window's CTAs waiting); the last windows' mesh runs everywhere
+        ctas, warps = C.c_int32(), C.c_int32()
+        n_sms = self.native.lib.k2b_chain_geometry(self.native.handle, S, C.byref(ctas), C.byref(warps))
+        free_sms = n_sms - ctas.value
+        capped = chunks - max(1, chunks // 4) if free_sms >= 8 else 0
+        bounds = [(T * c) // chunks for c in range(chunks + 1)]
+        init_c = (pose, betas, transl, expr if self.has_expr else None)
+        for c in range(chunks):
+            a0, b0 = bounds[c], bounds[c + 1]
+            rows = slice(a0 * S, b0 * S)
+            o = {k: (v[rows] if v is not None else None) for k, v in outs.items()}
+            with torch.cuda.stream(hp):
+                self._run_chain(S, T, targets, conf, conf_mode, *init_c, None, first_seq_ind, True, *common, outs=o,
+                                window=(a0, b0, T), time_major=tm)
+                done = torch.cuda.Event()
+                done.record(hp)
+            last = slice((b0 - 1) * S, b0 * S)      # the next window starts from this window's last frame
+            init_c = (outs["pose"][last], outs["betas"][last], outs["transl"][last],
+                      outs["expression"][last] if self.has_expr else None)
+            if c == chunks - 1:
+                if timing is not None:
+                    t1.record(hp)
+                    timing.append((t0, t1))
+                if params_ready is not None:
+                    params_ready.record(hp)
+            cur.wait_event(done)
+            if with_mesh:
+                self.forward_batch(params_of(rows), with_vertices=True, out_vertices=verts[rows], out_joints=joints[rows],
+                                   max_ctas=free_sms if c < capped else 0)
+        out["params"] = params_of(slice(0, F))
+        if with_mesh:
+            out["joints"], out["vertices"] = joints, verts
         return out
 
     def fit_frame(

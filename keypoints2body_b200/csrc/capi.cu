@@ -315,6 +315,15 @@ extern "C" size_t k2b_chain_workspace_bytes(const k2b_model* m, int64_t num_sequ
   return sizeof(float) * (size_t)grid * groups * (size_t)wc::hist_floats(lbfgs_history_capacity(max_iters));
 }
 
+extern "C" int k2b_chain_geometry(const k2b_model* m, int64_t num_sequences, int32_t* out_ctas, int32_t* out_warps) {
+  if (!m || num_sequences <= 0) return 0;
+  int grid, groups, helpers;
+  chain_geometry(m, num_sequences, grid, groups, helpers);
+  if (out_ctas) *out_ctas = grid;
+  if (out_warps) *out_warps = groups * (1 + helpers);
+  return m->num_sms;
+}
+
 extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* stream) {
   if (!a) return fail(K2B_EINVAL, "null args");
   int rc = check_common(m, a->num_sequences, a->num_obs, a->init_expr);
@@ -336,6 +345,10 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   wc::ChainParams p{};
   p.num_seq = a->num_sequences;
   p.frames = a->frames_per_sequence;
+  p.in_seq_stride = a->in_sequence_stride > 0 ? a->in_sequence_stride : a->frames_per_sequence;
+  if (p.in_seq_stride < p.frames) return fail(K2B_EINVAL, "in_sequence_stride must be >= frames_per_sequence");
+  p.out_seq_stride = a->out_time_major ? 1 : a->frames_per_sequence;
+  p.out_frame_stride = a->out_time_major ? a->num_sequences : 1;
   p.first_seq_ind = a->first_seq_ind;
   p.chain = a->chain_init;
   p.iters_first = a->num_iters_first;

@@ -678,6 +678,9 @@ constexpr int kAdamTableW = 64;
 struct ChainParams {
   long num_seq;            // S sequences, one warp each
   int frames;              // T frames per sequence, walked serially
+  long in_seq_stride;      // frames between consecutive sequences in targets / conf / preserve_pose (>= T)
+  long out_seq_stride;     // output row of (sequence s, frame t) = s * out_seq_stride + t * out_frame_stride:
+  long out_frame_stride;   //   (T, 1) sequence-major, (1, S) time-major
   long first_seq_ind;      // seq_ind of frame 0 (0: first-frame budget, no temporal term; world_space.py:211,214)
   int chain;               // 1: frame t starts from frame t-1's result (use_previous_frame_init); 0: from the init
   int iters_first, iters_follow;
@@ -737,7 +740,8 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
   const bool body_owner = lane >= 1 && lane < 24;
 #pragma unroll 1
   for (int t = 0; t < p.frames; ++t) {
-    const long f = seq * p.frames + t;
+    const long f = seq * p.in_seq_stride + t;                               // input row
+    const long frow = seq * p.out_seq_stride + (long)t * p.out_frame_stride;  // output row
     if (!p.chain) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) xr[c] = x0[c];
@@ -758,12 +762,12 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
     fo.iters = first ? p.iters_first : p.iters_follow;
     int evals = 0;
     const float loss = fit_warp<NS, K>(tb, wm, ob, xr, fo, hist, ro, al, p.hmax,
-                                       p.out_joints ? p.out_joints + f * K * 3 : nullptr, &evals);
+                                       p.out_joints ? p.out_joints + frow * K * 3 : nullptr, &evals);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) store_elem<NS>(p, f, 3 * lane + c, xr[c]);
+    for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, xr[c]);
     if (lane == 0) {
-      p.out_loss[f] = loss;
-      if (p.out_evals) p.out_evals[f] = evals;
+      p.out_loss[frow] = loss;
+      if (p.out_evals) p.out_evals[frow] = evals;
     }
   }
 }

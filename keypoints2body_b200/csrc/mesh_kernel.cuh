@@ -482,6 +482,7 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
     BlendParams bp{posefeat, a.shape, m.b_tiles, 1.f / m.dir_scale, m.v_template, (const float4*)skin, a.transl, m.ell_idx, m.ell_w,
                    a.out_vertices, B, m.npose, m.ns, m.kpad, m.nv, m.nj, m.ell, m.n_tiles, dbg ? atoi(dbg) : 0};
     const long passes = Bp / fr;
+    if (a.max_ctas > 0 && a.max_ctas < sms) sms = a.max_ctas;
     kern<<<(unsigned)(passes < sms ? passes : sms), kTcThreads, tsm, st>>>(bp);
     ++launches;
     if (!m.fused) {

@@ -195,6 +195,7 @@ extern "C" int wemu_chain(void* model, int K, int S, int T, long first_seq_ind, 
   wc::ChainParams& p = g.p;
   p = wc::ChainParams{};
   p.num_seq = S; p.frames = T; p.first_seq_ind = first_seq_ind; p.chain = chain;
+  p.in_seq_stride = T; p.out_seq_stride = T; p.out_frame_stride = 1;
   p.iters_first = iters_first; p.iters_follow = iters_follow; p.lbfgs = lbfgs; p.freeze_betas = freeze_betas;
   p.conf_mode = conf ? conf_mode : 0;
   p.lr = lr; p.joint_w2 = joint_w * joint_w; p.keep_w2 = keep_w * keep_w;

@@ -425,3 +425,24 @@ def test_chain_kernel_lbfgs_sequence_statistics(fitters, weights):
     print("chain lbfgs median loss per frame", np.median(ours, axis=0), "frame kernel", np.median(ref, axis=0))
     assert np.median(ours[:, -1]) <= 1.25 * np.median(ref[:, -1])
     assert np.median(ours) <= 1.25 * np.median(ref)
+
+
+@pytest.mark.parametrize("lbfgs", [False, True])
+def test_chain_windows_time_major_identical_to_one_launch(goldens, fitters, shims, lbfgs):
+    """Cutting the time axis into windows (one launch each, continuing from the previous window's last frame, mesh
+    of a finished window overlapping the next fit) and writing time-major must not change a single bit."""
+    g, S = goldens, 4
+    init, tgt = _chain_init(g, shims, S)
+    tgt = tgt[None].expand(S, -1, -1, -1) + 0.01 * torch.arange(S).view(S, 1, 1, 1)
+    f = fitters("smpl", use_lbfgs=lbfgs)
+    one = f.fit_chain(init, tgt, None)
+    win = f.fit_chain(init, tgt, None, time_major=True, chunks=3)
+    Tn = tgt.shape[1]
+    for k in ("global_orient", "body_pose", "betas", "transl"):
+        a = cpu(one["params"][k]).reshape(S, Tn, -1)
+        b = cpu(win["params"][k]).reshape(Tn, S, -1).transpose(1, 0, 2)
+        assert np.array_equal(a, b), k
+    for k in ("loss", "joints", "vertices", "fit_joints"):
+        a = cpu(one[k]).reshape(S, Tn, -1)
+        b = cpu(win[k]).reshape(Tn, S, -1).transpose(1, 0, 2)
+        assert np.array_equal(a, b), k

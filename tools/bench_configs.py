@@ -74,7 +74,7 @@ def main():
         for name, kw in (("S2 two_sweep", dict(schedule="two_sweep")),
                          ("S0 independent", dict(schedule="reference", use_previous_frame_init=False)),
                          ("S1 serial chain (reference default)", dict(schedule="reference", use_previous_frame_init=True))):
-            T = 4096 if not name.startswith("S1") else 256       # the chain is latency-bound: a 256-frame sample
+            T = 4096       # S1 runs as one launch of the warp-per-sequence kernel (k2b_fit_chain)
             cfg = SequenceOptimizeConfig(frame=FrameOptimizeConfig(use_lbfgs=lb), use_shape_optimization=False, **kw)
             ms = wall_ms(lambda: k2b.optimize_params_sequence(tgt[:T], body_model="smpl", joint_layout="AMASS", model=w,
                                                               config=cfg), warm=1, reps=2)
