@@ -286,9 +286,11 @@ extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, vo
 namespace {
 // groups = sequences walked concurrently by one CTA; a group is 1 + helpers warps
 void chain_geometry(const k2b_model* m, long S, int& grid, int& groups, int& helpers) {
-  // few sequences: the launch is latency-bound and most schedulers idle, so a second warp per sequence takes
-  // the mixture prior; with enough sequences to fill the SMs one warp per sequence has the best throughput
-  helpers = S <= (long)m->num_sms * 6 ? 1 : 0;
+  // few sequences: the launch is latency-bound and most schedulers idle, so helper warps take the mixture prior
+  // (measured on B200, L-BFGS, us per frame: 1 sequence 106 / 80 / 66 with 0 / 1 / 2 helpers; 256 sequences
+  // 113 / 86 / 80; 512 sequences 128 / 110 / 114); with enough sequences to fill the SMs one warp per sequence
+  // has the best throughput
+  helpers = S <= (long)m->num_sms * 2 ? 2 : (S <= (long)m->num_sms * 6 ? 1 : 0);
   if (const char* e = getenv("K2B_CHAIN_HELPERS")) helpers = atoi(e);
   if (helpers < 0) helpers = 0;
   if (helpers > 3) helpers = 3;

@@ -64,8 +64,10 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
   const int wmf = wc::warp_mem_floats(p.hmax);
   // a group = the warp that walks the sequence + p.helpers warps that scan the mixture components for it
   const int G = 1 + p.helpers, ngroups = nwarps / G;
-  const int group = warp / G, role = warp - group * G;
-  float* w = s_warp + (size_t)warp * wmf;
+  // the walking warp's position inside its group rotates with the group index, so the (latency-critical) walkers
+  // of neighbouring groups sit on different schedulers (warp id mod 4)
+  const int group = warp / G, role = (warp - group * G - group % G + G) % G;
+  float* w = s_warp + (size_t)(group * G + role) * wmf;     // shared-memory blocks are laid out by role
   wc::WarpMem wm = wc::make_warp_mem(w);
   const int bar = 1 + 2 * group;          // named barriers bar (work posted) and bar + 1 (results ready)
   if (role == 0) {

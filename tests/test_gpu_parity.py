@@ -346,10 +346,12 @@ def test_extreme_inputs_terminate_and_match_oracle(fitters, shims, oracle_prior,
     bad[0, 3, 1] = float("nan")
     bad[1, 7, 0] = float("inf")
     for lb in (False, True):
-        out = fitters("smpl", use_lbfgs=lb).fit_batch(params, bad, None, seq_ind=0, num_iters=10, with_mesh=False)
-        ev = cpu(out["evals"])
-        assert ev.max() <= 10 * 5 // 4 + 2 and ev.min() >= 1
-        assert np.isfinite(cpu(out["loss"])[2:]).all()           # finite frames are unaffected by their neighbours
+        for kern in KERNELS:
+            out = fitters("smpl", use_lbfgs=lb).fit_batch(params, bad, None, seq_ind=0, num_iters=10, with_mesh=False,
+                                                          kernel=kern)
+            ev = cpu(out["evals"])
+            assert ev.max() <= 10 * 5 // 4 + 2 and ev.min() >= 1
+            assert np.isfinite(cpu(out["loss"])[2:]).all()       # finite frames are unaffected by their neighbours
 
 
 # ---- warp-per-sequence kernel (k2b_fit_chain): the reference's serial frame loop in one launch ----------
@@ -446,3 +448,28 @@ def test_chain_windows_time_major_identical_to_one_launch(goldens, fitters, shim
         a = cpu(one[k]).reshape(S, Tn, -1)
         b = cpu(win[k]).reshape(Tn, S, -1).transpose(1, 0, 2)
         assert np.array_equal(a, b), k
+
+
+@pytest.mark.parametrize("lbfgs", [False, True])
+def test_warp_kernel_edge_cases(fitters, weights, lbfgs):
+    """Zero iterations pass the parameters through; a zero-confidence joint does not influence the fit; an explicit
+    temporal anchor (preserve_pose) and per-frame confidences are honoured exactly like the per-thread kernel does."""
+    tgt, init = make_problem(weights, 7, seed=707)
+    f = fitters("smpl", use_lbfgs=lbfgs)
+    out = f.fit_batch(init, tgt, None, seq_ind=0, num_iters=0, with_mesh=False, kernel="warp")
+    assert torch.equal(out["params"]["body_pose"].cpu(), init["body_pose"])
+    assert torch.equal(out["params"]["transl"].cpu(), init["transl"])
+    conf = torch.ones(7, 22)
+    conf[:, 20] = 0.0
+    tgt2 = tgt.clone()
+    tgt2[:, 20] += 5.0
+    a = f.fit_batch(init, tgt, conf, seq_ind=2, num_iters=4, with_mesh=False, kernel="warp")
+    b = f.fit_batch(init, tgt2, conf, seq_ind=2, num_iters=4, with_mesh=False, kernel="warp")
+    assert torch.equal(a["params"]["body_pose"], b["params"]["body_pose"]) and torch.equal(a["loss"], b["loss"])
+    if not lbfgs:
+        keep = init["body_pose"] + 0.05
+        w = f.fit_batch(init, tgt, conf, seq_ind=2, num_iters=6, with_mesh=False, kernel="warp", preserve_pose=keep)
+        t = f.fit_batch(init, tgt, conf, seq_ind=2, num_iters=6, with_mesh=False, kernel="frame", preserve_pose=keep)
+        assert (w["params"]["body_pose"] - t["params"]["body_pose"]).abs().max() < 1e-4
+        assert (w["params"]["body_pose"] - a["params"]["body_pose"]).abs().max() > 1e-4     # the anchor matters
+        np.testing.assert_allclose(cpu(w["loss"]), cpu(t["loss"]), rtol=1e-4)
