@@ -277,7 +277,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     F = args.frames_per_gpu
     lo, hi = rank * F, (rank + 1) * F
 
@@ -385,8 +387,15 @@ def run_ours(args):
     except Exception:
         pass
     mesh_ms = ms_step - fit_ms_step
-    if chain:     # the mesh pass overlaps the fit inside the step; for its roofline it is timed alone
-        mesh_ms = timed(lambda: fitter.forward_batch(out["params"], out_vertices=sf.vertices), 1)
+    if chain:     # the mesh pass overlaps the fit inside the step; for its roofline it is timed alone (rank 0
+        # only: no collective here, the other ranks have already returned)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        fitter.forward_batch(out["params"], out_vertices=sf.vertices)
+        e1.record()
+        torch.cuda.synchronize()
+        mesh_ms = e0.elapsed_time(e1)
     mesh_bytes = F * (6890 * 3 * 4 + n_j * 3 * 4) if not args.no_vertices else F * n_j * 12
     line = {
         "metric": METRIC, "value": world * F / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -388,7 +388,7 @@ class WorldSpaceFitter:
 
     def fit_chain(self, init: dict, j3d, conf=None, *, first_seq_ind=0, chain=True, joint_loss_weight=600.0,
                   pose_preserve_weight=5.0, freeze_betas=False, use_lbfgs=None, with_mesh=True, out_vertices=None,
-                  time_major=False, chunks=1, params_ready=None):
+                  time_major=False, chunks=1, params_ready=None, mesh_capped_fraction=None):
         """Fit S sequences of T frames each the way the reference's sequence loop does (api/sequence.py:214-281):
         serially in t, frame t starting from frame t-1's result (``chain=True``) or from the sequence's
         initialisation (``chain=False``) -- one warp per sequence, all frames inside one launch.
@@ -402,6 +402,9 @@ class WorldSpaceFitter:
         (same arithmetic, same results), and the mesh pass of a finished window runs on the caller's stream
         while the next window is being fitted -- the fit leaves most of every SM idle when there are few
         sequences.  ``params_ready``: optional event recorded when the fitted parameters are final.
+        ``mesh_capped_fraction``: share of the windows whose mesh pass is held to the SMs the fit leaves free
+        (the rest, at the end, run on all SMs); default 0.75 for L-BFGS, 0.45 for Adam, whose fit is shorter
+        relative to the mesh.
         """
         dev = self.device
         targets = _f32(j3d, dev)
@@ -484,7 +487,8 @@ class WorldSpaceFitter:
         ctas, warps = C.c_int32(), C.c_int32()
         n_sms = self.native.lib.k2b_chain_geometry(self.native.handle, S, C.byref(ctas), C.byref(warps))
         free_sms = n_sms - ctas.value
-        capped = chunks - max(1, chunks // 4) if free_sms >= 8 else 0
+        frac = mesh_capped_fraction if mesh_capped_fraction is not None else (0.75 if lbfgs else 0.45)
+        capped = min(chunks - 1, int(round(chunks * frac))) if free_sms >= 8 else 0
         bounds = [(T * c) // chunks for c in range(chunks + 1)]
         init_c = (pose, betas, transl, expr if self.has_expr else None)
         for c in range(chunks):
