@@ -279,6 +279,8 @@ def run_ours(args):
     if world > 1:
         import datetime
 
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version banner off stdout (one JSON line)
+
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     F = args.frames_per_gpu
     lo, hi = rank * F, (rank + 1) * F
@@ -390,6 +392,7 @@ def run_ours(args):
     if chain:     # the mesh pass overlaps the fit inside the step; for its roofline it is timed alone (rank 0
         # only: no collective here, the other ranks have already returned)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fitter.forward_batch(out["params"], out_vertices=sf.vertices)      # sizes the workspace for one full pass
         torch.cuda.synchronize()
         e0.record()
         fitter.forward_batch(out["params"], out_vertices=sf.vertices)
