@@ -181,6 +181,9 @@ def optimize_params_sequence(
         init["transl"] = default_init_params(pose, init["betas"], xyz[0:1], fitter, seq_cfg.frame.joints_category,
                                              seq_cfg.frame.coordinate_mode).transl
 
+    if model_indices is not None and body_model in SMPL_FAMILY:
+        # dict-block observations: into the fitter's observation slots (unobserved joints get confidence 0)
+        xyz, conf = fitter.scatter_observations(xyz, conf, model_indices)
     out = fit_sequence_batched(fitter, xyz, conf, init, seq_cfg)
     # per-frame views in one C++ pass per field (split / unbind), not 8 Python slicing calls per frame
     rows = {k: v.split(1) for k, v in out["params"].items() if v is not None}

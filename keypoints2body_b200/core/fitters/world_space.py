@@ -82,11 +82,7 @@ class WorldSpaceFitter:
             raise ValueError(f"keypoints2body_b200 runs on CUDA devices only, got device={device}")
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        if joints_category == "GENERIC":
-            raise NotImplementedError(
-                "GENERIC / dict-block observations need vertex-picked joints inside the loop; "
-                "not built yet (SURVEY.md section 8f row 2)")
-        if joints_category not in ("SMPL24", "AMASS"):
+        if joints_category not in ("SMPL24", "AMASS", "GENERIC"):
             raise ValueError("No such joints category!")
         self.smpl = smpl_model
         self.step_size = float(step_size)
@@ -115,6 +111,10 @@ class WorldSpaceFitter:
                     pass
         self.model_type = self.native.weights.model_type
         self.has_expr = self.native.num_shape == 20
+        if joints_category == "GENERIC":
+            # dict-block / explicit-index observations (world_space.py:198-201): supported where every index addresses
+            # a body joint the kernels fit (see scatter_observations); the observation slots are the model's own
+            self.num_obs = 24 if self.model_type == "smpl" else 22
 
     # ------------------------------------------------------------------ kernels
     def _run_fit(self, B, targets, conf, conf_per_frame, pose, betas, transl, expr, preserve, frame_iters,
@@ -300,6 +300,39 @@ class WorldSpaceFitter:
             nat.check(lib.k2b_shape_pass(self.native.handle, C.byref(a), nat.current_stream()))
         self.last_shape_evals = out_evals
         return out_betas
+
+    def scatter_observations(self, j3d, conf, model_indices):
+        """Observations given against explicit model-joint indices (``target_model_indices``, the reference's
+        GENERIC path, world_space.py:198-201) -> this fitter's fixed observation slots.
+
+        ``j3d`` (B,K,3), ``conf`` (K,) | (B,K) | None, ``model_indices`` (K,).  Slot i of the result holds the
+        observation of model joint i; joints nobody observed get confidence 0, i.e. no loss and no gradient,
+        which is exactly the sum the reference forms over the observed joints only.  Indices beyond the fitted
+        body joints (SMPL-H / SMPL-X hand joints, vertex-picked fingertips and face landmarks) need the finger
+        chains and the vertex branch inside the loop and are refused.
+        """
+        dev = self.device
+        idx = [int(i) for i in torch.as_tensor(model_indices).reshape(-1).tolist()]
+        if any(i < 0 or i >= self.num_obs for i in idx):
+            raise NotImplementedError(
+                f"observations of model joints >= {self.num_obs} (hand joints, vertex-picked fingertips / face "
+                "landmarks) are not built yet: they need the finger chains and the vertex branch inside the "
+                "fitting loop (SURVEY.md section 8f row 2)")
+        if len(set(idx)) != len(idx):
+            raise NotImplementedError("a model joint observed more than once is not supported")
+        j3d = _f32(j3d, dev)
+        if j3d.dim() != 3 or j3d.shape[1] != len(idx):
+            raise ValueError(f"j3d must be (B, {len(idx)}, 3) for {len(idx)} model indices, got {tuple(j3d.shape)}")
+        B = j3d.shape[0]
+        sel = torch.tensor(idx, device=dev, dtype=torch.long)
+        full = torch.zeros(B, self.num_obs, 3, device=dev)
+        full[:, sel] = j3d
+        conf = _f32(conf, dev)
+        if conf is None:
+            conf = torch.ones(len(idx), device=dev)
+        cfull = torch.zeros(conf.shape[:-1] + (self.num_obs,), device=dev)
+        cfull[..., sel] = conf
+        return full, cfull
 
     # ------------------------------------------------------------------ public
     def fit_batch(self, init: dict, j3d, conf=None, *, seq_ind=0, preserve_pose=None, num_iters=None,
@@ -533,7 +566,9 @@ class WorldSpaceFitter:
         if init_params.transl is None:
             raise ValueError("init_params.transl must be provided")
         if target_model_indices is not None:
-            raise NotImplementedError("explicit target_model_indices (GENERIC observations) are not built yet")
+            j3d, conf_3d = self.scatter_observations(j3d, conf_3d, target_model_indices)
+        elif self.joints_category == "GENERIC":
+            raise ValueError("joints_category='GENERIC' needs target_model_indices")
         init = {k: getattr(init_params, k) for k in ("global_orient", "body_pose", "betas", "transl")}
         if isinstance(init_params, SMPLHData):
             init["left_hand_pose"] = init_params.left_hand_pose

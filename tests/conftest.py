@@ -30,6 +30,13 @@ def goldens():
 
 
 @pytest.fixture(scope="session")
+def generic_goldens():
+    """Dict-block / explicit-index observations through the unmodified reference (make_goldens_generic.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "ref_goldens_generic.npz")
+    return dict(np.load(path))
+
+
+@pytest.fixture(scope="session")
 def weights():
     from keypoints2body_b200 import synthetic as syn
 

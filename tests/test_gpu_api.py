@@ -168,3 +168,54 @@ def test_mpjae_matches_reference(goldens):
     assert abs(float(a[:4096].double().mean().item()) - o_mean) < 1e-3
     with pytest.raises(ValueError):
         evaluate_pose_pair(np.zeros((0, 72), np.float32), np.zeros((0, 72), np.float32))
+
+
+def test_dict_body_block_frame_and_sequence(generic_goldens, weights, asset_cwd):
+    """Dict-block observations (``{"body": (K,4)}``: the reference's GENERIC layout with explicit model indices,
+    adapters.py:224-304) through the public API, against goldens from the unmodified reference."""
+    import keypoints2body_b200 as k2b
+
+    g = generic_goldens
+    block = g["gen_in_block"]
+    r = k2b.optimize_params_frame({"body": block[0]}, body_model="smpl", model=weights("smpl"),
+                                  config=dict(use_lbfgs=False))
+    assert np.abs(r.params.pose.cpu().numpy() - g["gen_frame_pose"]).max() < 1e-4
+    assert np.abs(r.params.betas.cpu().numpy() - g["gen_frame_betas"]).max() < 1e-4
+    assert np.abs(r.params.transl.cpu().numpy() - g["gen_frame_transl"]).max() < 1e-5
+    np.testing.assert_allclose(float(r.loss), float(g["gen_frame_loss"]), rtol=1e-4)
+    res = k2b.optimize_params_sequence({"body": block}, body_model="smpl", model=weights("smpl"),
+                                       config=dict(frame=dict(use_lbfgs=False), use_shape_optimization=False))
+    pose = np.concatenate([cat(res, "global_orient"), cat(res, "body_pose")], axis=1)
+    assert np.abs(pose - g["gen_seq_pose"]).max() < 1e-4
+    assert np.abs(cat(res, "betas") - g["gen_seq_betas"]).max() < 1e-4
+    assert np.abs(cat(res, "transl") - g["gen_seq_transl"]).max() < 1e-5
+    np.testing.assert_allclose(np.array([float(x.loss) for x in res]), g["gen_seq_loss"], rtol=1e-4)
+
+
+def test_explicit_target_model_indices(generic_goldens, weights, gmm):
+    """``fit_frame(target_model_indices=...)`` with a partial, permuted index set (world_space.py:198-201); indices
+    beyond the fitted body joints are refused."""
+    from keypoints2body_b200.core.fitters.world_space import WorldSpaceFitter
+    from keypoints2body_b200.models.smpl_data import SMPLData, SMPLXData
+
+    g = generic_goldens
+    idx = torch.as_tensor(g["gen_idx"]).long()
+    block = torch.as_tensor(g["gen_in_block"])
+    pose = torch.as_tensor(g["gen_idx_in_pose"])
+    f = WorldSpaceFitter(weights("smpl"), num_iters_first=12, use_lbfgs=False, joints_category="GENERIC",
+                         model_type="smpl", gmm=gmm)
+    init = SMPLData(betas=torch.zeros(1, 10), global_orient=pose[:, :3], body_pose=pose[:, 3:],
+                    transl=torch.as_tensor(g["gen_idx_in_transl"]))
+    r = f.fit_frame(init, block[1:2, idx, :3], block[1, idx, 3], seq_ind=0, target_model_indices=idx)
+    assert np.abs(r.params.pose.cpu().numpy() - g["gen_idx_pose"]).max() < 1e-4
+    assert np.abs(r.params.transl.cpu().numpy() - g["gen_idx_transl"]).max() < 1e-5
+    np.testing.assert_allclose(float(r.loss), float(g["gen_idx_loss"]), rtol=1e-4)
+    with pytest.raises(ValueError):
+        f.fit_frame(init, block[1:2, idx, :3], block[1, idx, 3], seq_ind=0)
+    fx = WorldSpaceFitter(weights("smplx"), use_lbfgs=False, joints_category="GENERIC", model_type="smplx", gmm=gmm)
+    xinit = SMPLXData(betas=torch.zeros(1, 10), global_orient=pose[:, :3], body_pose=pose[:, 3:],
+                      transl=torch.zeros(1, 3), left_hand_pose=torch.zeros(1, 45), right_hand_pose=torch.zeros(1, 45),
+                      expression=torch.zeros(1, 10), jaw_pose=torch.zeros(1, 3), leye_pose=torch.zeros(1, 3),
+                      reye_pose=torch.zeros(1, 3))
+    with pytest.raises(NotImplementedError):     # a hand joint of SMPL-X
+        fx.fit_frame(xinit, torch.zeros(1, 2, 3), torch.ones(2), target_model_indices=torch.tensor([0, 30]))
