@@ -172,6 +172,7 @@ typedef struct k2b_chain_args {
   const float* init_transl;     /* [S][3] */
   const float* init_expr;       /* [S][10] or NULL (required iff model num_shape == 20) */
   const float* preserve_pose;   /* [S][stride][69] or NULL = each frame's initial body pose */
+  const int32_t* seq_first_ind; /* [S] per-sequence seq_ind of frame 0, or NULL = first_seq_ind for all */
   float* out_pose;              /* [S][T][72] ([T][S][72] if out_time_major; likewise below) */
   float* out_betas;             /* [S][T][10] */
   float* out_transl;            /* [S][T][3] */

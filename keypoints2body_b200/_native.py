@@ -62,6 +62,7 @@ class ChainArgs(C.Structure):
         ("lr", C.c_float), ("joint_loss_weight", C.c_float), ("pose_preserve_weight", C.c_float),
         ("targets", C.c_void_p), ("conf", C.c_void_p), ("init_pose", C.c_void_p), ("init_betas", C.c_void_p),
         ("init_transl", C.c_void_p), ("init_expr", C.c_void_p), ("preserve_pose", C.c_void_p),
+        ("seq_first_ind", C.c_void_p),
         ("out_pose", C.c_void_p), ("out_betas", C.c_void_p), ("out_transl", C.c_void_p), ("out_expr", C.c_void_p),
         ("out_loss", C.c_void_p), ("out_joints", C.c_void_p), ("out_evals", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),

@@ -152,7 +152,7 @@ class WorldSpaceFitter:
 
     def _run_chain(self, S, T, targets, conf, conf_mode, pose, betas, transl, expr, preserve, first_seq_ind, chain,
                    iters_first, iters_follow, optimizer, joint_loss_weight, pose_preserve_weight, freeze_betas,
-                   want_joints=True, outs=None, window=None, time_major=False):
+                   want_joints=True, outs=None, window=None, time_major=False, seq_first=None):
         """One launch of the warp-per-sequence kernel (``k2b_fit_chain``): S sequences x T frames, serial in t.
 
         ``outs``: preallocated output dict (rows of this launch), else allocated here.  ``window = (a, b, T_total)``:
@@ -185,7 +185,7 @@ class WorldSpaceFitter:
             pose_preserve_weight=float(pose_preserve_weight),
             targets=tgt_ptr, conf=conf_ptr, init_pose=nat.ptr(pose), init_betas=nat.ptr(betas),
             init_transl=nat.ptr(transl), init_expr=nat.ptr(expr), preserve_pose=keep_ptr,
-            out_pose=nat.ptr(outs["pose"]), out_betas=nat.ptr(outs["betas"]), out_transl=nat.ptr(outs["transl"]),
+            seq_first_ind=nat.ptr(seq_first), out_pose=nat.ptr(outs["pose"]), out_betas=nat.ptr(outs["betas"]), out_transl=nat.ptr(outs["transl"]),
             out_expr=nat.ptr(outs["expression"]), out_loss=nat.ptr(outs["loss"]),
             out_joints=nat.ptr(outs["fit_joints"]), out_evals=nat.ptr(outs["evals"]), workspace=nat.ptr(ws),
             workspace_bytes=ws.numel(),
@@ -391,17 +391,19 @@ class WorldSpaceFitter:
         if kernel == "auto":
             # few frames: one thread per frame leaves the GPU idle and a frame takes ~1.3 ms; a warp per frame
             # (k2b_fit_chain with one-frame sequences) finishes in a fraction of that
-            kernel = "warp" if (frame_iters is None and B <= self.warp_kernel_max_frames) else "frame"
+            kernel = "warp" if B <= self.warp_kernel_max_frames else "frame"
         if kernel == "warp":
-            if frame_iters is not None:
-                raise ValueError("kernel='warp' needs a scalar seq_ind")
             if conf is not None and conf_pf:
                 conf = conf.reshape(B, 1, self.num_obs)
+            if frame_iters is not None:      # per-frame seq_ind: every frame is a one-frame sequence with its own index
+                seq_first, i_first, i_follow, s0 = seq.to(torch.int32).contiguous(), n_first, n_follow, 0
+            else:
+                seq_first, i_first, i_follow, s0 = None, budget, budget, (1 if preserve_all else 0)
             res = self._run_chain(B, 1, targets.reshape(B, 1, self.num_obs, 3), conf,
                                   0 if conf is None else (2 if conf_pf else 1), pose, betas, transl,
-                                  expr if self.has_expr else None, keep_pose, 0 if not preserve_all else 1, True,
-                                  budget, budget, nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight,
-                                  pose_preserve_weight, freeze_betas)
+                                  expr if self.has_expr else None, keep_pose, s0, True, i_first, i_follow,
+                                  nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight,
+                                  pose_preserve_weight, freeze_betas, seq_first=seq_first)
         else:
             res = self._run_fit(B, targets, conf, conf_pf, pose, betas, transl, expr if self.has_expr else None,
                                 keep_pose, frame_iters, frame_preserve, preserve_all, budget,

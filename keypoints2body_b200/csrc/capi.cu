@@ -352,6 +352,7 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   p.out_seq_stride = a->out_time_major ? 1 : a->frames_per_sequence;
   p.out_frame_stride = a->out_time_major ? a->num_sequences : 1;
   p.first_seq_ind = a->first_seq_ind;
+  p.seq_first = a->seq_first_ind;
   p.chain = a->chain_init;
   p.iters_first = a->num_iters_first;
   p.iters_follow = a->num_iters_followup;

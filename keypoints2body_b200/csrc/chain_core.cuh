@@ -682,6 +682,7 @@ struct ChainParams {
   long out_seq_stride;     // output row of (sequence s, frame t) = s * out_seq_stride + t * out_frame_stride:
   long out_frame_stride;   //   (T, 1) sequence-major, (1, S) time-major
   long first_seq_ind;      // seq_ind of frame 0 (0: first-frame budget, no temporal term; world_space.py:211,214)
+  const int* seq_first;    // optional [S]: per-sequence seq_ind of frame 0 (overrides first_seq_ind)
   int chain;               // 1: frame t starts from frame t-1's result (use_previous_frame_init); 0: from the init
   int iters_first, iters_follow;
   int lbfgs, freeze_betas;
@@ -757,7 +758,7 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[f * kBodyDim + 3 * lane - 3 + c] : xr[c];
-    const bool first = p.first_seq_ind + t == 0;
+    const bool first = (p.seq_first ? (long)p.seq_first[seq] : p.first_seq_ind) + t == 0;
     ob.keep_w2 = first ? 0.f : p.keep_w2;
     fo.iters = first ? p.iters_first : p.iters_follow;
     int evals = 0;

@@ -181,3 +181,21 @@ if what == "chainprof":
         o = f.fit_chain(init, tgt, None, with_mesh=False)
     torch.cuda.synchronize()
     print("ok", float(o["loss"].mean()))
+if what == "cross":
+    # where does the warp-per-frame kernel stop beating the thread-per-frame kernel?
+    for opt in ("lbfgs", "adam"):
+        f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=opt == "lbfgs")
+        for B in (1024, 4096, 8192, 16384, 32768, 65536):
+            mo = syn.make_motion(B, seed=3)
+            tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22).cuda()
+            init = dict(global_orient=torch.zeros(B, 3), body_pose=torch.zeros(B, 69), betas=torch.zeros(B, 10), transl=mo["transl"])
+            init = {k: v.cuda() for k, v in init.items()}
+            for seq in (0, 1):
+                row = []
+                for kern in ("frame", "warp"):
+                    f.fit_batch(init, tgt, None, seq_ind=seq, with_mesh=False, kernel=kern)
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    for _ in range(3):
+                        f.fit_batch(init, tgt, None, seq_ind=seq, with_mesh=False, kernel=kern)
+                    torch.cuda.synchronize(); row.append((time.perf_counter() - t0) / 3 * 1e3)
+                print(f"cross {opt} B={B} seq_ind={seq}: frame {row[0]:.2f} ms, warp {row[1]:.2f} ms", flush=True)
