@@ -92,7 +92,11 @@ class WorldSpaceFitter:
         self.device = device
         self.joints_category = joints_category
         self.num_obs = 24 if joints_category == "SMPL24" else 22
-        self.warp_kernel_max_frames = int(os.environ.get("K2B_WARP_MAX_FRAMES", "1024"))
+        # fit_batch(kernel="auto"): up to this many frames the warp-per-frame kernel is faster than the thread-per-frame
+        # one, whose time is flat up to a full grid (measured on B200, 30 / 10 iterations, ms: L-BFGS B=4096 2.1 / 0.7
+        # vs 8.8 / 2.9, B=16384 6.9 / 2.3 vs 9.7 / 2.8, B=32768 13.0 / 4.4 vs 10.8 / 3.1; Adam B=8192 2.3 / 0.8 vs
+        # 4.2 / 1.6, B=16384 4.5 / 1.5 vs 4.3 / 1.6)
+        self.warp_kernel_max_frames = int(os.environ.get("K2B_WARP_MAX_FRAMES", "16384" if use_lbfgs else "12288"))
 
         if isinstance(smpl_model, nat.NativeModel):
             self.native = smpl_model

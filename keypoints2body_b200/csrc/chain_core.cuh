@@ -312,20 +312,33 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
   Rod o;
   const V3 r = v3(xr[0], xr[1], xr[2]);
   const M3 R = rodrigues(r, o);
-  M3 Rw = R, Rp = eye3();
+  // World transforms by pointer doubling: after round r a lane holds the transform from its ancestor 2^(r+1)
+  // levels up (exclusive) down to itself, so 3 rounds (4 for the SMPL hands at depth 8) of 12 shuffles reach the
+  // root, instead of one round per tree level.  The products associate differently from a root-to-leaf walk
+  // (rounding-level differences, ~1e-7 m on the joints).
+  M3 Rw = R;
   V3 t = rel;
-#pragma unroll 1
-  for (int lev = 1; lev <= MAXD; ++lev) {
-    M3 Rq;
+  {
+    int up = (isj && j > 0) ? par : -1;          // ancestor the accumulated transform hangs from; -1: reached the root
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Rq.m[i] = shfl(Rw.m[i], par);
-    const V3 tq = v3(shfl(t.x, par), shfl(t.y, par), shfl(t.z, par));
-    if (dep == lev) {
-      Rp = Rq;
-      t = matvec(Rq, rel) + tq;
-      Rw = matmul(Rq, R);
+    for (int r = 0; r < ((MAXD > 7) ? 4 : 3); ++r) {
+      const int src = up >= 0 ? up : lane;
+      M3 Ru;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Ru.m[i] = shfl(Rw.m[i], src);
+      const V3 tu = v3(shfl(t.x, src), shfl(t.y, src), shfl(t.z, src));
+      const int upu = (int)shfl((float)up, src);
+      if (up >= 0) {
+        t = matvec(Ru, t) + tu;
+        Rw = matmul(Ru, Rw);
+        up = upu;
+      }
     }
   }
+  M3 Rp;                                          // the parent's world rotation (identity for the root)
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rp.m[i] = shfl(Rw.m[i], par);
+  if (!isj || j == 0) Rp = eye3();
 
   // ---- residuals (gmof, losses.py:6-10) ----------------------------------------------------------
   V3 g = v3(0.f, 0.f, 0.f);
