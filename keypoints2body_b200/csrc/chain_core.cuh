@@ -14,9 +14,9 @@
 // Ownership: element e of the parameter vector [go 3 | body 69 | transl 3 | shape NS] belongs to lane
 // e / 3, register e % 3 -- lane j < 24 owns the rotation of joint j, lane 24 the translation, lanes
 // 25.. the shape coefficients.
-//   kinematic tree   lane = joint; world transforms level by level (parent state fetched with
-//                    shuffles), subtree sums of the world-frame backward gathered child -> parent the
-//                    same way;
+//   kinematic tree   lane = joint; world transforms by pointer doubling towards the root (3-4 rounds of
+//                    shuffles), subtree sums of the world-frame backward by suffix scans along the
+//                    first-child chains plus the four side-branch additions;
 //   GMM prior        y = P_m d with the symmetric precision P_m = L_m L_m^T in shared memory: 27 lanes
 //                    as 3 row groups x 9 column chunks of 8; q_m = d.y needs no cross-group exchange,
 //                    only the arg-min component's y is combined (its gradient is P d itself).
@@ -291,10 +291,7 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
   const bool isj = lane < NJ;
   const int j = isj ? lane : 0;
   const int par = tree_parent(j);
-  const int dep = isj ? tree_depth(j) : 99;
   const int c0 = isj ? tree_first_child<NJ>(j) : -1;
-  const int c1 = (lane == 0) ? 2 : (lane == 9 ? 13 : -1);
-  const int c2 = (lane == 0) ? 3 : (lane == 9 ? 14 : -1);
   V3 rel;
   {
     const float4* e = tb.rel + j * (1 + NS);
@@ -362,17 +359,31 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
   if (with_grad) {
     Acc a{zero3(), v3(0.f, 0.f, 0.f)};
     if (lane < K) acc_point(a, g, t);
-#pragma unroll 1
-    for (int lev = MAXD; lev >= 1; --lev) {
-      const bool mine = dep == lev - 1;
-      Acc v = shfl_acc(a, c0 >= 0 ? c0 : lane);
-      if (mine && c0 >= 0) acc_add(a, v);
-      if (lev == 1 || lev == 4) {       // joints 0 and 9 have three children
-        v = shfl_acc(a, c1 >= 0 ? c1 : lane);
-        if (mine && c1 >= 0) acc_add(a, v);
-        v = shfl_acc(a, c2 >= 0 ? c2 : lane);
-        if (mine && c2 >= 0) acc_add(a, v);
+    // Subtree sums.  Following first children the tree is five chains (0-1-4-7-10, 2-5-8-11, 3-6-9-12-15 and the
+    // two arms from 13 / 14); three pointer-doubling rounds give every joint the sum over the rest of its chain,
+    // then the arm chains are added to 9, 6, 3 and the chains headed by 2 and 3 to the root: 7 exchanges of 12
+    // values instead of one per tree level plus the side branches (11).
+    {
+      int nx = c0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int src = nx >= 0 ? nx : lane;
+        const Acc v = shfl_acc(a, src);
+        const int nxn = (int)shfl((float)nx, src);
+        if (nx >= 0) {
+          acc_add(a, v);
+          nx = nxn;
+        }
       }
+      const bool spine = lane == 3 || lane == 6 || lane == 9;
+      Acc v = shfl_acc(a, 13);
+      if (spine) acc_add(a, v);
+      v = shfl_acc(a, 14);
+      if (spine) acc_add(a, v);
+      v = shfl_acc(a, 2);
+      if (lane == 0) acc_add(a, v);
+      v = shfl_acc(a, 3);
+      if (lane == 0) acc_add(a, v);
     }
     V3 rb = v3(0.f, 0.f, 0.f);           // a leaf's own rotation moves nothing observed
     V3 drel = v3(0.f, 0.f, 0.f);
