@@ -442,7 +442,7 @@ class WorldSpaceFitter:
         while the next window is being fitted -- the fit leaves most of every SM idle when there are few
         sequences.  ``params_ready``: optional event recorded when the fitted parameters are final.
         ``mesh_capped_fraction``: share of the windows whose mesh pass is held to the SMs the fit leaves free
-        (the rest, at the end, run on all SMs); default 0.75 for L-BFGS, 0.45 for Adam, whose fit is shorter
+        (the rest, at the end, run on all SMs); default 0.7 for L-BFGS, 0.45 for Adam, whose fit is shorter
         relative to the mesh.
         """
         dev = self.device
@@ -526,7 +526,9 @@ class WorldSpaceFitter:
         ctas, warps = C.c_int32(), C.c_int32()
         n_sms = self.native.lib.k2b_chain_geometry(self.native.handle, S, C.byref(ctas), C.byref(warps))
         free_sms = n_sms - ctas.value
-        frac = mesh_capped_fraction if mesh_capped_fraction is not None else (0.75 if lbfgs else 0.45)
+        frac = mesh_capped_fraction
+        if frac is None:
+            frac = float(os.environ.get("K2B_MESH_CAPPED_FRACTION", "0.7" if lbfgs else "0.45"))
         capped = min(chunks - 1, int(round(chunks * frac))) if free_sms >= 8 else 0
         bounds = [(T * c) // chunks for c in range(chunks + 1)]
         init_c = (pose, betas, transl, expr if self.has_expr else None)
