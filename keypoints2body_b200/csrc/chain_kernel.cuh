@@ -1,12 +1,13 @@
 // chain_kernel.cuh -- the warp-per-sequence fitting kernel (K5).
 //
-// One warp walks one sequence frame by frame (chain_core.cuh); a CTA holds up to 16 such warps next to
-// the tables they share: the eight symmetric 69 x 69 precision matrices (159 KB), the mixture means and
-// the rest-offset table.  Per-warp shared memory: the evaluation point, the GMM difference / gradient
-// staging vectors, four gradient slots and the L-BFGS rho / alpha arrays (~2.7 KB).  The L-BFGS (y, s)
-// history lives in global scratch (one block per resident warp, L2-resident), read one pair ahead.
-// With few sequences a second warp per sequence scans the mixture prior (FMA-bound, a third of an evaluation)
-// while the first walks the kinematic tree; the two meet through named barriers.
+// One warp walks one sequence frame by frame (chain_core.cuh); a CTA holds up to 12 warps next to the
+// tables they share: the eight symmetric 69 x 69 precision matrices (159 KB), the mixture means and the
+// rest-offset table.  Per-warp shared memory (~4 KB): the evaluation point, the double-buffered GMM
+// difference vectors, the per-lane partial sums of the eight components, the arg-min component's gradient,
+// four L-BFGS gradient slots and the rho / alpha arrays.  The L-BFGS (y, s) history lives in global scratch
+// (one block per walking warp, L2-resident), read one pair ahead.
+// With few sequences up to three helper warps per sequence scan the mixture prior (bound by the FMA pipe of
+// one scheduler per warp) while the first warp walks the kinematic tree; they meet through named barriers.
 // Used for the reference's default sequence schedule (serial in t) and for small batches, where the
 // one-thread-per-frame kernel is latency-bound.
 #pragma once
