@@ -44,6 +44,24 @@ SEQ_LEN = 4096
 EVAL_FLOP = {"smpl": 98e3, "smplh": 110e3, "smplx": 115e3}   # algorithmic flop / evaluation, SURVEY.md 8(d)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner under torchrun)
+    is sent to stderr instead."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,7 +235,7 @@ def run_reference(args):
     sched = "S2 (30 + 10 iteration budgets)" if args.schedule == "two_sweep" else "S1 (serial chain, 30 then 10 iterations)"
     sample = (f"{n} frames/step, schedule {sched}, {args.optimizer}, B=1 per frame, "
               f"torch {torch.__version__} CPU, full-mesh forward per evaluation")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -226,7 +244,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "cpu_baseline_batched_adam": cpu_reference_batched_adam(1024, threads),
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 class ChainRunner:
@@ -279,7 +297,6 @@ def run_ours(args):
     if world > 1:
         import datetime
 
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version banner off stdout (one JSON line)
 
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     F = args.frames_per_gpu
@@ -469,7 +486,7 @@ def run_ours(args):
             "sample": f"{n} frames, schedule {'S1 (serial chain)' if chain else 'S2 (30 + 10 budgets)'}, {args.optimizer}, B=1 per frame, torch CPU, "
                       "full-mesh forward per evaluation like the reference"}
         line["cpu_baseline_batched_adam"] = cpu_reference_batched_adam(1024, threads)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -530,6 +547,7 @@ def fma_peak(lib):
 
 if __name__ == "__main__":
     a = parse()
+    claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
