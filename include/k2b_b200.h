@@ -182,6 +182,11 @@ typedef struct k2b_chain_args {
   int32_t* out_evals;           /* [S][T] or NULL */
   void* workspace;              /* L-BFGS history; may be NULL for Adam */
   size_t workspace_bytes;       /* >= k2b_chain_workspace_bytes(m, S, optimizer, max(num_iters_*)) */
+  /* camera-space fitter stages, same meaning as in k2b_fit_args; all zero / NULL for the world-space fitter */
+  int32_t loss_kind;
+  int32_t final_loss_mode;
+  float depth_weight;
+  const float* depth_ref;       /* [S][stride][3], required for loss_kind 1 */
 } k2b_chain_args;
 
 size_t k2b_chain_workspace_bytes(const k2b_model* m, int64_t num_sequences, int32_t optimizer,

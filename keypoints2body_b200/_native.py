@@ -66,6 +66,8 @@ class ChainArgs(C.Structure):
         ("out_pose", C.c_void_p), ("out_betas", C.c_void_p), ("out_transl", C.c_void_p), ("out_expr", C.c_void_p),
         ("out_loss", C.c_void_p), ("out_joints", C.c_void_p), ("out_evals", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("loss_kind", C.c_int32), ("final_loss_mode", C.c_int32), ("depth_weight", C.c_float),
+        ("depth_ref", C.c_void_p),
     ]
 
 

@@ -69,20 +69,40 @@ class CameraSpaceFitter(WorldSpaceFitter):
         cam_t0 = _f32(init_cam_t, dev).contiguous()
         opt = nat.OPT_LBFGS if self.use_lbfgs else nat.OPT_ADAM
         pose = torch.cat([go, bp], dim=1).contiguous()
-        # stage 1: orientation + camera translation against the torso joints
-        s1 = self._run_fit(B, targets, conf, conf_pf, pose, betas, cam_t0, None, None, None, None, 0, self.num_iters,
-                           opt, joint_loss_weight, 0.0, True, want_joints=False, loss_kind=1, depth_ref=cam_t0)
-        # stage 2: full body fit; the temporal anchor is the INITIAL body pose (camera_space.py:136)
         move_betas = seq_ind == 0 or not freeze_betas
-        s2 = self._run_fit(B, targets, conf, conf_pf, s1["pose"], betas, s1["transl"], None, bp.contiguous(), None, None,
-                           int(seq_ind > 0), self.num_iters, opt, joint_loss_weight, pose_preserve_weight,
-                           not move_betas, want_joints=True, final_loss_mode=1)
+        if B <= self.warp_kernel_max_frames:
+            # few frames (the reference's camera fits are B = 1): one warp per frame (k2b_fit_chain with one-frame
+            # sequences) instead of one thread per frame
+            tg = targets.reshape(B, 1, self.num_obs, 3)
+            cm = 0 if conf is None else (2 if conf_pf else 1)
+            cf = conf.reshape(B, 1, self.num_obs) if conf_pf else conf
+            s1 = self._run_chain(B, 1, tg, cf, cm, pose, betas, cam_t0, None, None, 0, True, self.num_iters,
+                                 self.num_iters, opt, joint_loss_weight, 0.0, True, want_joints=False, loss_kind=1,
+                                 depth_ref=cam_t0)
+            s2 = self._run_chain(B, 1, tg, cf, cm, s1["pose"], betas, s1["transl"], None, bp.contiguous(),
+                                 int(seq_ind > 0), True, self.num_iters, self.num_iters, opt, joint_loss_weight,
+                                 pose_preserve_weight, not move_betas, final_loss_mode=1)
+        else:
+            s1, s2 = self._fit_two_stage_frames(B, targets, conf, conf_pf, pose, betas, cam_t0, bp, seq_ind, opt,
+                                                joint_loss_weight, pose_preserve_weight, move_betas)
         params = {"global_orient": s2["pose"][:, :3], "body_pose": s2["pose"][:, 3:], "betas": s2["betas"],
                   "transl": s2["transl"]}
         out = {"params": params, "loss": s2["loss"], "evals": s1["evals"] + s2["evals"], "fit_joints": s2["fit_joints"]}
         if with_mesh:
             out.update(self.forward_batch({k: v for k, v in params.items() if k != "transl"}))
         return out
+
+    def _fit_two_stage_frames(self, B, targets, conf, conf_pf, pose, betas, cam_t0, bp, seq_ind, opt, joint_loss_weight,
+                              pose_preserve_weight, move_betas):
+        """Both stages on the one-thread-per-frame kernel (large batches)."""
+        # stage 1: orientation + camera translation against the torso joints
+        s1 = self._run_fit(B, targets, conf, conf_pf, pose, betas, cam_t0, None, None, None, None, 0, self.num_iters,
+                           opt, joint_loss_weight, 0.0, True, want_joints=False, loss_kind=1, depth_ref=cam_t0)
+        # stage 2: full body fit; the temporal anchor is the INITIAL body pose (camera_space.py:136)
+        s2 = self._run_fit(B, targets, conf, conf_pf, s1["pose"], betas, s1["transl"], None, bp.contiguous(), None, None,
+                           int(seq_ind > 0), self.num_iters, opt, joint_loss_weight, pose_preserve_weight,
+                           not move_betas, want_joints=True, final_loss_mode=1)
+        return s1, s2
 
     def fit_frame(self, init_params: SMPLData, j3d: torch.Tensor, conf_3d: Optional[torch.Tensor] = None,
                   seq_ind: int = 0, target_model_indices: Optional[torch.Tensor] = None,

@@ -156,7 +156,8 @@ class WorldSpaceFitter:
 
     def _run_chain(self, S, T, targets, conf, conf_mode, pose, betas, transl, expr, preserve, first_seq_ind, chain,
                    iters_first, iters_follow, optimizer, joint_loss_weight, pose_preserve_weight, freeze_betas,
-                   want_joints=True, outs=None, window=None, time_major=False, seq_first=None):
+                   want_joints=True, outs=None, window=None, time_major=False, seq_first=None, loss_kind=0,
+                   final_loss_mode=0, depth_ref=None, depth_weight=100.0):
         """One launch of the warp-per-sequence kernel (``k2b_fit_chain``): S sequences x T frames, serial in t.
 
         ``outs``: preallocated output dict (rows of this launch), else allocated here.  ``window = (a, b, T_total)``:
@@ -192,7 +193,8 @@ class WorldSpaceFitter:
             seq_first_ind=nat.ptr(seq_first), out_pose=nat.ptr(outs["pose"]), out_betas=nat.ptr(outs["betas"]), out_transl=nat.ptr(outs["transl"]),
             out_expr=nat.ptr(outs["expression"]), out_loss=nat.ptr(outs["loss"]),
             out_joints=nat.ptr(outs["fit_joints"]), out_evals=nat.ptr(outs["evals"]), workspace=nat.ptr(ws),
-            workspace_bytes=ws.numel(),
+            workspace_bytes=ws.numel(), loss_kind=int(loss_kind), final_loss_mode=int(final_loss_mode),
+            depth_weight=float(depth_weight), depth_ref=nat.ptr(depth_ref),
         )
         with torch.cuda.device(dev):
             nat.check(lib.k2b_fit_chain(self.native.handle, C.byref(a), nat.current_stream()))

@@ -367,6 +367,12 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   p.preserve_pose = a->preserve_pose;
   p.out_pose = a->out_pose; p.out_betas = a->out_betas; p.out_transl = a->out_transl; p.out_expr = a->out_expr;
   p.out_loss = a->out_loss; p.out_joints = a->out_joints; p.out_evals = a->out_evals;
+  if (a->loss_kind != 0 && a->loss_kind != 1) return fail(K2B_EINVAL, "unknown loss_kind");
+  if (a->loss_kind == 1 && !a->depth_ref) return fail(K2B_EINVAL, "loss_kind 1 needs depth_ref");
+  p.loss_kind = a->loss_kind;
+  p.final_mode = a->final_loss_mode;
+  p.depth_w2 = 4.f * a->depth_weight * a->depth_weight;   // added to each of the 4 joint rows by the reference's broadcast
+  p.depth_ref = a->depth_ref;
   p.hmax = hmax;
   p.helpers = helpers;
   p.hist = nullptr;

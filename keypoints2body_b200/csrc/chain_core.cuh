@@ -248,6 +248,11 @@ struct FrameObs {      // this lane's share of the frame's observations
   float tx, ty, tz, w; // lane j < K: target and weight joint_w^2 conf_j^2 of joint j
   float keep[3];       // preserve pose of the owned body-pose entries
   float keep_w2;       // pose_preserve_weight^2 or 0
+  // camera-space stage 1 (camera_fitting_loss_3d, core/losses.py:70-93): plain squared joint error instead of GMoF,
+  // plus depth_w2 * |transl - dref|^2 (lane 24 holds dref)
+  bool plain_sq;
+  float depth_w2;
+  float dref[3];
 };
 
 K2B_HD Acc shfl_acc(const Acc& a, int src) {
@@ -347,11 +352,16 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
       joints_out[3 * lane + 2] = p.z;
     }
     const float ex = p.x - ob.tx, ey = p.y - ob.ty, ez = p.z - ob.tz;
-    const float ix = fdiv(1.f, kSigma2 + ex * ex), iy = fdiv(1.f, kSigma2 + ey * ey), iz = fdiv(1.f, kSigma2 + ez * ez);
-    const float gx = kSigma2 * ex * ex * ix, gy = kSigma2 * ey * ey * iy, gz = kSigma2 * ez * ez * iz;
-    lsum = ob.w * ((gx + gy) + gz);
-    const float c2w = 2.f * kSigma2 * kSigma2 * ob.w;
-    g = v3(c2w * ex * ix * ix, c2w * ey * iy * iy, c2w * ez * iz * iz);
+    if (ob.plain_sq) {
+      lsum = ob.w * fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+      g = v3(2.f * ob.w * ex, 2.f * ob.w * ey, 2.f * ob.w * ez);
+    } else {
+      const float ix = fdiv(1.f, kSigma2 + ex * ex), iy = fdiv(1.f, kSigma2 + ey * ey), iz = fdiv(1.f, kSigma2 + ez * ez);
+      const float gx = kSigma2 * ex * ex * ix, gy = kSigma2 * ey * ey * iy, gz = kSigma2 * ez * ez * iz;
+      lsum = ob.w * ((gx + gy) + gz);
+      const float c2w = 2.f * kSigma2 * kSigma2 * ob.w;
+      g = v3(c2w * ex * ix * ix, c2w * ey * iy * iy, c2w * ez * iz * iz);
+    }
   }
   gr[0] = gr[1] = gr[2] = 0.f;
 
@@ -413,6 +423,15 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
         for (int c = 0; c < 3; ++c)
           if (3 * lane + c == kShapeOff + s) gr[c] = v;
       }
+    }
+  }
+
+  if (ob.depth_w2 != 0.f && lane == 24) {   // camera-space stage 1: keep the translation near its initial estimate
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = xr[c] - ob.dref[c];
+      lsum = fmaf(ob.depth_w2 * d, d, lsum);
+      if (with_grad) gr[c] = fmaf(2.f * ob.depth_w2, d, gr[c]);
     }
   }
 
@@ -623,6 +642,8 @@ struct FitOpts {
   int iters;
   bool lbfgs;
   bool freeze_betas;
+  bool stage1;              // camera-space stage 1: only global_orient and the translation move, no priors
+  bool final_mode;          // returned loss = priors + joints at the final parameters, no preserve (camera_space.py:316-326)
   float lr;
   const float* adam_step;   // [kAdamTableW] lr / (1 - 0.9^k)
   const float* adam_bc2;    // sqrt(1 - 0.999^k)
@@ -637,8 +658,12 @@ K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& o
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const int e = 3 * lane + c;
-    frozen[c] = e >= 75 + NS || (fo.freeze_betas && e >= kShapeOff && e < kShapeOff + 10);
+    frozen[c] = e >= 75 + NS || (fo.freeze_betas && e >= kShapeOff && e < kShapeOff + 10) ||
+                (fo.stage1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
   }
+  const bool priors = !fo.stage1;
+  FrameObs obf = ob;        // observations of the final evaluation
+  if (fo.final_mode) obf.keep_w2 = 0.f;
   float gr[3];
   float out_loss = 0.f;
   int evals = 0;
@@ -654,14 +679,17 @@ K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& o
         step_k = (float)((double)fo.lr / (1.0 - pow(0.9, (double)k)));
         bc2_k = (float)sqrt(1.0 - pow(0.999, (double)k));
       }
-      out_loss = eval_warp<NS, K>(tb, wm, ob, xr, true, true, gr, nullptr, nullptr);   // loss before the step
+      out_loss = eval_warp<NS, K>(tb, wm, ob, xr, true, priors, gr, nullptr, nullptr);   // loss before the step
       ++evals;
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         if (!frozen[c]) adam_update(xr[c], m1[c], m2[c], gr[c], step_k, bc2_k);
     }
     // joints at the final parameters (world_space.py:258-278)
-    if (joints_out) eval_warp<NS, K>(tb, wm, ob, xr, false, false, gr, joints_out, nullptr);
+    if (joints_out || fo.final_mode) {
+      const float fl = eval_warp<NS, K>(tb, wm, obf, xr, false, priors && fo.final_mode, gr, joints_out, nullptr);
+      if (fo.final_mode) out_loss = fl;
+    }
   } else {
     WVec v;
     v.gs = wm.gs;
@@ -676,7 +704,7 @@ K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& o
     bool first = true;
 #pragma unroll 1
     while (true) {
-      const float loss = eval_warp<NS, K>(tb, wm, ob, v.x, true, true, gr, nullptr, nullptr);
+      const float loss = eval_warp<NS, K>(tb, wm, ob, v.x, true, priors, gr, nullptr, nullptr);
 #pragma unroll
       for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
       wsync();
@@ -688,7 +716,7 @@ K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& o
 #pragma unroll
     for (int c = 0; c < 3; ++c) xr[c] = v.xk[c];
     // loss (and joints) re-evaluated at the returned parameters (world_space.py:246-247)
-    out_loss = eval_warp<NS, K>(tb, wm, ob, xr, false, true, gr, joints_out, nullptr);
+    out_loss = eval_warp<NS, K>(tb, wm, obf, xr, false, priors, gr, joints_out, nullptr);
   }
   if (evals_out) *evals_out = evals;
   return out_loss;
@@ -724,6 +752,10 @@ struct ChainParams {
   float* hist;             // L-BFGS (y, s) history, hist_floats(hmax) per resident warp
   int hmax;
   int helpers;             // helper warps per sequence that scan the mixture components (0 = the walking warp does it)
+  // camera-space fitter (core/fitters/camera_space.py:81-339), see k2b_fit_args: loss_kind 1 = stage 1, final_mode 1 = stage 2
+  int loss_kind, final_mode;
+  float depth_w2;
+  const float* depth_ref;  // [S][stride][3] initial camera translation (loss_kind 1)
   float adam_step[kAdamTableW], adam_bc2[kAdamTableW];
 };
 K2B_HD constexpr long hist_floats(int hmax) { return (long)hmax * 2 * kWarpVec; }
@@ -762,6 +794,8 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
   fo.adam_step = p.adam_step;
   fo.adam_bc2 = p.adam_bc2;
   fo.adam_table = kAdamTableW;
+  fo.stage1 = p.loss_kind == 1;
+  fo.final_mode = p.final_mode != 0;
   const bool body_owner = lane >= 1 && lane < 24;
 #pragma unroll 1
   for (int t = 0; t < p.frames; ++t) {
@@ -778,7 +812,13 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
       ob.tx = tg[0]; ob.ty = tg[1]; ob.tz = tg[2];
       const float cf = p.conf_mode == 0 ? 1.f : (p.conf_mode == 1 ? p.conf[lane] : p.conf[f * K + lane]);
       ob.w = p.joint_w2 * cf * cf;
+      // camera stage 1 looks at RHip, LHip, RShoulder, LShoulder only, unweighted (losses.py:80-92)
+      if (fo.stage1) ob.w = (lane == 1 || lane == 2 || lane == 16 || lane == 17) ? 1.f : 0.f;
     }
+    ob.plain_sq = fo.stage1;
+    ob.depth_w2 = fo.stage1 ? p.depth_w2 : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ob.dref[c] = (fo.stage1 && lane == 24) ? p.depth_ref[f * 3 + c] : 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[f * kBodyDim + 3 * lane - 3 + c] : xr[c];

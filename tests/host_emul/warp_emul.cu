@@ -146,6 +146,9 @@ void lane_job() {
     for (int c = 0; c < 3; ++c)
       ob.keep[c] = (lane >= 1 && lane < 24) ? g.p.preserve_pose[3 * lane - 3 + c] : 0.f;
     ob.keep_w2 = g.p.keep_w2;
+    ob.plain_sq = false;
+    ob.depth_w2 = 0.f;
+    ob.dref[0] = ob.dref[1] = ob.dref[2] = 0.f;
     int comp = 0;
     const float loss = wc::eval_warp<NS, K>(tb, wm, ob, xr, true, true, gr, g.joints, &comp);
     for (int c = 0; c < 3; ++c)
@@ -188,7 +191,7 @@ extern "C" int wemu_chain(void* model, int K, int S, int T, long first_seq_ind, 
                           const float* conf, int conf_mode, const float* init_pose, const float* init_betas,
                           const float* init_transl, const float* init_expr, const float* preserve_pose, float* out_pose,
                           float* out_betas, float* out_transl, float* out_expr, float* out_loss, float* out_joints,
-                          int* out_evals) {
+                          int* out_evals, int loss_kind, int final_mode, float depth_weight, const float* depth_ref) {
   g.m = (WEmuModel*)model;
   g.K = K;
   g.eval_only = false;
@@ -202,6 +205,9 @@ extern "C" int wemu_chain(void* model, int K, int S, int T, long first_seq_ind, 
   p.targets = targets; p.conf = conf;
   p.init_pose = init_pose; p.init_betas = init_betas; p.init_transl = init_transl; p.init_expr = init_expr;
   p.preserve_pose = preserve_pose;
+  p.loss_kind = loss_kind; p.final_mode = final_mode;
+  p.depth_w2 = 4.f * depth_weight * depth_weight;   // the reference's (B,4,3)+(B,3) broadcast counts the depth term per joint row
+  p.depth_ref = depth_ref;
   p.out_pose = out_pose; p.out_betas = out_betas; p.out_transl = out_transl; p.out_expr = out_expr;
   p.out_loss = out_loss; p.out_joints = out_joints; p.out_evals = out_evals;
   const int max_it = iters_first > iters_follow ? iters_first : iters_follow;

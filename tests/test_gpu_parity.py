@@ -279,9 +279,10 @@ def test_edge_cases(fitters, weights):
         f.fit_batch({k: v for k, v in init.items() if k != "transl"}, tgt, None)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("tag,iters,seq_ind", [("cam_given_adam", 15, 0), ("cam_given_adam_follow", 15, 2),
                                                ("cam_adam", 15, 0), ("cam_adam_follow", 15, 2)])
-def test_camera_fitter_adam_vs_reference_goldens(goldens, weights, gmm, tag, iters, seq_ind):
+def test_camera_fitter_adam_vs_reference_goldens(goldens, weights, gmm, tag, iters, seq_ind, kernel):
     """Camera-space two-stage fitter, Adam: reference CameraSpaceFitter goldens.  Strict from a
     caller-supplied ``init_cam_t``; from the stage-0 estimate (zero translation gradient -> Adam's first
     step is rounding noise in the reference too) only the outcome is compared."""
@@ -291,6 +292,7 @@ def test_camera_fitter_adam_vs_reference_goldens(goldens, weights, gmm, tag, ite
     g = goldens
     f = CameraSpaceFitter(weights("smpl"), num_iters=iters, use_lbfgs=False, joints_category="AMASS",
                           model_type="smpl", gmm=gmm)
+    f.warp_kernel_max_frames = 0 if kernel == "frame" else 1 << 20     # both stages on that kernel
     pose, tgt = T(g["cam_in_pose"]), T(g["cam_in_target"])
     strict = "given" in tag
     for b in range(3):
@@ -309,11 +311,13 @@ def test_camera_fitter_adam_vs_reference_goldens(goldens, weights, gmm, tag, ite
             assert np.abs(cpu(r.params.pose) - g[tag + "_pose"][b:b + 1]).max() < 0.1
 
 
-def test_camera_fitter_lbfgs_statistics(goldens, weights, gmm):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_camera_fitter_lbfgs_statistics(goldens, weights, gmm, kernel):
     from keypoints2body_b200.core.fitters.camera_space import CameraSpaceFitter
 
     g = goldens
     f = CameraSpaceFitter(weights("smpl"), num_iters=20, use_lbfgs=True, joints_category="AMASS", model_type="smpl", gmm=gmm)
+    f.warp_kernel_max_frames = 0 if kernel == "frame" else 1 << 20
     pose, tgt = T(g["cam_in_pose"]), T(g["cam_in_target"])
     out = f.fit_batch(dict(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=torch.zeros(3, 10)), tgt,
                       torch.ones(22), seq_ind=0, freeze_betas=True)

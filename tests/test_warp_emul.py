@@ -50,7 +50,7 @@ def wemu():
     lib.wemu_eval.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, fp, fp, fp, fp, fp, fp, fp, ip]
     lib.wemu_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_float, C.c_float, C.c_float, fp, fp, C.c_int, fp, fp, fp, fp, fp,
-                               fp, fp, fp, fp, fp, fp, ip]
+                               fp, fp, fp, fp, fp, fp, ip, C.c_int, C.c_int, C.c_float, fp]
     return lib
 
 
@@ -79,7 +79,8 @@ class WModel:
         return dict(grad=grad, loss=float(loss[0]), joints=joints, comp=int(comp[0]))
 
     def chain(self, x0, targets, conf=None, first_seq_ind=0, chain=True, lbfgs=False, iters_first=30,
-              iters_follow=10, freeze=False, lr=1e-2, joint_w=600.0, keep_w=5.0, keep=None):
+              iters_follow=10, freeze=False, lr=1e-2, joint_w=600.0, keep_w=5.0, keep=None, loss_kind=0,
+              final_mode=0, depth_ref=None):
         """x0 (S,NX); targets (S,T,K,3); returns arrays shaped (S,T,..)."""
         S, T, K = targets.shape[:3]
         x0, targets = f32(x0), f32(targets)
@@ -95,7 +96,8 @@ class WModel:
                             int(freeze), lr, joint_w, keep_w, _p(targets), _p(conf),
                             0 if conf is None else (1 if conf.ndim == 1 else 2), _p(pose), _p(betas), _p(transl),
                             _p(expr), _p(keep), _p(o["pose"]), _p(o["betas"]), _p(o["transl"]), _p(o["expr"]),
-                            _p(o["loss"]), _p(o["joints"]), o["evals"].ctypes.data_as(ip))
+                            _p(o["loss"]), _p(o["joints"]), o["evals"].ctypes.data_as(ip), loss_kind, final_mode, 100.0,
+                            None if depth_ref is None else _p(f32(depth_ref)))
         return o
 
 
@@ -195,3 +197,26 @@ def test_warp_sequence_chain_matches_reference(goldens, wmodels, shims, name, ch
     assert np.abs(out["transl"][0] - g[name + "_transl"]).max() < 1e-5
     assert np.abs(out["joints"][0] - g[name + "_joints"][:, :22]).max() < 1e-4
     np.testing.assert_allclose(out["loss"][0], g[name + "_loss"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("tag,iters,seq_ind", [("cam_given_adam", 15, 0), ("cam_given_adam_follow", 15, 2)])
+def test_warp_camera_two_stage_adam_matches_reference(goldens, wmodels, tag, iters, seq_ind):
+    """Camera-space fitter (camera_space.py:81-339) on the warp-cooperative path: stage 1 (loss_kind 1: torso joints,
+    plain squared error, depth anchor, only orientation + translation move) then stage 2 (world loss with the
+    initial body pose as temporal anchor, loss re-evaluated without it), against the reference goldens made with a
+    caller-supplied ``init_cam_t``."""
+    g = goldens
+    m = wmodels("smpl")
+    pose, tgt, cam0 = g["cam_in_pose"], g["cam_in_target"], g["cam_given_init"]
+    x0 = pack_x(pose, cam0, np.zeros((len(pose), 10), np.float32))
+    s1 = m.chain(x0, tgt[:, None], np.ones(22), first_seq_ind=0, iters_first=iters, iters_follow=iters, freeze=True,
+                 loss_kind=1, depth_ref=cam0)
+    assert np.abs(s1["pose"][:, 0, 3:] - pose[:, 3:]).max() == 0          # stage 1 moves orientation + translation only
+    assert np.abs(s1["betas"][:, 0]).max() == 0
+    x1 = pack_x(s1["pose"][:, 0], s1["transl"][:, 0], s1["betas"][:, 0])
+    s2 = m.chain(x1, tgt[:, None], np.ones(22), first_seq_ind=1 if seq_ind > 0 else 0, iters_first=iters,
+                 iters_follow=iters, freeze=seq_ind > 0, keep=pose[:, None, 3:], final_mode=1)
+    assert np.abs(s2["pose"][:, 0] - g[tag + "_pose"]).max() < 1e-4
+    assert np.abs(s2["transl"][:, 0] - g[tag + "_transl"]).max() < 1e-4
+    assert np.abs(s2["betas"][:, 0] - g[tag + "_betas"]).max() < 1e-4
+    np.testing.assert_allclose(s2["loss"][:, 0], g[tag + "_loss"].reshape(-1), rtol=1e-4)

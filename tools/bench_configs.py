@@ -81,6 +81,22 @@ def main():
             emit(config=f"config2 optimize_params_sequence SMPL T={T} {name}", optimizer="lbfgs" if lb else "adam",
                  ms_per_call=ms, frames_per_s=T * 1e3 / ms, timing="wall clock through the public API (results as per-frame objects)")
 
+    # ---- row f1: camera-space two-stage fitter through the public API (B = 1 per frame by construction) -----
+    for lb in (True, False):
+        cfgc = dict(use_lbfgs=lb, coordinate_mode="camera", num_iters=30)
+        ms = wall_ms(lambda: k2b.optimize_params_frame(tgt[0], body_model="smpl", joint_layout="AMASS", model=w, config=cfgc))
+        emit(config="f1 camera-space optimize_params_frame SMPL AMASS B=1 (2 stages x 30 its, full mesh)",
+             optimizer="lbfgs" if lb else "adam", ms_per_call=ms, frames_per_s=1e3 / ms,
+             timing="wall clock incl. Python, model/prior construction per call")
+        Tc = 128
+        scfg = SequenceOptimizeConfig(frame=FrameOptimizeConfig(use_lbfgs=lb, coordinate_mode="camera", num_iters=30),
+                                      use_shape_optimization=False)
+        ms = wall_ms(lambda: k2b.optimize_params_sequence(tgt[:Tc], body_model="smpl", joint_layout="AMASS", model=w,
+                                                          config=scfg), warm=1, reps=2)
+        emit(config=f"f1 camera-space optimize_params_sequence SMPL T={Tc} (serial, 2 launches per frame)",
+             optimizer="lbfgs" if lb else "adam", ms_per_call=ms, frames_per_s=Tc * 1e3 / ms,
+             timing="wall clock through the public API")
+
     # ---- config 3: SMPL-X, 65 536 independent frames, 5 iterations -------------------------------------
     wx = syn.make_body_model("smplx")
     B = 65536
