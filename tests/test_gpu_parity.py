@@ -477,3 +477,39 @@ def test_warp_kernel_edge_cases(fitters, weights, lbfgs):
         assert (w["params"]["body_pose"] - t["params"]["body_pose"]).abs().max() < 1e-4
         assert (w["params"]["body_pose"] - a["params"]["body_pose"]).abs().max() > 1e-4     # the anchor matters
         np.testing.assert_allclose(cpu(w["loss"]), cpu(t["loss"]), rtol=1e-4)
+
+
+@pytest.mark.parametrize("mt", ["smplh", "smplx"])
+def test_chain_kernel_smplh_smplx_vs_oracle(fitters, shims, oracle_prior, weights, mt):
+    """Serial chains on the 52- / 55-joint models (expression is optimised for SMPL-X, hands / jaw / eyes pass
+    through): 3 sequences x 3 frames, Adam, against the oracle's frame-by-frame loop."""
+    from keypoints2body_b200 import synthetic as syn
+
+    S, Tn = 3, 3
+    w = weights(mt)
+    mo = syn.make_motion(Tn, seed=808, num_sequences=S)
+    g = torch.Generator().manual_seed(809)
+    tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22)
+    tgt = (tgt + 0.005 * torch.randn(tgt.shape, generator=g)).reshape(S, Tn, 22, 3)
+    pose0 = mo["pose"].reshape(S, Tn, 72)[:, 0] + 0.05 * torch.randn(S, 72, generator=g)
+    init = dict(global_orient=pose0[:, :3].contiguous(), body_pose=pose0[:, 3:].contiguous(), betas=torch.zeros(S, 10),
+                transl=mo["transl"].reshape(S, Tn, 3)[:, 0].contiguous(),
+                left_hand_pose=0.1 * torch.randn(S, 45, generator=g), right_hand_pose=0.1 * torch.randn(S, 45, generator=g))
+    if mt == "smplx":
+        init.update(expression=0.2 * torch.randn(S, 10, generator=g), jaw_pose=0.05 * torch.randn(S, 3, generator=g),
+                    leye_pose=torch.zeros(S, 3), reye_pose=torch.zeros(S, 3))
+    f = fitters(mt, use_lbfgs=False)
+    out = f.fit_chain(init, tgt, torch.ones(22))
+    prev = {k: None for k in rp.PARAM_ORDER}
+    prev.update(init)
+    for t in range(Tn):
+        r = rp.fit_frame(shims(mt), oracle_prior, prev, tgt[:, t], torch.ones(22), seq_ind=t, use_lbfgs=False)
+        prev = r["params"]
+        rows = torch.arange(S) * Tn + t
+        assert (cpu(out["params"]["body_pose"][rows]) - prev["body_pose"].numpy()).__abs__().max() < 1e-4
+        assert (cpu(out["params"]["transl"][rows]) - prev["transl"].numpy()).__abs__().max() < 1e-5
+        assert (cpu(out["joints"][rows]) - r["joints"].numpy()).__abs__().max() < 1e-4
+        assert (cpu(out["vertices"][rows]) - r["vertices"].numpy()).__abs__().max() < 1e-4
+        if mt == "smplx":
+            assert (cpu(out["params"]["expression"][rows]) - prev["expression"].numpy()).__abs__().max() < 1e-4
+    assert torch.equal(out["params"]["left_hand_pose"].cpu(), init["left_hand_pose"].repeat_interleave(Tn, dim=0))
