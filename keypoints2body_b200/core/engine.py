@@ -8,6 +8,7 @@ numeric step runs on the GPU through the fitter's kernels.
 
 from __future__ import annotations
 
+import importlib.util
 import os
 from typing import Optional
 
@@ -40,6 +41,9 @@ class OptimizeEngine:
                                         target_model_indices=target_model_indices)
 
 
+_MEAN_CACHE: dict = {}
+
+
 def load_mean_pose_shape(mean_file: str, device) -> tuple[torch.Tensor, torch.Tensor]:
     """Mean pose (1,72) and shape (1,10) from ``neutral_smpl_mean_params.h5``.
 
@@ -47,22 +51,30 @@ def load_mean_pose_shape(mean_file: str, device) -> tuple[torch.Tensor, torch.Te
     absent, an ``.npz`` with the same stem and the same ``pose`` / ``shape`` keys is read.
     """
     stem = os.path.splitext(mean_file)[0]
-    pose = shape = None
-    if os.path.exists(mean_file):
-        try:
+    use_h5 = os.path.exists(mean_file) and importlib.util.find_spec("h5py") is not None
+    src = mean_file if use_h5 else stem + ".npz"
+    if not os.path.exists(src):
+        raise FileNotFoundError(f"mean-parameter file not found: {mean_file} (or {stem}.npz)")
+    # the reference re-reads the file on every call (sequence.py:139-141, frame.py:113-115); here the parsed arrays are
+    # kept per (file, modification time, size, device): the zip / HDF5 reader was a fifth of a single-frame call
+    st = os.stat(src)
+    key = (os.path.abspath(src), st.st_mtime_ns, st.st_size, str(device))
+    hit = _MEAN_CACHE.get(key)
+    if hit is None:
+        if use_h5:
             import h5py  # noqa: WPS433
 
-            with h5py.File(mean_file, "r") as f:
+            with h5py.File(src, "r") as f:
                 pose, shape = np.asarray(f["pose"][:]), np.asarray(f["shape"][:])
-        except ImportError:
-            pose = None
-    if pose is None:
-        if not os.path.exists(stem + ".npz"):
-            raise FileNotFoundError(f"mean-parameter file not found: {mean_file} (or {stem}.npz)")
-        with np.load(stem + ".npz") as f:
-            pose, shape = f["pose"], f["shape"]
-    to = dict(device=device, dtype=torch.float32)
-    return torch.as_tensor(pose).reshape(1, -1).to(**to), torch.as_tensor(shape).reshape(1, -1).to(**to)
+        else:
+            with np.load(src) as f:
+                pose, shape = f["pose"], f["shape"]
+        to = dict(device=device, dtype=torch.float32)
+        hit = (torch.as_tensor(pose).reshape(1, -1).to(**to), torch.as_tensor(shape).reshape(1, -1).to(**to))
+        if len(_MEAN_CACHE) > 16:
+            _MEAN_CACHE.clear()
+        _MEAN_CACHE[key] = hit
+    return hit[0].clone(), hit[1].clone()
 
 
 def default_init_params(mean_pose, mean_shape, joints_frame, fitter, joints_category: str,
