@@ -81,6 +81,7 @@ int k2b_model_create(const k2b_model_desc* desc, k2b_model** out);
 void k2b_model_destroy(k2b_model* m);
 
 enum { K2B_OPT_ADAM = 0, K2B_OPT_LBFGS = 1 };
+enum { K2B_FREEZE_BETAS = 1, K2B_FREEZE_EXPR = 2 };
 
 /* One batched fit = B independent WorldSpaceFitter.fit_frame calls.
  * Flat parameter blocks follow the reference's optimiser order
@@ -91,7 +92,9 @@ typedef struct k2b_fit_args {
   int32_t num_obs;           /* K: 22 (AMASS) or 24 (SMPL24, SMPL only) */
   int32_t optimizer;         /* K2B_OPT_* */
   int32_t num_iters;         /* iteration budget (max_iter for L-BFGS) when frame_iters == NULL */
-  int32_t freeze_betas;      /* betas kept at their initial value */
+  int32_t freeze_betas;      /* bit 0 (K2B_FREEZE_BETAS): betas kept at their initial value; bit 1 (K2B_FREEZE_EXPR):
+                                expression kept (the reference optimises it only when the caller supplied one,
+                                world_space.py:222-223) */
   int32_t conf_per_frame;    /* conf is [B][K] (1) or [K] shared (0) */
   float lr;                  /* step_size, reference default 1e-2 */
   float joint_loss_weight;   /* reference default 600 */
@@ -156,7 +159,7 @@ typedef struct k2b_chain_args {
   int32_t num_iters_followup;   /* reference default 10 */
   int64_t first_seq_ind;        /* seq_ind of every sequence's frame 0 */
   int32_t chain_init;           /* 1 = use_previous_frame_init */
-  int32_t freeze_betas;
+  int32_t freeze_betas;         /* K2B_FREEZE_* bits, as in k2b_fit_args */
   int32_t conf_mode;            /* 0 none, 1 conf is [K], 2 conf is [S][stride][K] */
   int32_t out_time_major;       /* 0: outputs are [S][T][..]; 1: [T][S][..] (a time chunk of every sequence is contiguous) */
   int64_t in_sequence_stride;   /* frames between consecutive sequences in targets / conf / preserve_pose; 0 = T.

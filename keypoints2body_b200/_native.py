@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("K2B_LIB", os.path.join(_HERE, "libk2b_b200.so"))
 
 OPT_ADAM, OPT_LBFGS = 0, 1
+FREEZE_BETAS, FREEZE_EXPR = 1, 2      # k2b_fit_args.freeze_betas bits
 
 _c_float_p = C.POINTER(C.c_float)
 _c_int_p = C.POINTER(C.c_int32)

@@ -3,9 +3,9 @@
 Signature, argument meaning, error behaviour and result contract follow
 /root/reference/keypoints2body/api/frame.py:34-219.  Differences, all deliberate:
 results live on the CUDA device; ``device=None`` means the current CUDA device; numpy
-``prev_params`` are converted instead of crashing; MANO / FLAME,
-camera mode, dict observations and IK-GAT raise ``NotImplementedError`` (outside the
-accelerated path).
+``prev_params`` are converted instead of crashing.  World and camera
+coordinate modes and dict-block / explicit-index observations are served by the CUDA path; what
+still raises ``NotImplementedError`` is listed in DESIGN.md section 7.
 """
 
 from __future__ import annotations

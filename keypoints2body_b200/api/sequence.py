@@ -161,9 +161,12 @@ def optimize_params_sequence(
     fitter = engine.fitter
 
     mean_pose, mean_shape = load_mean_pose_shape(DEFAULT_MEAN_FILE, device)   # always, like sequence.py:139-141
-    betas_opt = optimize_shape_pass(fitter=fitter, seq_config=seq_cfg, init_mean_shape=mean_shape,
-                                    init_mean_pose=mean_pose, data_tensor=xyz, confidence_input=conf[0],
-                                    device=device)
+    if seq_cfg.frame.joints_category != "GENERIC":
+        betas_opt = optimize_shape_pass(fitter=fitter, seq_config=seq_cfg, init_mean_shape=mean_shape,
+                                        init_mean_pose=mean_pose, data_tensor=xyz, confidence_input=conf[0],
+                                        device=device)
+    else:       # dict-block / explicit-index observations skip the shape pre-pass (sequence.py:142-153)
+        betas_opt = mean_shape
     if init_params is None:
         base = default_init_params(mean_pose, betas_opt, xyz[0:1], fitter,
                                    joints_category=seq_cfg.frame.joints_category,

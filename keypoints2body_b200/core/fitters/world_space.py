@@ -10,9 +10,12 @@ the Adam / L-BFGS update for every iteration on chip, followed by one mesh pass
 (``k2b_mesh_batch``) for the returned vertices / joints.
 
 ``fit_batch`` is the batched entry the sequence driver and the benchmark use;
-``fit_frame`` is the reference-shaped call (it also accepts B > 1 like the
-reference does, with the reference's quirk that a 2-D confidence collapses to
-its first row, world_space.py:163-164).
+``fit_frame`` is the reference-shaped call.  It accepts B > 1 like the reference
+does (with the reference's quirk that a 2-D confidence collapses to its first
+row, world_space.py:163-164); for Adam that is identical to the reference (Adam is
+batch-separable), for L-BFGS the B frames are B INDEPENDENT fits here, whereas the
+reference runs one joint L-BFGS over the summed loss (one line search for all
+frames) -- the API path is B = 1, where the two coincide.
 """
 
 from __future__ import annotations
@@ -38,6 +41,18 @@ def _f32(t, device):
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(t)       # numpy prev_params are accepted (the reference crashes on them)
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _check_widths(B, **blocks):
+    """The kernels read fixed strides (72 / 69 / 10 / 3 floats per row): anything else would be read misaligned and
+    out of bounds, so widths are validated before raw pointers cross the C ABI."""
+    for name, (t, width) in blocks.items():
+        if t is None:
+            continue
+        if t.dim() != 2 or t.shape[1] != width or t.shape[0] not in (1, B):
+            raise ValueError(f"{name} must be (B={B}, {width}), got {tuple(t.shape)}"
+                             + (" -- body_pose is the reference's 69-D block for every SMPL-family model "
+                                "(SURVEY.md section 8c)" if name == "body_pose" else ""))
 
 
 def guess_init_transl_from_root(fitter_or_model, pose_aa, betas, j3d_world_frame, joints_category="SMPL24"):
@@ -137,7 +152,7 @@ class WorldSpaceFitter:
         ws = self.native.workspace("fit", ws_bytes)
         a = nat.FitArgs(
             num_frames=B, num_obs=self.num_obs, optimizer=optimizer, num_iters=int(num_iters),
-            freeze_betas=int(bool(freeze_betas)), conf_per_frame=int(conf_per_frame), lr=self.step_size,
+            freeze_betas=int(freeze_betas), conf_per_frame=int(conf_per_frame), lr=self.step_size,
             joint_loss_weight=float(joint_loss_weight), pose_preserve_weight=float(pose_preserve_weight),
             targets=nat.ptr(targets), conf=nat.ptr(conf), init_pose=nat.ptr(pose), init_betas=nat.ptr(betas),
             init_transl=nat.ptr(transl), init_expr=nat.ptr(expr), preserve_pose=nat.ptr(preserve),
@@ -184,7 +199,7 @@ class WorldSpaceFitter:
         a = nat.ChainArgs(
             num_sequences=S, frames_per_sequence=Tw, num_obs=K, optimizer=optimizer,
             num_iters_first=int(iters_first), num_iters_followup=int(iters_follow),
-            first_seq_ind=int(first_seq_ind) + a0, chain_init=int(bool(chain)), freeze_betas=int(bool(freeze_betas)),
+            first_seq_ind=int(first_seq_ind) + a0, chain_init=int(bool(chain)), freeze_betas=int(freeze_betas),
             conf_mode=int(conf_mode), out_time_major=int(bool(time_major)), in_sequence_stride=int(t_total),
             lr=self.step_size, joint_loss_weight=float(joint_loss_weight),
             pose_preserve_weight=float(pose_preserve_weight),
@@ -204,8 +219,11 @@ class WorldSpaceFitter:
                        joint_loss_weight=600.0, pose_preserve_weight=5.0):
         """One evaluation of the loss and its gradient (parity / debugging entry)."""
         dev = self.device
-        pose = torch.cat([_f32(params["global_orient"], dev), _f32(params["body_pose"], dev)], dim=1).contiguous()
-        B = pose.shape[0]
+        go, bp = _f32(params["global_orient"], dev), _f32(params["body_pose"], dev)
+        B = go.shape[0]
+        _check_widths(B, global_orient=(go, 3), body_pose=(bp, 69), betas=(_f32(params["betas"], dev), 10),
+                      transl=(_f32(params["transl"], dev), 3), preserve_pose=(_f32(preserve_pose, dev), 69))
+        pose = torch.cat([go, bp], dim=1).contiguous()
         targets = _f32(j3d, dev)[:, : self.num_obs].contiguous()
         conf = _f32(conf, dev)
         conf_pf = conf is not None and conf.dim() == 2
@@ -360,12 +378,17 @@ class WorldSpaceFitter:
         transl = init.get("transl")
         if transl is None:
             raise ValueError("init_params.transl must be provided")
-        pose = torch.cat([go, bp], dim=1).contiguous()
-        B = pose.shape[0]
+        B = go.shape[0]
         betas = _f32(init["betas"], dev)
+        transl = _f32(transl, dev)
+        keep_pose = _f32(preserve_pose, dev)
+        _check_widths(B, global_orient=(go, 3), body_pose=(bp, 69), betas=(betas, 10), transl=(transl, 3),
+                      preserve_pose=(keep_pose, 69), expression=(_f32(init.get("expression"), dev), 10))
+        if bp.shape[0] != B or transl.shape[0] != B or (keep_pose is not None and keep_pose.shape[0] != B):
+            raise ValueError("body_pose, transl and preserve_pose need one row per frame")
+        pose = torch.cat([go, bp], dim=1).contiguous()
         if betas.shape[0] != B:
             betas = betas.expand(B, -1).contiguous()
-        transl = _f32(transl, dev)
         targets = _f32(j3d, dev)
         if targets.dim() != 3 or targets.shape[0] != B or targets.shape[1] < self.num_obs:
             raise ValueError(f"j3d must be (B={B}, K>={self.num_obs}, 3), got {tuple(targets.shape)}")
@@ -376,8 +399,14 @@ class WorldSpaceFitter:
             conf = conf[..., : self.num_obs].contiguous()
         extras = {k: _f32(init.get(k), dev) for k in _EXTRA_BLOCKS}
         expr = extras["expression"]
+        freeze = int(bool(freeze_betas))
         if self.has_expr and expr is None:
+            # the reference optimises the expression only when the caller supplied one (world_space.py:222-223);
+            # otherwise the model's zero default stays fixed and the result carries expression=None
             expr = torch.zeros(B, 10, device=dev)
+            freeze |= nat.FREEZE_EXPR
+        elif self.has_expr and expr.shape[0] != B:
+            expr = expr.expand(B, -1).contiguous()
 
         frame_iters = frame_preserve = None
         if isinstance(seq_ind, torch.Tensor):
@@ -393,7 +422,6 @@ class WorldSpaceFitter:
                 self.num_iters_first if seq_ind == 0 else self.num_iters_followup)
             preserve_all = int(seq_ind > 0)
         lbfgs = self.use_lbfgs if use_lbfgs is None else use_lbfgs
-        keep_pose = _f32(preserve_pose, dev)
         if kernel == "auto":
             # few frames: one thread per frame leaves the GPU idle and a frame takes ~1.3 ms; a warp per frame
             # (k2b_fit_chain with one-frame sequences) finishes in a fraction of that
@@ -409,18 +437,18 @@ class WorldSpaceFitter:
                                   0 if conf is None else (2 if conf_pf else 1), pose, betas, transl,
                                   expr if self.has_expr else None, keep_pose, s0, True, i_first, i_follow,
                                   nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight,
-                                  pose_preserve_weight, freeze_betas, seq_first=seq_first)
+                                  pose_preserve_weight, freeze, seq_first=seq_first)
         else:
             res = self._run_fit(B, targets, conf, conf_pf, pose, betas, transl, expr if self.has_expr else None,
                                 keep_pose, frame_iters, frame_preserve, preserve_all, budget,
                                 nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight, pose_preserve_weight,
-                                freeze_betas)
+                                freeze)
         params = {"global_orient": res["pose"][:, :3], "body_pose": res["pose"][:, 3:], "betas": res["betas"],
                   "transl": res["transl"]}
         for k in _EXTRA_BLOCKS:
             if extras[k] is not None:
                 params[k] = extras[k]      # receive no gradient from body keypoints: passed through
-        if self.has_expr:
+        if self.has_expr and not (freeze & nat.FREEZE_EXPR):
             params["expression"] = res["expression"]
         out = {"params": params, "loss": res["loss"], "evals": res["evals"], "fit_joints": res["fit_joints"]}
         if with_mesh:
@@ -456,6 +484,8 @@ class WorldSpaceFitter:
         go, bp = _f32(init["global_orient"], dev), _f32(init["body_pose"], dev)
         if init.get("transl") is None:
             raise ValueError("init_params.transl must be provided")
+        _check_widths(S, global_orient=(go, 3), body_pose=(bp, 69), betas=(_f32(init["betas"], dev), 10),
+                      transl=(_f32(init["transl"], dev), 3), expression=(_f32(init.get("expression"), dev), 10))
         pose = torch.cat([go, bp], dim=1).expand(S, -1).contiguous()
         betas = _f32(init["betas"], dev).expand(S, -1).contiguous()
         transl = _f32(init["transl"], dev).expand(S, -1).contiguous()
@@ -468,7 +498,10 @@ class WorldSpaceFitter:
                 raise ValueError("per-frame confidences must be (S, T, K)")
         extras = {k: _f32(init.get(k), dev) for k in _EXTRA_BLOCKS}
         expr = extras["expression"]
+        freeze = int(bool(freeze_betas))
         if self.has_expr:
+            if expr is None:        # no expression supplied: it stays at the model's zero default (world_space.py:222-223)
+                freeze |= nat.FREEZE_EXPR
             expr = (expr if expr is not None else torch.zeros(S, 10, device=dev)).expand(S, -1).contiguous()
         lbfgs = self.use_lbfgs if use_lbfgs is None else use_lbfgs
         optimizer = nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM
@@ -483,7 +516,7 @@ class WorldSpaceFitter:
                     loss=torch.empty(F, device=dev), fit_joints=torch.empty(F, self.num_obs, 3, device=dev),
                     evals=torch.empty(F, dtype=torch.int32, device=dev))
         common = (self.num_iters_first, self.num_iters_followup, optimizer, joint_loss_weight, pose_preserve_weight,
-                  freeze_betas)
+                  freeze)
 
         def params_of(rows):
             p = {"global_orient": outs["pose"][rows, :3], "body_pose": outs["pose"][rows, 3:],
@@ -493,7 +526,7 @@ class WorldSpaceFitter:
                 if extras[k] is not None:    # receive no gradient from body keypoints: passed through to every frame
                     e = extras[k].expand(S, -1)
                     p[k] = e.repeat(n // S, 1) if tm else e.repeat_interleave(n // S, dim=0)
-            if self.has_expr:
+            if self.has_expr and not (freeze & nat.FREEZE_EXPR):
                 p["expression"] = outs["expression"][rows]
             return p
 

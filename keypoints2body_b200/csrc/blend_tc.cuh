@@ -31,6 +31,12 @@
 //   byte address(row r, k) = (k / 64) * rows*128 + r * 128 + ((((k % 64) / 8) ^ (r % 8)) * 16) + (k % 8) * 2
 #pragma once
 
+#ifdef K2B_DIAG
+#define K2B_TC_DBG(p) ((p).debug)
+#else
+#define K2B_TC_DBG(p) 0     // work-skipping diagnostics do not exist in the shipped library
+#endif
+
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -171,7 +177,8 @@ struct BlendParams {
   float* out;               // [B][3V] skinned vertices
   long num_frames;
   int npose, ns, kpad, nv, nj, ell, n_tiles;
-  int debug;   // K2B_TC_DEBUG: 1 = skip output stores, 3 = skip the epilogue (timing experiments only)
+  int debug;   // diagnostic builds only (-DK2B_DIAG, K2B_TC_DEBUG): 1 = skip output stores, 3 = skip the epilogue.
+               // The shipped library compiles the switch out (K2B_TC_DBG is the constant 0).
 };
 
 // Column tiles carry VERTICES, not raw columns: tile row n = 32 q + l holds coordinate l % 3 of vertex
@@ -350,8 +357,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
           ph_afull ^= 1u << a;
           tc::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * FR);
-          const bool st_ok = v_ok && p.debug != 1;
-          if (p.debug == 3) {                                      // timing experiment: no TMEM reads / stores
+          const bool st_ok = v_ok && K2B_TC_DBG(p) != 1;
+          if (K2B_TC_DBG(p) == 3) {                                      // timing experiment: no TMEM reads / stores
             tc::tc_fence_before();
             tc::mbar_arrive(BAR(16 + a));
             continue;
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * FR);
           const long ncols = 3L * p.nv;
           float* o = p.out + f0 * ncols + c;
-          if (p.debug == 3) {                                      // timing experiment: no TMEM reads / stores
+          if (K2B_TC_DBG(p) == 3) {                                      // timing experiment: no TMEM reads / stores
             tc::tc_fence_before();
             tc::mbar_arrive(BAR(16 + a));
             continue;
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
               tc::tc_fence_before();
               tc::mbar_arrive(BAR(16 + a));                        // accumulator may be overwritten
             }
-            if (col_ok && p.debug != 1) {
+            if (col_ok && K2B_TC_DBG(p) != 1) {
   #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const long fr = ch * 16 + i;

@@ -228,7 +228,9 @@ extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* st
   p.out_loss = a->out_loss; p.out_joints = a->out_joints; p.out_evals = a->out_evals;
   p.scratch = (float*)a->workspace;
   p.lbfgs_hmax = lbfgs_history_capacity(a->num_iters);
+#ifdef K2B_DIAG
   p.debug_rounds = getenv("K2B_DEBUG_ROUNDS") != nullptr;
+#endif
   {
     // Lanes waiting at an outer-iteration boundary that trigger the (warp-wide) direction update.  Measured on
     // B200 at 227 k frames: a 30-iteration budget runs 2.4 % faster at 28 than at 32 (fewer idle rounds), a

@@ -642,6 +642,7 @@ struct FitOpts {
   int iters;
   bool lbfgs;
   bool freeze_betas;
+  bool freeze_expr;         // expression kept at its initial value (NS == 20; the caller gave none, world_space.py:222-223)
   bool stage1;              // camera-space stage 1: only global_orient and the translation move, no priors
   bool final_mode;          // returned loss = priors + joints at the final parameters, no preserve (camera_space.py:316-326)
   float lr;
@@ -659,6 +660,7 @@ K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& o
   for (int c = 0; c < 3; ++c) {
     const int e = 3 * lane + c;
     frozen[c] = e >= 75 + NS || (fo.freeze_betas && e >= kShapeOff && e < kShapeOff + 10) ||
+                (fo.freeze_expr && e >= kShapeOff + 10) ||
                 (fo.stage1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
   }
   const bool priors = !fo.stage1;
@@ -789,7 +791,8 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
   }
   FitOpts fo;
   fo.lbfgs = p.lbfgs != 0;
-  fo.freeze_betas = p.freeze_betas != 0;
+  fo.freeze_betas = (p.freeze_betas & 1) != 0;
+  fo.freeze_expr = (p.freeze_betas & 2) != 0;
   fo.lr = p.lr;
   fo.adam_step = p.adam_step;
   fo.adam_bc2 = p.adam_bc2;

@@ -64,7 +64,7 @@ struct FitParams {
   int final_mode;          // 1: returned loss = priors + joints at the final parameters, no preserve (camera_space.py:316-326)
   const float* depth_ref;  // [B][3] initial camera translation (loss_kind 1)
   float depth_w2;
-  int debug_rounds;        // K2B_DEBUG_ROUNDS: pack the warp's round count into out_evals (diagnostics)
+  int debug_rounds;        // -DK2B_DIAG builds only (K2B_DEBUG_ROUNDS): pack the warp's round count into out_evals
   int outer_quorum;        // lanes waiting at an outer-iteration boundary that trigger the direction update
   int adam_fuse;           // 1: body-pose Adam steps inside the gradient pass (K2B_ADAM_FUSE=0 turns it off; same results)
 };
@@ -182,7 +182,8 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       fc.dref[0] = p.depth_ref[fr * 3]; fc.dref[1] = p.depth_ref[fr * 3 + 1]; fc.dref[2] = p.depth_ref[fr * 3 + 2];
     }
     const bool priors = !stage1;
-    const bool freeze_betas = p.freeze_betas != 0;
+    const bool freeze_betas = (p.freeze_betas & 1) != 0;    // bit 0: betas, bit 1: expression (NS == 20)
+    const bool freeze_expr = NS == 20 && (p.freeze_betas & 2) != 0;
 
     float out_loss = 0.f;
     int evals = 0;
@@ -249,6 +250,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
           for (int i = 0; i < NX; ++i) {
             if (fused && i >= 3 && i < kTranslOff) continue;
             if (freeze_betas && i >= kShapeOff && i < kShapeOff + 10) continue;
+            if (freeze_expr && i >= kShapeOff + 10) continue;
             if (stage1 && !(i < 3 || (i >= kTranslOff && i < kShapeOff))) continue;
             float mm = m1[i * kStride], vv = m2[i * kStride], x = c.X(i);
             adam_update(x, mm, vv, c.G(i), step_k, bc2_k);
@@ -286,6 +288,8 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         }
         if (freeze_betas)
           for (int i = 0; i < 10; ++i) ce.G(kShapeOff + i) = 0.f;
+        if (freeze_expr)
+          for (int i = 10; i < NS; ++i) ce.G(kShapeOff + i) = 0.f;
         if (stage1) {
 #pragma unroll 3
           for (int i = 3; i < kTranslOff; ++i) ce.G(i) = 0.f;
@@ -313,7 +317,9 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         }
       }
       evals = st.evals;
+#ifdef K2B_DIAG
       if (p.debug_rounds) evals |= rounds << 16;
+#endif
     }
 
     if (valid) {

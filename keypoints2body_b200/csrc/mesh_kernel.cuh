@@ -478,7 +478,11 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#ifdef K2B_DIAG
     const char* dbg = getenv("K2B_TC_DEBUG");
+#else
+    const char* dbg = nullptr;
+#endif
     BlendParams bp{posefeat, a.shape, m.b_tiles, 1.f / m.dir_scale, m.v_template, (const float4*)skin, a.transl, m.ell_idx, m.ell_w,
                    a.out_vertices, B, m.npose, m.ns, m.kpad, m.nv, m.nj, m.ell, m.n_tiles, dbg ? atoi(dbg) : 0};
     const long passes = Bp / fr;

@@ -115,3 +115,30 @@ def test_prior_constants(tmp_path, gmm, goldens):
         assert np.allclose(np.triu(c.chol[m], 1), 0)
     with pytest.raises(FileNotFoundError):
         load_gmm(str(tmp_path), 6)
+
+
+def test_torch_lbfgs_line_search_budget_is_max_eval_minus_evals():
+    """The device machine caps a line search at ``max_ls = max_eval - evals`` (csrc/lbfgs_core.cuh, start_outer).
+    That is what the torch build the reference runs on does: LBFGS.step passes ``max_ls=max_eval - current_evals``
+    to _strong_wolfe (its signature default of 25 is never used by step).  Pinned here so a torch upgrade that
+    changes it is noticed."""
+    import inspect
+
+    import torch.optim.lbfgs as L
+
+    src = inspect.getsource(L.LBFGS.step)
+    assert "max_ls=max_eval - current_evals" in src.replace("\n", " ").replace("  ", " ")
+
+
+def test_parameter_width_validation():
+    """Raw pointers cross the C ABI with fixed strides, so widths are checked on the host first (a genuine smplx
+    SMPL-H / SMPL-X body_pose is 63 wide; this build follows the reference and expects 69)."""
+    from keypoints2body_b200.core.fitters.world_space import _check_widths
+
+    ok = dict(global_orient=(torch.zeros(4, 3), 3), body_pose=(torch.zeros(4, 69), 69), betas=(torch.zeros(1, 10), 10),
+              transl=(torch.zeros(4, 3), 3), preserve_pose=(None, 69))
+    _check_widths(4, **ok)
+    for name, bad in (("body_pose", torch.zeros(4, 63)), ("betas", torch.zeros(4, 16)), ("transl", torch.zeros(4)),
+                      ("global_orient", torch.zeros(3, 3)), ("preserve_pose", torch.zeros(4, 72))):
+        with pytest.raises(ValueError, match=name):
+            _check_widths(4, **dict(ok, **{name: (bad, ok[name][1])}))
