@@ -223,6 +223,9 @@ typedef struct k2b_eval_args {
   int32_t* out_gmm_component;/* [B] arg-min mixture component, or NULL */
   void* workspace;
   size_t workspace_bytes;
+  int32_t warp_evaluator;    /* 0: the one-thread-per-frame evaluator (the code k2b_fit_batch runs);
+                                1: the warp-per-frame evaluator (the code k2b_fit_chain runs, with the helper-warp
+                                   geometry k2b_fit_chain would pick for B sequences); workspace may be NULL */
 } k2b_eval_args;
 
 int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* args, void* cuda_stream);
@@ -279,6 +282,31 @@ int k2b_shape_pass(const k2b_model* m, const k2b_shape_args* args, void* cuda_st
  * Enqueues a memset of *out_sum_deg and one kernel on the stream; does not synchronise. */
 int k2b_mpjae(const float* pred_pose, int32_t pred_dims, const float* gt_pose, int32_t gt_dims, int64_t num_frames,
               float* out_angles_deg, double* out_sum_deg, void* cuda_stream);
+
+/* Line-search conformance (gate G3): replays N recorded strong-Wolfe line searches of torch.optim.LBFGS
+ * (torch/optim/lbfgs.py:40-209) through the device machine, the objective being a table of the recorded (f, g.d)
+ * responses.  The machine must propose the same trial steps and return the same (t, f).  All pointers are DEVICE
+ * arrays.  warp_policy 0: one thread per search (the vector policy of k2b_fit_batch); 1: one warp per search with
+ * lane-distributed vectors (the policy of k2b_fit_chain). */
+typedef struct k2b_replay_args {
+  int32_t num_searches;      /* N */
+  int32_t max_resp;          /* row length R of the response / output tables */
+  int32_t warp_policy;
+  const double* t0;          /* [N] first trial step */
+  const double* f0;          /* [N] loss at the iterate */
+  const float* gtd0;         /* [N] directional derivative at the iterate */
+  const double* d_norm;      /* [N] max |d| */
+  const int32_t* max_ls;     /* [N] line-search budget (max_eval - evaluations so far) */
+  const uint8_t* t_is_f32;   /* [N] 1: t is a float32 tensor (first outer iteration, lbfgs.py:396-401) */
+  const int32_t* n_resp;     /* [N] recorded evaluations */
+  const double* resp_f;      /* [N][R] recorded losses */
+  const float* resp_gtd;     /* [N][R] recorded directional derivatives */
+  double* out_t;             /* [N][R] trial steps the machine proposed */
+  double* out_final;         /* [N][3] returned t, returned f, evaluations used */
+  int32_t* out_k;            /* [N] responses consumed */
+} k2b_replay_args;
+
+int k2b_linesearch_replay(const k2b_replay_args* args, void* cuda_stream);
 
 /* FP32-FMA micro-benchmark used as the roofline denominator of the fit kernel:
  * returns achieved TFLOP/s (2 flop per FMA) over `iters` dependent-chain rounds. */

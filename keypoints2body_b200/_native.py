@@ -82,6 +82,16 @@ class EvalArgs(C.Structure):
         ("out_loss", C.c_void_p), ("out_grad_pose", C.c_void_p), ("out_grad_betas", C.c_void_p),
         ("out_grad_transl", C.c_void_p), ("out_grad_expr", C.c_void_p), ("out_joints", C.c_void_p),
         ("out_gmm_component", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("warp_evaluator", C.c_int32),
+    ]
+
+
+class ReplayArgs(C.Structure):
+    _fields_ = [
+        ("num_searches", C.c_int32), ("max_resp", C.c_int32), ("warp_policy", C.c_int32),
+        ("t0", C.c_void_p), ("f0", C.c_void_p), ("gtd0", C.c_void_p), ("d_norm", C.c_void_p), ("max_ls", C.c_void_p),
+        ("t_is_f32", C.c_void_p), ("n_resp", C.c_void_p), ("resp_f", C.c_void_p), ("resp_gtd", C.c_void_p),
+        ("out_t", C.c_void_p), ("out_final", C.c_void_p), ("out_k", C.c_void_p),
     ]
 
 
@@ -106,7 +116,7 @@ class ShapeArgs(C.Structure):
 
 EXPORTS = (
     "k2b_model_create", "k2b_model_destroy", "k2b_fit_workspace_bytes", "k2b_fit_batch",
-    "k2b_fit_batch_host", "k2b_chain_workspace_bytes", "k2b_chain_geometry", "k2b_fit_chain", "k2b_evaluate_batch", "k2b_mesh_workspace_bytes", "k2b_mesh_batch",
+    "k2b_fit_batch_host", "k2b_chain_workspace_bytes", "k2b_chain_geometry", "k2b_fit_chain", "k2b_evaluate_batch", "k2b_linesearch_replay", "k2b_mesh_workspace_bytes", "k2b_mesh_batch",
     "k2b_shape_workspace_bytes", "k2b_shape_pass", "k2b_mpjae", "k2b_fma_peak", "k2b_launch_count", "k2b_last_error", "k2b_version",
 )
 
@@ -140,6 +150,8 @@ def load_library():
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p, C.POINTER(st), C.c_void_p]
         fn.restype = C.c_int
+    lib.k2b_linesearch_replay.argtypes = [C.POINTER(ReplayArgs), C.c_void_p]
+    lib.k2b_linesearch_replay.restype = C.c_int
     lib.k2b_shape_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.k2b_shape_workspace_bytes.restype = C.c_size_t
     lib.k2b_mesh_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]

@@ -216,8 +216,10 @@ class WorldSpaceFitter:
         return outs
 
     def evaluate_batch(self, params: dict, j3d, conf=None, preserve_pose=None, preserve_on=False,
-                       joint_loss_weight=600.0, pose_preserve_weight=5.0):
-        """One evaluation of the loss and its gradient (parity / debugging entry)."""
+                       joint_loss_weight=600.0, pose_preserve_weight=5.0, kernel="frame"):
+        """One evaluation of the loss and its gradient (parity / debugging entry).  ``kernel``: "frame" = the
+        one-thread-per-frame evaluator (what ``k2b_fit_batch`` runs), "warp" = the warp-per-frame evaluator (what
+        ``k2b_fit_chain`` runs)."""
         dev = self.device
         go, bp = _f32(params["global_orient"], dev), _f32(params["body_pose"], dev)
         B = go.shape[0]
@@ -250,6 +252,7 @@ class WorldSpaceFitter:
             out_grad_betas=nat.ptr(outs["grad_betas"]), out_grad_transl=nat.ptr(outs["grad_transl"]),
             out_grad_expr=nat.ptr(outs["grad_expression"]), out_joints=nat.ptr(outs["joints"]),
             out_gmm_component=nat.ptr(outs["gmm_component"]), workspace=nat.ptr(ws), workspace_bytes=ws.numel(),
+            warp_evaluator=int(kernel == "warp"),
         )
         with torch.cuda.device(dev):
             nat.check(lib.k2b_evaluate_batch(self.native.handle, C.byref(a), nat.current_stream()))

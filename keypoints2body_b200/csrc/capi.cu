@@ -15,6 +15,7 @@
 #include "chain_kernel.cuh"
 #include "eval_kernel.cuh"
 #include "mesh_kernel.cuh"
+#include "replay_kernel.cuh"
 #include "shape_kernel.cuh"
 
 using namespace k2b;
@@ -253,6 +254,10 @@ extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* st
   return launch_fit_ns<kModeLbfgs>(m->num_shape, p, at, grid, st);
 }
 
+namespace {
+int evaluate_warp(const k2b_model* m, const k2b_eval_args* a, cudaStream_t st);
+}
+
 extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, void* stream) {
   if (!a) return fail(K2B_EINVAL, "null args");
   int rc = check_common(m, a->num_frames, a->num_obs, a->expr);
@@ -260,6 +265,7 @@ extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, vo
   if (!a->targets || !a->pose || !a->betas || !a->transl || !a->out_loss || !a->out_grad_pose ||
       !a->out_grad_betas || !a->out_grad_transl)
     return fail(K2B_EINVAL, "missing required array");
+  if (a->warp_evaluator) return evaluate_warp(m, a, (cudaStream_t)stream);
   const int grid = fit_grid(m, a->num_frames);
   const size_t need = (size_t)scratch_rows(m->num_shape, kModeEval, 0) * grid * fit_threads_rt(m->num_shape) * sizeof(float);
   if (!a->workspace || a->workspace_bytes < need) return fail(K2B_ENOMEM, "workspace too small");
@@ -395,6 +401,64 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   else e = launch_chain<10, 22>(p, tab, grid, warps, st);
   g_launches.fetch_add(1);
   if (e != cudaSuccess) return fail(K2B_ECUDA, std::string("chain kernel launch: ") + cudaGetErrorString(e));
+  return K2B_OK;
+}
+
+// one evaluation per frame through the warp-per-frame evaluator: chain_kernel in eval_only mode, every frame a
+// one-frame sequence (the gradient lands in the out_* parameter arrays, the mixture component in out_evals)
+namespace {
+int evaluate_warp(const k2b_model* m, const k2b_eval_args* a, cudaStream_t st) {
+  int grid, groups, helpers;
+  chain_geometry(m, a->num_frames, grid, groups, helpers);
+  const int warps = groups * (1 + helpers);
+  wc::ChainParams p{};
+  p.num_seq = a->num_frames;
+  p.frames = 1;
+  p.in_seq_stride = 1;
+  p.out_seq_stride = 1;
+  p.out_frame_stride = 1;
+  p.first_seq_ind = a->preserve_all ? 1 : 0;     // the temporal term is on for seq_ind > 0
+  p.chain = 1;
+  p.conf_mode = a->conf ? (a->conf_per_frame ? 2 : 1) : 0;
+  p.joint_w2 = a->joint_loss_weight * a->joint_loss_weight;
+  p.keep_w2 = a->pose_preserve_weight * a->pose_preserve_weight;
+  p.targets = a->targets; p.conf = a->conf;
+  p.init_pose = a->pose; p.init_betas = a->betas; p.init_transl = a->transl; p.init_expr = a->expr;
+  p.preserve_pose = a->preserve_pose;
+  p.out_pose = a->out_grad_pose; p.out_betas = a->out_grad_betas; p.out_transl = a->out_grad_transl;
+  p.out_expr = a->out_grad_expr;
+  p.out_loss = a->out_loss; p.out_joints = a->out_joints; p.out_evals = a->out_gmm_component;
+  p.hmax = 1;
+  p.helpers = helpers;
+  p.eval_only = 1;
+  const ChainTables tab{m->prec, m->mu, m->nlw, m->rel};
+  cudaError_t e;
+  if (a->num_obs == 24) e = launch_chain<10, 24>(p, tab, grid, warps, st);
+  else if (m->num_shape == 20) e = launch_chain<20, 22>(p, tab, grid, warps, st);
+  else e = launch_chain<10, 22>(p, tab, grid, warps, st);
+  g_launches.fetch_add(1);
+  if (e != cudaSuccess) return fail(K2B_ECUDA, std::string("chain kernel launch: ") + cudaGetErrorString(e));
+  return K2B_OK;
+}
+}  // namespace
+
+extern "C" int k2b_linesearch_replay(const k2b_replay_args* a, void* stream) {
+  if (!a) return fail(K2B_EINVAL, "null args");
+  if (a->num_searches <= 0 || a->max_resp <= 0) return fail(K2B_EINVAL, "num_searches and max_resp must be positive");
+  if (!a->t0 || !a->f0 || !a->gtd0 || !a->d_norm || !a->max_ls || !a->t_is_f32 || !a->n_resp || !a->resp_f ||
+      !a->resp_gtd || !a->out_t || !a->out_final || !a->out_k)
+    return fail(K2B_EINVAL, "missing required array");
+  const ReplayParams p{a->num_searches, a->max_resp, a->t0, a->f0, a->gtd0, a->d_norm, a->max_ls, a->t_is_f32,
+                       a->n_resp, a->resp_f, a->resp_gtd, a->out_t, a->out_final, a->out_k};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->warp_policy) {
+    const int per = kReplayThreads / 32;
+    replay_warp_kernel<<<(a->num_searches + per - 1) / per, kReplayThreads, 0, st>>>(p);
+  } else {
+    replay_thread_kernel<<<(a->num_searches + kReplayThreads - 1) / kReplayThreads, kReplayThreads, 0, st>>>(p);
+  }
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
   return K2B_OK;
 }
 

@@ -31,6 +31,10 @@
 int k2b_emul_lane();
 float k2b_emul_shfl(float v, int src);
 void k2b_emul_sync();
+// optional line-search trace of the emulated warp: rows of (t, f, g.d) per trial evaluation (tests only)
+extern float* k2b_emul_trace;
+extern int k2b_emul_trace_cap;
+extern int* k2b_emul_trace_n;
 #endif
 
 namespace k2b {
@@ -631,6 +635,24 @@ struct WarpOps {
     for (int c = 0; c < 3; ++c) gm = fmaxf(gm, fabsf(v.G(slot, c)));
     return wmax(gm);
   }
+  // line-search replay (1-D surrogate): element 0 (lane 0, register 0) carries the problem, the rest is zero
+  static K2B_HD void replay_seed(const C&, const V& v, float gtd0) {
+    const bool e0 = lane_id() == 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v.x[c] = 0.f;
+      v.xk[c] = 0.f;
+      v.d[c] = (e0 && c == 0) ? 1.f : 0.f;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) v.G(s, c) = 0.f;
+    }
+    if (e0) v.G(0, 0) = gtd0;
+    wsync();
+  }
+  static K2B_HD void replay_response(const V& v, int cur, float gtd) {
+    if (lane_id() == 0) v.G(cur, 0) = gtd;
+    wsync();
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -710,6 +732,15 @@ K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& o
 #pragma unroll
       for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
       wsync();
+#if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
+      if (k2b_emul_trace && !first) {
+        const float gtd = st.dot_cur_d(v);
+        if (lane == 0 && *k2b_emul_trace_n < k2b_emul_trace_cap) {
+          float* row = k2b_emul_trace + 3 * (*k2b_emul_trace_n)++;
+          row[0] = (float)st.t; row[1] = loss; row[2] = gtd;
+        }
+      }
+#endif
       st.advance_now(v, v, loss, first, fo.iters, fo.lr);
       first = false;
       if (st.done) break;
@@ -758,6 +789,8 @@ struct ChainParams {
   int loss_kind, final_mode;
   float depth_w2;
   const float* depth_ref;  // [S][stride][3] initial camera translation (loss_kind 1)
+  int eval_only;           // 1: no fit -- one evaluation at the initial parameters per frame; out_pose / out_betas / out_transl /
+                           // out_expr receive the GRADIENT, out_evals the arg-min mixture component (k2b_evaluate_batch, warp evaluator)
   float adam_step[kAdamTableW], adam_bc2[kAdamTableW];
 };
 K2B_HD constexpr long hist_floats(int hmax) { return (long)hmax * 2 * kWarpVec; }
@@ -828,6 +861,19 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
     const bool first = (p.seq_first ? (long)p.seq_first[seq] : p.first_seq_ind) + t == 0;
     ob.keep_w2 = first ? 0.f : p.keep_w2;
     fo.iters = first ? p.iters_first : p.iters_follow;
+    if (p.eval_only) {
+      float gr[3];
+      int comp = 0;
+      const float l = eval_warp<NS, K>(tb, wm, ob, xr, true, !fo.stage1, gr, p.out_joints ? p.out_joints + frow * K * 3 : nullptr,
+                                       &comp);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, gr[c]);
+      if (lane == 0) {
+        p.out_loss[frow] = l;
+        if (p.out_evals) p.out_evals[frow] = comp;
+      }
+      continue;
+    }
     int evals = 0;
     const float loss = fit_warp<NS, K>(tb, wm, ob, xr, fo, hist, ro, al, p.hmax,
                                        p.out_joints ? p.out_joints + frow * K * 3 : nullptr, &evals);

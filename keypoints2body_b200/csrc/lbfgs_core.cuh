@@ -227,6 +227,13 @@ struct ThreadOps {
     for (int i = 0; i < N; ++i) gmax = fmaxf(gmax, fabsf(v.at(og + i)));
     return gmax;
   }
+  // line-search replay (1-D surrogate, N == 1): iterate 0, direction 1, flat_grad = g.d
+  static K2B_HD void replay_seed(const C&, const V& v, float gtd0) {
+    v.at(v.xk()) = 0.f;
+    v.at(v.d()) = 1.f;
+    v.at(v.gslot(0)) = gtd0;
+  }
+  static K2B_HD void replay_response(const V& v, int cur, float gtd) { v.at(v.gslot(cur)) = gtd; }
 };
 
 template <int N, class Ops = ThreadOps<N>>
@@ -509,14 +516,15 @@ struct Lbfgs {
     }
   }
 
-  // ---- test hook: run only the line search on a 1-D surrogate (tests/host_emul) ----------
+  // ---- conformance hook: run only the line search on a 1-D surrogate whose objective is a table of recorded
+  // (f, g.d) responses (tests/host_emul on the CPU, k2b_linesearch_replay on the device) ----------
   bool ls_replay_finished;
-  K2B_HD void ls_replay_begin(const Cols& c, const Vecs& v, double t0, double f0_, float gtd0_, double d_norm_,
+  K2B_HD void ls_replay_begin(const C& c, const V& v, double t0, double f0_, float gtd0_, double d_norm_,
                               int max_ls_, bool t_is_f32) {
     max_iter = 1; max_eval = max_ls_ + 1; lr = 1.f;
     n_iter = 1; evals = 1; num_old = 0; head = 0; done = false;
     loss = f0_; prev_loss = f0_; t = t0; H_diag = 1.f; g0 = 0; slot_prev_grad = 0; cur = 1;
-    v.at(v.xk()) = 0.f; v.at(v.d()) = 1.f; v.at(v.gslot(0)) = gtd0_;
+    Ops::replay_seed(c, v, gtd0_);      // iterate 0, direction 1, flat_grad (slot 0) = g.d
     d_norm = d_norm_; f0 = f0_; gtd0 = gtd0_; max_ls = max_ls_; ls_evals = 0;
     t_prev = 0.0; f_prev = f0_; gtd_prev = gtd0_; slot_prev = 0; ls_iter = 0; phase = 0;
     first_eval = true; ls_done = false; insuf = false; br_n = 0; ls_replay_finished = false;

@@ -195,7 +195,7 @@ extern "C" int emu_linesearch_replay(double t0, double f0, float gtd0, double d_
   int k = 0;
   while (!st.ls_replay_finished && k < n_resp) {
     out_t[k] = st.t;
-    st.eval_cols(c, v).G(0) = resp_gtd[k];
+    ThreadOps<1>::replay_response(v, st.cur, resp_gtd[k]);
     st.after_eval(c, v, (float)resp_f[k]);
     ++k;
   }

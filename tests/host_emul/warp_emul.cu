@@ -60,6 +60,16 @@ void run_warp(void (*job)()) {
 }
 }  // namespace
 
+float* k2b_emul_trace = nullptr;
+int k2b_emul_trace_cap = 0;
+int* k2b_emul_trace_n = nullptr;
+// rows of (t, f, g.d) for every line-search trial of the next wemu_chain call(s); pass nulls to stop tracing
+extern "C" void wemu_set_trace(float* rows, int cap, int* count) {
+  k2b_emul_trace = rows;
+  k2b_emul_trace_cap = cap;
+  k2b_emul_trace_n = count;
+}
+
 int k2b_emul_lane() { return g_lane; }
 float k2b_emul_shfl(float v, int src) {
   const int me = g_lane, p = g_par[me];
@@ -224,4 +234,54 @@ extern "C" int wemu_chain(void* model, int K, int S, int T, long first_seq_ind, 
     run_warp(pick_job(g.m->ns, K));
   }
   return 0;
+}
+
+// Line-search replay through the lane-distributed vector policy (WarpOps): the same conformance hook as
+// host_emul.cu's emu_linesearch_replay / the device's k2b_linesearch_replay(warp_policy = 1).
+namespace {
+struct ReplayJob {
+  double t0, f0, d_norm;
+  float gtd0;
+  int max_ls, t_is_f32, n_resp;
+  const double* resp_f;
+  const float* resp_gtd;
+  double* out_t;
+  double* out_final;
+  int k;
+  std::vector<float> gs;
+} r;
+
+void replay_lane_job() {
+  wc::WVec v;
+  v.gs = r.gs.data();
+  v.hist = nullptr;
+  v.ro = nullptr;
+  v.al = nullptr;
+  v.hmax = 1;
+  Lbfgs<85, wc::WarpOps> st;
+  st.init();
+  st.ls_replay_begin(v, v, r.t0, r.f0, r.gtd0, r.d_norm, r.max_ls, r.t_is_f32 != 0);
+  int k = 0;
+  while (!st.ls_replay_finished && k < r.n_resp) {
+    if (wc::lane_id() == 0) r.out_t[k] = st.t;
+    wc::WarpOps::replay_response(v, st.cur, r.resp_gtd[k]);
+    st.after_eval(v, v, (float)r.resp_f[k]);
+    ++k;
+  }
+  if (wc::lane_id() == 0) {
+    r.out_final[0] = st.t;
+    r.out_final[1] = st.loss;
+    r.out_final[2] = (double)st.ls_evals;
+    r.k = k;
+  }
+}
+}  // namespace
+
+extern "C" int wemu_linesearch_replay(double t0, double f0, float gtd0, double d_norm, int max_ls, int t_is_f32, int n_resp,
+                                      const double* resp_f, const float* resp_gtd, double* out_t, double* out_final) {
+  r.t0 = t0; r.f0 = f0; r.gtd0 = gtd0; r.d_norm = d_norm; r.max_ls = max_ls; r.t_is_f32 = t_is_f32; r.n_resp = n_resp;
+  r.resp_f = resp_f; r.resp_gtd = resp_gtd; r.out_t = out_t; r.out_final = out_final; r.k = 0;
+  r.gs.assign(4 * wc::kWarpVec, 0.f);
+  run_warp(replay_lane_job);
+  return r.k;
 }

@@ -1,0 +1,316 @@
+"""GPU parity of the L-BFGS path -- the reference's default optimiser and the path bench.py times -- and of long
+chains, against goldens the UNMODIFIED reference produced (tests/golden/make_goldens_r2.py) and the oracle.
+
+SURVEY.md section 8(c) gates, all through the C ABI, for BOTH kernels (k2b_fit_batch: one thread per frame;
+k2b_fit_chain: one warp per frame, with and without helper warps -- the geometry the benchmark runs):
+  G1'      teacher-forced evaluation parity at every trial point x the reference's L-BFGS visited
+  G3       torch's recorded line searches replayed on the device (both vector policies of the machine)
+  G4(ii)   distribution of final loss / mean joint error / evaluations over 512 independent fits (both budgets) and
+           32 chains x 64 frames, against the reference's own numbers on the same inputs
+  G4(iii)  distance to a float64 run of the oracle not larger than the float32 reference's own distance to it
+  G2-long  Adam chains (strict, every frame): the reference's two demo sequences (real AMASS-22 keypoints, 195 and
+           116 frames) and a 512-frame synthetic chain
+(G4(i), trial-by-trial agreement up to a noise-level decision, needs the line-search trace and runs on the CPU
+emulation of the same device code: tests/test_lbfgs_conformance.py.)
+
+Reference self-noise, measured when the goldens were made (tests/golden/r2_dist.npz): the same 128 follow-up fits on
+1 vs 4 CPU threads differ per frame by a median 6.5 % in final loss (1.6 % of the fits are identical), and their
+medians by 3.0 %; float32 vs float64: 14.8 % per frame, 13 % on the median.  Resampling 512 fits moves the median
+by 2.1 % (1 sigma).  The distribution bars below are set from these figures.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import problems
+from oracle import reference_port as rp
+
+pytestmark = pytest.mark.gpu
+T = torch.as_tensor
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def cpu(x):
+    return x.detach().cpu().numpy()
+
+
+def load(name):
+    return dict(np.load(os.path.join(HERE, "golden", name)))
+
+
+@pytest.fixture(scope="module")
+def fitters(weights, gmm):
+    from keypoints2body_b200.core.fitters.world_space import WorldSpaceFitter
+
+    cache = {}
+
+    def get(mt, **kw):
+        key = (mt, tuple(sorted(kw.items())))
+        if key not in cache:
+            cache[key] = WorldSpaceFitter(weights(mt), joints_category="AMASS", model_type=mt, gmm=gmm, **kw)
+        return cache[key]
+
+    return get
+
+
+# ---- G1': teacher-forced evaluation parity ---------------------------------------------------------------------
+EVALUATORS = [("frame", None), ("warp", "0"), ("warp", "2")]      # (kernel, helper warps per frame)
+
+
+@pytest.mark.parametrize("kernel,helpers", EVALUATORS)
+@pytest.mark.parametrize("tag,mt", [("first", "smpl"), ("follow", "smpl"), ("smplx", "smplx")])
+def test_teacher_forced_evaluation_parity(fitters, monkeypatch, tag, mt, kernel, helpers):
+    """Every point the reference's line searches evaluated (150 + 50 + 19 points of 11 fits): our loss and gradient at
+    the reference's x.  Loss rel <= 1e-5; gradient <= 1e-4 |g|_inf against the float64 oracle where the float32
+    reference is itself at its noise floor (see tests/test_lbfgs_conformance.py), <= 2e-4 against the reference."""
+    from test_lbfgs_conformance import oracle64_gradient, split_flat
+
+    if helpers is not None:
+        monkeypatch.setenv("K2B_CHAIN_HELPERS", helpers)
+    pts = load("r2_points.npz")
+    x, f, g = pts[tag + "_x"], pts[tag + "_f"], pts[tag + "_g"]
+    frame, tgt, keep = pts[tag + "_frame"], pts[tag + "_target"], pts[tag + "_keep"]
+    keep_w = 5.0 if int(pts[tag + "_seq_ind"]) > 0 else 0.0
+    xk, gk = split_flat(x, mt), split_flat(g, mt)
+    params = dict(global_orient=T(xk[:, :3]), body_pose=T(xk[:, 3:72]), transl=T(xk[:, 72:75]), betas=T(xk[:, 75:85]))
+    if mt == "smplx":
+        params["expression"] = T(xk[:, 85:95])
+    out = fitters(mt).evaluate_batch(params, T(tgt[frame]), torch.ones(22), preserve_pose=T(keep[frame]),
+                                     preserve_on=keep_w > 0, pose_preserve_weight=keep_w, kernel=kernel)
+    loss = cpu(out["loss"])
+    grad = np.concatenate([cpu(out["grad_pose"]), cpu(out["grad_transl"]), cpu(out["grad_betas"])]
+                          + ([cpu(out["grad_expression"])] if mt == "smplx" else []), axis=1)
+    assert (np.abs(loss - f) / np.abs(f)).max() <= 1e-5
+    gmax = np.abs(gk).max(axis=1)
+    rel = np.abs(grad - gk).max(axis=1) / gmax
+    assert rel.max() <= 2e-4
+    for i in np.nonzero(rel > 5e-5)[0]:
+        g64 = oracle64_gradient(mt, x[i], tgt[frame[i]], keep[frame[i]], keep_w)
+        assert np.abs(grad[i] - g64).max() / gmax[i] <= 1e-4, (i, rel[i])
+    print(tag, kernel, helpers, "points", len(f), "worst loss rel", (np.abs(loss - f) / np.abs(f)).max(), "worst grad rel", rel.max())
+
+
+# ---- G3 on the device --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("warp_policy", [0, 1])
+def test_linesearch_replay_on_device(goldens, fitters, warp_policy):
+    """Every strong-Wolfe line search torch performed in the L-BFGS golden runs (first-frame, follow-up and SMPL-X
+    budgets), replayed by the device machine with the recorded (f, g.d) as the objective: same trial steps
+    (1e-6 rel), same number of evaluations, same returned (t, f)."""
+    from keypoints2body_b200 import _native as nat
+
+    recs, resps = [], []
+    for tag in ("lbfgs_smpl_first", "lbfgs_smpl_follow", "lbfgs_smplx"):
+        for b in range(goldens[tag + "_linesearch"].shape[0]):
+            for rec in goldens[tag + "_linesearch"][b]:
+                if np.isnan(rec[0]):
+                    break
+                recs.append(rec)
+                resps.append(goldens[tag + "_trace"][b, int(rec[5]):int(rec[5]) + int(rec[6])])
+    N, R = len(recs), max(len(r) for r in resps)
+    assert N >= 60
+    rec = np.asarray(recs, np.float64)
+    rf, rg, n_resp = np.zeros((N, R)), np.zeros((N, R), np.float32), np.zeros(N, np.int32)
+    for i, r in enumerate(resps):
+        n_resp[i] = len(r)
+        rf[i, :len(r)], rg[i, :len(r)] = r[:, 1], r[:, 2]
+    dev = torch.device("cuda")
+    d = dict(t0=T(rec[:, 0]), f0=T(rec[:, 1]), gtd0=T(rec[:, 2].astype(np.float32)), d_norm=T(rec[:, 3]),
+             max_ls=T(rec[:, 4].astype(np.int32)), t_is_f32=T(rec[:, 9].astype(np.uint8)), n_resp=T(n_resp),
+             resp_f=T(rf), resp_gtd=T(rg))
+    d = {k: v.to(dev).contiguous() for k, v in d.items()}
+    out_t = torch.zeros(N, R, dtype=torch.float64, device=dev)
+    out_final = torch.zeros(N, 3, dtype=torch.float64, device=dev)
+    out_k = torch.zeros(N, dtype=torch.int32, device=dev)
+    a = nat.ReplayArgs(num_searches=N, max_resp=R, warp_policy=warp_policy, **{k: v.data_ptr() for k, v in d.items()},
+                       out_t=out_t.data_ptr(), out_final=out_final.data_ptr(), out_k=out_k.data_ptr())
+    nat.check(fitters("smpl").native.lib.k2b_linesearch_replay(C.byref(a), nat.current_stream()))
+    torch.cuda.synchronize()
+    out_t, out_final, out_k = cpu(out_t), cpu(out_final), cpu(out_k)
+    assert (out_k == n_resp).all()
+    assert (out_final[:, 2] == n_resp).all()
+    for i, r in enumerate(resps):
+        np.testing.assert_allclose(out_t[i, :len(r)], r[:, 0], rtol=1e-6)
+    np.testing.assert_allclose(out_final[:, 0], rec[:, 7], rtol=1e-6)
+    np.testing.assert_allclose(out_final[:, 1], rec[:, 8], rtol=1e-7)
+
+
+# ---- G4(ii), G4(iii): distributions ------------------------------------------------------------------------------
+# Bars from the reference's own noise (module docstring): medians within 4 %, 95th percentiles within 8 % (a tail
+# statistic of 512 chaotic fits: the reference's float64 run moves it by 22 %), mean evaluations within 1 %.
+MED_TOL, P95_TOL, EVAL_TOL = 0.04, 0.08, 0.01
+
+
+def _compare_distribution(label, loss, err, evals, ref_loss, ref_err, ref_evals):
+    stats = {}
+    for name, ours, ref, tol in (("loss median", np.median(loss), np.median(ref_loss), MED_TOL),
+                                 ("loss p95", np.percentile(loss, 95), np.percentile(ref_loss, 95), P95_TOL),
+                                 ("error median", np.median(err), np.median(ref_err), MED_TOL),
+                                 ("error p95", np.percentile(err, 95), np.percentile(ref_err, 95), P95_TOL),
+                                 ("evaluations mean", np.mean(evals), np.mean(ref_evals), EVAL_TOL)):
+        stats[name] = (float(ours), float(ref), float(ours / ref - 1.0))
+        assert abs(ours / ref - 1.0) <= tol, (label, name, ours, ref)
+    print(label, {k: (round(v[0], 5), round(v[1], 5), f"{100 * v[2]:+.2f}%") for k, v in stats.items()})
+    return stats
+
+
+@pytest.mark.parametrize("kernel", ["frame", "warp"])
+@pytest.mark.parametrize("seq_ind", [0, 1])
+def test_lbfgs_distribution_512_frames(fitters, weights, kernel, seq_ind):
+    """512 independent fits (30-iteration and 10-iteration budgets) against the reference's WorldSpaceFitter on the
+    same inputs (r2_dist.npz), and against the oracle in float64 (r2_dist64.npz)."""
+    ref, ref64 = load("r2_dist.npz"), load("r2_dist64.npz")
+    tgt, init = problems.frame_problem(weights("smpl"), int(ref["n"]), int(ref["seed"]))
+    assert abs(float(tgt.double().sum()) - float(ref["target_sum"])) < 1e-6       # same inputs as the golden run
+    f = fitters("smpl", use_lbfgs=True)
+    out = f.fit_batch(init, tgt, torch.ones(22), seq_ind=seq_ind, kernel=kernel, with_mesh=False)
+    loss, evals = cpu(out["loss"]).astype(np.float64), cpu(out["evals"])
+    err = problems.mean_joint_error(out["fit_joints"].cpu(), tgt).numpy().astype(np.float64)
+    s = f"s{seq_ind}"
+    _compare_distribution(f"512 fits, seq_ind {seq_ind}, {kernel} kernel", loss, err, evals, ref[s + "_loss"],
+                          ref[s + "_err"], ref[s + "_evals"])
+    budget = (30 if seq_ind == 0 else 10) * 5 // 4
+    assert evals.max() <= budget + 1 and np.array_equal(np.unique(evals), np.unique(ref[s + "_evals"]))
+    # G4(iii): per-frame distance to the float64 run, ours vs the float32 reference's own
+    d_ours = np.median(np.abs(loss - ref64[s + "_loss"]) / ref64[s + "_loss"])
+    d_ref = np.median(np.abs(ref[s + "_loss"] - ref64[s + "_loss"]) / ref64[s + "_loss"])
+    e_ours = np.median(np.abs(err - ref64[s + "_err"]))
+    e_ref = np.median(np.abs(ref[s + "_err"] - ref64[s + "_err"]))
+    print(f"  distance to float64: loss ours {d_ours:.4f} vs reference {d_ref:.4f}; error ours {e_ours:.5f} m vs "
+          f"reference {e_ref:.5f} m")
+    assert d_ours <= 1.15 * d_ref and e_ours <= 1.15 * e_ref
+    # the reported loss is the loss AT the returned parameters (world_space.py:246-247)
+    chk = f.evaluate_batch(out["params"], tgt, torch.ones(22), preserve_pose=init["body_pose"], preserve_on=seq_ind > 0)
+    np.testing.assert_allclose(cpu(chk["loss"]), loss, rtol=1e-5)
+
+
+@pytest.mark.parametrize("kernel", ["warp", "frame"])
+def test_lbfgs_chains_32x64(fitters, weights, shims, kernel):
+    """32 chains of 64 frames, L-BFGS, the reference's default schedule (frame t starts from frame t-1's result)
+    against the reference's own optimize_params_sequence on the same sequences (r2_chains.npz): one launch of the
+    warp-per-sequence kernel, and the same chain walked by 64 launches of the one-thread-per-frame kernel."""
+    ref = load("r2_chains.npz")
+    S, Tn = int(ref["S"]), int(ref["T"])
+    w = weights("smpl")
+    tgt = problems.chain_problem(w, S, Tn, int(ref["seed"]))
+    assert abs(float(tgt.double().sum()) - float(ref["target_sum"])) < 1e-6
+    with torch.no_grad():
+        root = shims("smpl")(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10)).joints[0, 0]
+    init = dict(global_orient=torch.zeros(S, 3), body_pose=torch.zeros(S, 69), betas=torch.zeros(S, 10),
+                transl=(tgt[:, 0, 0] - root).contiguous())
+    f = fitters("smpl", use_lbfgs=True)
+    if kernel == "warp":
+        out = f.fit_chain(init, tgt, None, with_mesh=False)
+        loss, evals = cpu(out["loss"]).reshape(S, Tn), cpu(out["evals"]).reshape(S, Tn)
+        err = problems.mean_joint_error(out["fit_joints"].cpu().reshape(S, Tn, 22, 3), tgt).numpy()
+    else:
+        prev, loss, evals, err = init, [], [], []
+        for t in range(Tn):
+            r = f.fit_batch(prev, tgt[:, t], None, seq_ind=t, with_mesh=False, kernel="frame")
+            prev = r["params"]
+            loss.append(cpu(r["loss"])); evals.append(cpu(r["evals"]))
+            err.append(problems.mean_joint_error(r["fit_joints"].cpu(), tgt[:, t]).numpy())
+        loss, evals, err = np.stack(loss, 1), np.stack(evals, 1), np.stack(err, 1)
+    _compare_distribution(f"32 x 64 chains, follow-up frames, {kernel} kernel", loss[:, 1:].ravel().astype(np.float64),
+                          err[:, 1:].ravel().astype(np.float64), evals[:, 1:].ravel(), ref["loss"][:, 1:].ravel(),
+                          ref["err"][:, 1:].ravel(), ref["evals"][:, 1:].ravel())
+    assert abs(evals[:, 0].mean() / ref["evals"][:, 0].mean() - 1.0) <= 0.02
+    # no drift along the chain: the last 16 frames are fitted as well as the reference fits them
+    assert abs(np.median(err[:, -16:]) / np.median(ref["err"][:, -16:]) - 1.0) <= 0.06
+
+
+# ---- G2 on long chains ---------------------------------------------------------------------------------------------
+def _sequence_init(shims, tgt):
+    with torch.no_grad():
+        root = shims("smpl")(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10)).joints[0, 0]
+    return dict(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10),
+                transl=(tgt[0:1, 0] - root).contiguous())
+
+
+def _check_adam_chain(label, pose, betas, transl, joints22, loss, g, name):
+    d_pose = np.abs(pose - g[name + "_pose"]).max(axis=1)
+    d_j = np.abs(joints22 - g[name + "_joints22"]).reshape(len(pose), -1).max(axis=1)
+    d_t = np.abs(transl - g[name + "_transl"]).max(axis=1)
+    d_b = np.abs(betas - g[name + "_betas"]).max(axis=1)
+    n = len(pose)
+    q = [slice(0, n // 4), slice(n // 4, n // 2), slice(n // 2, 3 * n // 4), slice(3 * n // 4, n)]
+    print(label, name, f"{n} frames: worst pose {d_pose.max():.2e} rad, joints {d_j.max():.2e} m, transl {d_t.max():.2e} m, "
+          f"betas {d_b.max():.2e}; worst joints per quarter of the chain",
+          [f"{d_j[s].max():.1e}" for s in q])
+    assert d_pose.max() < 1e-4 and d_j.max() < 1e-4 and d_t.max() < 1e-5 and d_b.max() < 1e-4
+    np.testing.assert_allclose(loss, g[name + "_loss"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("chunks", [1, 5])
+@pytest.mark.parametrize("name", ["demo1", "demo2", "long512"])
+def test_adam_long_chain_every_frame(fitters, weights, shims, name, chunks):
+    """Adam, schedule S1, every frame of a long chain against the reference's optimize_params_sequence: the two demo
+    sequences (real AMASS-22 keypoints shipped with the reference) and a 512-frame synthetic chain; one launch and
+    time windows.  1e-6-level per-frame differences must not grow along thousands of warm-started iterations."""
+    g = load("r2_adam.npz")
+    tgt = T(g[name + "_in"]) if name.startswith("demo") else problems.chain_problem(weights("smpl"), 1, 512, 4040)[0]
+    f = fitters("smpl", use_lbfgs=False)
+    out = f.fit_chain(_sequence_init(shims, tgt), tgt[None], None, time_major=chunks > 1, chunks=chunks, with_mesh=True)
+    p = out["params"]
+    pose = np.concatenate([cpu(p["global_orient"]), cpu(p["body_pose"])], axis=1)
+    _check_adam_chain(f"fit_chain(chunks={chunks})", pose, cpu(p["betas"]), cpu(p["transl"]), cpu(out["joints"])[:, :22],
+                      cpu(out["loss"]), g, name)
+
+
+@pytest.mark.parametrize("name", ["demo1", "demo2"])
+def test_adam_demo_sequence_through_public_api(weights, gmm, tmp_path, monkeypatch, name):
+    """The same through optimize_params_sequence (public API, reference config dict)."""
+    from keypoints2body_b200 import optimize_params_sequence
+    from keypoints2body_b200 import synthetic as syn
+
+    g = load("r2_adam.npz")
+    syn.write_assets(str(tmp_path / "data" / "models"), seed=0)
+    monkeypatch.chdir(tmp_path)
+    res = optimize_params_sequence(g[name + "_in"], body_model="smpl", joint_layout="AMASS", model=weights("smpl"),
+                                   config=dict(frame=dict(use_lbfgs=False), use_shape_optimization=False))
+    pose = np.concatenate([cpu(r.params.pose) for r in res])
+    _check_adam_chain("optimize_params_sequence", pose, np.concatenate([cpu(r.params.betas) for r in res]),
+                      np.concatenate([cpu(r.params.transl) for r in res]),
+                      np.concatenate([cpu(r.joints[:, :22]) for r in res]), np.stack([float(r.loss) for r in res]), g, name)
+
+
+def test_demo_sequence_default_config_through_public_api(weights, tmp_path, monkeypatch):
+    """Default configuration (L-BFGS, shape pre-pass over the first 50 frames) on the 195-frame demo sequence: the shape
+    pass reproduces the reference's betas, the per-frame fits its loss / error distribution and evaluation counts."""
+    from keypoints2body_b200 import optimize_params_sequence
+    from keypoints2body_b200 import synthetic as syn
+
+    g = load("r2_adam.npz")
+    syn.write_assets(str(tmp_path / "data" / "models"), seed=0)
+    monkeypatch.chdir(tmp_path)
+    tgt = g["demo1_in"]
+    res = optimize_params_sequence(tgt, body_model="smpl", joint_layout="AMASS", model=weights("smpl"))
+    loss = np.array([float(r.loss) for r in res])
+    err = np.array([float(problems.mean_joint_error(r.joints[:, :22].cpu(), T(tgt[t:t + 1]))) for t, r in enumerate(res)])
+    ref_loss, ref_err = g["demo1_default_loss"], g["demo1_default_err"]
+    print("demo1, defaults: loss median ours / ref", np.median(loss), np.median(ref_loss), "error median", np.median(err),
+          np.median(ref_err))
+    assert abs(np.median(loss[1:]) / np.median(ref_loss[1:]) - 1.0) <= 0.06      # 194 fits: twice the 512-fit bar
+    assert abs(np.median(err[1:]) / np.median(ref_err[1:]) - 1.0) <= 0.06
+
+
+def test_dict_block_sequence_with_default_config(weights, tmp_path, monkeypatch):
+    """Dict-block observations with the DEFAULT sequence config (use_shape_optimization=True): the reference skips
+    the shape pre-pass for GENERIC observations (api/sequence.py:142-153) and starts from the mean shape."""
+    from keypoints2body_b200 import optimize_params_sequence
+    from keypoints2body_b200 import synthetic as syn
+
+    syn.write_assets(str(tmp_path / "data" / "models"), seed=0)
+    monkeypatch.chdir(tmp_path)
+    tgt = problems.chain_problem(weights("smpl"), 1, 4, 99)[0]
+    block = np.concatenate([tgt.numpy(), np.ones((4, 22, 1), np.float32)], axis=2)       # (T, 22, 4): xyz + confidence
+    a = optimize_params_sequence({"body": block}, body_model="smpl", model=weights("smpl"),
+                                 config=dict(frame=dict(use_lbfgs=False)))
+    b = optimize_params_sequence(tgt.numpy(), body_model="smpl", joint_layout="AMASS", model=weights("smpl"),
+                                 config=dict(frame=dict(use_lbfgs=False), use_shape_optimization=False))
+    assert len(a) == 4
+    for ra, rb in zip(a, b):       # all 22 body joints observed through the dict = the AMASS fit without a shape pass
+        assert torch.allclose(ra.params.pose, rb.params.pose, atol=2e-5)
