@@ -292,22 +292,35 @@ extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, vo
 
 // ---- warp-per-sequence fit (serial chains, small batches) ------------------------------------
 namespace {
-// groups = sequences walked concurrently by one CTA; a group is 1 + helpers warps
-void chain_geometry(const k2b_model* m, long S, int& grid, int& groups, int& helpers) {
-  // few sequences: the launch is latency-bound and most schedulers idle, so helper warps take the mixture prior
-  // (measured on B200, L-BFGS, us per frame: 1 sequence 106 / 80 / 66 with 0 / 1 / 2 helpers; 256 sequences
-  // 113 / 86 / 80; 512 sequences 128 / 110 / 114); with enough sequences to fill the SMs one warp per sequence
-  // has the best throughput
-  helpers = S <= (long)m->num_sms * 2 ? 2 : (S <= (long)m->num_sms * 6 ? 1 : 0);
+// Launch geometry of the warp-per-sequence kernel.  teams = sequences walked concurrently by one CTA; a team is
+// `evals` evaluator warps (> 1: speculative line-search evaluation, L-BFGS only) x (1 + helpers) warps.
+void chain_geometry(const k2b_model* m, long S, bool lbfgs, int hmax, int& grid, int& teams, int& helpers, int& evals) {
+  // Few sequences: the launch is latency-bound and most schedulers idle.  Helper warps take the mixture prior off the
+  // evaluator (measured on B200, L-BFGS, us per frame: 1 sequence 106 / 80 / 66 with 0 / 1 / 2 helpers; 256 sequences
+  // 113 / 86 / 80; 512 sequences 128 / 110 / 114), and with L-BFGS further evaluators try the line search's next
+  // steps in the same round (chain_core.cuh, TeamMem).  With enough sequences to fill the SMs one warp per sequence
+  // has the best throughput.  12 warps of 168 registers fill an SM's register file.
+  const long per_sm = (S + m->num_sms - 1) / m->num_sms;       // sequences an SM has to host
+  if (per_sm <= 1) { evals = lbfgs ? 5 : 1; helpers = lbfgs ? 1 : 2; }
+  else if (per_sm <= 2) { evals = lbfgs ? 5 : 1; helpers = lbfgs ? 0 : 2; }
+  else { evals = 1; helpers = per_sm <= 6 ? 1 : 0; }
   if (const char* e = getenv("K2B_CHAIN_HELPERS")) helpers = atoi(e);
-  if (helpers < 0) helpers = 0;
-  if (helpers > 3) helpers = 3;
-  int cap = kChainMaxWarps / (1 + helpers);
-  if (helpers > 0 && cap > 7) cap = 7;            // two named barriers per group, ids 1..15
-  long g = (S + m->num_sms - 1) / m->num_sms;
+  if (const char* e = getenv("K2B_CHAIN_TEAM")) evals = atoi(e);
+  if (!lbfgs) evals = 1;
+  helpers = helpers < 0 ? 0 : (helpers > 3 ? 3 : helpers);
+  evals = evals < 1 ? 1 : (evals > wc::kMaxCand ? wc::kMaxCand : evals);
+  while (evals * (1 + helpers) > kChainMaxWarps) {
+    if (helpers > 0) --helpers; else --evals;
+  }
+  const int tw = evals * (1 + helpers);
+  int cap = kChainMaxWarps / tw;
+  const int bar_cap = evals == 1 ? (helpers > 0 ? 7 : kChainMaxWarps) : 3;      // named barrier ids 1..15
+  if (cap > bar_cap) cap = bar_cap;
+  long g = per_sm;
   if (const char* e = getenv("K2B_CHAIN_WARPS")) g = atoi(e);
-  groups = (int)(g < 1 ? 1 : (g > cap ? cap : g));
-  const long ctas = (S + groups - 1) / groups;
+  teams = (int)(g < 1 ? 1 : (g > cap ? cap : g));
+  while (teams > 1 && chain_smem_bytes(m->num_shape, teams, evals, helpers, hmax) > 227 * 1024) --teams;
+  const long ctas = (S + teams - 1) / teams;
   grid = (int)(ctas < m->num_sms ? ctas : m->num_sms);
 }
 int chain_hmax(const k2b_chain_args* a) {
@@ -320,17 +333,18 @@ extern "C" size_t k2b_chain_workspace_bytes(const k2b_model* m, int64_t num_sequ
                                             int32_t max_iters) {
   if (!m || num_sequences <= 0) return 0;
   if (optimizer != K2B_OPT_LBFGS) return 256;
-  int grid, groups, helpers;
-  chain_geometry(m, num_sequences, grid, groups, helpers);
-  return sizeof(float) * (size_t)grid * groups * (size_t)wc::hist_floats(lbfgs_history_capacity(max_iters));
+  int grid, teams, helpers, evals;
+  const int hmax = lbfgs_history_capacity(max_iters);
+  chain_geometry(m, num_sequences, true, hmax, grid, teams, helpers, evals);
+  return sizeof(float) * (size_t)grid * teams * (size_t)wc::hist_floats(hmax);
 }
 
 extern "C" int k2b_chain_geometry(const k2b_model* m, int64_t num_sequences, int32_t* out_ctas, int32_t* out_warps) {
   if (!m || num_sequences <= 0) return 0;
-  int grid, groups, helpers;
-  chain_geometry(m, num_sequences, grid, groups, helpers);
+  int grid, teams, helpers, evals;
+  chain_geometry(m, num_sequences, true, lbfgs_history_capacity(30), grid, teams, helpers, evals);
   if (out_ctas) *out_ctas = grid;
-  if (out_warps) *out_warps = groups * (1 + helpers);
+  if (out_warps) *out_warps = teams * evals * (1 + helpers);
   return m->num_sms;
 }
 
@@ -346,12 +360,10 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   if (a->num_iters_first < 0 || a->num_iters_followup < 0) return fail(K2B_EINVAL, "iteration budgets must be >= 0");
   if (a->conf_mode < 0 || a->conf_mode > 2) return fail(K2B_EINVAL, "conf_mode must be 0, 1 or 2");
   const int hmax = chain_hmax(a);
-  int grid, groups, helpers;
-  chain_geometry(m, a->num_sequences, grid, groups, helpers);
-  while (groups > 1 && chain_smem_bytes(m->num_shape, groups * (1 + helpers), hmax) > 227 * 1024) --groups;   // very long budgets
-  if (chain_smem_bytes(m->num_shape, groups * (1 + helpers), hmax) > 227 * 1024)
+  int grid, teams, helpers, evals;
+  chain_geometry(m, a->num_sequences, a->optimizer == K2B_OPT_LBFGS, hmax, grid, teams, helpers, evals);
+  if (chain_smem_bytes(m->num_shape, teams, evals, helpers, hmax) > 227 * 1024)
     return fail(K2B_EUNSUPPORTED, "iteration budget too large");
-  const int warps = groups * (1 + helpers);
   wc::ChainParams p{};
   p.num_seq = a->num_sequences;
   p.frames = a->frames_per_sequence;
@@ -383,9 +395,10 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   p.depth_ref = a->depth_ref;
   p.hmax = hmax;
   p.helpers = helpers;
+  p.team = evals;
   p.hist = nullptr;
   if (p.lbfgs) {
-    const size_t need = sizeof(float) * (size_t)grid * groups * (size_t)wc::hist_floats(hmax);
+    const size_t need = sizeof(float) * (size_t)grid * teams * (size_t)wc::hist_floats(hmax);
     if (!a->workspace || a->workspace_bytes < need) return fail(K2B_ENOMEM, "workspace too small");
     p.hist = (float*)a->workspace;
   }
@@ -396,9 +409,9 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   const ChainTables tab{m->prec, m->mu, m->nlw, m->rel};
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (a->num_obs == 24) e = launch_chain<10, 24>(p, tab, grid, warps, st);
-  else if (m->num_shape == 20) e = launch_chain<20, 22>(p, tab, grid, warps, st);
-  else e = launch_chain<10, 22>(p, tab, grid, warps, st);
+  if (a->num_obs == 24) e = launch_chain<10, 24>(p, tab, grid, teams, st);
+  else if (m->num_shape == 20) e = launch_chain<20, 22>(p, tab, grid, teams, st);
+  else e = launch_chain<10, 22>(p, tab, grid, teams, st);
   g_launches.fetch_add(1);
   if (e != cudaSuccess) return fail(K2B_ECUDA, std::string("chain kernel launch: ") + cudaGetErrorString(e));
   return K2B_OK;
@@ -408,9 +421,8 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
 // one-frame sequence (the gradient lands in the out_* parameter arrays, the mixture component in out_evals)
 namespace {
 int evaluate_warp(const k2b_model* m, const k2b_eval_args* a, cudaStream_t st) {
-  int grid, groups, helpers;
-  chain_geometry(m, a->num_frames, grid, groups, helpers);
-  const int warps = groups * (1 + helpers);
+  int grid, teams, helpers, evals;
+  chain_geometry(m, a->num_frames, false, 1, grid, teams, helpers, evals);
   wc::ChainParams p{};
   p.num_seq = a->num_frames;
   p.frames = 1;
@@ -430,12 +442,13 @@ int evaluate_warp(const k2b_model* m, const k2b_eval_args* a, cudaStream_t st) {
   p.out_loss = a->out_loss; p.out_joints = a->out_joints; p.out_evals = a->out_gmm_component;
   p.hmax = 1;
   p.helpers = helpers;
+  p.team = 1;
   p.eval_only = 1;
   const ChainTables tab{m->prec, m->mu, m->nlw, m->rel};
   cudaError_t e;
-  if (a->num_obs == 24) e = launch_chain<10, 24>(p, tab, grid, warps, st);
-  else if (m->num_shape == 20) e = launch_chain<20, 22>(p, tab, grid, warps, st);
-  else e = launch_chain<10, 22>(p, tab, grid, warps, st);
+  if (a->num_obs == 24) e = launch_chain<10, 24>(p, tab, grid, teams, st);
+  else if (m->num_shape == 20) e = launch_chain<20, 22>(p, tab, grid, teams, st);
+  else e = launch_chain<10, 22>(p, tab, grid, teams, st);
   g_launches.fetch_add(1);
   if (e != cudaSuccess) return fail(K2B_ECUDA, std::string("chain kernel launch: ") + cudaGetErrorString(e));
   return K2B_OK;

@@ -31,10 +31,12 @@
 int k2b_emul_lane();
 float k2b_emul_shfl(float v, int src);
 void k2b_emul_sync();
+void k2b_emul_bar(int id, int threads, int blocking);   // named barrier among the emulated warps (lanes are coroutines)
 // optional line-search trace of the emulated warp: rows of (t, f, g.d) per trial evaluation (tests only)
 extern float* k2b_emul_trace;
 extern int k2b_emul_trace_cap;
 extern int* k2b_emul_trace_n;
+extern long k2b_emul_rounds;      // team rounds (serial evaluation steps) of the emulated leader
 #endif
 
 namespace k2b {
@@ -44,7 +46,8 @@ constexpr int kPStride = 72;                       // row stride of a precision 
 constexpr int kPFloats = kBodyDim * kPStride;      // per component
 constexpr int kWarpVec = 96;                       // 32 lanes x 3 elements
 constexpr int kDbufStride = 80;                    // one staged difference vector (72 used)
-constexpr int kWarpMemFloats = 96 + 2 * kDbufStride + 80 + 256 + 4 * kWarpVec;   // xs, dbuf x2, ybuf, qbuf, 4 gradient slots
+constexpr int kEvalMemFloats = 96 + 2 * kDbufStride + 80 + 256;   // per-warp block: xs, dbuf x2, ybuf, qbuf
+constexpr int kMaxCand = 6;                        // candidate steps a team evaluates per round (<= evaluators)
 
 K2B_HD int lane_id() {
 #if defined(__CUDA_ARCH__)
@@ -116,30 +119,84 @@ struct WarpMem {       // per-warp shared memory, kWarpMemFloats floats
   float* dbuf;         // [2][kDbufStride] x_body - mu_m, double-buffered over the components
   float* ybuf;         // [72] P d of the arg-min component
   float* qbuf;         // [8][32] per-lane partial sums of d.P_m d
-  float* gs;           // [4][96] gradient slots (L-BFGS)
-  // GMM delegation (chain_kernel.cuh, device only): `helpers` > 0 means this warp leads a group whose other
-  // warps scan the mixture components while it walks the kinematic tree.  Named barriers bar_id (work posted)
-  // and bar_id + 1 (results ready); helper h's shared-memory block starts at helper_mem + h * helper_stride.
+  float* gs;           // [4][96] gradient slots (L-BFGS; the sequence's leading warp only, in the team area)
+  // GMM delegation: `helpers` > 0 means other warps scan the mixture components for this evaluator while it walks the
+  // kinematic tree.  Named barriers bar_id (points posted) and bar_id + 1 (results ready) are shared by every evaluator
+  // and helper of the team (bar_threads threads in all): the evaluators of a round run the same code, so they post
+  // and collect together.  Helper h's shared-memory block starts at helper_mem + h * helper_stride.
   int helpers;
   int bar_id;
+  int bar_threads;
   float* helper_mem;
   int helper_stride;
 };
 constexpr int kYbufOff = 96 + 2 * kDbufStride;
-K2B_HD WarpMem make_warp_mem(float* w) {
-  return WarpMem{w, w + 96, w + kYbufOff, w + kYbufOff + 80, w + kYbufOff + 80 + 256, 0, 0, nullptr, 0};
+K2B_HD WarpMem make_warp_mem(float* w, float* gs) {
+  return WarpMem{w, w + 96, w + kYbufOff, w + kYbufOff + 80, gs, 0, 0, 32, nullptr, 0};
 }
 K2B_HD void bar_arrive(int id, int threads) {
 #if defined(__CUDA_ARCH__)
   __threadfence_block();
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+#elif defined(K2B_WARP_EMUL)
+  k2b_emul_bar(id, threads, 0);
 #endif
 }
 K2B_HD void bar_sync(int id, int threads) {
 #if defined(__CUDA_ARCH__)
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+#elif defined(K2B_WARP_EMUL)
+  k2b_emul_bar(id, threads, 1);
 #endif
 }
+
+// ---- a sequence's team --------------------------------------------------------------------------------------------
+// One sequence is served by E evaluator warps (the first one leads: it owns the iterate and runs the L-BFGS machine)
+// and E x H helper warps (H per evaluator, scanning the mixture components).  With E > 1 the line search is evaluated
+// speculatively: torch's bracket phase almost always walks t -> 10 t (or the mid-point 5.505 t) -> 10x that
+// (lbfgs.py:76-94), so while the leader evaluates the step the machine asked for, the other evaluators evaluate the
+// steps it would ask for next; when the machine then asks for one of them, bit for bit, the result is already there.
+// Evaluations are pure functions of the point, so the fit is bit-identical to the one-evaluator kernel; only the
+// number of serial rounds per frame drops (about 13 -> 7 at the reference's 10-iteration budget).
+// Team shared memory: [E (1 + H) warp blocks of kEvalMemFloats][team area].
+struct TeamMem {
+  float* gs;      // [4][96] gradient slots of the leader
+  float* ro;      // [hmax]
+  float* al;      // [hmax]
+  float* xk;      // [96] base point of the posted candidates (the iterate; the point itself when `point_is_base`)
+  float* d;       // [96] search direction
+  float* tval;    // [8] candidate steps
+  int* cmd;       // [8] kind, n_c, flags, row lo, row hi
+  float* res_f;   // [8] losses of candidates 1..
+  float* res_g;   // [E][96] gradients of candidates 1..
+  int E, H;
+  int bar_go, bar_done;   // named barriers: round posted (leader arrives, siblings wait) / results ready
+};
+K2B_HD constexpr int team_area_floats(int E, int hmax) {
+  return 4 * kWarpVec + 2 * ((hmax + 3) & ~3) + 96 + 96 + 8 + 8 + 8 + E * kWarpVec;
+}
+K2B_HD constexpr int team_floats(int E, int H, int hmax) { return E * (1 + H) * kEvalMemFloats + team_area_floats(E, hmax); }
+K2B_HD TeamMem make_team_mem(float* team_base, int E, int H, int hmax) {
+  float* a = team_base + E * (1 + H) * kEvalMemFloats;
+  const int hp = (hmax + 3) & ~3;
+  TeamMem t;
+  t.gs = a;
+  t.ro = a + 4 * kWarpVec;
+  t.al = t.ro + hp;
+  t.xk = t.al + hp;
+  t.d = t.xk + 96;
+  t.tval = t.d + 96;
+  t.cmd = reinterpret_cast<int*>(t.tval + 8);
+  t.res_f = t.tval + 16;
+  t.res_g = t.tval + 24;
+  t.E = E;
+  t.H = H;
+  t.bar_go = 0;
+  t.bar_done = 0;
+  return t;
+}
+enum { kCmdExit = 0, kCmdEval = 1 };
+enum { kFlagGrad = 1, kFlagPriors = 2, kFlagKeep = 4, kFlagFinal = 8, kFlagBase = 16 };
 
 // ---- GMM prior pieces ----------------------------------------------------------------------------
 // Lane -> (row group rg, column chunk cc): lanes 0-7 / 8-15 / 16-23 are row groups 0 / 1 / 2 with chunks 0..7,
@@ -280,7 +337,7 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
   for (int c = 0; c < 3; ++c) wm.xs[3 * lane + c] = xr[c];
   if (with_priors && wm.helpers > 0) {   // hand the point to the helper warps (they read xs and dbuf[0])
     if (lane == 0) wm.dbuf[0] = with_grad ? 2.f : 1.f;
-    bar_arrive(wm.bar_id, 32 * (1 + wm.helpers));
+    bar_arrive(wm.bar_id, wm.bar_threads);
   }
   wsync();
   float shape[NS];
@@ -448,7 +505,7 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
     const float* ysrc = wm.ybuf;
     if (wm.helpers > 0) {
       // the helper warps were handed this point at the top of the evaluation; collect their results
-      bar_sync(wm.bar_id + 1, 32 * (1 + wm.helpers));
+      bar_sync(wm.bar_id + 1, wm.bar_threads);
       for (int h = 0; h < wm.helpers; ++h) {
         const float* hm = wm.helper_mem + h * wm.helper_stride;
         const float ll = hm[0];
@@ -756,6 +813,173 @@ K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& o
 }
 
 // ---------------------------------------------------------------------------------------------
+// Team protocol (see TeamMem).  A round: the leader posts the candidate steps and, when they changed, the base point
+// and direction; every evaluator computes its point x = xk + t d, evaluates it and publishes loss and gradient; the
+// leader feeds the machine with its own result and then with every published result the machine asks for next.
+// ---------------------------------------------------------------------------------------------
+K2B_HD void team_post(const TeamMem& tm, int kind, int n_c, int flags, long row) {
+  if (lane_id() == 0) {
+    tm.cmd[0] = kind;
+    tm.cmd[1] = n_c;
+    tm.cmd[2] = flags;
+    tm.cmd[3] = (int)(row & 0xffffffffl);
+    tm.cmd[4] = (int)(row >> 32);
+  }
+}
+// an evaluator without a candidate this round still takes part in the helpers' handshake
+K2B_HD void team_idle_round(const WarpMem& wm) {
+  if (wm.helpers > 0) {
+    if (lane_id() == 0) wm.dbuf[0] = 3.f;      // helpers: nothing to scan
+    bar_arrive(wm.bar_id, wm.bar_threads);
+    bar_sync(wm.bar_id + 1, wm.bar_threads);
+  }
+}
+K2B_HD void team_release_helpers(const WarpMem& wm) {
+  if (wm.helpers > 0) {
+    if (lane_id() == 0) wm.dbuf[0] = 0.f;
+    bar_arrive(wm.bar_id, wm.bar_threads);
+  }
+}
+
+// Helper warp: scans components h, h + H, .. of the mixture prior at the point its evaluator posted.
+K2B_HD void team_helper(const WarpTables& tb, const WarpMem& wm, float* own, const float* lead, int h, int H, int bar_b,
+                        int bar_threads) {
+  const int lane = lane_id();
+  while (true) {
+    bar_sync(bar_b, bar_threads);
+    const float cmd = *reinterpret_cast<const volatile float*>(lead + 96);
+    if (cmd == 0.f) break;
+    if (cmd != 3.f) {
+      float xr[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) xr[c] = *reinterpret_cast<const volatile float*>(lead + 3 * lane + c);
+      float best;
+      int bm;
+      gmm_scan(tb, wm, xr, h, H, cmd == 2.f, best, bm);
+      if (lane == 0) {
+        own[0] = best;
+        own[1] = (float)bm;
+      }
+    }
+    bar_arrive(bar_b + 1, bar_threads);
+  }
+}
+
+// The steps the team evaluates this round: the one the machine asked for, then the ones it would ask for next.
+template <class Machine>
+K2B_HD int team_candidates(const Machine& st, int E, float (&tc)[kMaxCand]) {
+  tc[0] = (float)st.t;
+  int n = 1;
+  if (E > 1 && st.phase == 0) {       // bracket phase (lbfgs.py:57-94); the zoom phase is not predictable
+    double a, b, a2, b2, a3, b3;
+    st.predict_extrapolation(st.t, st.t_prev, a, b);
+    st.predict_extrapolation(a, st.t, a2, b2);
+    st.predict_extrapolation(b, st.t, a3, b3);
+    const double order[5] = {a, b, a2, a3, b3};       // by frequency in the reference's runs: 10 t, 5.5 t, 100 t, 55 t, 30 t
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float f = (float)order[k];
+      bool dup = !(fabsf(f) <= 3.0e38f);
+      for (int i = 0; i < n; ++i) dup = dup || tc[i] == f;
+      if (!dup && n < E && n < kMaxCand) tc[n++] = f;
+    }
+  }
+  return n;
+}
+
+// WorldSpaceFitter.fit_frame (L-BFGS) by the leader of a team.  Same arguments as fit_warp plus the team.
+template <int NS, int K>
+K2B_HD float fit_warp_team(const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, const FrameObs& ob, float (&xr)[3],
+                           const FitOpts& fo, float* hist, int hmax, float* joints_out, int* evals_out, long row) {
+  const int lane = lane_id();
+  bool frozen[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int e = 3 * lane + c;
+    frozen[c] = e >= 75 + NS || (fo.freeze_betas && e >= kShapeOff && e < kShapeOff + 10) ||
+                (fo.freeze_expr && e >= kShapeOff + 10) ||
+                (fo.stage1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
+  }
+  const bool priors = !fo.stage1;
+  FrameObs obf = ob;
+  if (fo.final_mode) obf.keep_w2 = 0.f;
+  const int base_flags = (priors ? kFlagPriors : 0) | (ob.keep_w2 != 0.f ? kFlagKeep : 0);
+  float gr[3];
+  WVec v;
+  v.gs = tm.gs;
+  v.hist = hist;
+  v.ro = tm.ro;
+  v.al = tm.al;
+  v.hmax = hmax;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { v.x[c] = xr[c]; v.xk[c] = xr[c]; v.d[c] = 0.f; }
+  Lbfgs<75 + NS, WarpOps> st;
+  st.init();
+  bool first = true;
+  int posted_iter = -1;
+#pragma unroll 1
+  while (true) {
+    // ---- post the round ---------------------------------------------------------------------------
+#if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
+    if (lane == 0) ++k2b_emul_rounds;
+#endif
+    float tc[kMaxCand];
+    int n_c = 1;
+    if (!first) n_c = team_candidates(st, tm.E, tc);
+    if (first || posted_iter != st.n_iter) {          // base point and direction of this line search
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tm.xk[3 * lane + c] = first ? v.x[c] : v.xk[c];
+        tm.d[3 * lane + c] = v.d[c];
+      }
+      posted_iter = first ? -1 : st.n_iter;
+    }
+    if (lane < kMaxCand) tm.tval[lane] = lane < n_c && !first ? tc[lane] : 0.f;
+    team_post(tm, kCmdEval, n_c, base_flags | kFlagGrad | (first ? kFlagBase : 0), row);
+    wsync();
+    bar_arrive(tm.bar_go, 32 * tm.E);
+    // ---- the step the machine asked for ------------------------------------------------------------
+    const float loss = eval_warp<NS, K>(tb, wm, ob, v.x, true, priors, gr, nullptr, nullptr);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
+    wsync();
+    bar_sync(tm.bar_done, 32 * tm.E);
+    // ---- feed the machine: own result, then every published result it asks for --------------------
+    const int line = st.n_iter;
+    st.advance_now(v, v, loss, first, fo.iters, fo.lr);
+    unsigned used = 1u;
+#pragma unroll 1
+    while (!first && !st.done && st.n_iter == line) {
+      const float want = (float)st.t;
+      int j = -1;
+      for (int i = 1; i < n_c; ++i)
+        if (!((used >> i) & 1u) && tc[i] == want) j = i;
+      if (j < 0) break;
+      used |= 1u << j;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v.G(st.cur, c) = tm.res_g[j * kWarpVec + 3 * lane + c];
+      const float lj = tm.res_f[j];
+      wsync();
+      st.advance_now(v, v, lj, false, fo.iters, fo.lr);
+    }
+    first = false;
+    if (st.done) break;
+  }
+  if (evals_out) *evals_out = st.evals;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) xr[c] = v.xk[c];
+  // loss (and joints) re-evaluated at the returned parameters (world_space.py:246-247): a round of its own
+#pragma unroll
+  for (int c = 0; c < 3; ++c) tm.xk[3 * lane + c] = xr[c];
+  team_post(tm, kCmdEval, 1, (priors ? kFlagPriors : 0) | (obf.keep_w2 != 0.f ? kFlagKeep : 0) | kFlagBase, row);
+  wsync();
+  bar_arrive(tm.bar_go, 32 * tm.E);
+  const float out_loss = eval_warp<NS, K>(tb, wm, obf, xr, false, priors, gr, joints_out, nullptr);
+  bar_sync(tm.bar_done, 32 * tm.E);
+  return out_loss;
+}
+
+// ---------------------------------------------------------------------------------------------
 // A whole sequence by one warp: the reference's frame loop (api/sequence.py:214-281).
 // ---------------------------------------------------------------------------------------------
 constexpr int kAdamTableW = 64;
@@ -784,7 +1008,8 @@ struct ChainParams {
   float* out_loss; float* out_joints; int* out_evals;
   float* hist;             // L-BFGS (y, s) history, hist_floats(hmax) per resident warp
   int hmax;
-  int helpers;             // helper warps per sequence that scan the mixture components (0 = the walking warp does it)
+  int helpers;             // helper warps per evaluator that scan the mixture components (0 = the evaluator does it)
+  int team;                // evaluator warps per sequence (>= 1; > 1: speculative line-search evaluation, L-BFGS only)
   // camera-space fitter (core/fitters/camera_space.py:81-339), see k2b_fit_args: loss_kind 1 = stage 1, final_mode 1 = stage 2
   int loss_kind, final_mode;
   float depth_w2;
@@ -794,7 +1019,6 @@ struct ChainParams {
   float adam_step[kAdamTableW], adam_bc2[kAdamTableW];
 };
 K2B_HD constexpr long hist_floats(int hmax) { return (long)hmax * 2 * kWarpVec; }
-K2B_HD constexpr int warp_mem_floats(int hmax) { return kWarpMemFloats + ((2 * hmax + 3) & ~3); }
 
 template <int NS>
 K2B_HD float load_elem(const ChainParams& p, long s, int e) {
@@ -812,9 +1036,97 @@ K2B_HD void store_elem(const ChainParams& p, long f, int e, float v) {
   else if (NS == 20 && e < kShapeOff + 20 && p.out_expr) p.out_expr[f * 10 + (e - kShapeOff - 10)] = v;
 }
 
+// This lane's share of the observations of input row f (targets, joint weights, camera-stage extras); the temporal
+// anchor (keep) is filled in by the caller.
+template <int K>
+K2B_HD void load_frame_obs(const ChainParams& p, long f, bool stage1, FrameObs& ob) {
+  const int lane = lane_id();
+  ob.tx = ob.ty = ob.tz = ob.w = 0.f;
+  if (lane < K) {
+    const float* tg = p.targets + (f * K + lane) * 3;
+    ob.tx = tg[0]; ob.ty = tg[1]; ob.tz = tg[2];
+    const float cf = p.conf_mode == 0 ? 1.f : (p.conf_mode == 1 ? p.conf[lane] : p.conf[f * K + lane]);
+    ob.w = p.joint_w2 * cf * cf;
+    // camera stage 1 looks at RHip, LHip, RShoulder, LShoulder only, unweighted (losses.py:80-92)
+    if (stage1) ob.w = (lane == 1 || lane == 2 || lane == 16 || lane == 17) ? 1.f : 0.f;
+  }
+  ob.plain_sq = stage1;
+  ob.depth_w2 = stage1 ? p.depth_w2 : 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) ob.dref[c] = (stage1 && lane == 24) ? p.depth_ref[f * 3 + c] : 0.f;
+}
+
+// Evaluator warp `idx` >= 1 of a team: evaluates candidate idx of every round the leader posts.
 template <int NS, int K>
-K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb, const WarpMem& wm, float* hist,
-                           float* ro, float* al) {
+K2B_HD void team_sibling(const ChainParams& p, const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, int idx) {
+  const int lane = lane_id();
+  const bool stage1 = p.loss_kind == 1;
+  const bool body_owner = lane >= 1 && lane < 24;
+  bool frozen[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int e = 3 * lane + c;
+    frozen[c] = e >= 75 + NS || ((p.freeze_betas & 1) && e >= kShapeOff && e < kShapeOff + 10) ||
+                ((p.freeze_betas & 2) && e >= kShapeOff + 10) ||
+                (stage1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
+  }
+  FrameObs ob;
+  ob.keep[0] = ob.keep[1] = ob.keep[2] = 0.f;
+  long cur_row = -1;
+#pragma unroll 1
+  while (true) {
+    bar_sync(tm.bar_go, 32 * tm.E);
+    const int kind = *reinterpret_cast<const volatile int*>(tm.cmd);
+    if (kind == kCmdExit) break;
+    const int n_c = *reinterpret_cast<const volatile int*>(tm.cmd + 1);
+    const int flags = *reinterpret_cast<const volatile int*>(tm.cmd + 2);
+    const long row = (long)(unsigned)*reinterpret_cast<const volatile int*>(tm.cmd + 3) |
+                     ((long)*reinterpret_cast<const volatile int*>(tm.cmd + 4) << 32);
+    if (row != cur_row) {       // first round of a frame: the posted point is the frame's initial parameters
+      load_frame_obs<K>(p, row, stage1, ob);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[row * kBodyDim + 3 * lane - 3 + c]
+                                                     : *reinterpret_cast<const volatile float*>(tm.xk + 3 * lane + c);
+      cur_row = row;
+    }
+    ob.keep_w2 = (flags & kFlagKeep) ? p.keep_w2 : 0.f;
+    const bool priors = (flags & kFlagPriors) != 0;
+    if (idx < n_c) {
+      const float t = *reinterpret_cast<const volatile float*>(tm.tval + idx);
+      float x[3], gr[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xk = *reinterpret_cast<const volatile float*>(tm.xk + 3 * lane + c);
+        const float d = *reinterpret_cast<const volatile float*>(tm.d + 3 * lane + c);
+        x[c] = (flags & kFlagBase) ? xk : fmaf(t, d, xk);
+      }
+      const float loss = eval_warp<NS, K>(tb, wm, ob, x, (flags & kFlagGrad) != 0, priors, gr, nullptr, nullptr);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tm.res_g[idx * kWarpVec + 3 * lane + c] = frozen[c] ? 0.f : gr[c];
+      if (lane == 0) tm.res_f[idx] = loss;
+    } else if (priors) {
+      team_idle_round(wm);
+    }
+    wsync();
+    bar_arrive(tm.bar_done, 32 * tm.E);
+  }
+  team_release_helpers(wm);
+}
+
+// Leader's last act: let the other evaluators (and through them their helpers) go.
+K2B_HD void team_dismiss(const WarpMem& wm, const TeamMem& tm) {
+  if (tm.E > 1) {
+    team_post(tm, kCmdExit, 0, 0, 0);
+    wsync();
+    bar_arrive(tm.bar_go, 32 * tm.E);
+  }
+  team_release_helpers(wm);
+}
+
+template <int NS, int K>
+K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb, const WarpMem& wm, const TeamMem& tm,
+                           float* hist) {
   const int lane = lane_id();
   float x0[3], xr[3];
 #pragma unroll
@@ -842,19 +1154,7 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
       for (int c = 0; c < 3; ++c) xr[c] = x0[c];
     }
     FrameObs ob;
-    ob.tx = ob.ty = ob.tz = ob.w = 0.f;
-    if (lane < K) {
-      const float* tg = p.targets + (f * K + lane) * 3;
-      ob.tx = tg[0]; ob.ty = tg[1]; ob.tz = tg[2];
-      const float cf = p.conf_mode == 0 ? 1.f : (p.conf_mode == 1 ? p.conf[lane] : p.conf[f * K + lane]);
-      ob.w = p.joint_w2 * cf * cf;
-      // camera stage 1 looks at RHip, LHip, RShoulder, LShoulder only, unweighted (losses.py:80-92)
-      if (fo.stage1) ob.w = (lane == 1 || lane == 2 || lane == 16 || lane == 17) ? 1.f : 0.f;
-    }
-    ob.plain_sq = fo.stage1;
-    ob.depth_w2 = fo.stage1 ? p.depth_w2 : 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) ob.dref[c] = (fo.stage1 && lane == 24) ? p.depth_ref[f * 3 + c] : 0.f;
+    load_frame_obs<K>(p, f, fo.stage1, ob);
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[f * kBodyDim + 3 * lane - 3 + c] : xr[c];
@@ -875,8 +1175,9 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
       continue;
     }
     int evals = 0;
-    const float loss = fit_warp<NS, K>(tb, wm, ob, xr, fo, hist, ro, al, p.hmax,
-                                       p.out_joints ? p.out_joints + frow * K * 3 : nullptr, &evals);
+    float* jout = p.out_joints ? p.out_joints + frow * K * 3 : nullptr;
+    const float loss = (tm.E > 1 && fo.lbfgs) ? fit_warp_team<NS, K>(tb, wm, tm, ob, xr, fo, hist, p.hmax, jout, &evals, f)
+                                              : fit_warp<NS, K>(tb, wm, ob, xr, fo, hist, tm.ro, tm.al, p.hmax, jout, &evals);
 #pragma unroll
     for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, xr[c]);
     if (lane == 0) {

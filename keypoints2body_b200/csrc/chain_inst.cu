@@ -9,10 +9,11 @@
 namespace k2b {
 
 template <>
-cudaError_t launch_chain<K2B_NS, K2B_K>(const wc::ChainParams& p, const ChainTables& tab, int grid, int warps,
+cudaError_t launch_chain<K2B_NS, K2B_K>(const wc::ChainParams& p, const ChainTables& tab, int grid, int teams,
                                         cudaStream_t st) {
   auto kern = chain_kernel<K2B_NS, K2B_K>;
-  const size_t smem = chain_smem_bytes(K2B_NS, warps, p.hmax);
+  const int warps = teams * p.team * (1 + p.helpers);
+  const size_t smem = chain_smem_bytes(K2B_NS, teams, p.team, p.helpers, p.hmax);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

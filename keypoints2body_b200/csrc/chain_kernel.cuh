@@ -31,9 +31,10 @@ template <int NS>
 constexpr size_t chain_table_floats() {
   return (size_t)kGmmM * wc::kPFloats + kGmmM * kMuStride + kGmmM + kMaxFitJoints * (1 + NS) * 4;
 }
-inline size_t chain_smem_bytes(int ns, int warps, int hmax) {
+// shared memory of a launch: tables + `teams` teams of E evaluators x (1 + H) warps each
+inline size_t chain_smem_bytes(int ns, int teams, int E, int H, int hmax) {
   const size_t tab = ns == 20 ? chain_table_floats<20>() : chain_table_floats<10>();
-  return sizeof(float) * (tab + (size_t)warps * wc::warp_mem_floats(hmax));
+  return sizeof(float) * (tab + (size_t)teams * wc::team_floats(E, H, hmax));
 }
 
 template <int NS, int K>
@@ -44,7 +45,7 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
   float* s_mu = s_P + kGmmM * wc::kPFloats;
   float* s_nlw = s_mu + kGmmM * kMuStride;
   float* s_rel = s_nlw + kGmmM;
-  float* s_warp = s_rel + kMaxFitJoints * (1 + NS) * 4;
+  float* s_team = s_rel + kMaxFitJoints * (1 + NS) * 4;
   const int tid = threadIdx.x, nthr = blockDim.x;
   {
     const float4* src = reinterpret_cast<const float4*>(tab.P);
@@ -62,54 +63,44 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
 
   const int warp = tid >> 5, nwarps = nthr >> 5;
   const wc::WarpTables tb{s_P, s_mu, s_nlw, reinterpret_cast<const float4*>(s_rel)};
-  const int wmf = wc::warp_mem_floats(p.hmax);
-  // a group = the warp that walks the sequence + p.helpers warps that scan the mixture components for it
-  const int G = 1 + p.helpers, ngroups = nwarps / G;
-  // the walking warp's position inside its group rotates with the group index, so the (latency-critical) walkers
-  // of neighbouring groups sit on different schedulers (warp id mod 4)
-  const int group = warp / G, role = (warp - group * G - group % G + G) % G;
-  float* w = s_warp + (size_t)(group * G + role) * wmf;     // shared-memory blocks are laid out by role
-  wc::WarpMem wm = wc::make_warp_mem(w);
-  const int bar = 1 + 2 * group;          // named barriers bar (work posted) and bar + 1 (results ready)
-  if (role == 0) {
-    wm.helpers = p.helpers;
-    wm.bar_id = bar;
-    wm.helper_mem = w + wmf;
-    wm.helper_stride = wmf;
-    float* ro = w + wc::kWarpMemFloats;
-    float* al = ro + p.hmax;
-    const long slot = (long)blockIdx.x * ngroups + group;
-    float* hist = p.hist ? p.hist + slot * wc::hist_floats(p.hmax) : nullptr;
-    for (long seq = slot; seq < p.num_seq; seq += (long)gridDim.x * ngroups)
-      wc::run_chain_warp<NS, K>(p, seq, tb, wm, hist, ro, al);
-    if (p.helpers > 0) {                  // release the helpers
-      if ((tid & 31) == 0) wm.dbuf[0] = 0.f;
-      wc::bar_arrive(bar, 32 * G);
+  // a team = E evaluator warps (the first one leads the sequence) + E x H helper warps that scan the mixture
+  // components for them; warps of a team are consecutive, evaluators first, so that the (latency-critical)
+  // evaluators of a team sit on different schedulers (warp id mod 4)
+  const int E = p.team, H = p.helpers, TW = E * (1 + H), nteams = nwarps / TW;
+  const int team = warp / TW, member = warp - team * TW;
+  float* base = s_team + (size_t)team * wc::team_floats(E, H, p.hmax);
+  wc::TeamMem tm = wc::make_team_mem(base, E, H, p.hmax);
+  // named barriers: one evaluator per sequence keeps the ids of the helper pair dense (up to 7 teams per CTA);
+  // teams of several evaluators use four ids each (up to 3 teams per CTA)
+  const int bar_b = E == 1 ? 1 + 2 * team : 2 + 4 * team;
+  tm.bar_go = 1 + 4 * team;
+  tm.bar_done = 4 + 4 * team;
+  if (member < E) {
+    wc::WarpMem wm = wc::make_warp_mem(base + (size_t)member * wc::kEvalMemFloats, tm.gs);
+    wm.helpers = H;
+    wm.bar_id = bar_b;
+    wm.bar_threads = 32 * TW;
+    wm.helper_mem = base + (size_t)(E + member * H) * wc::kEvalMemFloats;
+    wm.helper_stride = wc::kEvalMemFloats;
+    if (member == 0) {
+      const long slot = (long)blockIdx.x * nteams + team;
+      float* hist = p.hist ? p.hist + slot * wc::hist_floats(p.hmax) : nullptr;
+      for (long seq = slot; seq < p.num_seq; seq += (long)gridDim.x * nteams)
+        wc::run_chain_warp<NS, K>(p, seq, tb, wm, tm, hist);
+      wc::team_dismiss(wm, tm);
+    } else {
+      wc::team_sibling<NS, K>(p, tb, wm, tm, member);
     }
   } else {
-    const float* lead = w - (size_t)role * wmf;       // the leader's block: xs at 0, command word at dbuf[0]
-    const int lane = tid & 31;
-    while (true) {
-      wc::bar_sync(bar, 32 * G);
-      const float cmd = *reinterpret_cast<const volatile float*>(lead + 96);
-      if (cmd == 0.f) break;
-      float xr[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) xr[c] = *reinterpret_cast<const volatile float*>(lead + 3 * lane + c);
-      float best;
-      int bm;
-      wc::gmm_scan(tb, wm, xr, role - 1, p.helpers, cmd == 2.f, best, bm);
-      if (lane == 0) {
-        w[0] = best;
-        w[1] = (float)bm;
-      }
-      wc::bar_arrive(bar + 1, 32 * G);
-    }
+    const int e = (member - E) / H, h = (member - E) % H;
+    float* own = base + (size_t)member * wc::kEvalMemFloats;
+    const wc::WarpMem wm = wc::make_warp_mem(own, nullptr);
+    wc::team_helper(tb, wm, own, base + (size_t)e * wc::kEvalMemFloats, h, H, bar_b, 32 * TW);
   }
 }
 
 // NS: shape coefficients (10 | 20); K: observed joints (22 | 24).  Specialised in chain_inst.cu.
 template <int NS, int K>
-cudaError_t launch_chain(const wc::ChainParams& p, const ChainTables& tab, int grid, int warps, cudaStream_t st);
+cudaError_t launch_chain(const wc::ChainParams& p, const ChainTables& tab, int grid, int teams, cudaStream_t st);
 
 }  // namespace k2b

@@ -516,6 +516,22 @@ struct Lbfgs {
     }
   }
 
+  // Where the bracket phase goes from a trial at `tt` (predecessor `tp`) in its two common outcomes: the cubic's
+  // minimiser lies at or beyond the upper bound (-> the bound, 10 t), or the cubic has no real root (-> the middle of the
+  // bounds).  Same arithmetic as the extrapolation branch of after_eval (lbfgs.py:76-94, 27-37), so a point evaluated
+  // speculatively at one of these steps is bit for bit the point the machine asks for when it takes that branch.
+  K2B_HD void predict_extrapolation(double tt, double tp, double& t_max, double& t_mid) const {
+    double min_step = tt + 0.01 * (tt - tp);
+    double max_step = tt * 10.0;
+    if (t_f32) {
+      const float tf = (float)tt;
+      min_step = (double)(tf + 0.01f * (tf - (float)tp));
+      max_step = (double)(tf * 10.f);
+    }
+    t_max = max_step;
+    t_mid = (min_step + max_step) / 2.0;
+  }
+
   // ---- conformance hook: run only the line search on a 1-D surrogate whose objective is a table of recorded
   // (f, g.d) responses (tests/host_emul on the CPU, k2b_linesearch_replay on the device) ----------
   bool ls_replay_finished;

@@ -19,17 +19,19 @@
 using namespace k2b;
 
 namespace {
-constexpr int kLanes = 32;
+constexpr int kMaxWarps = 16;
+constexpr int kMaxLanes = 32 * kMaxWarps;
 constexpr size_t kStack = 1 << 20;
-ucontext_t g_ctx[kLanes], g_main;
+ucontext_t g_ctx[kMaxLanes], g_main;
 char* g_stacks = nullptr;
-int g_lane = 0, g_done = 0;
-float g_buf[2][kLanes];
-int g_par[kLanes];
+int g_lane = 0, g_done = 0, kLanes = 32;     // kLanes: coroutines of the current run (32 per emulated warp)
+float g_buf[2][kMaxLanes];
+int g_par[kMaxLanes];
+int g_bar_cnt[16], g_bar_gen[16];
 void (*g_job)() = nullptr;
 
 void yield_next() {
-  const int cur = g_lane, nxt = (cur + 1) & 31;
+  const int cur = g_lane, nxt = (cur + 1) % kLanes;
   g_lane = nxt;
   swapcontext(&g_ctx[cur], &g_ctx[nxt]);
   g_lane = cur;
@@ -43,10 +45,13 @@ void lane_entry() {
     yield_next();
   }
 }
-void run_warp(void (*job)()) {
-  if (!g_stacks) g_stacks = (char*)malloc(kStack * kLanes);
+// runs `job` on `warps` emulated warps (32 coroutines each) that share named barriers
+void run_warps(void (*job)(), int warps) {
+  if (!g_stacks) g_stacks = (char*)malloc(kStack * kMaxLanes);
+  kLanes = 32 * warps;
   g_job = job;
   g_done = 0;
+  for (int i = 0; i < 16; ++i) g_bar_cnt[i] = g_bar_gen[i] = 0;
   for (int l = 0; l < kLanes; ++l) {
     g_par[l] = 0;
     getcontext(&g_ctx[l]);
@@ -58,11 +63,19 @@ void run_warp(void (*job)()) {
   g_lane = 0;
   swapcontext(&g_main, &g_ctx[0]);
 }
+void run_warp(void (*job)()) { run_warps(job, 1); }
+int emul_warp() { return g_lane >> 5; }
 }  // namespace
 
 float* k2b_emul_trace = nullptr;
 int k2b_emul_trace_cap = 0;
 int* k2b_emul_trace_n = nullptr;
+long k2b_emul_rounds = 0;
+extern "C" long wemu_rounds(int reset) {
+  const long r = k2b_emul_rounds;
+  if (reset) k2b_emul_rounds = 0;
+  return r;
+}
 // rows of (t, f, g.d) for every line-search trial of the next wemu_chain call(s); pass nulls to stop tracing
 extern "C" void wemu_set_trace(float* rows, int cap, int* count) {
   k2b_emul_trace = rows;
@@ -70,15 +83,25 @@ extern "C" void wemu_set_trace(float* rows, int cap, int* count) {
   k2b_emul_trace_n = count;
 }
 
-int k2b_emul_lane() { return g_lane; }
+int k2b_emul_lane() { return g_lane & 31; }
 float k2b_emul_shfl(float v, int src) {
   const int me = g_lane, p = g_par[me];
   g_buf[p][me] = v;
   g_par[me] = p ^ 1;
   yield_next();
-  return g_buf[p][src];
+  return g_buf[p][(me & ~31) + src];
 }
 void k2b_emul_sync() { yield_next(); }
+// bar.arrive / bar.sync among the emulated warps: a generation barrier counted in threads
+void k2b_emul_bar(int id, int threads, int blocking) {
+  const int gen = g_bar_gen[id];
+  if (++g_bar_cnt[id] == threads) {
+    g_bar_cnt[id] = 0;
+    ++g_bar_gen[id];
+  } else if (blocking) {
+    while (g_bar_gen[id] == gen) yield_next();
+  }
+}
 
 struct WEmuModel {
   int ns;
@@ -135,13 +158,30 @@ struct Job {
   float* joints;
   int* comp;
   std::vector<float> wmem, hist;
+  int E = 1, H = 0;     // team: evaluators, helpers per evaluator
 } g;
 
 template <int NS, int K>
 void lane_job() {
   wc::WarpTables tb{g.m->P.data(), g.m->mu.data(), g.m->nlw.data(), (const float4*)g.m->rel.data()};
-  float* w = g.wmem.data();
-  const wc::WarpMem wm = wc::make_warp_mem(w);
+  float* base = g.wmem.data();
+  const int E = g.E, H = g.H, TW = E * (1 + H), member = emul_warp();
+  wc::TeamMem tm = wc::make_team_mem(base, E, H, g.p.hmax > 0 ? g.p.hmax : 1);
+  const int bar_b = E == 1 ? 1 : 2;          // the kernel's ids for team 0
+  tm.bar_go = 1;
+  tm.bar_done = 4;
+  if (member >= E) {                          // helper warp
+    const int e = (member - E) / H, h = (member - E) % H;
+    float* own = base + (size_t)member * wc::kEvalMemFloats;
+    wc::team_helper(tb, wc::make_warp_mem(own, nullptr), own, base + (size_t)e * wc::kEvalMemFloats, h, H, bar_b, 32 * TW);
+    return;
+  }
+  wc::WarpMem wm = wc::make_warp_mem(base + (size_t)member * wc::kEvalMemFloats, tm.gs);
+  wm.helpers = H;
+  wm.bar_id = bar_b;
+  wm.bar_threads = 32 * TW;
+  wm.helper_mem = base + (size_t)(E + member * H) * wc::kEvalMemFloats;
+  wm.helper_stride = wc::kEvalMemFloats;
   if (g.eval_only) {
     const int lane = wc::lane_id();
     float xr[3], gr[3];
@@ -164,10 +204,15 @@ void lane_job() {
     for (int c = 0; c < 3; ++c)
       if (3 * lane + c < 75 + NS) g.grad[3 * lane + c] = gr[c];
     if (lane == 0) { *g.loss = loss; *g.comp = comp; }
+    wc::team_release_helpers(wm);
     return;
   }
-  float* ro = w + wc::kWarpMemFloats;
-  wc::run_chain_warp<NS, K>(g.p, g.seq, tb, wm, g.hist.data(), ro, ro + g.p.hmax);
+  if (member == 0) {
+    wc::run_chain_warp<NS, K>(g.p, g.seq, tb, wm, tm, g.hist.data());
+    wc::team_dismiss(wm, tm);
+  } else {
+    wc::team_sibling<NS, K>(g.p, tb, wm, tm, member);
+  }
 }
 
 void (*pick_job(int ns, int K))() {
@@ -190,9 +235,20 @@ extern "C" int wemu_eval(void* model, int K, float joint_w, float keep_w, const 
   g.p.keep_w2 = keep_w * keep_w;
   g.p.preserve_pose = keep_pose;
   g.x = x; g.grad = out_grad; g.loss = out_loss; g.joints = out_joints; g.comp = out_comp;
-  g.wmem.assign(wc::warp_mem_floats(1), 0.f);
-  run_warp(pick_job(g.m->ns, K));
+  g.p.hmax = 1;
+  g.E = 1;
+  g.p.team = 1;
+  g.p.helpers = g.H;
+  g.wmem.assign(wc::team_floats(1, g.H, 1), 0.f);
+  run_warps(pick_job(g.m->ns, K), 1 + g.H);
   return 0;
+}
+
+// Team of the following wemu_eval / wemu_chain calls: E evaluator warps (> 1: speculative line-search evaluation,
+// L-BFGS chains only) and H helper warps per evaluator (mixture prior scanned by other warps).
+extern "C" void wemu_set_team(int evaluators, int helpers) {
+  g.E = evaluators < 1 ? 1 : evaluators;
+  g.H = helpers < 0 ? 0 : helpers;
 }
 
 // S sequences of T frames each, walked by one (emulated) warp per sequence.
@@ -226,13 +282,19 @@ extern "C" int wemu_chain(void* model, int K, int S, int T, long first_seq_ind, 
     p.adam_step[k - 1] = (float)((double)lr / (1.0 - std::pow(0.9, (double)k)));
     p.adam_bc2[k - 1] = (float)std::sqrt(1.0 - std::pow(0.999, (double)k));
   }
-  g.wmem.assign(wc::warp_mem_floats(p.hmax), 0.f);
+  const int E = lbfgs ? g.E : 1;
+  p.team = E;
+  p.helpers = g.H;
+  const int keepE = g.E;
+  g.E = E;
+  g.wmem.assign(wc::team_floats(E, g.H, p.hmax), 0.f);
   g.hist.assign(wc::hist_floats(p.hmax), 0.f);
   p.hist = g.hist.data();
   for (long s = 0; s < S; ++s) {
     g.seq = s;
-    run_warp(pick_job(g.m->ns, K));
+    run_warps(pick_job(g.m->ns, K), E * (1 + g.H));
   }
+  g.E = keepE;
   return 0;
 }
 

@@ -59,6 +59,10 @@ def fitters(weights, gmm):
 
 # ---- G1': teacher-forced evaluation parity ---------------------------------------------------------------------
 EVALUATORS = [("frame", None), ("warp", "0"), ("warp", "2")]      # (kernel, helper warps per frame)
+# Absolute float32 floor of the gradient: joint positions carry ~2e-7 m of forward-kinematics rounding, the joint term
+# turns that into 2 * 600^2 * 2e-7 = 0.14 per joint coordinate, and the translation gradient sums 22 of them.  The
+# float32 reference is itself up to 0.43 away from the float64 oracle at these points (tests/test_lbfgs_conformance.py).
+GRAD_NOISE_FLOOR = 0.5
 
 
 @pytest.mark.parametrize("kernel,helpers", EVALUATORS)
@@ -90,7 +94,7 @@ def test_teacher_forced_evaluation_parity(fitters, monkeypatch, tag, mt, kernel,
     assert rel.max() <= 2e-4
     for i in np.nonzero(rel > 5e-5)[0]:
         g64 = oracle64_gradient(mt, x[i], tgt[frame[i]], keep[frame[i]], keep_w)
-        assert np.abs(grad[i] - g64).max() / gmax[i] <= 1e-4, (i, rel[i])
+        assert np.abs(grad[i] - g64).max() <= max(1e-4 * gmax[i], GRAD_NOISE_FLOOR), (i, rel[i])
     print(tag, kernel, helpers, "points", len(f), "worst loss rel", (np.abs(loss - f) / np.abs(f)).max(), "worst grad rel", rel.max())
 
 
@@ -314,3 +318,29 @@ def test_dict_block_sequence_with_default_config(weights, tmp_path, monkeypatch)
     assert len(a) == 4
     for ra, rb in zip(a, b):       # all 22 body joints observed through the dict = the AMASS fit without a shape pass
         assert torch.allclose(ra.params.pose, rb.params.pose, atol=2e-5)
+
+
+@pytest.mark.parametrize("S,Tn", [(3, 12), (40, 6)])
+def test_team_evaluation_is_bit_identical(fitters, weights, shims, monkeypatch, S, Tn):
+    """Speculative line-search teams (several evaluator warps per sequence, csrc/chain_core.cuh TeamMem) and helper
+    warps change WHEN an evaluation happens, never its value: every team shape returns the bits one warp returns."""
+    w = weights("smpl")
+    tgt = problems.chain_problem(w, S, Tn, 5150)
+    with torch.no_grad():
+        root = shims("smpl")(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10)).joints[0, 0]
+    init = dict(global_orient=torch.zeros(S, 3), body_pose=torch.zeros(S, 69), betas=torch.zeros(S, 10),
+                transl=(tgt[:, 0, 0] - root).contiguous())
+    f = fitters("smpl", use_lbfgs=True)
+    outs = {}
+    for E, H in ((1, 0), (1, 2), (5, 0), (3, 1), (6, 1), (4, 2), (None, None)):
+        if E is None:
+            monkeypatch.delenv("K2B_CHAIN_TEAM"); monkeypatch.delenv("K2B_CHAIN_HELPERS")     # the library's own choice
+        else:
+            monkeypatch.setenv("K2B_CHAIN_TEAM", str(E)); monkeypatch.setenv("K2B_CHAIN_HELPERS", str(H))
+        o = f.fit_chain(init, tgt, None, with_mesh=False)
+        outs[(E, H)] = {k: cpu(o[k]) for k in ("loss", "evals", "fit_joints")}
+        outs[(E, H)].update({k: cpu(v) for k, v in o["params"].items()})
+    ref = outs[(1, 0)]
+    for key, o in outs.items():
+        for k, v in ref.items():
+            assert np.array_equal(v, o[k]), (key, k)

@@ -222,3 +222,30 @@ def test_warp_camera_two_stage_adam_matches_reference(goldens, wmodels, tag, ite
     assert np.abs(s2["transl"][:, 0] - g[tag + "_transl"]).max() < 1e-4
     assert np.abs(s2["betas"][:, 0] - g[tag + "_betas"]).max() < 1e-4
     np.testing.assert_allclose(s2["loss"][:, 0], g[tag + "_loss"].reshape(-1), rtol=1e-4)
+
+
+@pytest.mark.parametrize("E,H", [(1, 2), (5, 0), (3, 1), (6, 1), (2, 2)])
+def test_team_is_bit_identical_to_one_warp(goldens, wemu, wmodels, shims, E, H):
+    """A sequence served by a team -- E evaluator warps trying the line search's next steps in the same round, H helper
+    warps per evaluator scanning the mixture prior -- must return exactly what one warp returns: evaluations are pure
+    functions of the point, and the machine consumes the same (loss, gradient) sequence either way.  L-BFGS chain of 6
+    frames (30-iteration first frame, 10-iteration follow-ups with the temporal term) and the SMPL-X 5-iteration case."""
+    g = goldens
+    wemu.wemu_set_team.argtypes = [C.c_int, C.c_int]
+    x0, tgt = _sequence_init(g, shims)
+    xx = pack_x(g["lbfgs_smplx_in_pose"], g["lbfgs_smplx_in_transl"], g["lbfgs_smplx_in_betas"], np.zeros((3, 10), np.float32))
+    try:
+        wemu.wemu_set_team(1, 0)
+        ref = wmodels("smpl").chain(x0, tgt[None], np.ones(22), lbfgs=True)
+        refx = wmodels("smplx").chain(xx, g["lbfgs_smplx_in_target"][:, None], np.ones(22), lbfgs=True, iters_first=5, iters_follow=5)
+        wemu.wemu_set_team(E, H)
+        out = wmodels("smpl").chain(x0, tgt[None], np.ones(22), lbfgs=True)
+        outx = wmodels("smplx").chain(xx, g["lbfgs_smplx_in_target"][:, None], np.ones(22), lbfgs=True, iters_first=5, iters_follow=5)
+        adam = wmodels("smpl").chain(x0, tgt[None], np.ones(22), lbfgs=False)        # helpers only (teams are L-BFGS)
+    finally:
+        wemu.wemu_set_team(1, 0)
+    for a, b in ((ref, out), (refx, outx)):
+        for k in ("pose", "betas", "transl", "expr", "loss", "joints", "evals"):
+            assert np.array_equal(a[k], b[k]), (E, H, k)
+    assert np.abs(adam["pose"][0] - g["seq_adam_chain_pose"]).max() < 1e-4
+    print("evaluations per frame", ref["evals"].ravel())
