@@ -301,12 +301,14 @@ void chain_geometry(const k2b_model* m, long S, bool lbfgs, int hmax, int& grid,
   // steps in the same round (chain_core.cuh, TeamMem).  With enough sequences to fill the SMs one warp per sequence
   // has the best throughput.  12 warps of 168 registers fill an SM's register file.
   const long per_sm = (S + m->num_sms - 1) / m->num_sms;       // sequences an SM has to host
-  if (per_sm <= 1) { evals = lbfgs ? 5 : 1; helpers = lbfgs ? 1 : 2; }
-  else if (per_sm <= 2) { evals = lbfgs ? 5 : 1; helpers = lbfgs ? 0 : 2; }
-  else { evals = 1; helpers = per_sm <= 6 ? 1 : 0; }
+  if (per_sm <= 1) { evals = 6; helpers = 2; }
+  else if (per_sm <= 2) { evals = 6; helpers = 2; }
+  else { evals = per_sm <= 4 ? 3 : 1; helpers = per_sm <= 6 ? 1 : 0; }
   if (const char* e = getenv("K2B_CHAIN_HELPERS")) helpers = atoi(e);
   if (const char* e = getenv("K2B_CHAIN_TEAM")) evals = atoi(e);
-  if (!lbfgs) evals = 1;
+  // L-BFGS evaluates the mixture prior in line form (chain_core.cuh, LineEval): the evaluators share the matrix
+  // products, there is nothing for helper warps to do; Adam has no line search to speculate on
+  if (lbfgs) helpers = 0; else evals = 1;
   helpers = helpers < 0 ? 0 : (helpers > 3 ? 3 : helpers);
   evals = evals < 1 ? 1 : (evals > wc::kMaxCand ? wc::kMaxCand : evals);
   while (evals * (1 + helpers) > kChainMaxWarps) {

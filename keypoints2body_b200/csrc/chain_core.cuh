@@ -169,11 +169,14 @@ struct TeamMem {
   int* cmd;       // [8] kind, n_c, flags, row lo, row hi
   float* res_f;   // [8] losses of candidates 1..
   float* res_g;   // [E][96] gradients of candidates 1..
+  float* lu;      // [8][72] u_m = P_m (xk - mu_m)      (LineEval)
+  float* lw;      // [8][72] w_m = P_m d
+  float* labc;    // [8][4]  A_m, B_m, C_m
   int E, H;
-  int bar_go, bar_done;   // named barriers: round posted (leader arrives, siblings wait) / results ready
+  int bar_go, bar_tab, bar_done;   // named barriers: round posted / line tables ready / results ready
 };
 K2B_HD constexpr int team_area_floats(int E, int hmax) {
-  return 4 * kWarpVec + 2 * ((hmax + 3) & ~3) + 96 + 96 + 8 + 8 + 8 + E * kWarpVec;
+  return 4 * kWarpVec + 2 * ((hmax + 3) & ~3) + 96 + 96 + 8 + 8 + 8 + E * kWarpVec + 2 * kGmmM * kPStride + 4 * kGmmM;
 }
 K2B_HD constexpr int team_floats(int E, int H, int hmax) { return E * (1 + H) * kEvalMemFloats + team_area_floats(E, hmax); }
 K2B_HD TeamMem make_team_mem(float* team_base, int E, int H, int hmax) {
@@ -189,14 +192,21 @@ K2B_HD TeamMem make_team_mem(float* team_base, int E, int H, int hmax) {
   t.cmd = reinterpret_cast<int*>(t.tval + 8);
   t.res_f = t.tval + 16;
   t.res_g = t.tval + 24;
+  t.lu = t.res_g + E * kWarpVec;
+  t.lw = t.lu + kGmmM * kPStride;
+  t.labc = t.lw + kGmmM * kPStride;
   t.E = E;
   t.H = H;
   t.bar_go = 0;
+  t.bar_tab = 0;
   t.bar_done = 0;
   return t;
 }
 enum { kCmdExit = 0, kCmdEval = 1 };
 enum { kFlagGrad = 1, kFlagPriors = 2, kFlagKeep = 4, kFlagFinal = 8, kFlagBase = 16 };
+// what a round does to the line tables before evaluating: nothing (same line search continues), rebuild u at the
+// posted point (a frame's first evaluation), follow the iterate and take the new direction, or follow the iterate only
+enum { kTabKeep = 0, kTabRefresh = 1, kTabLine = 2, kTabPoint = 3 };
 
 // ---- GMM prior pieces ----------------------------------------------------------------------------
 // Lane -> (row group rg, column chunk cc): lanes 0-7 / 8-15 / 16-23 are row groups 0 / 1 / 2 with chunks 0..7,
@@ -305,6 +315,44 @@ K2B_HD void gmm_scan(const WarpTables& tb, const WarpMem& wm, const float (&xr)[
   }
 }
 
+// out[0..71] = P_m dvec for a vector staged in shared memory (72 floats, entries 69..71 zero).  Same row / column
+// ownership as gmm_scan; the three row groups are combined by shuffles.
+K2B_HD void gmm_matvec(const WarpTables& tb, const float* dvec, int m, float* out) {
+  const int lane = lane_id();
+  const int rg = lane < 24 ? lane >> 3 : lane - 24;
+  const int cc = lane < 24 ? lane & 7 : 8;
+  const bool act = lane < 27;
+  float2 acc[4];
+  if (act) gmm_rows(tb, dvec, m, rg, cc, acc);
+  else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+  }
+  float y[8] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, acc[3].x, acc[3].y};
+  const int p1 = lane < 24 ? (lane + 8) % 24 : 24 + (lane - 23) % 3;
+  const int p2 = lane < 24 ? (lane + 16) % 24 : 24 + (lane - 22) % 3;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) y[k] = (y[k] + shfl(y[k], p1)) + shfl(y[k], p2);
+  if (act && rg == 0) {
+    *reinterpret_cast<float4*>(out + 4 * cc) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(out + 36 + 4 * cc) = make_float4(y[4], y[5], y[6], y[7]);
+  }
+  wsync();
+}
+
+// The mixture prior along a line.  On x(t) = xk + t d the Mahalanobis form of component m is the quadratic
+//   q_m(t) = A_m + 2 t B_m + t^2 C_m,   A_m = a.u_m, B_m = d.u_m, C_m = d.w_m,   a = xk - mu_m, u_m = P_m a, w_m = P_m d,
+// and its gradient is u_m + t w_m.  Every evaluation of an L-BFGS line search lies on one line, so the eight
+// precision-matrix products are done once per line search (w_m; u_m follows the iterate: u_m += t_accepted w_m, and
+// is recomputed from scratch at every frame's first evaluation) instead of once per evaluation, and an evaluation at
+// any step t costs 8 fused multiply-adds for the arg-min and one axpy for the gradient.
+struct LineEval {
+  const float* u;     // [8][72]
+  const float* w;     // [8][72]
+  const float* abc;   // [8][4] A, B, C
+  float t;
+};
+
 struct FrameObs {      // this lane's share of the frame's observations
   float tx, ty, tz, w; // lane j < K: target and weight joint_w^2 conf_j^2 of joint j
   float keep[3];       // preserve pose of the owned body-pose entries
@@ -329,13 +377,14 @@ K2B_HD Acc shfl_acc(const Acc& a, int src) {
 // gradient of the owned elements (zero for unowned ones).  joints_out: global [K][3] or null.
 template <int NS, int K>
 K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& ob, const float (&xr)[3],
-                       bool with_grad, bool with_priors, float (&gr)[3], float* joints_out, int* gmm_component) {
+                       bool with_grad, bool with_priors, float (&gr)[3], float* joints_out, int* gmm_component,
+                       const LineEval* le = nullptr) {
   constexpr int NJ = (K == 24) ? 24 : 22;
   constexpr int MAXD = (K == 24) ? 8 : 7;
   const int lane = lane_id();
 #pragma unroll
   for (int c = 0; c < 3; ++c) wm.xs[3 * lane + c] = xr[c];
-  if (with_priors && wm.helpers > 0) {   // hand the point to the helper warps (they read xs and dbuf[0])
+  if (with_priors && wm.helpers > 0 && !le) {   // hand the point to the helper warps (they read xs and dbuf[0])
     if (lane == 0) wm.dbuf[0] = with_grad ? 2.f : 1.f;
     bar_arrive(wm.bar_id, wm.bar_threads);
   }
@@ -503,7 +552,21 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
     float best = INFINITY;
     int bm = 0;
     const float* ysrc = wm.ybuf;
-    if (wm.helpers > 0) {
+    const float* yw = nullptr;          // line form: gradient = ysrc + t yw
+    if (le) {
+      // every lane evaluates the eight quadratics (first minimum wins, like torch.min)
+#pragma unroll
+      for (int m = 0; m < kGmmM; ++m) {
+        const float q = fmaf(le->t, fmaf(le->t, le->abc[4 * m + 2], 2.f * le->abc[4 * m + 1]), le->abc[4 * m]);
+        const float ll = fmaf(0.5f, q, tb.nlw[m]);
+        if (ll < best) {
+          best = ll;
+          bm = m;
+        }
+      }
+      ysrc = le->u + bm * kPStride;
+      yw = le->w + bm * kPStride;
+    } else if (wm.helpers > 0) {
       // the helper warps were handed this point at the top of the evaluation; collect their results
       bar_sync(wm.bar_id + 1, wm.bar_threads);
       for (int h = 0; h < wm.helpers; ++h) {
@@ -527,7 +590,7 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
         const int i = i0 + c;
         const float xi = xr[c];
         float gi = gr[c];
-        if (with_grad) gi = fmaf(kPosePriorW2, ysrc[i], gi);
+        if (with_grad) gi = fmaf(kPosePriorW2, yw ? fmaf(le->t, yw[i], ysrc[i]) : ysrc[i], gi);
         if (ob.keep_w2 != 0.f) {      // temporal pose-preserve term (losses.py:57-59)
           const float d = xi - ob.keep[c];
           lsum = fmaf(ob.keep_w2 * d, d, lsum);
@@ -817,15 +880,91 @@ K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& o
 // and direction; every evaluator computes its point x = xk + t d, evaluates it and publishes loss and gradient; the
 // leader feeds the machine with its own result and then with every published result the machine asks for next.
 // ---------------------------------------------------------------------------------------------
-K2B_HD void team_post(const TeamMem& tm, int kind, int n_c, int flags, long row) {
+K2B_HD void team_post(const TeamMem& tm, int kind, int n_c, int flags, long row, int tab_mode, float t_step) {
   if (lane_id() == 0) {
     tm.cmd[0] = kind;
     tm.cmd[1] = n_c;
     tm.cmd[2] = flags;
     tm.cmd[3] = (int)(row & 0xffffffffl);
     tm.cmd[4] = (int)(row >> 32);
+    tm.cmd[5] = tab_mode;
+    tm.tval[7] = t_step;
   }
 }
+
+// This warp's share (components idx, idx + E, ..) of a line-table update; every evaluator of the team calls it in the
+// same round, then the team meets at bar_tab.  dbuf: 72+ floats of this warp's scratch.
+K2B_HD void line_tables_update(const WarpTables& tb, float* dbuf, const TeamMem& tm, int mode, float t_step, int idx) {
+  const int lane = lane_id();
+#pragma unroll 1
+  for (int m = idx; m < kGmmM; m += tm.E) {
+    float* u = tm.lu + m * kPStride;
+    float* w = tm.lw + m * kPStride;
+    float* abc = tm.labc + 4 * m;
+    float A = abc[0];
+    const float B = abc[1], Cc = abc[2];
+    wsync();
+    float pa = 0.f, pb = 0.f, pc = 0.f;
+    if (mode == kTabRefresh) {
+      if (lane < 24) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int i = 3 * lane + c;
+          dbuf[i] = i < kBodyDim ? tm.xk[3 + i] - tb.mu[m * kMuStride + i] : 0.f;
+        }
+      }
+      wsync();
+      gmm_matvec(tb, dbuf, m, u);
+      if (lane < 24) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int i = 3 * lane + c;
+          pa = fmaf(dbuf[i], u[i], pa);
+          w[i] = 0.f;
+        }
+      }
+      A = wsum(pa);
+      if (lane == 0) { abc[0] = A; abc[1] = 0.f; abc[2] = 0.f; }
+    } else {
+      // follow the iterate: xk moved by t_step along the previous direction
+      A = fmaf(t_step, fmaf(t_step, Cc, 2.f * B), A);
+      if (lane < 24) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int i = 3 * lane + c;
+          u[i] = fmaf(t_step, w[i], u[i]);
+        }
+      }
+      if (mode == kTabLine) {
+        if (lane < 24) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int i = 3 * lane + c;
+            dbuf[i] = i < kBodyDim ? tm.d[3 + i] : 0.f;
+          }
+        }
+        wsync();
+        gmm_matvec(tb, dbuf, m, w);
+        if (lane < 24) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int i = 3 * lane + c;
+            pb = fmaf(dbuf[i], u[i], pb);
+            pc = fmaf(dbuf[i], w[i], pc);
+          }
+        }
+        pb = wsum(pb);
+        pc = wsum(pc);
+      } else if (lane < 24) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) w[3 * lane + c] = 0.f;
+      }
+      if (lane == 0) { abc[0] = A; abc[1] = pb; abc[2] = pc; }
+    }
+  }
+  wsync();
+}
+
 // an evaluator without a candidate this round still takes part in the helpers' handshake
 K2B_HD void team_idle_round(const WarpMem& wm) {
   if (wm.helpers > 0) {
@@ -887,7 +1026,8 @@ K2B_HD int team_candidates(const Machine& st, int E, float (&tc)[kMaxCand]) {
   return n;
 }
 
-// WorldSpaceFitter.fit_frame (L-BFGS) by the leader of a team.  Same arguments as fit_warp plus the team.
+// WorldSpaceFitter.fit_frame (L-BFGS) by the leader of a team (a team of one included).  Same arguments as fit_warp
+// plus the team.  The mixture prior is evaluated in line form (LineEval), the team maintains the tables.
 template <int NS, int K>
 K2B_HD float fit_warp_team(const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, const FrameObs& ob, float (&xr)[3],
                            const FitOpts& fo, float* hist, int hmax, float* joints_out, int* evals_out, long row) {
@@ -901,6 +1041,7 @@ K2B_HD float fit_warp_team(const WarpTables& tb, const WarpMem& wm, const TeamMe
                 (fo.stage1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
   }
   const bool priors = !fo.stage1;
+  const bool teamed = tm.E > 1;
   FrameObs obf = ob;
   if (fo.final_mode) obf.keep_w2 = 0.f;
   const int base_flags = (priors ? kFlagPriors : 0) | (ob.keep_w2 != 0.f ? kFlagKeep : 0);
@@ -915,41 +1056,60 @@ K2B_HD float fit_warp_team(const WarpTables& tb, const WarpMem& wm, const TeamMe
   for (int c = 0; c < 3; ++c) { v.x[c] = xr[c]; v.xk[c] = xr[c]; v.d[c] = 0.f; }
   Lbfgs<75 + NS, WarpOps> st;
   st.init();
+  LineEval le{tm.lu, tm.lw, tm.labc, 0.f};
   bool first = true;
-  int posted_iter = -1;
+  int tab_mode = kTabRefresh;       // what the next round does to the line tables
+  float t_pending = 0.f;            // step the iterate took since the tables were last brought up to date
 #pragma unroll 1
   while (true) {
-    // ---- post the round ---------------------------------------------------------------------------
 #if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
     if (lane == 0) ++k2b_emul_rounds;
 #endif
+    // ---- post the round ---------------------------------------------------------------------------
     float tc[kMaxCand];
     int n_c = 1;
+    tc[0] = 0.f;
     if (!first) n_c = team_candidates(st, tm.E, tc);
-    if (first || posted_iter != st.n_iter) {          // base point and direction of this line search
+    if (tab_mode != kTabKeep) {       // base point and direction of this line search
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         tm.xk[3 * lane + c] = first ? v.x[c] : v.xk[c];
         tm.d[3 * lane + c] = v.d[c];
       }
-      posted_iter = first ? -1 : st.n_iter;
     }
-    if (lane < kMaxCand) tm.tval[lane] = lane < n_c && !first ? tc[lane] : 0.f;
-    team_post(tm, kCmdEval, n_c, base_flags | kFlagGrad | (first ? kFlagBase : 0), row);
+    if (lane < kMaxCand) tm.tval[lane] = lane < n_c ? tc[lane] : 0.f;
+    team_post(tm, kCmdEval, n_c, base_flags | kFlagGrad | (first ? kFlagBase : 0), row, priors ? tab_mode : kTabKeep, t_pending);
     wsync();
-    bar_arrive(tm.bar_go, 32 * tm.E);
+    if (teamed) bar_arrive(tm.bar_go, 32 * tm.E);
+    if (priors && tab_mode != kTabKeep) {
+      line_tables_update(tb, wm.dbuf, tm, tab_mode, t_pending, 0);
+      if (teamed) bar_sync(tm.bar_tab, 32 * tm.E);
+    }
+    tab_mode = kTabKeep;
+    t_pending = 0.f;
     // ---- the step the machine asked for ------------------------------------------------------------
-    const float loss = eval_warp<NS, K>(tb, wm, ob, v.x, true, priors, gr, nullptr, nullptr);
+    le.t = tc[0];
+    const float loss = eval_warp<NS, K>(tb, wm, ob, v.x, true, priors, gr, nullptr, nullptr, &le);
 #pragma unroll
     for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
     wsync();
-    bar_sync(tm.bar_done, 32 * tm.E);
+    if (teamed) bar_sync(tm.bar_done, 32 * tm.E);
     // ---- feed the machine: own result, then every published result it asks for --------------------
-    const int line = st.n_iter;
-    st.advance_now(v, v, loss, first, fo.iters, fo.lr);
     unsigned used = 1u;
+    float next_loss = loss;
 #pragma unroll 1
-    while (!first && !st.done && st.n_iter == line) {
+    while (true) {
+      st.advance(v, v, next_loss, first, fo.iters, fo.lr);
+      first = false;
+      if (st.done || st.need_outer) {       // the line search is over (or never started): the iterate moved by t
+        t_pending = (float)st.t;
+        tab_mode = kTabPoint;
+        if (st.need_outer && !st.done) {
+          st.start_outer(v, v);
+          if (!st.done) tab_mode = kTabLine;
+        }
+        break;
+      }
       const float want = (float)st.t;
       int j = -1;
       for (int i = 1; i < n_c; ++i)
@@ -958,11 +1118,9 @@ K2B_HD float fit_warp_team(const WarpTables& tb, const WarpMem& wm, const TeamMe
       used |= 1u << j;
 #pragma unroll
       for (int c = 0; c < 3; ++c) v.G(st.cur, c) = tm.res_g[j * kWarpVec + 3 * lane + c];
-      const float lj = tm.res_f[j];
+      next_loss = tm.res_f[j];
       wsync();
-      st.advance_now(v, v, lj, false, fo.iters, fo.lr);
     }
-    first = false;
     if (st.done) break;
   }
   if (evals_out) *evals_out = st.evals;
@@ -971,11 +1129,18 @@ K2B_HD float fit_warp_team(const WarpTables& tb, const WarpMem& wm, const TeamMe
   // loss (and joints) re-evaluated at the returned parameters (world_space.py:246-247): a round of its own
 #pragma unroll
   for (int c = 0; c < 3; ++c) tm.xk[3 * lane + c] = xr[c];
-  team_post(tm, kCmdEval, 1, (priors ? kFlagPriors : 0) | (obf.keep_w2 != 0.f ? kFlagKeep : 0) | kFlagBase, row);
+  if (lane < kMaxCand) tm.tval[lane] = 0.f;
+  team_post(tm, kCmdEval, 1, (priors ? kFlagPriors : 0) | (obf.keep_w2 != 0.f ? kFlagKeep : 0) | kFlagBase, row,
+            priors ? tab_mode : kTabKeep, t_pending);
   wsync();
-  bar_arrive(tm.bar_go, 32 * tm.E);
-  const float out_loss = eval_warp<NS, K>(tb, wm, obf, xr, false, priors, gr, joints_out, nullptr);
-  bar_sync(tm.bar_done, 32 * tm.E);
+  if (teamed) bar_arrive(tm.bar_go, 32 * tm.E);
+  if (priors && tab_mode != kTabKeep) {
+    line_tables_update(tb, wm.dbuf, tm, tab_mode, t_pending, 0);
+    if (teamed) bar_sync(tm.bar_tab, 32 * tm.E);
+  }
+  le.t = 0.f;
+  const float out_loss = eval_warp<NS, K>(tb, wm, obf, xr, false, priors, gr, joints_out, nullptr, &le);
+  if (teamed) bar_sync(tm.bar_done, 32 * tm.E);
   return out_loss;
 }
 
@@ -1092,6 +1257,11 @@ K2B_HD void team_sibling(const ChainParams& p, const WarpTables& tb, const WarpM
     }
     ob.keep_w2 = (flags & kFlagKeep) ? p.keep_w2 : 0.f;
     const bool priors = (flags & kFlagPriors) != 0;
+    const int tab_mode = *reinterpret_cast<const volatile int*>(tm.cmd + 5);
+    if (tab_mode != kTabKeep) {
+      line_tables_update(tb, wm.dbuf, tm, tab_mode, *reinterpret_cast<const volatile float*>(tm.tval + 7), idx);
+      bar_sync(tm.bar_tab, 32 * tm.E);
+    }
     if (idx < n_c) {
       const float t = *reinterpret_cast<const volatile float*>(tm.tval + idx);
       float x[3], gr[3];
@@ -1101,12 +1271,11 @@ K2B_HD void team_sibling(const ChainParams& p, const WarpTables& tb, const WarpM
         const float d = *reinterpret_cast<const volatile float*>(tm.d + 3 * lane + c);
         x[c] = (flags & kFlagBase) ? xk : fmaf(t, d, xk);
       }
-      const float loss = eval_warp<NS, K>(tb, wm, ob, x, (flags & kFlagGrad) != 0, priors, gr, nullptr, nullptr);
+      const LineEval le{tm.lu, tm.lw, tm.labc, (flags & kFlagBase) ? 0.f : t};
+      const float loss = eval_warp<NS, K>(tb, wm, ob, x, (flags & kFlagGrad) != 0, priors, gr, nullptr, nullptr, &le);
 #pragma unroll
       for (int c = 0; c < 3; ++c) tm.res_g[idx * kWarpVec + 3 * lane + c] = frozen[c] ? 0.f : gr[c];
       if (lane == 0) tm.res_f[idx] = loss;
-    } else if (priors) {
-      team_idle_round(wm);
     }
     wsync();
     bar_arrive(tm.bar_done, 32 * tm.E);
@@ -1117,7 +1286,7 @@ K2B_HD void team_sibling(const ChainParams& p, const WarpTables& tb, const WarpM
 // Leader's last act: let the other evaluators (and through them their helpers) go.
 K2B_HD void team_dismiss(const WarpMem& wm, const TeamMem& tm) {
   if (tm.E > 1) {
-    team_post(tm, kCmdExit, 0, 0, 0);
+    team_post(tm, kCmdExit, 0, 0, 0, kTabKeep, 0.f);
     wsync();
     bar_arrive(tm.bar_go, 32 * tm.E);
   }
@@ -1176,7 +1345,7 @@ K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb,
     }
     int evals = 0;
     float* jout = p.out_joints ? p.out_joints + frow * K * 3 : nullptr;
-    const float loss = (tm.E > 1 && fo.lbfgs) ? fit_warp_team<NS, K>(tb, wm, tm, ob, xr, fo, hist, p.hmax, jout, &evals, f)
+    const float loss = fo.lbfgs ? fit_warp_team<NS, K>(tb, wm, tm, ob, xr, fo, hist, p.hmax, jout, &evals, f)
                                               : fit_warp<NS, K>(tb, wm, ob, xr, fo, hist, tm.ro, tm.al, p.hmax, jout, &evals);
 #pragma unroll
     for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, xr[c]);

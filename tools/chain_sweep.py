@@ -14,7 +14,7 @@ from keypoints2body_b200.core.fitters.world_space import WorldSpaceFitter  # noq
 
 w, gmm = syn.make_body_model("smpl"), syn.make_gmm()
 cfgs = [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]] or [(256, 64), (1, 256), (148, 64), (512, 32)]
-shapes = [(1, 0), (1, 1), (1, 2), (2, 2), (3, 1), (4, 0), (4, 1), (4, 2), (5, 0), (5, 1), (6, 0), (6, 1)]
+shapes = [(1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0)]
 f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=True)
 for S, Tn in cfgs:
     mo = syn.make_motion(S * Tn, seed=3)
