@@ -39,6 +39,12 @@ extern int* k2b_emul_trace_n;
 extern long k2b_emul_rounds;      // team rounds (serial evaluation steps) of the emulated leader
 #endif
 
+// Code size matters here: eval_warp is ~2 k instructions, and a kernel that inlines it at every use (Adam loop, final
+// forward, L-BFGS trial, team sibling, evaluate-only ...) outgrows the instruction cache and runs at half speed (measured:
+// 22 k instructions, 2.3x slower; out of line it was no better, the arguments then live in local memory).  So every
+// evaluator warp runs ONE loop with ONE call site (run_evaluator): what differs between the modes is how the next
+// point is chosen and where the result goes.
+
 namespace k2b {
 namespace wc {
 
@@ -776,106 +782,6 @@ struct WarpOps {
 };
 
 // ---------------------------------------------------------------------------------------------
-// One WorldSpaceFitter.fit_frame (world_space.py:93-257) by the warp.  xr: in = initial parameters,
-// out = fitted parameters (owned elements).  Returns the reported loss; *evals = closure evaluations
-// that count (Adam: iterations; L-BFGS: func_evals).
-// ---------------------------------------------------------------------------------------------
-struct FitOpts {
-  int iters;
-  bool lbfgs;
-  bool freeze_betas;
-  bool freeze_expr;         // expression kept at its initial value (NS == 20; the caller gave none, world_space.py:222-223)
-  bool stage1;              // camera-space stage 1: only global_orient and the translation move, no priors
-  bool final_mode;          // returned loss = priors + joints at the final parameters, no preserve (camera_space.py:316-326)
-  float lr;
-  const float* adam_step;   // [kAdamTableW] lr / (1 - 0.9^k)
-  const float* adam_bc2;    // sqrt(1 - 0.999^k)
-  int adam_table;
-};
-
-template <int NS, int K>
-K2B_HD float fit_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& ob, float (&xr)[3], const FitOpts& fo,
-                      float* hist, float* ro, float* al, int hmax, float* joints_out, int* evals_out) {
-  const int lane = lane_id();
-  bool frozen[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int e = 3 * lane + c;
-    frozen[c] = e >= 75 + NS || (fo.freeze_betas && e >= kShapeOff && e < kShapeOff + 10) ||
-                (fo.freeze_expr && e >= kShapeOff + 10) ||
-                (fo.stage1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
-  }
-  const bool priors = !fo.stage1;
-  FrameObs obf = ob;        // observations of the final evaluation
-  if (fo.final_mode) obf.keep_w2 = 0.f;
-  float gr[3];
-  float out_loss = 0.f;
-  int evals = 0;
-  if (!fo.lbfgs) {
-    float m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int k = 1; k <= fo.iters; ++k) {
-      float step_k, bc2_k;
-      if (k <= fo.adam_table) {
-        step_k = fo.adam_step[k - 1];
-        bc2_k = fo.adam_bc2[k - 1];
-      } else {
-        step_k = (float)((double)fo.lr / (1.0 - pow(0.9, (double)k)));
-        bc2_k = (float)sqrt(1.0 - pow(0.999, (double)k));
-      }
-      out_loss = eval_warp<NS, K>(tb, wm, ob, xr, true, priors, gr, nullptr, nullptr);   // loss before the step
-      ++evals;
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        if (!frozen[c]) adam_update(xr[c], m1[c], m2[c], gr[c], step_k, bc2_k);
-    }
-    // joints at the final parameters (world_space.py:258-278)
-    if (joints_out || fo.final_mode) {
-      const float fl = eval_warp<NS, K>(tb, wm, obf, xr, false, priors && fo.final_mode, gr, joints_out, nullptr);
-      if (fo.final_mode) out_loss = fl;
-    }
-  } else {
-    WVec v;
-    v.gs = wm.gs;
-    v.hist = hist;
-    v.ro = ro;
-    v.al = al;
-    v.hmax = hmax;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { v.x[c] = xr[c]; v.xk[c] = xr[c]; v.d[c] = 0.f; }
-    Lbfgs<75 + NS, WarpOps> st;
-    st.init();
-    bool first = true;
-#pragma unroll 1
-    while (true) {
-      const float loss = eval_warp<NS, K>(tb, wm, ob, v.x, true, priors, gr, nullptr, nullptr);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
-      wsync();
-#if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
-      if (k2b_emul_trace && !first) {
-        const float gtd = st.dot_cur_d(v);
-        if (lane == 0 && *k2b_emul_trace_n < k2b_emul_trace_cap) {
-          float* row = k2b_emul_trace + 3 * (*k2b_emul_trace_n)++;
-          row[0] = (float)st.t; row[1] = loss; row[2] = gtd;
-        }
-      }
-#endif
-      st.advance_now(v, v, loss, first, fo.iters, fo.lr);
-      first = false;
-      if (st.done) break;
-    }
-    evals = st.evals;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) xr[c] = v.xk[c];
-    // loss (and joints) re-evaluated at the returned parameters (world_space.py:246-247)
-    out_loss = eval_warp<NS, K>(tb, wm, obf, xr, false, priors, gr, joints_out, nullptr);
-  }
-  if (evals_out) *evals_out = evals;
-  return out_loss;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Team protocol (see TeamMem).  A round: the leader posts the candidate steps and, when they changed, the base point
 // and direction; every evaluator computes its point x = xk + t d, evaluates it and publishes loss and gradient; the
 // leader feeds the machine with its own result and then with every published result the machine asks for next.
@@ -905,27 +811,8 @@ K2B_HD void line_tables_update(const WarpTables& tb, float* dbuf, const TeamMem&
     const float B = abc[1], Cc = abc[2];
     wsync();
     float pa = 0.f, pb = 0.f, pc = 0.f;
-    if (mode == kTabRefresh) {
-      if (lane < 24) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int i = 3 * lane + c;
-          dbuf[i] = i < kBodyDim ? tm.xk[3 + i] - tb.mu[m * kMuStride + i] : 0.f;
-        }
-      }
-      wsync();
-      gmm_matvec(tb, dbuf, m, u);
-      if (lane < 24) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int i = 3 * lane + c;
-          pa = fmaf(dbuf[i], u[i], pa);
-          w[i] = 0.f;
-        }
-      }
-      A = wsum(pa);
-      if (lane == 0) { abc[0] = A; abc[1] = 0.f; abc[2] = 0.f; }
-    } else {
+    const bool refresh = mode == kTabRefresh, line = mode == kTabLine;
+    if (!refresh) {
       // follow the iterate: xk moved by t_step along the previous direction
       A = fmaf(t_step, fmaf(t_step, Cc, 2.f * B), A);
       if (lane < 24) {
@@ -935,32 +822,36 @@ K2B_HD void line_tables_update(const WarpTables& tb, float* dbuf, const TeamMem&
           u[i] = fmaf(t_step, w[i], u[i]);
         }
       }
-      if (mode == kTabLine) {
-        if (lane < 24) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int i = 3 * lane + c;
-            dbuf[i] = i < kBodyDim ? tm.d[3 + i] : 0.f;
-          }
-        }
-        wsync();
-        gmm_matvec(tb, dbuf, m, w);
-        if (lane < 24) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int i = 3 * lane + c;
-            pb = fmaf(dbuf[i], u[i], pb);
-            pc = fmaf(dbuf[i], w[i], pc);
-          }
-        }
-        pb = wsum(pb);
-        pc = wsum(pc);
-      } else if (lane < 24) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) w[3 * lane + c] = 0.f;
-      }
-      if (lane == 0) { abc[0] = A; abc[1] = pb; abc[2] = pc; }
     }
+    if (lane < 24) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int i = 3 * lane + c;
+        float dv = 0.f;
+        if (i < kBodyDim) dv = refresh ? tm.xk[3 + i] - tb.mu[m * kMuStride + i] : tm.d[3 + i];
+        dbuf[i] = dv;
+        if (!line) w[i] = 0.f;
+      }
+    }
+    wsync();
+    if (refresh || line) gmm_matvec(tb, dbuf, m, refresh ? u : w);      // the one precision-matrix product
+    if (lane < 24) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int i = 3 * lane + c;
+        if (refresh) pa = fmaf(dbuf[i], u[i], pa);
+        if (line) {
+          pb = fmaf(dbuf[i], u[i], pb);
+          pc = fmaf(dbuf[i], w[i], pc);
+        }
+      }
+    }
+    if (refresh) A = wsum(pa);
+    if (line) {
+      pb = wsum(pb);
+      pc = wsum(pc);
+    }
+    if (lane == 0) { abc[0] = A; abc[1] = pb; abc[2] = pc; }
   }
   wsync();
 }
@@ -1024,124 +915,6 @@ K2B_HD int team_candidates(const Machine& st, int E, float (&tc)[kMaxCand]) {
     }
   }
   return n;
-}
-
-// WorldSpaceFitter.fit_frame (L-BFGS) by the leader of a team (a team of one included).  Same arguments as fit_warp
-// plus the team.  The mixture prior is evaluated in line form (LineEval), the team maintains the tables.
-template <int NS, int K>
-K2B_HD float fit_warp_team(const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, const FrameObs& ob, float (&xr)[3],
-                           const FitOpts& fo, float* hist, int hmax, float* joints_out, int* evals_out, long row) {
-  const int lane = lane_id();
-  bool frozen[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int e = 3 * lane + c;
-    frozen[c] = e >= 75 + NS || (fo.freeze_betas && e >= kShapeOff && e < kShapeOff + 10) ||
-                (fo.freeze_expr && e >= kShapeOff + 10) ||
-                (fo.stage1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
-  }
-  const bool priors = !fo.stage1;
-  const bool teamed = tm.E > 1;
-  FrameObs obf = ob;
-  if (fo.final_mode) obf.keep_w2 = 0.f;
-  const int base_flags = (priors ? kFlagPriors : 0) | (ob.keep_w2 != 0.f ? kFlagKeep : 0);
-  float gr[3];
-  WVec v;
-  v.gs = tm.gs;
-  v.hist = hist;
-  v.ro = tm.ro;
-  v.al = tm.al;
-  v.hmax = hmax;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { v.x[c] = xr[c]; v.xk[c] = xr[c]; v.d[c] = 0.f; }
-  Lbfgs<75 + NS, WarpOps> st;
-  st.init();
-  LineEval le{tm.lu, tm.lw, tm.labc, 0.f};
-  bool first = true;
-  int tab_mode = kTabRefresh;       // what the next round does to the line tables
-  float t_pending = 0.f;            // step the iterate took since the tables were last brought up to date
-#pragma unroll 1
-  while (true) {
-#if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
-    if (lane == 0) ++k2b_emul_rounds;
-#endif
-    // ---- post the round ---------------------------------------------------------------------------
-    float tc[kMaxCand];
-    int n_c = 1;
-    tc[0] = 0.f;
-    if (!first) n_c = team_candidates(st, tm.E, tc);
-    if (tab_mode != kTabKeep) {       // base point and direction of this line search
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        tm.xk[3 * lane + c] = first ? v.x[c] : v.xk[c];
-        tm.d[3 * lane + c] = v.d[c];
-      }
-    }
-    if (lane < kMaxCand) tm.tval[lane] = lane < n_c ? tc[lane] : 0.f;
-    team_post(tm, kCmdEval, n_c, base_flags | kFlagGrad | (first ? kFlagBase : 0), row, priors ? tab_mode : kTabKeep, t_pending);
-    wsync();
-    if (teamed) bar_arrive(tm.bar_go, 32 * tm.E);
-    if (priors && tab_mode != kTabKeep) {
-      line_tables_update(tb, wm.dbuf, tm, tab_mode, t_pending, 0);
-      if (teamed) bar_sync(tm.bar_tab, 32 * tm.E);
-    }
-    tab_mode = kTabKeep;
-    t_pending = 0.f;
-    // ---- the step the machine asked for ------------------------------------------------------------
-    le.t = tc[0];
-    const float loss = eval_warp<NS, K>(tb, wm, ob, v.x, true, priors, gr, nullptr, nullptr, &le);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
-    wsync();
-    if (teamed) bar_sync(tm.bar_done, 32 * tm.E);
-    // ---- feed the machine: own result, then every published result it asks for --------------------
-    unsigned used = 1u;
-    float next_loss = loss;
-#pragma unroll 1
-    while (true) {
-      st.advance(v, v, next_loss, first, fo.iters, fo.lr);
-      first = false;
-      if (st.done || st.need_outer) {       // the line search is over (or never started): the iterate moved by t
-        t_pending = (float)st.t;
-        tab_mode = kTabPoint;
-        if (st.need_outer && !st.done) {
-          st.start_outer(v, v);
-          if (!st.done) tab_mode = kTabLine;
-        }
-        break;
-      }
-      const float want = (float)st.t;
-      int j = -1;
-      for (int i = 1; i < n_c; ++i)
-        if (!((used >> i) & 1u) && tc[i] == want) j = i;
-      if (j < 0) break;
-      used |= 1u << j;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) v.G(st.cur, c) = tm.res_g[j * kWarpVec + 3 * lane + c];
-      next_loss = tm.res_f[j];
-      wsync();
-    }
-    if (st.done) break;
-  }
-  if (evals_out) *evals_out = st.evals;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) xr[c] = v.xk[c];
-  // loss (and joints) re-evaluated at the returned parameters (world_space.py:246-247): a round of its own
-#pragma unroll
-  for (int c = 0; c < 3; ++c) tm.xk[3 * lane + c] = xr[c];
-  if (lane < kMaxCand) tm.tval[lane] = 0.f;
-  team_post(tm, kCmdEval, 1, (priors ? kFlagPriors : 0) | (obf.keep_w2 != 0.f ? kFlagKeep : 0) | kFlagBase, row,
-            priors ? tab_mode : kTabKeep, t_pending);
-  wsync();
-  if (teamed) bar_arrive(tm.bar_go, 32 * tm.E);
-  if (priors && tab_mode != kTabKeep) {
-    line_tables_update(tb, wm.dbuf, tm, tab_mode, t_pending, 0);
-    if (teamed) bar_sync(tm.bar_tab, 32 * tm.E);
-  }
-  le.t = 0.f;
-  const float out_loss = eval_warp<NS, K>(tb, wm, obf, xr, false, priors, gr, joints_out, nullptr, &le);
-  if (teamed) bar_sync(tm.bar_done, 32 * tm.E);
-  return out_loss;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1221,11 +994,21 @@ K2B_HD void load_frame_obs(const ChainParams& p, long f, bool stage1, FrameObs& 
   for (int c = 0; c < 3; ++c) ob.dref[c] = (stage1 && lane == 24) ? p.depth_ref[f * 3 + c] : 0.f;
 }
 
-// Evaluator warp `idx` >= 1 of a team: evaluates candidate idx of every round the leader posts.
+// ---------------------------------------------------------------------------------------------
+// An evaluator warp of a team.  idx 0 leads: it walks its sequences frame by frame (the reference's loop,
+// api/sequence.py:214-281; every frame one WorldSpaceFitter.fit_frame, world_space.py:93-257) and owns the optimiser
+// state -- Adam moments in registers, or the L-BFGS machine.  idx > 0 evaluates the speculative steps of the rounds the
+// leader posts.  All of them pass through the same evaluation call; see the note on code size at the top.
+// ---------------------------------------------------------------------------------------------
 template <int NS, int K>
-K2B_HD void team_sibling(const ChainParams& p, const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, int idx) {
+K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, int idx,
+                          long first_seq, long seq_stride, float* hist) {
   const int lane = lane_id();
-  const bool stage1 = p.loss_kind == 1;
+  const bool leader = idx == 0;
+  const bool teamed = tm.E > 1;
+  const bool stage1 = p.loss_kind == 1;       // camera-space stage 1: only global_orient and the translation move, no priors
+  const bool priors_on = !stage1;
+  const bool lbfgs = p.lbfgs != 0;
   const bool body_owner = lane >= 1 && lane < 24;
   bool frozen[3];
 #pragma unroll
@@ -1235,125 +1018,296 @@ K2B_HD void team_sibling(const ChainParams& p, const WarpTables& tb, const WarpM
                 ((p.freeze_betas & 2) && e >= kShapeOff + 10) ||
                 (stage1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
   }
+  enum { kNewFrame, kAdam, kAdamFinal, kRound, kFinal, kEvalOnly };
+  // ---- leader state ------------------------------------------------------------------------------------------
+  long seq = first_seq, f = 0, frow = 0;
+  int t = -1, phase = kNewFrame, iters = 0, evals = 0, k = 1;
+  float x0[3] = {0.f, 0.f, 0.f}, xr[3] = {0.f, 0.f, 0.f};
+  float out_loss = 0.f;
+  float m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f};
+  WVec v;
+  v.gs = tm.gs;
+  v.hist = hist;
+  v.ro = tm.ro;
+  v.al = tm.al;
+  v.hmax = p.hmax;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v.x[c] = v.xk[c] = v.d[c] = 0.f;
+  Lbfgs<75 + NS, WarpOps> st;
+  st.init();
+  bool lfirst = true;
+  int tab_next = kTabRefresh;       // what the next round does to the line tables
+  float t_pending = 0.f;            // step the iterate took since the tables were last brought up to date
+  float tc[kMaxCand];
+  int n_c = 1;
+#pragma unroll
+  for (int i = 0; i < kMaxCand; ++i) tc[i] = 0.f;
+  // ---- state of every evaluator ---------------------------------------------------------------------------------
   FrameObs ob;
+  ob.tx = ob.ty = ob.tz = ob.w = 0.f;
   ob.keep[0] = ob.keep[1] = ob.keep[2] = 0.f;
+  ob.keep_w2 = 0.f;
+  ob.plain_sq = stage1;
+  ob.depth_w2 = 0.f;
+  ob.dref[0] = ob.dref[1] = ob.dref[2] = 0.f;
   long cur_row = -1;
+  if (leader && seq < p.num_seq) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xr[c] = x0[c] = load_elem<NS>(p, seq, 3 * lane + c);
+  }
 #pragma unroll 1
   while (true) {
-    bar_sync(tm.bar_go, 32 * tm.E);
-    const int kind = *reinterpret_cast<const volatile int*>(tm.cmd);
-    if (kind == kCmdExit) break;
-    const int n_c = *reinterpret_cast<const volatile int*>(tm.cmd + 1);
-    const int flags = *reinterpret_cast<const volatile int*>(tm.cmd + 2);
-    const long row = (long)(unsigned)*reinterpret_cast<const volatile int*>(tm.cmd + 3) |
-                     ((long)*reinterpret_cast<const volatile int*>(tm.cmd + 4) << 32);
-    if (row != cur_row) {       // first round of a frame: the posted point is the frame's initial parameters
-      load_frame_obs<K>(p, row, stage1, ob);
+    // ===== 1. the next point ======================================================================================
+    float x[3] = {0.f, 0.f, 0.f};
+    bool with_grad = true, with_priors = priors_on, final_obs = false, do_eval = true, use_line = false, want_comp = false;
+    float* jout = nullptr;
+    int tab_mode = kTabKeep;
+    float t_step = 0.f, le_t = 0.f;
+    if (leader) {
+      if (phase == kNewFrame) {
+        if (++t >= p.frames) {
+          seq += seq_stride;
+          t = 0;
+          if (seq < p.num_seq) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[row * kBodyDim + 3 * lane - 3 + c]
-                                                     : *reinterpret_cast<const volatile float*>(tm.xk + 3 * lane + c);
-      cur_row = row;
-    }
-    ob.keep_w2 = (flags & kFlagKeep) ? p.keep_w2 : 0.f;
-    const bool priors = (flags & kFlagPriors) != 0;
-    const int tab_mode = *reinterpret_cast<const volatile int*>(tm.cmd + 5);
-    if (tab_mode != kTabKeep) {
-      line_tables_update(tb, wm.dbuf, tm, tab_mode, *reinterpret_cast<const volatile float*>(tm.tval + 7), idx);
-      bar_sync(tm.bar_tab, 32 * tm.E);
-    }
-    if (idx < n_c) {
-      const float t = *reinterpret_cast<const volatile float*>(tm.tval + idx);
-      float x[3], gr[3];
+            for (int c = 0; c < 3; ++c) xr[c] = x0[c] = load_elem<NS>(p, seq, 3 * lane + c);
+          }
+        }
+        if (seq >= p.num_seq) {       // all sequences done: let the other evaluators go
+          if (teamed) {
+            team_post(tm, kCmdExit, 0, 0, 0, kTabKeep, 0.f);
+            wsync();
+            bar_arrive(tm.bar_go, 32 * tm.E);
+          }
+          break;
+        }
+        f = seq * p.in_seq_stride + t;                                   // input row
+        frow = seq * p.out_seq_stride + (long)t * p.out_frame_stride;    // output row
+        if (!p.chain) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float xk = *reinterpret_cast<const volatile float*>(tm.xk + 3 * lane + c);
-        const float d = *reinterpret_cast<const volatile float*>(tm.d + 3 * lane + c);
-        x[c] = (flags & kFlagBase) ? xk : fmaf(t, d, xk);
+          for (int c = 0; c < 3; ++c) xr[c] = x0[c];
+        }
+        load_frame_obs<K>(p, f, stage1, ob);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[f * kBodyDim + 3 * lane - 3 + c] : xr[c];
+        const bool first = (p.seq_first ? (long)p.seq_first[seq] : p.first_seq_ind) + t == 0;
+        ob.keep_w2 = first ? 0.f : p.keep_w2;      // the temporal term is on for seq_ind > 0 (world_space.py:211)
+        iters = first ? p.iters_first : p.iters_follow;
+        evals = 0;
+        out_loss = 0.f;
+        if (p.eval_only) {
+          phase = kEvalOnly;
+        } else if (lbfgs) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { v.x[c] = xr[c]; v.xk[c] = xr[c]; v.d[c] = 0.f; }
+          st.init();
+          lfirst = true;
+          tab_next = kTabRefresh;
+          t_pending = 0.f;
+          phase = kRound;
+        } else {
+          k = 1;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) m1[c] = m2[c] = 0.f;
+          phase = iters > 0 ? kAdam : kAdamFinal;
+        }
       }
-      const LineEval le{tm.lu, tm.lw, tm.labc, (flags & kFlagBase) ? 0.f : t};
-      const float loss = eval_warp<NS, K>(tb, wm, ob, x, (flags & kFlagGrad) != 0, priors, gr, nullptr, nullptr, &le);
+      float* jframe = p.out_joints ? p.out_joints + frow * K * 3 : nullptr;
+      if (phase == kEvalOnly) {
+        jout = jframe;
+        want_comp = true;
+      } else if (phase == kAdamFinal) {
+        // joints at the final parameters (world_space.py:258-278); camera stage 2 also re-evaluates the loss there
+        do_eval = jframe != nullptr || p.final_mode != 0;
+        with_grad = false;
+        with_priors = priors_on && p.final_mode != 0;
+        final_obs = true;
+        jout = jframe;
+      } else if (phase == kRound || phase == kFinal) {
+        const bool fin = phase == kFinal;
+#if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
+        if (lane == 0 && !fin) ++k2b_emul_rounds;
+#endif
+        n_c = 1;
+        tc[0] = 0.f;
+        if (!fin && !lfirst) n_c = team_candidates(st, tm.E, tc);
+        tab_mode = priors_on ? tab_next : kTabKeep;
+        t_step = t_pending;
+        if (tab_next != kTabKeep || fin) {       // base point and direction of this line search
 #pragma unroll
-      for (int c = 0; c < 3; ++c) tm.res_g[idx * kWarpVec + 3 * lane + c] = frozen[c] ? 0.f : gr[c];
-      if (lane == 0) tm.res_f[idx] = loss;
+          for (int c = 0; c < 3; ++c) {
+            tm.xk[3 * lane + c] = fin ? xr[c] : (lfirst ? v.x[c] : v.xk[c]);
+            tm.d[3 * lane + c] = v.d[c];
+          }
+        }
+        if (lane < kMaxCand) tm.tval[lane] = lane < n_c ? tc[lane] : 0.f;
+        const bool keep_on = (fin && p.final_mode ? 0.f : ob.keep_w2) != 0.f;
+        team_post(tm, kCmdEval, n_c, (fin ? 0 : kFlagGrad) | (priors_on ? kFlagPriors : 0) | (keep_on ? kFlagKeep : 0) |
+                                         ((fin || lfirst) ? kFlagBase : 0), f, tab_mode, t_step);
+        wsync();
+        if (teamed) bar_arrive(tm.bar_go, 32 * tm.E);
+        tab_next = kTabKeep;
+        t_pending = 0.f;
+        with_grad = !fin;
+        final_obs = fin;
+        jout = fin ? jframe : nullptr;
+        use_line = priors_on;
+        le_t = tc[0];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[c] = phase == kRound ? v.x[c] : xr[c];
+    } else {
+      bar_sync(tm.bar_go, 32 * tm.E);
+      if (*reinterpret_cast<const volatile int*>(tm.cmd) == kCmdExit) break;
+      n_c = *reinterpret_cast<const volatile int*>(tm.cmd + 1);
+      const int flags = *reinterpret_cast<const volatile int*>(tm.cmd + 2);
+      const long row = (long)(unsigned)*reinterpret_cast<const volatile int*>(tm.cmd + 3) |
+                       ((long)*reinterpret_cast<const volatile int*>(tm.cmd + 4) << 32);
+      tab_mode = *reinterpret_cast<const volatile int*>(tm.cmd + 5);
+      t_step = *reinterpret_cast<const volatile float*>(tm.tval + 7);
+      if (row != cur_row) {       // first round of a frame: the posted point is the frame's initial parameters
+        load_frame_obs<K>(p, row, stage1, ob);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[row * kBodyDim + 3 * lane - 3 + c]
+                                                       : *reinterpret_cast<const volatile float*>(tm.xk + 3 * lane + c);
+        cur_row = row;
+      }
+      ob.keep_w2 = (flags & kFlagKeep) ? p.keep_w2 : 0.f;
+      with_grad = (flags & kFlagGrad) != 0;
+      with_priors = (flags & kFlagPriors) != 0;
+      use_line = with_priors;
+      do_eval = idx < n_c;
+      if (do_eval) {
+        const float ti = *reinterpret_cast<const volatile float*>(tm.tval + idx);
+        const bool base = (flags & kFlagBase) != 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float xk = *reinterpret_cast<const volatile float*>(tm.xk + 3 * lane + c);
+          const float d = *reinterpret_cast<const volatile float*>(tm.d + 3 * lane + c);
+          x[c] = base ? xk : fmaf(ti, d, xk);
+        }
+        le_t = base ? 0.f : ti;
+      }
     }
-    wsync();
-    bar_arrive(tm.bar_done, 32 * tm.E);
-  }
-  team_release_helpers(wm);
-}
-
-// Leader's last act: let the other evaluators (and through them their helpers) go.
-K2B_HD void team_dismiss(const WarpMem& wm, const TeamMem& tm) {
-  if (tm.E > 1) {
-    team_post(tm, kCmdExit, 0, 0, 0, kTabKeep, 0.f);
-    wsync();
-    bar_arrive(tm.bar_go, 32 * tm.E);
-  }
-  team_release_helpers(wm);
-}
-
-template <int NS, int K>
-K2B_HD void run_chain_warp(const ChainParams& p, long seq, const WarpTables& tb, const WarpMem& wm, const TeamMem& tm,
-                           float* hist) {
-  const int lane = lane_id();
-  float x0[3], xr[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    x0[c] = load_elem<NS>(p, seq, 3 * lane + c);
-    xr[c] = x0[c];
-  }
-  FitOpts fo;
-  fo.lbfgs = p.lbfgs != 0;
-  fo.freeze_betas = (p.freeze_betas & 1) != 0;
-  fo.freeze_expr = (p.freeze_betas & 2) != 0;
-  fo.lr = p.lr;
-  fo.adam_step = p.adam_step;
-  fo.adam_bc2 = p.adam_bc2;
-  fo.adam_table = kAdamTableW;
-  fo.stage1 = p.loss_kind == 1;
-  fo.final_mode = p.final_mode != 0;
-  const bool body_owner = lane >= 1 && lane < 24;
-#pragma unroll 1
-  for (int t = 0; t < p.frames; ++t) {
-    const long f = seq * p.in_seq_stride + t;                               // input row
-    const long frow = seq * p.out_seq_stride + (long)t * p.out_frame_stride;  // output row
-    if (!p.chain) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) xr[c] = x0[c];
+    // ===== 2. line tables: every evaluator of the team takes its share of the mixture components ====================
+    if (tab_mode != kTabKeep) {
+      line_tables_update(tb, wm.dbuf, tm, tab_mode, t_step, idx);
+      if (teamed) bar_sync(tm.bar_tab, 32 * tm.E);
     }
-    FrameObs ob;
-    load_frame_obs<K>(p, f, fo.stage1, ob);
+    // ===== 3. the evaluation (the kernel's only call site of eval_warp) =============================================
+    float gr[3] = {0.f, 0.f, 0.f};
+    float loss = 0.f;
+    int comp = 0;
+    if (do_eval) {
+      FrameObs oe = ob;
+      if (final_obs && p.final_mode) oe.keep_w2 = 0.f;      // camera_space.py:316-326
+      const LineEval le{tm.lu, tm.lw, tm.labc, le_t};
+      loss = eval_warp<NS, K>(tb, wm, oe, x, with_grad, with_priors, gr, jout, want_comp ? &comp : nullptr,
+                              use_line ? &le : nullptr);
+    }
+    // ===== 4. where the result goes ==================================================================================
+    if (!leader) {
+      if (do_eval) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[f * kBodyDim + 3 * lane - 3 + c] : xr[c];
-    const bool first = (p.seq_first ? (long)p.seq_first[seq] : p.first_seq_ind) + t == 0;
-    ob.keep_w2 = first ? 0.f : p.keep_w2;
-    fo.iters = first ? p.iters_first : p.iters_follow;
-    if (p.eval_only) {
-      float gr[3];
-      int comp = 0;
-      const float l = eval_warp<NS, K>(tb, wm, ob, xr, true, !fo.stage1, gr, p.out_joints ? p.out_joints + frow * K * 3 : nullptr,
-                                       &comp);
+        for (int c = 0; c < 3; ++c) tm.res_g[idx * kWarpVec + 3 * lane + c] = frozen[c] ? 0.f : gr[c];
+        if (lane == 0) tm.res_f[idx] = loss;
+      }
+      wsync();
+      bar_arrive(tm.bar_done, 32 * tm.E);
+      continue;
+    }
+    bool frame_done = false;
+    if (phase == kEvalOnly) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, gr[c]);
       if (lane == 0) {
-        p.out_loss[frow] = l;
+        p.out_loss[frow] = loss;
         if (p.out_evals) p.out_evals[frow] = comp;
       }
-      continue;
-    }
-    int evals = 0;
-    float* jout = p.out_joints ? p.out_joints + frow * K * 3 : nullptr;
-    const float loss = fo.lbfgs ? fit_warp_team<NS, K>(tb, wm, tm, ob, xr, fo, hist, p.hmax, jout, &evals, f)
-                                              : fit_warp<NS, K>(tb, wm, ob, xr, fo, hist, tm.ro, tm.al, p.hmax, jout, &evals);
+      phase = kNewFrame;
+    } else if (phase == kAdam) {
+      out_loss = loss;        // the loss of the last iteration, before its step (world_space.py:250-256)
+      ++evals;
+      float step_k, bc2_k;
+      if (k <= kAdamTableW) {
+        step_k = p.adam_step[k - 1];
+        bc2_k = p.adam_bc2[k - 1];
+      } else {
+        step_k = (float)((double)p.lr / (1.0 - pow(0.9, (double)k)));
+        bc2_k = (float)sqrt(1.0 - pow(0.999, (double)k));
+      }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, xr[c]);
-    if (lane == 0) {
-      p.out_loss[frow] = loss;
-      if (p.out_evals) p.out_evals[frow] = evals;
+      for (int c = 0; c < 3; ++c)
+        if (!frozen[c]) adam_update(xr[c], m1[c], m2[c], gr[c], step_k, bc2_k);
+      if (++k > iters) phase = kAdamFinal;
+    } else if (phase == kAdamFinal) {
+      if (do_eval && p.final_mode) out_loss = loss;
+      frame_done = true;
+    } else if (phase == kRound) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
+      wsync();
+      if (teamed) bar_sync(tm.bar_done, 32 * tm.E);
+      // feed the machine: own result, then every published result it asks for
+      unsigned used = 1u;
+      float next_loss = loss;
+#pragma unroll 1
+      while (true) {
+#if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
+        if (k2b_emul_trace && !lfirst) {
+          const float gtd = st.dot_cur_d(v);
+          if (lane == 0 && *k2b_emul_trace_n < k2b_emul_trace_cap) {
+            float* row = k2b_emul_trace + 3 * (*k2b_emul_trace_n)++;
+            row[0] = (float)st.t; row[1] = next_loss; row[2] = gtd;
+          }
+        }
+#endif
+        st.advance(v, v, next_loss, lfirst, iters, p.lr);
+        lfirst = false;
+        if (st.done || st.need_outer) {       // the line search is over (or never started): the iterate moved by t
+          t_pending = (float)st.t;
+          tab_next = kTabPoint;
+          if (st.need_outer && !st.done) {
+            st.start_outer(v, v);
+            if (!st.done) tab_next = kTabLine;
+          }
+          break;
+        }
+        const float want = (float)st.t;
+        int j = -1;
+        for (int i = 1; i < n_c; ++i)
+          if (!((used >> i) & 1u) && tc[i] == want) j = i;
+        if (j < 0) break;
+        used |= 1u << j;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v.G(st.cur, c) = tm.res_g[j * kWarpVec + 3 * lane + c];
+        next_loss = tm.res_f[j];
+        wsync();
+      }
+      if (st.done) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xr[c] = v.xk[c];
+        phase = kFinal;     // loss (and joints) re-evaluated at the returned parameters (world_space.py:246-247)
+      }
+    } else {                // kFinal
+      if (teamed) bar_sync(tm.bar_done, 32 * tm.E);
+      out_loss = loss;
+      evals = st.evals;
+      frame_done = true;
+    }
+    if (frame_done) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, xr[c]);
+      if (lane == 0) {
+        p.out_loss[frow] = out_loss;
+        if (p.out_evals) p.out_evals[frow] = evals;
+      }
+      phase = kNewFrame;
     }
   }
+  team_release_helpers(wm);
 }
 
 }  // namespace wc

@@ -71,10 +71,12 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
   float* base = s_team + (size_t)team * wc::team_floats(E, H, p.hmax);
   wc::TeamMem tm = wc::make_team_mem(base, E, H, p.hmax);
   // named barriers: one evaluator per sequence keeps the ids of the helper pair dense (up to 7 teams per CTA);
-  // teams of several evaluators use four ids each (up to 3 teams per CTA)
-  const int bar_b = E == 1 ? 1 + 2 * team : 2 + 4 * team;
-  tm.bar_go = 1 + 4 * team;
-  tm.bar_done = 4 + 4 * team;
+  // teams of several evaluators use five ids each (round posted, helper pair, tables ready, results ready; up to 3
+  // teams per CTA)
+  const int bar_b = E == 1 ? 1 + 2 * team : 2 + 5 * team;
+  tm.bar_go = 1 + 5 * team;
+  tm.bar_tab = 4 + 5 * team;
+  tm.bar_done = 5 + 5 * team;
   if (member < E) {
     wc::WarpMem wm = wc::make_warp_mem(base + (size_t)member * wc::kEvalMemFloats, tm.gs);
     wm.helpers = H;
@@ -82,15 +84,9 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
     wm.bar_threads = 32 * TW;
     wm.helper_mem = base + (size_t)(E + member * H) * wc::kEvalMemFloats;
     wm.helper_stride = wc::kEvalMemFloats;
-    if (member == 0) {
-      const long slot = (long)blockIdx.x * nteams + team;
-      float* hist = p.hist ? p.hist + slot * wc::hist_floats(p.hmax) : nullptr;
-      for (long seq = slot; seq < p.num_seq; seq += (long)gridDim.x * nteams)
-        wc::run_chain_warp<NS, K>(p, seq, tb, wm, tm, hist);
-      wc::team_dismiss(wm, tm);
-    } else {
-      wc::team_sibling<NS, K>(p, tb, wm, tm, member);
-    }
+    const long slot = (long)blockIdx.x * nteams + team;
+    float* hist = p.hist ? p.hist + slot * wc::hist_floats(p.hmax) : nullptr;
+    wc::run_evaluator<NS, K>(p, tb, wm, tm, member, slot, (long)gridDim.x * nteams, hist);
   } else {
     const int e = (member - E) / H, h = (member - E) % H;
     float* own = base + (size_t)member * wc::kEvalMemFloats;

@@ -6,6 +6,7 @@
     python tests/golden/make_goldens_r2.py chains   -> r2_chains.npz   32 chains x 64 frames, L-BFGS, reference sequence driver
     python tests/golden/make_goldens_r2.py adam     -> r2_adam.npz     Adam chains: the two demo sequences (195 / 116 real
                                                                        AMASS-22 frames) and a 512-frame synthetic chain
+    python tests/golden/make_goldens_r2.py adam_pert -> r2_adam_pert.npz  the same chains from an initial pose 1e-7 rad away
 
 What runs is the reference's own WorldSpaceFitter / optimize_params_sequence / torch.optim (imported through
 oracle.ref_loader's stubs; body model = oracle.smplx_shim on the seeded synthetic weights).  Inputs are regenerated
@@ -263,8 +264,35 @@ def section_adam():
     save("r2_adam.npz", G)
 
 
+def section_adam_pert():
+    """The reference against itself along the long Adam chains: the same runs from an initial body pose moved by 1e-7 rad.
+    Unobserved leaf joints (feet, head, hands) see only the priors, their gradients hover at rounding level, and Adam's
+    g / (sqrt(v) + eps) turns a sign flip there into a full-size step: the chain amplifies 1e-7 to centimetres within ~20
+    frames.  These runs are the yardstick for a free-running comparison (tests/test_gpu_lbfgs_parity.py)."""
+    ref, tmp = setup()
+    from keypoints2body.models.smpl_data import SMPLData
+
+    weights = syn.make_body_model("smpl", seed=0)
+    model = BodyModelShim(weights)
+    G = {}
+    demo = {n: np.load(f"/root/reference/data/demo/test_motion{n}.npy").astype(np.float32) for n in (1, 2)}
+    long_tgt = problems.chain_problem(weights, 1, LONG_T, LONG_SEED)[0].numpy()
+    with torch.no_grad():
+        root = model(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10)).joints[:, 0]
+    with ref_loader.reference_cwd(tmp):
+        for name, joints in (("demo1", demo[1]), ("demo2", demo[2]), ("long512", long_tgt)):
+            init = SMPLData(betas=torch.zeros(1, 10), global_orient=torch.zeros(1, 3), body_pose=torch.full((1, 69), 1e-7),
+                            transl=torch.as_tensor(joints[0:1, 0]) - root)
+            res = ref.optimize_params_sequence(joints, init_params=init, body_model="smpl", joint_layout="AMASS", model=model,
+                                               config=dict(frame=dict(use_lbfgs=False), use_shape_optimization=False))
+            G[f"{name}_pose"] = torch.cat([r.params.pose for r in res])
+            G[f"{name}_joints22"] = torch.cat([r.joints[:, :22] for r in res])
+            print(name, "done", flush=True)
+    save("r2_adam_pert.npz", G)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     sys.path.insert(0, HERE)
     {"points": section_points, "dist": section_dist, "dist64": section_dist64, "chains": section_chains,
-     "adam": section_adam}[sys.argv[1]]()
+     "adam": section_adam, "adam_pert": section_adam_pert}[sys.argv[1]]()

@@ -169,7 +169,8 @@ void lane_job() {
   wc::TeamMem tm = wc::make_team_mem(base, E, H, g.p.hmax > 0 ? g.p.hmax : 1);
   const int bar_b = E == 1 ? 1 : 2;          // the kernel's ids for team 0
   tm.bar_go = 1;
-  tm.bar_done = 4;
+  tm.bar_tab = 4;
+  tm.bar_done = 5;
   if (member >= E) {                          // helper warp
     const int e = (member - E) / H, h = (member - E) % H;
     float* own = base + (size_t)member * wc::kEvalMemFloats;
@@ -207,12 +208,7 @@ void lane_job() {
     wc::team_release_helpers(wm);
     return;
   }
-  if (member == 0) {
-    wc::run_chain_warp<NS, K>(g.p, g.seq, tb, wm, tm, g.hist.data());
-    wc::team_dismiss(wm, tm);
-  } else {
-    wc::team_sibling<NS, K>(g.p, tb, wm, tm, member);
-  }
+  wc::run_evaluator<NS, K>(g.p, tb, wm, tm, member, g.seq, g.p.num_seq, g.hist.data());      // one sequence per run
 }
 
 void (*pick_job(int ns, int K))() {
