@@ -271,7 +271,7 @@ class ChainRunner:
         init = dict(self.init, transl=tg[:, 0, 0] - self.root0)     # root alignment of frame 0 (engine.py:89-128)
         f.chain_events = self.kernel_events                          # (start, end) of the fit on its own stream
         out = f.fit_chain(init, tg, None, with_mesh=True, out_vertices=self.vertices, time_major=True,
-                          chunks=self.chunks, params_ready=params_ready)
+                          chunks=self.chunks, params_ready=params_ready, fit_joints=False)
         f.chain_events = None
         p = out["params"]
         out["pose"] = torch.cat([p["global_orient"], p["body_pose"]], dim=1)

@@ -460,7 +460,7 @@ class WorldSpaceFitter:
 
     def fit_chain(self, init: dict, j3d, conf=None, *, first_seq_ind=0, chain=True, joint_loss_weight=600.0,
                   pose_preserve_weight=5.0, freeze_betas=False, use_lbfgs=None, with_mesh=True, out_vertices=None,
-                  time_major=False, chunks=1, params_ready=None, mesh_capped_fraction=None):
+                  time_major=False, chunks=1, params_ready=None, mesh_capped_fraction=None, fit_joints=True):
         """Fit S sequences of T frames each the way the reference's sequence loop does (api/sequence.py:214-281):
         serially in t, frame t starting from frame t-1's result (``chain=True``) or from the sequence's
         initialisation (``chain=False``) -- one warp per sequence, all frames inside one launch.
@@ -476,7 +476,9 @@ class WorldSpaceFitter:
         sequences.  ``params_ready``: optional event recorded when the fitted parameters are final.
         ``mesh_capped_fraction``: share of the windows whose mesh pass is held to the SMs the fit leaves free
         (the rest, at the end, run on all SMs); default 0.7 for L-BFGS, 0.45 for Adam, whose fit is shorter
-        relative to the mesh.
+        relative to the mesh.  ``fit_joints=False``: the fit kernel does not return the posed kinematic joints
+        (``out["fit_joints"]`` is None; the mesh pass returns all joints anyway), which also spares the L-BFGS fit its
+        extra forward pass at the returned parameters -- the returned loss is the accepted trial's, bit for bit.
         """
         dev = self.device
         targets = _f32(j3d, dev)
@@ -516,7 +518,8 @@ class WorldSpaceFitter:
         outs = dict(pose=torch.empty(F, 72, device=dev), betas=torch.empty(F, 10, device=dev),
                     transl=torch.empty(F, 3, device=dev),
                     expression=torch.empty(F, 10, device=dev) if self.has_expr else None,
-                    loss=torch.empty(F, device=dev), fit_joints=torch.empty(F, self.num_obs, 3, device=dev),
+                    loss=torch.empty(F, device=dev),
+                    fit_joints=torch.empty(F, self.num_obs, 3, device=dev) if fit_joints else None,
                     evals=torch.empty(F, dtype=torch.int32, device=dev))
         common = (self.num_iters_first, self.num_iters_followup, optimizer, joint_loss_weight, pose_preserve_weight,
                   freeze)

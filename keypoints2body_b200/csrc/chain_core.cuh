@@ -1000,7 +1000,8 @@ K2B_HD void load_frame_obs(const ChainParams& p, long f, bool stage1, FrameObs& 
 // state -- Adam moments in registers, or the L-BFGS machine.  idx > 0 evaluates the speculative steps of the rounds the
 // leader posts.  All of them pass through the same evaluation call; see the note on code size at the top.
 // ---------------------------------------------------------------------------------------------
-template <int NS, int K>
+// LB: the optimiser is a compile-time choice, so that the other optimiser's state does not occupy registers.
+template <int NS, int K, bool LB>
 K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, int idx,
                           long first_seq, long seq_stride, float* hist) {
   const int lane = lane_id();
@@ -1008,7 +1009,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
   const bool teamed = tm.E > 1;
   const bool stage1 = p.loss_kind == 1;       // camera-space stage 1: only global_orient and the translation move, no priors
   const bool priors_on = !stage1;
-  const bool lbfgs = p.lbfgs != 0;
+  constexpr bool lbfgs = LB;
   const bool body_owner = lane >= 1 && lane < 24;
   bool frozen[3];
 #pragma unroll
@@ -1117,14 +1118,14 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       if (phase == kEvalOnly) {
         jout = jframe;
         want_comp = true;
-      } else if (phase == kAdamFinal) {
+      } else if (!LB && phase == kAdamFinal) {
         // joints at the final parameters (world_space.py:258-278); camera stage 2 also re-evaluates the loss there
         do_eval = jframe != nullptr || p.final_mode != 0;
         with_grad = false;
         with_priors = priors_on && p.final_mode != 0;
         final_obs = true;
         jout = jframe;
-      } else if (phase == kRound || phase == kFinal) {
+      } else if (LB && (phase == kRound || phase == kFinal)) {
         const bool fin = phase == kFinal;
 #if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
         if (lane == 0 && !fin) ++k2b_emul_rounds;
@@ -1156,7 +1157,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         le_t = tc[0];
       }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) x[c] = phase == kRound ? v.x[c] : xr[c];
+      for (int c = 0; c < 3; ++c) x[c] = (LB && phase == kRound) ? v.x[c] : xr[c];
     } else {
       bar_sync(tm.bar_go, 32 * tm.E);
       if (*reinterpret_cast<const volatile int*>(tm.cmd) == kCmdExit) break;
@@ -1227,7 +1228,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         if (p.out_evals) p.out_evals[frow] = comp;
       }
       phase = kNewFrame;
-    } else if (phase == kAdam) {
+    } else if (!LB && phase == kAdam) {
       out_loss = loss;        // the loss of the last iteration, before its step (world_space.py:250-256)
       ++evals;
       float step_k, bc2_k;
@@ -1242,10 +1243,10 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       for (int c = 0; c < 3; ++c)
         if (!frozen[c]) adam_update(xr[c], m1[c], m2[c], gr[c], step_k, bc2_k);
       if (++k > iters) phase = kAdamFinal;
-    } else if (phase == kAdamFinal) {
+    } else if (!LB && phase == kAdamFinal) {
       if (do_eval && p.final_mode) out_loss = loss;
       frame_done = true;
-    } else if (phase == kRound) {
+    } else if (LB && phase == kRound) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
       wsync();
@@ -1289,9 +1290,19 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       if (st.done) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) xr[c] = v.xk[c];
-        phase = kFinal;     // loss (and joints) re-evaluated at the returned parameters (world_space.py:246-247)
+        // loss (and joints) re-evaluated at the returned parameters (world_space.py:246-247).  The returned parameters
+        // ARE the accepted trial point (lbfgs.py:488-493 adds t d to the iterate the same way the trial was formed), so
+        // the loss is the machine's own, bit for bit; the extra forward pass is only run when joints are wanted or the
+        // camera stage re-evaluates without the temporal term.
+        if (p.out_joints || p.final_mode) {
+          phase = kFinal;
+        } else {
+          out_loss = (float)st.loss;
+          evals = st.evals;
+          frame_done = true;
+        }
       }
-    } else {                // kFinal
+    } else if (LB) {        // kFinal
       if (teamed) bar_sync(tm.bar_done, 32 * tm.E);
       out_loss = loss;
       evals = st.evals;

@@ -11,14 +11,16 @@ namespace k2b {
 template <>
 cudaError_t launch_chain<K2B_NS, K2B_K>(const wc::ChainParams& p, const ChainTables& tab, int grid, int teams,
                                         cudaStream_t st) {
-  auto kern = chain_kernel<K2B_NS, K2B_K>;
+  // the optimiser is a template parameter of the kernel (the other optimiser's state would only cost registers)
+  const bool lb = p.lbfgs != 0 && !p.eval_only;
+  auto kern = lb ? chain_kernel<K2B_NS, K2B_K, true> : chain_kernel<K2B_NS, K2B_K, false>;
   const int warps = teams * p.team * (1 + p.helpers);
   const size_t smem = chain_smem_bytes(K2B_NS, teams, p.team, p.helpers, p.hmax);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[lb]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured[lb] = smem;
   }
   kern<<<grid, 32 * warps, smem, st>>>(p, tab);
   return cudaGetLastError();

@@ -208,7 +208,8 @@ void lane_job() {
     wc::team_release_helpers(wm);
     return;
   }
-  wc::run_evaluator<NS, K>(g.p, tb, wm, tm, member, g.seq, g.p.num_seq, g.hist.data());      // one sequence per run
+  if (g.p.lbfgs) wc::run_evaluator<NS, K, true>(g.p, tb, wm, tm, member, g.seq, g.p.num_seq, g.hist.data());      // one sequence per run
+  else wc::run_evaluator<NS, K, false>(g.p, tb, wm, tm, member, g.seq, g.p.num_seq, g.hist.data());
 }
 
 void (*pick_job(int ns, int K))() {

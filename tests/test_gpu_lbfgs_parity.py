@@ -402,3 +402,23 @@ def test_team_evaluation_is_bit_identical(fitters, weights, shims, monkeypatch, 
     for key, o in outs.items():
         for k, v in ref.items():
             assert np.array_equal(v, o[k]), (key, k)
+
+
+def test_loss_without_the_final_forward_is_the_same_loss(fitters, weights, shims):
+    """fit_chain(fit_joints=False) skips the L-BFGS fit's forward pass at the returned parameters (the returned
+    parameters are the accepted trial point, so its loss is already known): parameters, loss and evaluation counts
+    must be bit-identical to the run that re-evaluates."""
+    w = weights("smpl")
+    S, Tn = 7, 9
+    tgt = problems.chain_problem(w, S, Tn, 6262)
+    with torch.no_grad():
+        root = shims("smpl")(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10)).joints[0, 0]
+    init = dict(global_orient=torch.zeros(S, 3), body_pose=torch.zeros(S, 69), betas=torch.zeros(S, 10),
+                transl=(tgt[:, 0, 0] - root).contiguous())
+    f = fitters("smpl", use_lbfgs=True)
+    a = f.fit_chain(init, tgt, None, with_mesh=False)
+    b = f.fit_chain(init, tgt, None, with_mesh=False, fit_joints=False)
+    assert b["fit_joints"] is None
+    assert torch.equal(a["loss"], b["loss"]) and torch.equal(a["evals"], b["evals"])
+    for k in a["params"]:
+        assert torch.equal(a["params"][k], b["params"][k]), k
