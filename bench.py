@@ -76,8 +76,11 @@ def parse():
                          "variant, frames sharded across GPUs with a one-frame NCCL halo exchange)")
     ap.add_argument("--chunks", type=int, default=16, help="schedule reference: time windows whose mesh pass overlaps the next window's fit")
     ap.add_argument("--no-vertices", action="store_true", help="skip the vertex output (joints only)")
-    ap.add_argument("--cpu-sample-frames", type=int, default=0, help="0 = choose for ~20 s of CPU work")
+    ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames of the first sequence the CPU arm fits (0 = 64)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--fp-steps", type=int, default=2, help="timed steps of the frame-parallel schedule measured beside S1")
+    ap.add_argument("--no-frame-parallel", action="store_true")
+    ap.add_argument("--no-e2e-vertices", action="store_true")
     return ap.parse_args()
 
 
@@ -146,43 +149,178 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(frames: int, threads: int, optimizer: str, seed: int = 77, schedule: str = "two_sweep"):
-    """Times the oracle port (the reference's algorithm on torch CPU, B = 1 per frame like the API,
-    full-mesh forward per evaluation like smplx) on `frames` frames with schedule S2 or S1."""
+CPU_SAMPLE_FRAMES = 64      # frames of the workload's first sequence the CPU arm fits per step (>= 64)
+
+
+def workload_config(args, mesh=True) -> dict:
+    """The workload definition, identical in both arms (`bench.py` and `bench.py --impl reference`)."""
+    F = args.frames_per_gpu
+    chain = args.schedule == "reference"
+    return {
+        "workload": (f"SMPL AMASS-22 sequence fit, {F} frames/GPU ({F // SEQ_LEN} sequences x {SEQ_LEN}; BASELINE "
+                     "configs[3] shard, each sequence = configs[1]), "
+                     + ("schedule S1 = the reference's own serial chain (frame t starts from frame t-1's result; 30 "
+                        "iterations for frame 0, 10 + pose-preserve after), whole sequences per GPU, " if chain else
+                        "schedule S2: sweep0 30-iteration budget + sweep1 10-iteration budget with pose-preserve, frames "
+                        "sharded across GPUs with a one-frame halo, ")
+                     + f"{args.optimizer}, " + ("full mesh (6890 verts + 45 joints) per frame" if mesh else "joints only")),
+        "optimizer": args.optimizer, "schedule": args.schedule, "frames_per_gpu": F, "seq_len": SEQ_LEN,
+        "l2_policy": "inputs larger than L2 (targets %.0f MB/GPU, outputs %.1f GB/GPU)"
+                     % (F * 22 * 12 / 1e6, F * (6890 * 12 + 45 * 12) / 1e9 if mesh else F * 45 * 12 / 1e9),
+    }
+
+
+class LbfgsEvalCounter:
+    """Counts closure evaluations of every torch.optim.LBFGS.step (both the reference and the port run torch's)."""
+
+    def __init__(self):
+        self.evals = []
+
+    def __enter__(self):
+        import torch.optim.lbfgs as L
+
+        self.L, self.orig = L, L.LBFGS.step
+        me = self
+
+        def step(opt, closure):
+            out = me.orig(opt, closure)
+            me.evals.append(int(opt.state[opt._params[0]]["func_evals"]))
+            return out
+
+        L.LBFGS.step = step
+        return self
+
+    def __exit__(self, *exc):
+        self.L.LBFGS.step = self.orig
+        return False
+
+
+class CpuArm:
+    """The reference's implementation of the path on the host cores.
+
+    kind "reference": the UNMODIFIED reference package (/root/reference in the authoring container, its copy
+    oracle/_ref on the GPU box -- oracle/make_ref.py) through its public ``optimize_params_sequence``, body model =
+    oracle/smplx_shim (smplx itself is not installable offline).  kind "port": oracle/reference_port.py, used only
+    when neither exists.  B = 1 per frame and a full-mesh forward per evaluation, exactly like the reference."""
+
+    def __init__(self, optimizer: str):
+        from keypoints2body_b200 import synthetic as syn
+        from oracle import ref_loader
+        from oracle.smplx_shim import BodyModelShim
+
+        self.lbfgs = optimizer == "lbfgs"
+        self.weights = syn.make_body_model("smpl", seed=0)
+        self.model = BodyModelShim(self.weights)
+        self.gmm = syn.make_gmm(seed=0)
+        self.kind = "port"
+        self.ref = None
+        if ref_loader.available():
+            try:
+                import tempfile
+
+                self.ref = ref_loader.load_reference()
+                self.cwd = tempfile.mkdtemp()
+                syn.write_assets(os.path.join(self.cwd, "data/models"), seed=0)
+                self.kind = "reference"
+            except Exception as e:        # noqa: BLE001
+                print("reference import failed, timing the port:", e, file=sys.stderr)
+                self.ref = None
+
+    def fit_chain(self, joints: torch.Tensor, threads: int) -> dict:
+        """Schedule S1 on one sequence (T,22,3): frames/s, evaluations per frame, per-frame loss and joints."""
+        from oracle import problems, ref_loader
+        from oracle import reference_port as rp
+
+        torch.set_num_threads(threads)
+        T = joints.shape[0]
+        with LbfgsEvalCounter() as cnt:
+            t0 = time.perf_counter()
+            if self.ref is not None:
+                cfg = dict(frame=dict(use_lbfgs=self.lbfgs), use_shape_optimization=False)
+                with ref_loader.reference_cwd(self.cwd):
+                    res = self.ref.optimize_params_sequence(joints.numpy(), body_model="smpl", joint_layout="AMASS",
+                                                            model=self.model, config=cfg)
+                loss = torch.stack([r.loss.reshape(()) for r in res])
+                j22 = torch.cat([r.joints[:, :22] for r in res])
+                pose = torch.cat([r.params.pose for r in res])
+            else:
+                prior = rp.GMMPrior(self.gmm)
+                z = dict(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10))
+                prev = {k: None for k in rp.PARAM_ORDER}
+                prev.update(z, transl=joints[0:1, 0] - self.model(**z).joints[:, 0])
+                loss, j22, pose = [], [], []
+                for t in range(T):
+                    r = rp.fit_frame(self.model, prior, prev, joints[t:t + 1], torch.ones(22), seq_ind=t, use_lbfgs=self.lbfgs)
+                    prev = r["params"]
+                    loss.append(r["loss"].reshape(()))
+                    j22.append(r["joints"][:, :22])
+                    pose.append(torch.cat([prev["global_orient"], prev["body_pose"]], dim=1))
+                loss, j22, pose = torch.stack(loss), torch.cat(j22), torch.cat(pose)
+            dt = time.perf_counter() - t0
+        evals = cnt.evals if self.lbfgs else [30] + [10] * (T - 1)
+        return {"seconds": dt, "frames_per_s": T / dt, "evals_per_frame": float(sum(evals)) / T, "loss": loss,
+                "joints22": j22, "pose": pose, "err": problems.mean_joint_error(j22, joints)}
+
+    def describe(self, frames: int) -> str:
+        return (f"{frames} frames of the workload's first sequence, schedule S1 (serial chain, 30 then 10 iterations), "
+                f"{'lbfgs' if self.lbfgs else 'adam'}, B=1 per frame, "
+                + ("the unmodified reference's optimize_params_sequence" if self.kind == "reference" else "oracle port")
+                + f", torch {torch.__version__} CPU, full-mesh forward per evaluation")
+
+
+def cpu_sample_targets(args) -> torch.Tensor:
+    """The first CPU_SAMPLE_FRAMES frames of global sequence 0 -- the frames rank 0's first sequence starts with."""
     from keypoints2body_b200 import synthetic as syn
-    from oracle import reference_port as rp
-    from oracle.smplx_shim import BodyModelShim
 
-    torch.set_num_threads(threads)
-    weights = syn.make_body_model("smpl", seed=0)
-    model, prior = BodyModelShim(weights), rp.GMMPrior(syn.make_gmm(seed=0))
-    mo = syn.make_motion(frames, seed=seed)
-    tgt = syn.kinematic_joints(weights, mo["pose"][:, :66], mo["betas"], mo["transl"], 22)
-    lbfgs = optimizer == "lbfgs"
-    conf = torch.ones(22)
-    root0 = model(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10)).joints[:, 0]
+    n = args.cpu_sample_frames or CPU_SAMPLE_FRAMES
+    return make_targets(syn.make_body_model("smpl", seed=0), 0, n, torch.device("cpu"))
 
-    def chain_pass():      # S1: api/sequence.py:214-281
-        prev = {k: None for k in rp.PARAM_ORDER}
-        prev.update(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10),
-                    transl=tgt[0:1, 0] - root0)
-        for t in range(frames):
-            prev = rp.fit_frame(model, prior, prev, tgt[t:t + 1], conf, seq_ind=t, use_lbfgs=lbfgs)["params"]
 
-    if schedule == "reference":
-        return chain_pass
+def cpu_baseline_block(arm: CpuArm, sample: torch.Tensor, threads: int, all_thread_run: dict, with_demo: bool) -> dict:
+    one = arm.fit_chain(sample[: max(16, len(sample) // 2)], 1)          # 1 thread: half the sample keeps the run short
+    blk = {"value": all_thread_run["frames_per_s"], "unit": UNIT, "cores": threads, "kind": arm.kind,
+           "sample": arm.describe(len(sample)), "evals_per_frame": all_thread_run["evals_per_frame"],
+           "value_1_thread": one["frames_per_s"], "sample_1_thread": f"{len(one['loss'])} frames"}
+    if with_demo:
+        try:       # the reference's own demo sequence (real AMASS-22 keypoints; stored with the goldens)
+            import numpy as np
 
-    def one_pass():
-        s0 = []
-        for t in range(frames):
-            init = {k: None for k in rp.PARAM_ORDER}
-            init.update(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10),
-                        transl=tgt[t:t + 1, 0] - root0)
-            s0.append(rp.fit_frame(model, prior, init, tgt[t:t + 1], conf, seq_ind=0, use_lbfgs=lbfgs))
-        for t in range(1, frames):
-            rp.fit_frame(model, prior, s0[t - 1]["params"], tgt[t:t + 1], conf, seq_ind=t, use_lbfgs=lbfgs)
+            demo = torch.as_tensor(np.load(os.path.join(ROOT, "tests", "golden", "r2_adam.npz"))["demo1_in"])
+            d = arm.fit_chain(demo, threads)
+            blk["demo_sequence"] = {"value": d["frames_per_s"], "unit": UNIT, "frames": len(demo),
+                                    "evals_per_frame": d["evals_per_frame"],
+                                    "what": "data/demo/test_motion1.npy (195 real AMASS-22 frames), same call"}
+        except Exception as e:      # noqa: BLE001
+            blk["demo_sequence"] = {"unavailable": str(e)}
+    return blk
 
-    return one_pass
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if args.schedule != "reference":
+        raise SystemExit("--impl reference times schedule S1 (the reference has no other)")
+    threads = os.cpu_count() or 1
+    arm = CpuArm(args.optimizer)
+    sample = cpu_sample_targets(args)
+    n = len(sample)
+    for _ in range(args.warmup):
+        arm.fit_chain(sample, threads)
+    runs = [arm.fit_chain(sample, threads) for _ in range(args.steps)]
+    dt = sum(r["seconds"] for r in runs) / len(runs)
+    val = n / dt
+    last = dict(runs[-1], frames_per_s=val)
+    blk = cpu_baseline_block(arm, sample, threads, last, with_demo=True)
+    emit({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": blk,
+        "cpu_baseline_batched_adam": cpu_reference_batched_adam(1024, threads),
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    })
 
 
 def cpu_reference_batched_adam(frames: int, threads: int, seed: int = 78) -> dict:
@@ -211,40 +349,6 @@ def cpu_reference_batched_adam(frames: int, threads: int, seed: int = 78) -> dic
     return {"value": frames / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{frames} frames in one batched call per sweep (S2, 30 + 10 iterations), adam, torch CPU, "
                       "full-mesh forward per evaluation"}
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    probe = cpu_reference_rate(2, threads, args.optimizer, schedule=args.schedule)
-    t0 = time.perf_counter()
-    probe()
-    per_frame = (time.perf_counter() - t0) / 2
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    n = args.cpu_sample_frames or int(max(2, min(64, budget / per_frame)))
-    one_pass = cpu_reference_rate(n, threads, args.optimizer, schedule=args.schedule)
-    for _ in range(args.warmup):
-        one_pass()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one_pass()
-    dt = (time.perf_counter() - t0) / args.steps
-    val = n / dt
-    sched = "S2 (30 + 10 iteration budgets)" if args.schedule == "two_sweep" else "S1 (serial chain, 30 then 10 iterations)"
-    sample = (f"{n} frames/step, schedule {sched}, {args.optimizer}, B=1 per frame, "
-              f"torch {torch.__version__} CPU, full-mesh forward per evaluation")
-    emit({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "bounded sample of the ours-arm workload: " + sample, "optimizer": args.optimizer,
-                   "schedule": args.schedule},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "cpu_baseline_batched_adam": cpu_reference_batched_adam(1024, threads),
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    })
 
 
 class ChainRunner:
@@ -281,6 +385,7 @@ class ChainRunner:
 
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import numpy as np
     import torch.distributed as dist
 
     from keypoints2body_b200 import _native as nat
@@ -297,7 +402,6 @@ def run_ours(args):
     if world > 1:
         import datetime
 
-
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     F = args.frames_per_gpu
     lo, hi = rank * F, (rank + 1) * F
@@ -309,10 +413,17 @@ def run_ours(args):
     chain = args.schedule == "reference"
     if chain and F % SEQ_LEN:
         raise SystemExit("--schedule reference needs whole sequences per GPU")
-    sf = ChainRunner(fitter, F, not args.no_vertices, args.chunks) if chain else SequenceBatchFitter(
-        fitter, F, cfg, with_vertices=not args.no_vertices)
+    with_verts = not args.no_vertices
+    if chain:
+        sf = ChainRunner(fitter, F, with_verts, args.chunks)
+        # the frame-parallel schedule (S2) is measured beside it, into the same vertex buffer
+        sf2 = None if args.no_frame_parallel else SequenceBatchFitter(fitter, F, cfg, with_vertices=False)
+        if sf2 is not None:
+            sf2.vertices = sf.vertices
+    else:
+        sf, sf2 = SequenceBatchFitter(fitter, F, cfg, with_vertices=with_verts), None
     targets = make_targets(weights, lo, hi, dev)
-    seq_ind = seq_index(lo, hi, dev)       # S2 only; S1 takes [lo, hi) as F / 4096 whole sequences
+    seq_ind = seq_index(lo, hi, dev)       # S2: frames shard across GPUs, boundaries fall mid-sequence; S1: whole sequences
     lib = fitter.native.lib
 
     def barrier():
@@ -384,6 +495,7 @@ def run_ours(args):
             h_loss.copy_(o["loss"], non_blocking=True)
         h_joints.copy_(o["joints"], non_blocking=True)
         torch.cuda.current_stream().wait_stream(side)
+        return o
 
     for _ in range(max(1, args.warmup // 2)):
         step_host()
@@ -391,12 +503,32 @@ def run_ours(args):
     h2d = h_targets.numel() * 4
     d2h = 4 * (h_pose.numel() + h_betas.numel() + h_transl.numel() + h_loss.numel() + h_joints.numel())
 
+    # ---- frame-parallel schedule S2 beside it: frames sharded across the ranks, one-frame NCCL halo ------------
+    fp = None
+    if sf2 is not None:
+        sf2.run(targets, seq_ind)
+        sf2.kernel_events, sf2.halo_events = [], []
+        ms_fp = timed(lambda: sf2.run(targets, seq_ind), args.fp_steps)
+        torch.cuda.synchronize()
+        fp_fit_ms = sum(a.elapsed_time(b) for a, b in sf2.kernel_events) / args.fp_steps
+        halo_ms = sum(a.elapsed_time(b) for a, b in sf2.halo_events) / max(1, args.fp_steps)
+        sf2.kernel_events = sf2.halo_events = None
+        o2 = sf2.run(targets, seq_ind)
+        fp = {"ms_per_step": ms_fp, "fit_ms": fp_fit_ms, "halo_ms": halo_ms,
+              "evals": float(sf2.evals0.sum()) + float(sf2.evals1.sum()),
+              "mean_err": float((o2["joints"][:, :22] - targets).norm(dim=-1).mean())}
+        del o2
+
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (fused fit kernel, two launches per step) -------------------
-    tf = ctypes_double()
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
     peak_tflops, _ = fma_peak(lib)
     flop_step = (evals0 + evals1 + F) * EVAL_FLOP["smpl"]     # + one final (loss / joints) forward per frame/sweep
+    if chain and args.optimizer == "lbfgs":
+        flop_step = evals0 * EVAL_FLOP["smpl"]                  # no extra forward: the returned loss is the accepted trial's
     fit_ms_step = sum(fit_ms) / max(1, args.steps)
     achieved = flop_step / (fit_ms_step * 1e-3) / 1e12 if fit_ms_step > 0 else None
     nominal = 148 * 128 * 2 * 1.965e9 / 1e12
@@ -406,8 +538,7 @@ def run_ours(args):
     except Exception:
         pass
     mesh_ms = ms_step - fit_ms_step
-    if chain:     # the mesh pass overlaps the fit inside the step; for its roofline it is timed alone (rank 0
-        # only: no collective here, the other ranks have already returned)
+    if chain:     # the mesh pass overlaps the fit inside the step; for its roofline it is timed alone
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fitter.forward_batch(out["params"], out_vertices=sf.vertices)      # sizes the workspace for one full pass
         torch.cuda.synchronize()
@@ -416,47 +547,32 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         mesh_ms = e0.elapsed_time(e1)
-    mesh_bytes = F * (6890 * 3 * 4 + n_j * 3 * 4) if not args.no_vertices else F * n_j * 12
+    mesh_bytes = F * (6890 * 3 * 4 + n_j * 3 * 4) if with_verts else F * n_j * 12
+    kernel_name = ("chain_kernel<10,22,%s> (warp-per-sequence; %d window launches per step)" % (args.optimizer, args.chunks)
+                   if chain else "fit_kernel<10,22,%s> (sweep 0 + sweep 1)" % args.optimizer)
+    traffic, traffic_note = ncu_traffic("chain" if chain else "fit", args, F)
     line = {
         "metric": METRIC, "value": world * F / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": (f"SMPL AMASS-22 sequence fit, {F} frames/GPU ({F // SEQ_LEN} sequences x {SEQ_LEN}; "
-                         "BASELINE configs[3] shard, each sequence = configs[1]), "
-                         + ("schedule S1 = the reference's own serial chain (frame t starts from frame t-1's result; 30 "
-                            "iterations for frame 0, 10 + pose-preserve after), one warp group per sequence, whole "
-                            f"sequences per GPU, {args.chunks} time windows (mesh of window c overlaps the fit of c+1), " if chain else
-                            "schedule S2: sweep0 30-iteration budget + sweep1 10-iteration budget with pose-preserve, ")
-                         + f"{args.optimizer}, "
-                         + ("full mesh (6890 verts + 45 joints) per frame" if not args.no_vertices else "joints only")),
-            "optimizer": args.optimizer, "schedule": args.schedule, "frames_per_gpu": F, "seq_len": SEQ_LEN,
-            "l2_policy": "inputs larger than L2 (targets %.0f MB/GPU, outputs %.1f GB/GPU)" % (h2d / 1e6, mesh_bytes / 1e9),
-            "evals_per_frame": evals_total / F, "mean_joint_error_m": mean_err,
-        },
+        "vs_baseline": None, "dtype": "f32 (fit); fp16 x fp16 -> fp32 tcgen05 blend in the mesh pass", "data": "synthetic",
+        "config": workload_config(args, with_verts),
+        "fit_quality": {"evals_per_frame": evals_total / F, "mean_joint_error_m": mean_err},
         "e2e": {"value": world * F / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-                "note": "vertices stay in HBM (%.1f GB/GPU); params, loss and 45 joints are copied back" % (mesh_bytes / 1e9)},
+                "note": "vertices stay in HBM (%.1f GB/GPU); params, loss and 45 joints are copied back; see "
+                        "e2e_with_vertices" % (mesh_bytes / 1e9)},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
         "roofline": {
-            "kernel": ("chain_kernel<10,22> (%s; one launch, latency-bound: F/4096 warps)" if chain else
-                       "fit_kernel<10,22,%s> (sweep 0 + sweep 1)") % ("lbfgs" if args.optimizer == "lbfgs" else "adam"),
-            "bound": "fp32_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            "kernel": kernel_name, "bound": "fp32_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops if achieved and peak_tflops else None,
             "peak_source": "in-run FFMA micro-benchmark (k2b_fma_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f" % nominal,
             "frac_of_nominal": achieved / nominal if achieved else None,
-            "flop_per_eval": EVAL_FLOP["smpl"], "evals_per_launch": [evals0 + F] if chain else [evals0 + F, evals1 + F],
-            "ms_per_launch_pair": fit_ms_step, "share_of_step": fit_ms_step / ms_step,
-            "traffic": ncu_chain_traffic(args.optimizer, F, args.chunks) if chain else ncu_fit_traffic(args.optimizer, F),
-            "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of ONE of the %d window launches of a step, from "
-                             "the committed ncu --set full capture of this command (profiles/r01_chain_ncu_metrics.txt): "
-                             "the window's keypoints are read once (17.3 MB), everything else stays on chip or in L2"
-                             % args.chunks) if chain else
-                            "dram__bytes_read.sum + dram__bytes_write.sum of the sweep-0 launch from the committed ncu "
-                            "--set full capture (profiles/r01_fit_lbfgs_ncu_metrics.txt, same frame count); the "
-                            "algorithmic HBM bytes are ~1.5 KB/frame, the rest is L-BFGS (s, y) history that does not fit L2",
-            "launches_per_step": args.chunks if chain else 2,
+            "flop_per_eval": EVAL_FLOP["smpl"], "evals_per_step": flop_step / EVAL_FLOP["smpl"],
+            "ms_per_step_in_kernel": fit_ms_step, "share_of_step": fit_ms_step / ms_step,
+            "traffic": traffic, "traffic_note": traffic_note, "launches_per_step": args.chunks if chain else 2,
+            "note": ("latency-bound by construction: %d serial chains per GPU; the throughput kernel is under frame_parallel"
+                     % (F // SEQ_LEN)) if chain else None,
         },
         "roofline_mesh": {
             "kernel": "mesh_pose_kernel + blend_skin_tc_kernel (tcgen05 blend, LBS in the epilogue) + gather_extra_kernel", "bound": "hbm",
@@ -469,72 +585,106 @@ def run_ours(args):
                     if chain else "step time minus the fit launches",
         },
     }
-    del tf
+    if fp is not None:
+        fp_flop = (fp["evals"] + 2 * F) * EVAL_FLOP["smpl"]
+        fp_ach = fp_flop / (fp["fit_ms"] * 1e-3) / 1e12
+        t2, n2 = ncu_traffic("fit", args, F)
+        line["frame_parallel"] = {
+            "what": "schedule S2 on the same keypoints: frames sharded across the ranks (each shard boundary falls inside a "
+                    "sequence), sweep 0 + one-frame halo over NCCL + sweep 1, full mesh; one thread per frame (fit_kernel)",
+            "value": world * F / (fp["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": fp["ms_per_step"],
+            "steps": args.fp_steps, "evals_per_frame": fp["evals"] / F, "mean_joint_error_m": fp["mean_err"],
+            "halo_ms_per_step": fp["halo_ms"], "halo_bytes_per_boundary": 95 * 4, "n_boundaries": world - 1,
+            "roofline": {"kernel": "fit_kernel<10,22,%s> (sweep 0 + sweep 1)" % args.optimizer, "bound": "fp32_fma",
+                         "achieved": fp_ach, "peak": peak_tflops, "unit": "TFLOP/s",
+                         "frac": fp_ach / peak_tflops if peak_tflops else None, "flop_per_eval": EVAL_FLOP["smpl"],
+                         "ms_per_step_in_kernel": fp["fit_ms"], "share_of_step": fp["fit_ms"] / fp["ms_per_step"],
+                         "traffic": t2, "traffic_note": n2},
+        }
+    # ---- the vertices were written: a sample re-evaluated by the FP32 CUDA-core mesh path ---------------------------
+    if with_verts:
+        g = torch.Generator().manual_seed(11)
+        idx = torch.randint(0, F, (256,), generator=g).to(dev)
+        sub = {k: v[idx].contiguous() for k, v in out["params"].items()}
+        os.environ["K2B_MESH_FP32"] = "1"
+        chk = fitter.forward_batch(sub)["vertices"]
+        os.environ["K2B_MESH_FP32"] = "0"
+        got = sf.vertices[idx]
+        line["vertex_check"] = {"frames": 256, "max_abs_diff_m": float((chk - got).abs().max()),
+                                "checksum": float(got.double().sum()),
+                                "what": "256 random frames of the step's vertex output against the FP32 CUDA-core mesh path"}
+        del chk, got
+    # ---- e2e with the vertices streamed to pinned host memory in windows (PCIe-bound) ------------------------------
+    if with_verts and world == 1 and not args.no_e2e_vertices:
+        win = 16384
+        pin = [torch.empty(win, 6890, 3, pin_memory=True) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def step_host_vertices():
+            step_host()
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                for i, a0 in enumerate(range(0, F, win)):
+                    b0 = min(F, a0 + win)
+                    pin[i % 2][: b0 - a0].copy_(sf.vertices[a0:b0], non_blocking=True)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+
+        ms_v = timed(step_host_vertices, 1)
+        line["e2e_with_vertices"] = {"value": F / (ms_v * 1e-3), "unit": UNIT, "ms_per_step": ms_v, "steps": 1,
+                                     "d2h_bytes_per_step": d2h + F * 6890 * 12,
+                                     "note": "every vertex leaves the GPU too (%.1f GB through two 1.35 GB pinned windows): "
+                                             "PCIe-bound, %.1f GB/s" % (F * 6890 * 12 / 1e9, F * 6890 * 12 / (ms_v * 1e-3) / 1e9)}
+        del pin
+    # ---- CPU baseline on the same frames, and our result on them against it ------------------------------------------
     if world == 1 and not args.skip_cpu_baseline:
         threads = os.cpu_count() or 1
-        probe = cpu_reference_rate(2, threads, args.optimizer, schedule=args.schedule)
-        t0 = time.perf_counter()
-        probe()
-        per_frame = (time.perf_counter() - t0) / 2
-        n = args.cpu_sample_frames or int(max(2, min(64, 20.0 / per_frame)))
-        one_pass = cpu_reference_rate(n, threads, args.optimizer, schedule=args.schedule)
-        t0 = time.perf_counter()
-        one_pass()
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {
-            "value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} frames, schedule {'S1 (serial chain)' if chain else 'S2 (30 + 10 budgets)'}, {args.optimizer}, B=1 per frame, torch CPU, "
-                      "full-mesh forward per evaluation like the reference"}
-        line["cpu_baseline_batched_adam"] = cpu_reference_batched_adam(1024, threads)
+        arm = CpuArm(args.optimizer)
+        sample = cpu_sample_targets(args)
+        arm.fit_chain(sample[:8], threads)          # warm-up (thread pool, allocator)
+        ref_run = arm.fit_chain(sample, threads)
+        line["cpu_baseline"] = cpu_baseline_block(arm, sample, threads, ref_run, with_demo=False)
+        n = len(sample)
+        z = {"global_orient": torch.zeros(1, 3), "body_pose": torch.zeros(1, 69), "betas": torch.zeros(1, 10)}
+        init = dict(z, transl=(sample[0:1, 0].to(dev) - sf.root0).cpu() if chain else sample[0:1, 0])
+        if not chain:
+            init["transl"] = sample[0:1, 0] - fitter.forward_batch(z, with_vertices=False)["joints"][:, 0].cpu()
+        ours = fitter.fit_chain(init, sample[None].to(dev), None, with_mesh=False)
+        pose = torch.cat([ours["params"]["global_orient"], ours["params"]["body_pose"]], dim=1).cpu()
+        o_err = (ours["fit_joints"].cpu() - sample).norm(dim=-1).mean(dim=-1)
+        line["parity_check"] = {
+            "what": "our chain fit of the CPU sample's frames against the CPU arm's result on them (L-BFGS: distribution; "
+                    "the reference differs from itself by a median 6.5 % per frame across thread counts)",
+            "frames": n, "loss_median_ratio": float(ours["loss"].cpu().median() / ref_run["loss"].median()),
+            "joint_error_median_ratio": float(o_err.median() / ref_run["err"].median()),
+            "evals_per_frame": [float(ours["evals"].float().mean()), ref_run["evals_per_frame"]],
+            "first_frames_pose_max_abs_diff": float((pose[:2] - ref_run["pose"][:2]).abs().max()),
+        }
     emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def ncu_chain_traffic(optimizer: str, frames: int, chunks: int):
-    """DRAM bytes of one window launch of the chain kernel from the committed ncu capture of the default bench; null
-    when the configuration differs from the captured one."""
-    if optimizer != "lbfgs" or frames != 256 * SEQ_LEN or chunks != 16:
-        return None
-    try:
-        total, seen, inside = 0.0, 0, False
-        for ln in open(os.path.join(ROOT, "profiles", "r01_chain_ncu_metrics.txt")):
-            if ln.startswith("## bench launch 0"):
-                inside = True
-            elif ln.startswith("## bench launch 1"):
-                break
-            elif inside and (ln.startswith("dram__bytes_read.sum") or ln.startswith("dram__bytes_write.sum")):
-                val, unit = ln.split("=")[1].split()
-                total += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
-                seen += 1
-        return total if seen == 2 else None
-    except Exception:
-        return None
-
-
-def ncu_fit_traffic(optimizer: str, frames: int):
-    """DRAM bytes of the dominant launch (sweep 0 of the L-BFGS fit kernel) from the committed ncu capture; null
-    when there is no capture for this optimiser / frame count."""
-    if optimizer != "lbfgs" or frames != 256 * SEQ_LEN:
-        return None
+def ncu_traffic(which: str, args, frames: int):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` capture of this workload (profiles/r02_*_ncu_metrics.txt); null when the configuration differs."""
+    name = {"chain": "r02_chain_ncu_metrics.txt", "fit": "r02_fit_ncu_metrics.txt"}[which]
+    if args.optimizer != "lbfgs" or frames != 256 * SEQ_LEN:
+        return None, "no committed capture for this configuration"
     try:
         total, seen = 0.0, 0
-        for ln in open(os.path.join(ROOT, "profiles", "r01_fit_lbfgs_ncu_metrics.txt")):
+        for ln in open(os.path.join(ROOT, "profiles", name)):
             if ln.startswith("## launch 1"):
                 break
             if ln.startswith("dram__bytes_read.sum") or ln.startswith("dram__bytes_write.sum"):
-                val, unit = ln.split("=")[1].split()
+                val, unit = ln.split("=")[1].split()[:2]
                 total += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
                 seen += 1
-        return total if seen == 2 else None
+        if seen == 2:
+            return total, f"first launch in profiles/{name} (ncu --set full capture of this command)"
     except Exception:
-        return None
-
-
-def ctypes_double():
-    import ctypes
-
-    return ctypes.c_double()
+        pass
+    return None, "no committed capture"
 
 
 def fma_peak(lib):

@@ -119,7 +119,14 @@ class SequenceBatchFitter:
                 "betas": self.s0["betas"][F:F + 1], "transl": self.s0["transl"][F:F + 1]}
         if self.s0["expr"] is not None:
             last["expression"] = self.s0["expr"][F:F + 1]
+        hev = getattr(self, "halo_events", None)      # bench.py: device time of the exchange
+        if hev is not None:
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
         halo = exchange_halo(last, group)
+        if hev is not None:
+            h1.record()
+            hev.append((h0, h1))
         if halo is None:
             # no left neighbour: a shard that starts mid-sequence falls back to its own first frame
             for k in ("pose", "betas", "transl", "expr"):

@@ -303,7 +303,7 @@ void chain_geometry(const k2b_model* m, long S, bool lbfgs, int hmax, int& grid,
   const long per_sm = (S + m->num_sms - 1) / m->num_sms;       // sequences an SM has to host
   if (per_sm <= 1) { evals = 6; helpers = 2; }
   else if (per_sm <= 2) { evals = 6; helpers = 2; }
-  else { evals = per_sm <= 4 ? 3 : 1; helpers = per_sm <= 6 ? 1 : 0; }
+  else { evals = per_sm <= 3 ? 4 : (per_sm <= 4 ? 3 : (per_sm <= 6 ? 2 : 1)); helpers = per_sm <= 6 ? 1 : 0; }
   if (const char* e = getenv("K2B_CHAIN_HELPERS")) helpers = atoi(e);
   if (const char* e = getenv("K2B_CHAIN_TEAM")) evals = atoi(e);
   // L-BFGS evaluates the mixture prior in line form (chain_core.cuh, LineEval): the evaluators share the matrix
@@ -316,7 +316,7 @@ void chain_geometry(const k2b_model* m, long S, bool lbfgs, int hmax, int& grid,
   }
   const int tw = evals * (1 + helpers);
   int cap = kChainMaxWarps / tw;
-  const int bar_cap = evals == 1 ? (helpers > 0 ? 7 : kChainMaxWarps) : 3;      // named barrier ids 1..15
+  const int bar_cap = evals == 1 ? (helpers > 0 ? 7 : kChainMaxWarps) : 5;      // named barrier ids 1..15
   if (cap > bar_cap) cap = bar_cap;
   long g = per_sm;
   if (const char* e = getenv("K2B_CHAIN_WARPS")) g = atoi(e);

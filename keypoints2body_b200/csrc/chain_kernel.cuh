@@ -70,13 +70,13 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
   const int team = warp / TW, member = warp - team * TW;
   float* base = s_team + (size_t)team * wc::team_floats(E, H, p.hmax);
   wc::TeamMem tm = wc::make_team_mem(base, E, H, p.hmax);
-  // named barriers: one evaluator per sequence keeps the ids of the helper pair dense (up to 7 teams per CTA);
-  // teams of several evaluators use five ids each (round posted, helper pair, tables ready, results ready; up to 3
-  // teams per CTA)
-  const int bar_b = E == 1 ? 1 + 2 * team : 2 + 5 * team;
-  tm.bar_go = 1 + 5 * team;
-  tm.bar_tab = 4 + 5 * team;
-  tm.bar_done = 5 + 5 * team;
+  // named barriers (ids 1..15): a lone evaluator with helpers (Adam) uses the helper pair, ids 1 + 2 team, + 1 (up to
+  // 7 teams per CTA); a team of several evaluators (L-BFGS, no helpers: k2b_fit_chain never combines the two) uses three:
+  // round posted, tables ready, results ready (up to 5 teams per CTA)
+  const int bar_b = 1 + 2 * team;
+  tm.bar_go = 1 + 3 * team;
+  tm.bar_tab = 2 + 3 * team;
+  tm.bar_done = 3 + 3 * team;
   if (member < E) {
     wc::WarpMem wm = wc::make_warp_mem(base + (size_t)member * wc::kEvalMemFloats, tm.gs);
     wm.helpers = H;

@@ -27,10 +27,21 @@ import types
 import numpy as np
 
 REFERENCE_ROOT = "/root/reference"
+VENDORED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+"""``oracle/_ref``: an unmodified copy of the reference's Python package made by ``oracle/make_ref.py`` (git-ignored,
+travels to the GPU box with the snapshot) so that ``bench.py --impl reference`` times the reference itself there."""
+
+
+def reference_root():
+    """/root/reference in the authoring container, else the vendored copy, else None."""
+    for root in (REFERENCE_ROOT, VENDORED_ROOT):
+        if os.path.isdir(os.path.join(root, "keypoints2body")):
+            return root
+    return None
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "keypoints2body"))
+    return reference_root() is not None
 
 
 class _NpzAsH5:
@@ -64,11 +75,12 @@ def _install_stubs():
 
 def load_reference():
     """Return the reference's top-level ``keypoints2body`` module (unmodified)."""
-    if not available():
-        raise RuntimeError(f"{REFERENCE_ROOT} is not present (GPU box?)")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError(f"neither {REFERENCE_ROOT} nor {VENDORED_ROOT} holds the reference package")
     _install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import keypoints2body  # noqa: WPS433  (the reference, not this repo's package)
 
     return keypoints2body
