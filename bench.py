@@ -302,9 +302,16 @@ def run_reference(args):
     if args.schedule != "reference":
         raise SystemExit("--impl reference times schedule S1 (the reference has no other)")
     threads = os.cpu_count() or 1
+    os.environ.pop("OMP_NUM_THREADS", None)        # torchrun pins it to 1; torch.set_num_threads decides here
     arm = CpuArm(args.optimizer)
     sample = cpu_sample_targets(args)
     n = len(sample)
+    # B = 1 work is a stream of tiny ops: more threads are not always faster.  The arm gets the better of "all
+    # host threads" and "one thread" (probe on 16 frames), and reports both.
+    arm.fit_chain(sample[:4], threads)
+    probe = {th: arm.fit_chain(sample[:16], th)["frames_per_s"] for th in (threads, 1)}
+    if probe[1] > probe[threads]:
+        threads = 1
     for _ in range(args.warmup):
         arm.fit_chain(sample, threads)
     runs = [arm.fit_chain(sample, threads) for _ in range(args.steps)]
@@ -312,6 +319,7 @@ def run_reference(args):
     val = n / dt
     last = dict(runs[-1], frames_per_s=val)
     blk = cpu_baseline_block(arm, sample, threads, last, with_demo=True)
+    blk["probe_frames_per_s"] = {"all_threads_%d" % (os.cpu_count() or 1): probe[os.cpu_count() or 1], "one_thread": probe[1]}
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",

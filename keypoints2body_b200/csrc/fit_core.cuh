@@ -255,6 +255,8 @@ struct Cols {
 // z = L^T d is accumulated in 72 registers by a rolled loop over the rows of each panel; the
 // arg-min component's z is recomputed in a 9th pass (cheaper than keeping a second register
 // set alive), then G(3..71) = kPosePriorW2 * L z.  Returns kPosePriorW2 * min.
+// (Tried in round 2: scanning the previous evaluation's winner last so that its z is still in registers and the
+// ninth pass can be skipped.  The extra live state pushed the Adam kernel from 68 to 520 bytes of spills and cost 25 %.)
 // ---------------------------------------------------------------------------------
 template <int P>
 K2B_HD void gmm_zpanel(const Cols& c, const float* __restrict__ Lm, const float* __restrict__ mum, float2 (&z)[36]) {

@@ -312,7 +312,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         }
         if (!__any_sync(0xffffffffu, !st.done)) {
           stage = 2;
-#pragma unroll 17
+#pragma unroll kVecUnroll
           for (int i = 0; i < NX; ++i) c.X(i) = v.at(i);
         }
       }

@@ -19,8 +19,14 @@
 
 #include "fit_core.cuh"
 
+// unroll factor of the per-frame vector passes (one thread per frame): loads in flight vs code size
+#ifndef K2B_VEC_UNROLL
+#define K2B_VEC_UNROLL 17
+#endif
+
 namespace k2b {
 
+constexpr int kVecUnroll = K2B_VEC_UNROLL;
 constexpr double kTolGrad = 1e-7;
 constexpr double kTolChange = 1e-9;
 constexpr double kC1 = 1e-4;
@@ -97,7 +103,7 @@ struct ThreadOps {
   static K2B_HD float dot_cur_d(const V& v, int cur) {
     const int og = v.gslot(cur), od = v.d();
     float a0 = 0.f, a1 = 0.f;
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) {
       if (i & 1) a1 = fmaf(v.at(og + i), v.at(od + i), a1);
       else a0 = fmaf(v.at(og + i), v.at(od + i), a0);
@@ -106,14 +112,14 @@ struct ThreadOps {
   }
   static K2B_HD void set_trial(const C& c, const V& v, float tf) {
     const int od = v.d();
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, v.at(od + i), v.at(i));
   }
   // xk = x; returns max |flat_grad| (slot 0)
   static K2B_HD float begin_copy(const C& c, const V& v) {
     float gmax = 0.f;
     const int og = v.gslot(0);
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) {
       v.at(i) = c.X(i);
       gmax = fmaxf(gmax, fabsf(v.at(og + i)));
@@ -123,7 +129,7 @@ struct ThreadOps {
   // first outer iteration: q = -flat_grad (q lives in the x column)
   static K2B_HD void neg_grad(const C& c, const V& v, int g0) {
     const int og = v.gslot(g0);
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) c.X(i) = -v.at(og + i);
   }
   // later outer iterations: history update + two-loop recursion (lbfgs.py:399-442); leaves q in the x column
@@ -136,7 +142,7 @@ struct ThreadOps {
     if (num_old == v.hmax) h = head;
     const int oy = v.y(h), os = v.s(h);
     float ys0 = 0.f, ys1 = 0.f, yy0 = 0.f, yy1 = 0.f;
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) {
       const float gi = v.at(og + i);
       const float yi = gi - v.at(op + i);
@@ -160,30 +166,30 @@ struct ThreadOps {
       const int hk = (head + k) % v.hmax;
       const int oyk = v.y(hk), osk = v.s(hk);
       float a0 = 0.f, a1 = 0.f;
-#pragma unroll 17
+#pragma unroll kVecUnroll
       for (int i = 0; i < N; ++i) {
         if (i & 1) a1 = fmaf(v.at(osk + i), c.X(i), a1);
         else a0 = fmaf(v.at(osk + i), c.X(i), a0);
       }
       const float a = (a0 + a1) * v.at(v.ro(hk));
       v.at(v.al(hk)) = a;
-#pragma unroll 17
+#pragma unroll kVecUnroll
       for (int i = 0; i < N; ++i) c.X(i) = fmaf(-a, v.at(oyk + i), c.X(i));
     }
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) c.X(i) *= H_diag;
 #pragma unroll 1
     for (int k = 0; k < num_old; ++k) {
       const int hk = (head + k) % v.hmax;
       const int oyk = v.y(hk), osk = v.s(hk);
       float b0 = 0.f, b1 = 0.f;
-#pragma unroll 17
+#pragma unroll kVecUnroll
       for (int i = 0; i < N; ++i) {
         if (i & 1) b1 = fmaf(v.at(oyk + i), c.X(i), b1);
         else b0 = fmaf(v.at(oyk + i), c.X(i), b0);
       }
       const float coef = v.at(v.al(hk)) - (b0 + b1) * v.at(v.ro(hk));
-#pragma unroll 17
+#pragma unroll kVecUnroll
       for (int i = 0; i < N; ++i) c.X(i) = fmaf(coef, v.at(osk + i), c.X(i));
     }
   }
@@ -193,7 +199,7 @@ struct ThreadOps {
     float gtd0a = 0.f, gtd1a = 0.f;
     gsum = 0.f;
     dmax = 0.f;
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) {
       const float gi = v.at(og + i), di = c.X(i);
       v.at(od + i) = di;
@@ -205,14 +211,14 @@ struct ThreadOps {
   }
   // first trial point: x = xk + t d with d still in the x column
   static K2B_HD void first_trial(const C& c, const V& v, float tf) {
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, c.X(i), v.at(i));
   }
   // xk += t d (_add_grad); returns max |t d|
   static K2B_HD float move_iterate(const C& c, const V& v, float tf) {
     const int od = v.d();
     float dtmax = 0.f;
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) {
       const float di = v.at(od + i);
       v.at(i) = fmaf(tf, di, v.at(i));
@@ -223,7 +229,7 @@ struct ThreadOps {
   static K2B_HD float grad_max(const V& v, int slot) {
     float gmax = 0.f;
     const int og = v.gslot(slot);
-#pragma unroll 17
+#pragma unroll kVecUnroll
     for (int i = 0; i < N; ++i) gmax = fmaxf(gmax, fabsf(v.at(og + i)));
     return gmax;
   }
