@@ -308,6 +308,74 @@ typedef struct k2b_replay_args {
 
 int k2b_linesearch_replay(const k2b_replay_args* args, void* cuda_stream);
 
+/* ---- general articulated fit: hands / face observations, MANO, FLAME ------------------------------------------
+ * Replaces, for inputs the body-keypoint kernels do not cover:
+ *   WorldSpaceFitter.fit_frame with target_model_indices addressing hand joints / vertex-picked landmarks
+ *       (core/fitters/world_space.py:198-201, core/joints/adapters.py:224-380, core/constants.py:65-71),
+ *   MANOFitter.fit_frame and FLAMEFitter.fit_frame (core/fitters/misc_models.py:18-359; generic_keypoint_loss_3d,
+ *       core/losses.py:96-112).
+ * A model is any kinematic tree (<= 56 joints) with <= 20 shape coefficients; the parameter vector x [num_params] is
+ * the concatenation of the caller's blocks, pose_src / shape_src / transl_src say where the model reads its pose,
+ * shape and translation in it (-1 = fixed zero).  Observable points: kinematic joint j (index j) and picked vertex p
+ * (index num_joints + p), for which the host passes the rows of v_template / shapedirs / posedirs and the non-zero
+ * skinning weights.  Loss = joint_w^2 sum conf^2 gmof(point - target) + sum reg_w[i] x_i^2
+ *   + [temporal] keep_scale sum keep_w[i] (x_i - keep_i)^2 + [body_off >= 0] the SMPL pose prior and angle prior on
+ * x[body_off .. body_off + 69) (core/losses.py:24-67).  All host pointers are copied. */
+typedef struct k2b_artic k2b_artic;
+typedef struct k2b_artic_desc {
+  int32_t num_joints;
+  int32_t num_shape;
+  int32_t num_params;
+  int32_t num_picked;
+  const int32_t* parents;        /* [n_j] */
+  const float* J0;               /* [n_j][3]  J_regressor . v_template */
+  const float* JS;               /* [n_j][3][num_shape]  J_regressor . shapedirs */
+  const int32_t* pose_src;       /* [3 n_j] */
+  const int32_t* shape_src;      /* [num_shape] */
+  int32_t transl_src;
+  const float* pv_template;      /* [P][3] */
+  const float* pv_shapedirs;     /* [P][3][num_shape] */
+  const float* pv_posedirs;      /* [P][3][9 (n_j - 1)] */
+  const int32_t* pv_skin_idx;    /* [P][8] */
+  const float* pv_skin_w;        /* [P][8], 0 = unused slot */
+  const float* reg_w;            /* [num_params] */
+  const float* keep_w;           /* [num_params] */
+  int32_t body_off;              /* -1 = no SMPL body priors */
+  const k2b_model* prior_model;  /* supplies the max-mixture prior when body_off >= 0 */
+} k2b_artic_desc;
+
+int k2b_artic_create(const k2b_artic_desc* desc, k2b_artic** out);
+void k2b_artic_destroy(k2b_artic* m);
+
+enum { K2B_ARTIC_EVAL = 0, K2B_ARTIC_ADAM = 1, K2B_ARTIC_LBFGS = 2 };
+typedef struct k2b_artic_fit_args {
+  int64_t num_frames;          /* B */
+  int32_t num_obs;             /* K <= 128 */
+  int32_t mode;                /* K2B_ARTIC_* */
+  int32_t num_iters;
+  int32_t conf_per_frame;
+  float lr;
+  float joint_loss_weight;
+  float keep_scale;            /* pose_preserve_weight^2 when the temporal term is on (seq_ind > 0), else 0 */
+  const int32_t* obs_idx;      /* [K] (device) */
+  const float* targets;        /* [B][K][3] */
+  const float* conf;           /* [K] | [B][K] | NULL */
+  const float* init_x;         /* [B][num_params] */
+  const float* keep_x;         /* [B][num_params] or NULL = init_x */
+  const uint8_t* frozen;       /* [num_params] 1 = not optimised, or NULL */
+  float* out_x;                /* [B][num_params] */
+  float* out_loss;             /* [B] */
+  float* out_grad;             /* [B][num_params], required for K2B_ARTIC_EVAL */
+  float* out_points;           /* [B][K][3] model points at the returned parameters, or NULL */
+  int32_t* out_evals;          /* [B] or NULL */
+  int32_t* out_gmm_component;  /* [B] or NULL (K2B_ARTIC_EVAL) */
+  void* workspace;
+  size_t workspace_bytes;      /* >= k2b_artic_workspace_bytes(...) */
+} k2b_artic_fit_args;
+
+size_t k2b_artic_workspace_bytes(const k2b_artic* m, int64_t num_frames, int32_t mode, int32_t num_iters);
+int k2b_artic_fit(const k2b_artic* m, const k2b_artic_fit_args* args, void* cuda_stream);
+
 /* FP32-FMA micro-benchmark used as the roofline denominator of the fit kernel:
  * returns achieved TFLOP/s (2 flop per FMA) over `iters` dependent-chain rounds. */
 int k2b_fma_peak(int iters, double* out_tflops, double* out_ms, void* cuda_stream);

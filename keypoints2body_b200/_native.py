@@ -95,6 +95,31 @@ class ReplayArgs(C.Structure):
     ]
 
 
+class ArticDesc(C.Structure):
+    _fields_ = [
+        ("num_joints", C.c_int32), ("num_shape", C.c_int32), ("num_params", C.c_int32), ("num_picked", C.c_int32),
+        ("parents", _c_int_p), ("J0", _c_float_p), ("JS", _c_float_p), ("pose_src", _c_int_p), ("shape_src", _c_int_p),
+        ("transl_src", C.c_int32),
+        ("pv_template", _c_float_p), ("pv_shapedirs", _c_float_p), ("pv_posedirs", _c_float_p),
+        ("pv_skin_idx", _c_int_p), ("pv_skin_w", _c_float_p), ("reg_w", _c_float_p), ("keep_w", _c_float_p),
+        ("body_off", C.c_int32), ("prior_model", C.c_void_p),
+    ]
+
+
+class ArticFitArgs(C.Structure):
+    _fields_ = [
+        ("num_frames", C.c_int64), ("num_obs", C.c_int32), ("mode", C.c_int32), ("num_iters", C.c_int32),
+        ("conf_per_frame", C.c_int32), ("lr", C.c_float), ("joint_loss_weight", C.c_float), ("keep_scale", C.c_float),
+        ("obs_idx", C.c_void_p), ("targets", C.c_void_p), ("conf", C.c_void_p), ("init_x", C.c_void_p),
+        ("keep_x", C.c_void_p), ("frozen", C.c_void_p), ("out_x", C.c_void_p), ("out_loss", C.c_void_p),
+        ("out_grad", C.c_void_p), ("out_points", C.c_void_p), ("out_evals", C.c_void_p),
+        ("out_gmm_component", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+ARTIC_EVAL, ARTIC_ADAM, ARTIC_LBFGS = 0, 1, 2
+
+
 class MeshArgs(C.Structure):
     _fields_ = [
         ("num_frames", C.c_int64), ("full_pose", C.c_void_p), ("shape", C.c_void_p),
@@ -117,7 +142,8 @@ class ShapeArgs(C.Structure):
 EXPORTS = (
     "k2b_model_create", "k2b_model_destroy", "k2b_fit_workspace_bytes", "k2b_fit_batch",
     "k2b_fit_batch_host", "k2b_chain_workspace_bytes", "k2b_chain_geometry", "k2b_fit_chain", "k2b_evaluate_batch", "k2b_linesearch_replay", "k2b_mesh_workspace_bytes", "k2b_mesh_batch",
-    "k2b_shape_workspace_bytes", "k2b_shape_pass", "k2b_mpjae", "k2b_fma_peak", "k2b_launch_count", "k2b_last_error", "k2b_version",
+    "k2b_shape_workspace_bytes", "k2b_shape_pass", "k2b_artic_create", "k2b_artic_destroy", "k2b_artic_workspace_bytes",
+    "k2b_artic_fit", "k2b_mpjae", "k2b_fma_peak", "k2b_launch_count", "k2b_last_error", "k2b_version",
 )
 
 _lib = None
@@ -150,6 +176,14 @@ def load_library():
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p, C.POINTER(st), C.c_void_p]
         fn.restype = C.c_int
+    lib.k2b_artic_create.argtypes = [C.POINTER(ArticDesc), C.POINTER(C.c_void_p)]
+    lib.k2b_artic_create.restype = C.c_int
+    lib.k2b_artic_destroy.argtypes = [C.c_void_p]
+    lib.k2b_artic_destroy.restype = None
+    lib.k2b_artic_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
+    lib.k2b_artic_workspace_bytes.restype = C.c_size_t
+    lib.k2b_artic_fit.argtypes = [C.c_void_p, C.POINTER(ArticFitArgs), C.c_void_p]
+    lib.k2b_artic_fit.restype = C.c_int
     lib.k2b_linesearch_replay.argtypes = [C.POINTER(ReplayArgs), C.c_void_p]
     lib.k2b_linesearch_replay.restype = C.c_int
     lib.k2b_shape_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
@@ -209,13 +243,13 @@ class NativeModel:
         self.num_vertices = weights.num_vertices
         self.num_extra = weights.num_extra
         keep = [weights.parents, weights.v_template, weights.shapedirs, weights.posedirs,
-                weights.J_regressor, weights.lbs_weights, weights.extra_vertex_ids,
-                np.ascontiguousarray(gmm.means), np.ascontiguousarray(gmm.chol),
-                np.ascontiguousarray(gmm.neg_log_w)]
+                weights.J_regressor, weights.lbs_weights, weights.extra_vertex_ids]
+        if gmm is not None:       # None: a mesh-only model (MANO, FLAME -- fitted through k2b_artic_fit)
+            keep += [np.ascontiguousarray(gmm.means), np.ascontiguousarray(gmm.chol), np.ascontiguousarray(gmm.neg_log_w)]
         desc = ModelDesc(
             weights.num_joints, weights.num_vertices, weights.num_shape, weights.num_extra,
             _ip(keep[0]), _fp(keep[1]), _fp(keep[2]), _fp(keep[3]), _fp(keep[4]), _fp(keep[5]),
-            _ip(keep[6]), _fp(keep[7]), _fp(keep[8]), _fp(keep[9]),
+            _ip(keep[6]), *( [_fp(keep[7]), _fp(keep[8]), _fp(keep[9])] if gmm is not None else [None, None, None]),
         )
         handle = C.c_void_p()
         with torch.cuda.device(self.device):

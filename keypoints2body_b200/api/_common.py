@@ -5,11 +5,12 @@ from __future__ import annotations
 import torch
 
 from ..core.joints.adapters import adapt_layout_and_conf
-from ..models.smpl_data import SMPLData, SMPLHData, SMPLXData
+from ..models.smpl_data import FLAMEData, MANOData, SMPLData, SMPLHData, SMPLXData
 
 OPTIMIZATION_BODY_MODELS = {"smpl", "smplh", "smplx", "mano", "flame"}
 SMPL_FAMILY = {"smpl", "smplh", "smplx"}
 PARAM_TYPES = {"smpl": SMPLData, "smplh": SMPLHData, "smplx": SMPLXData}
+MISC_PARAM_TYPES = {"mano": MANOData, "flame": FLAMEData}
 DEFAULT_MEAN_FILE = "./data/models/neutral_smpl_mean_params.h5"
 
 

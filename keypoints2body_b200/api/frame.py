@@ -15,10 +15,11 @@ from typing import Optional
 import torch
 
 from ..core.config import BodyModelConfig, FrameOptimizeConfig, ModelType
-from ..core.engine import OptimizeEngine, default_init_params, load_mean_pose_shape, upgrade_smpl_family_init_params
+from ..core.engine import (OptimizeEngine, default_init_params, default_init_params_for_model, load_mean_pose_shape,
+                           upgrade_smpl_family_init_params)
 from ..core.joints.adapters import normalize_frame_observations
 from ..models.smpl_data import BodyModelFitResult, BodyModelParams
-from ._common import (DEFAULT_MEAN_FILE, PARAM_TYPES, SMPL_FAMILY, canonical_layout, check_request,
+from ._common import (DEFAULT_MEAN_FILE, MISC_PARAM_TYPES, PARAM_TYPES, SMPL_FAMILY, canonical_layout, check_request,
                       dict_to_params, params_to_dict, resolve_device)
 from .model_factory import load_body_model
 
@@ -60,6 +61,20 @@ def optimize_params_frame(
         model = load_body_model(BodyModelConfig(model_type=body_model), device)
     engine = OptimizeEngine(model=model, frame_config=frame_cfg, device=device, model_type=body_model)
     fitter = engine.fitter
+
+    if body_model not in SMPL_FAMILY:          # MANO / FLAME (frame.py:144-150, 209-211)
+        j3d, conf_3d = j3d.to(device), conf_3d.to(device)
+        if prev_params is None:
+            init_params = default_init_params_for_model(body_model, model, j3d, device, frame_cfg.coordinate_mode)
+        else:
+            expected = MISC_PARAM_TYPES[body_model]
+            if not isinstance(prev_params, expected):
+                raise ValueError(f"prev_params must be {expected.__name__} for body_model={body_model}.")
+            init_params = prev_params.to(device)
+            if frame_cfg.coordinate_mode == "world" and init_params.transl is None:
+                init_params.transl = j3d[:, 0, :].detach()
+        return engine.fit_frame(init_params=init_params, j3d=j3d, conf_3d=conf_3d, seq_ind=0,
+                                target_model_indices=model_indices)
 
     if prev_params is None:
         mean_pose, mean_shape = load_mean_pose_shape(DEFAULT_MEAN_FILE, device)

@@ -27,11 +27,11 @@ import torch
 
 from ..core.config import BodyModelConfig, FrameOptimizeConfig, ModelType, SequenceOptimizeConfig
 from ..core.constants import FIX_FOOT_CONF, FIX_FOOT_IDX
-from ..core.engine import (OptimizeEngine, default_init_params, load_mean_pose_shape, optimize_shape_pass,
-                           upgrade_smpl_family_init_params)
+from ..core.engine import (OptimizeEngine, default_init_params, default_init_params_for_model, load_mean_pose_shape,
+                           optimize_shape_pass, upgrade_smpl_family_init_params)
 from ..core.joints.adapters import normalize_sequence_observations
 from ..models.smpl_data import BodyModelFitResult, BodyModelParams
-from ._common import (DEFAULT_MEAN_FILE, PARAM_TYPES, SMPL_FAMILY, canonical_layout, check_request,
+from ._common import (DEFAULT_MEAN_FILE, MISC_PARAM_TYPES, PARAM_TYPES, SMPL_FAMILY, canonical_layout, check_request,
                       dict_to_params, params_to_dict, resolve_device)
 from .model_factory import load_body_model
 
@@ -122,6 +122,22 @@ def fit_sequence_batched(fitter, xyz, conf, init: dict, seq_cfg: SequenceOptimiz
     return out
 
 
+def _fit_sequence_serial(engine, xyz, conf, prev, model_indices, seq_cfg) -> list[BodyModelFitResult]:
+    """The reference's frame loop as written (sequence.py:214-281): one ``fit_frame`` per frame, frame t starting from
+    frame t-1's result.  Used where the observations need the general articulated fit (MANO, FLAME, hand / face blocks of
+    SMPL-H / SMPL-X): one launch of ``k2b_artic_fit`` and one mesh pass per frame."""
+    results = []
+    for t in range(xyz.shape[0]):
+        frame = xyz[t:t + 1]
+        if seq_cfg.frame.coordinate_mode == "world" and prev.transl is None:
+            prev.transl = frame[:, 0, :].detach()
+        res = engine.fit_frame(init_params=prev, j3d=frame, conf_3d=conf[t], seq_ind=t, target_model_indices=model_indices)
+        results.append(res)
+        if seq_cfg.use_previous_frame_init:
+            prev = res.params
+    return results
+
+
 def optimize_params_sequence(
     joints_seq,
     *,
@@ -160,6 +176,17 @@ def optimize_params_sequence(
     engine = OptimizeEngine(model=model, frame_config=seq_cfg.frame, device=device, model_type=body_model)
     fitter = engine.fitter
 
+    if body_model not in SMPL_FAMILY:          # MANO / FLAME (sequence.py:155-158, 192-212)
+        xyz, conf = xyz.to(device), conf.to(device)
+        if init_params is None:
+            prev = default_init_params_for_model(body_model, model, xyz[0:1], device, seq_cfg.frame.coordinate_mode)
+        else:
+            expected = MISC_PARAM_TYPES[body_model]
+            if not isinstance(init_params, expected):
+                raise ValueError(f"init_params must be {expected.__name__} for body_model={body_model}.")
+            prev = init_params.to(device)
+        return _fit_sequence_serial(engine, xyz, conf, prev, model_indices, seq_cfg)
+
     mean_pose, mean_shape = load_mean_pose_shape(DEFAULT_MEAN_FILE, device)   # always, like sequence.py:139-141
     if seq_cfg.frame.joints_category != "GENERIC":
         betas_opt = optimize_shape_pass(fitter=fitter, seq_config=seq_cfg, init_mean_shape=mean_shape,
@@ -184,7 +211,14 @@ def optimize_params_sequence(
         init["transl"] = default_init_params(pose, init["betas"], xyz[0:1], fitter, seq_cfg.frame.joints_category,
                                              seq_cfg.frame.coordinate_mode).transl
 
-    if model_indices is not None and body_model in SMPL_FAMILY:
+    if model_indices is not None and not fitter.body_joints_only(model_indices):
+        # hand joints / vertex-picked landmarks among the observations: the general articulated fit, frame by frame
+        if seq_cfg.frame.coordinate_mode != "world":
+            raise NotImplementedError("hand / face observations are fitted in world coordinates (like the reference's "
+                                      "CameraSpaceFitter, which takes SMPL body joints only)")
+        start = dict_to_params(body_model, init)
+        return _fit_sequence_serial(engine, xyz.to(device), conf.to(device), start, model_indices, seq_cfg)
+    if model_indices is not None:
         # dict-block observations: into the fitter's observation slots (unobserved joints get confidence 0)
         xyz, conf = fitter.scatter_observations(xyz, conf, model_indices)
     out = fit_sequence_batched(fitter, xyz, conf, init, seq_cfg)

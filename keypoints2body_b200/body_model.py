@@ -58,7 +58,7 @@ def infer_model_type(model) -> str:
     if isinstance(mt, str):
         return mt
     n_j = int(_np(model.parents, np.int64).shape[0])
-    return {24: "smpl", 52: "smplh", 55: "smplx"}.get(n_j, "smpl")
+    return {24: "smpl", 52: "smplh", 55: "smplx", 16: "mano", 5: "flame"}.get(n_j, "smpl")
 
 
 def extract_weights(model, model_type: str | None = None, num_betas: int = 10,
@@ -73,13 +73,13 @@ def extract_weights(model, model_type: str | None = None, num_betas: int = 10,
     shapedirs = _np(model.shapedirs)
     if shapedirs.ndim != 3:
         raise ValueError("shapedirs must be (V,3,S)")
-    if model_type == "smplx":
+    if model_type in ("smplx", "flame"):
         expr_dirs = getattr(model, "expr_dirs", None)
         if expr_dirs is not None and shapedirs.shape[2] <= num_betas:
             shapedirs = np.concatenate([shapedirs[..., :num_betas], _np(expr_dirs)[..., :num_expression]], axis=2)
         shapedirs = shapedirs[..., : num_betas + num_expression]
         if shapedirs.shape[2] != num_betas + num_expression:
-            raise ValueError("SMPL-X needs betas + expression shape directions")
+            raise ValueError("SMPL-X / FLAME need betas + expression shape directions")
     else:
         shapedirs = shapedirs[..., :num_betas]
     if shapedirs.shape[2] not in (10, 20):

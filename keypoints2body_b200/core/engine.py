@@ -15,7 +15,8 @@ from typing import Optional
 import numpy as np
 import torch
 
-from ..models.smpl_data import BodyModelFitResult, BodyModelParams, SMPLData, SMPLHData, SMPLXData
+from ..models.smpl_data import (BodyModelFitResult, BodyModelParams, FLAMEData, MANOData, SMPLData, SMPLHData,
+                                SMPLXData)
 from .config import FrameOptimizeConfig, SequenceOptimizeConfig
 from .estimators.factory import create_estimator
 from .fitters.world_space import guess_init_transl_from_root
@@ -91,6 +92,22 @@ def default_init_params(mean_pose, mean_shape, joints_frame, fitter, joints_cate
         transl = guess_init_transl_from_root(fitter, pose, betas, joints_frame,
                                              joints_category="AMASS" if joints_category == "GENERIC" else joints_category)
     return SMPLData(betas=betas, global_orient=pose[:, :3], body_pose=pose[:, 3:], transl=transl)
+
+
+def default_init_params_for_model(model_type: str, model, joints_frame: torch.Tensor, device, coordinate_mode: str):
+    """Zero initialisation for the MANO / FLAME fitters, translation = the first observed joint (engine.py:131-167)."""
+    batch = joints_frame.shape[0]
+    num_betas = int(getattr(model, "num_betas", 10))
+    transl = joints_frame[:, 0, :].clone().detach().to(device) if coordinate_mode == "world" else None
+    z = lambda d: torch.zeros((batch, d), device=device)  # noqa: E731
+    if model_type == "mano":
+        return MANOData(betas=z(num_betas), global_orient=z(3), body_pose=z(0), transl=transl,
+                        hand_pose=z(int(getattr(model, "NUM_HAND_JOINTS", 15)) * 3))
+    if model_type == "flame":
+        return FLAMEData(betas=z(num_betas), global_orient=z(3), body_pose=z(0), transl=transl,
+                         expression=z(int(getattr(model, "num_expression_coeffs", 10)) or 10), jaw_pose=z(3),
+                         neck_pose=z(3), leye_pose=z(3), reye_pose=z(3))
+    raise ValueError(f"default_init_params_for_model is unsupported for {model_type}")
 
 
 def upgrade_smpl_family_init_params(base_params: SMPLData, model_type: str, model, device) -> BodyModelParams:

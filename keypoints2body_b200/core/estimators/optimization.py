@@ -22,9 +22,13 @@ class OptimizationEstimator:
     def __init__(self, model, frame_config: FrameOptimizeConfig, device, model_type: str = "smpl"):
         self.frame_config = frame_config
         if model_type in ("mano", "flame"):
-            raise NotImplementedError(
-                f"body_model='{model_type}' fitters are outside the accelerated path "
-                "(SURVEY.md section 8f row 4); use the reference implementation for them")
+            from ..fitters.misc_models import FLAMEFitter, MANOFitter
+
+            self._fitter = (MANOFitter if model_type == "mano" else FLAMEFitter)(
+                model=model, coordinate_mode=frame_config.coordinate_mode, step_size=frame_config.step_size,
+                num_iters_first=frame_config.num_iters_first, num_iters_followup=frame_config.num_iters_followup,
+                use_lbfgs=frame_config.use_lbfgs, device=device)
+            return
         common = dict(model_type=model_type, prior_folder=getattr(frame_config, "prior_folder", "./data/models/"))
         if frame_config.coordinate_mode == "camera":
             if model_type != "smpl":

@@ -328,6 +328,12 @@ class WorldSpaceFitter:
         self.last_shape_evals = out_evals
         return out_betas
 
+    def body_joints_only(self, model_indices) -> bool:
+        """True when every index addresses a fitted body joint exactly once: the body-keypoint kernels apply
+        (observations scattered into their slots); otherwise the general articulated fit takes the call."""
+        idx = [int(i) for i in torch.as_tensor(model_indices).reshape(-1).tolist()]
+        return all(0 <= i < self.num_obs for i in idx) and len(set(idx)) == len(idx)
+
     def scatter_observations(self, j3d, conf, model_indices):
         """Observations given against explicit model-joint indices (``target_model_indices``, the reference's
         GENERIC path, world_space.py:198-201) -> this fitter's fixed observation slots.
@@ -335,18 +341,18 @@ class WorldSpaceFitter:
         ``j3d`` (B,K,3), ``conf`` (K,) | (B,K) | None, ``model_indices`` (K,).  Slot i of the result holds the
         observation of model joint i; joints nobody observed get confidence 0, i.e. no loss and no gradient,
         which is exactly the sum the reference forms over the observed joints only.  Indices beyond the fitted
-        body joints (SMPL-H / SMPL-X hand joints, vertex-picked fingertips and face landmarks) need the finger
-        chains and the vertex branch inside the loop and are refused.
+        body joints (SMPL-H / SMPL-X hand joints, vertex-picked fingertips and face landmarks) are served by
+        ``fit_frame`` through the general articulated fit (csrc/artic_core.cuh), not by the batched kernels.
         """
         dev = self.device
         idx = [int(i) for i in torch.as_tensor(model_indices).reshape(-1).tolist()]
         if any(i < 0 or i >= self.num_obs for i in idx):
             raise NotImplementedError(
                 f"observations of model joints >= {self.num_obs} (hand joints, vertex-picked fingertips / face "
-                "landmarks) are not built yet: they need the finger chains and the vertex branch inside the "
-                "fitting loop (SURVEY.md section 8f row 2)")
+                "landmarks) go through fit_frame / optimize_params_frame / optimize_params_sequence (the general "
+                "articulated fit); the batched body-keypoint entry points take body joints only")
         if len(set(idx)) != len(idx):
-            raise NotImplementedError("a model joint observed more than once is not supported")
+            raise NotImplementedError("a model joint observed more than once: use fit_frame (general articulated fit)")
         j3d = _f32(j3d, dev)
         if j3d.dim() != 3 or j3d.shape[1] != len(idx):
             raise ValueError(f"j3d must be (B, {len(idx)}, 3) for {len(idx)} model indices, got {tuple(j3d.shape)}")
@@ -360,6 +366,36 @@ class WorldSpaceFitter:
         cfull = torch.zeros(conf.shape[:-1] + (self.num_obs,), device=dev)
         cfull[..., sel] = conf
         return full, cfull
+
+    def _fit_frame_articulated(self, init_params, j3d, conf_3d, seq_ind, idx, joint_loss_weight, pose_preserve_weight,
+                               freeze_betas) -> BodyModelFitResult:
+        """``fit_frame`` for observations beyond the body joints (world_space.py:198-201): every block the caller
+        supplied is optimised, in the reference's order; blocks left at None stay at the model's zero default."""
+        from .articulated import articulated_fit, get_articulated
+
+        am = get_articulated(self.native, with_body_priors=True)
+        blocks = {k: getattr(init_params, k, None) for k, _ in am.blocks}
+        if conf_3d is not None:
+            conf_3d = _f32(conf_3d, self.device)
+            if conf_3d.dim() == 2:
+                conf_3d = conf_3d[0]       # reference quirk, world_space.py:163-164
+            conf_3d = conf_3d[: len(idx)].contiguous()
+        iters = self.num_iters_first if seq_ind == 0 else self.num_iters_followup
+        p, loss, _evals, _pts = articulated_fit(am, blocks, j3d, conf_3d, idx, seq_ind=int(seq_ind), num_iters=iters,
+                                                use_lbfgs=self.use_lbfgs, lr=self.step_size,
+                                                joint_loss_weight=joint_loss_weight,
+                                                pose_preserve_weight=pose_preserve_weight, freeze_betas=freeze_betas)
+        given = {k: v for k, v in p.items() if blocks.get(k) is not None}
+        mesh = self.forward_batch(dict(p))
+        base = dict(betas=p["betas"], global_orient=p["global_orient"], body_pose=p["body_pose"], transl=p["transl"])
+        if isinstance(init_params, SMPLXData):
+            fitted = SMPLXData(**base, **{k: given.get(k) for k in ("left_hand_pose", "right_hand_pose", "expression",
+                                                                    "jaw_pose", "leye_pose", "reye_pose")})
+        elif isinstance(init_params, SMPLHData):
+            fitted = SMPLHData(**base, left_hand_pose=given.get("left_hand_pose"), right_hand_pose=given.get("right_hand_pose"))
+        else:
+            fitted = SMPLData(**base)
+        return BodyModelFitResult(params=fitted, vertices=mesh["vertices"], joints=mesh["joints"], loss=loss.sum())
 
     # ------------------------------------------------------------------ public
     def fit_batch(self, init: dict, j3d, conf=None, *, seq_ind=0, preserve_pose=None, num_iters=None,
@@ -615,6 +651,12 @@ class WorldSpaceFitter:
         if init_params.transl is None:
             raise ValueError("init_params.transl must be provided")
         if target_model_indices is not None:
+            idx = [int(i) for i in torch.as_tensor(target_model_indices).reshape(-1).tolist()]
+            if not self.body_joints_only(idx):
+                # hand joints, vertex-picked finger tips / face landmarks (or repeated indices): the general
+                # articulated fit (csrc/artic_core.cuh) instead of the body-keypoint kernels
+                return self._fit_frame_articulated(init_params, j3d, conf_3d, seq_ind, idx, joint_loss_weight,
+                                                   pose_preserve_weight, freeze_betas)
             j3d, conf_3d = self.scatter_observations(j3d, conf_3d, target_model_indices)
         elif self.joints_category == "GENERIC":
             raise ValueError("joints_category='GENERIC' needs target_model_indices")

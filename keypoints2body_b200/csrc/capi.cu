@@ -16,6 +16,7 @@
 #include "eval_kernel.cuh"
 #include "mesh_kernel.cuh"
 #include "replay_kernel.cuh"
+#include "artic_kernel.cuh"
 #include "shape_kernel.cuh"
 
 using namespace k2b;
@@ -46,6 +47,7 @@ cudaError_t upload(const std::vector<T>& h, T** d) {
 struct k2b_model {
   int num_joints = 0, num_vertices = 0, num_shape = 0, num_extra = 0;
   bool smpl24_ok = false;
+  bool fit_ok = false;     // SMPL body tree + pose prior present: the body-keypoint fit kernels apply
   int device = 0, num_sms = 0;
   float *chol = nullptr, *mu = nullptr, *nlw = nullptr, *rel = nullptr;
   float* prec = nullptr;   // [8][69][72] symmetric precisions L L^T (warp-per-sequence kernel)
@@ -72,11 +74,13 @@ extern "C" void k2b_model_destroy(k2b_model* m) {
 extern "C" int k2b_model_create(const k2b_model_desc* d, k2b_model** out) {
   if (!d || !out) return fail(K2B_EINVAL, "null argument");
   if (d->num_shape != 10 && d->num_shape != 20) return fail(K2B_EINVAL, "num_shape must be 10 or 20");
-  if (d->num_joints < 22) return fail(K2B_EINVAL, "need at least the 22 body joints");
+  // The body-keypoint fit kernels are written for the SMPL body tree (first 22 joints) and need the pose prior; any
+  // other model (MANO, FLAME) is a mesh-only model here: k2b_mesh_batch works, fits go through k2b_artic_fit.
   static const int body[22] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
-  for (int j = 0; j < 22; ++j)
-    if (d->parents[j] != body[j]) return fail(K2B_EUNSUPPORTED, "first 22 parents are not the SMPL body tree");
+  bool fit_ok = d->num_joints >= 22 && d->gmm_chol && d->gmm_means && d->gmm_neg_log_w;
+  for (int j = 0; fit_ok && j < 22; ++j) fit_ok = d->parents[j] == body[j];
   k2b_model* m = new k2b_model();
+  m->fit_ok = fit_ok;
   m->num_joints = d->num_joints;
   m->num_vertices = d->num_vertices;
   m->num_shape = d->num_shape;
@@ -88,7 +92,7 @@ extern "C" int k2b_model_create(const k2b_model_desc* d, k2b_model** out) {
   const int NS = d->num_shape;
   // packed Cholesky rows
   std::vector<float> chol((size_t)kGmmM * kCholStride, 0.f), mu((size_t)kGmmM * kMuStride, 0.f), nlw(kGmmM);
-  for (int c = 0; c < kGmmM; ++c) {
+  for (int c = 0; fit_ok && c < kGmmM; ++c) {
     for (int j = 0; j < kBodyDim; ++j) {
       for (int i = 0; i <= j; ++i)
         chol[(size_t)c * kCholStride + chol_row_off(j) + i] = d->gmm_chol[((size_t)c * kBodyDim + j) * kBodyDim + i];
@@ -98,7 +102,7 @@ extern "C" int k2b_model_create(const k2b_model_desc* d, k2b_model** out) {
   }
   // the same precisions as dense symmetric matrices P = L L^T (float64 product), rows padded to 72
   std::vector<float> prec((size_t)kGmmM * wc::kPFloats, 0.f);
-  for (int c = 0; c < kGmmM; ++c) {
+  for (int c = 0; fit_ok && c < kGmmM; ++c) {
     const float* L = d->gmm_chol + (size_t)c * kBodyDim * kBodyDim;
     for (int i = 0; i < kBodyDim; ++i)
       for (int j = 0; j <= i; ++j) {
@@ -175,6 +179,8 @@ void fill_adam_table(AdamTable& at, double lr) {
 
 int check_common(const k2b_model* m, long B, int num_obs, const void* expr) {
   if (!m) return fail(K2B_EINVAL, "null model");
+  if (!m->fit_ok)
+    return fail(K2B_EUNSUPPORTED, "this model is not an SMPL-family body with a pose prior: fit it with k2b_artic_fit");
   if (B <= 0) return fail(K2B_EINVAL, "num_frames must be positive");
   if (num_obs != 22 && num_obs != 24) return fail(K2B_EINVAL, "num_obs must be 22 (AMASS) or 24 (SMPL24)");
   if (num_obs == 24 && !m->smpl24_ok)
@@ -613,6 +619,127 @@ extern "C" int k2b_shape_pass(const k2b_model* m, const k2b_shape_args* a, void*
   p.hmax = lbfgs_history_capacity(a->num_iters);
   const int grid = (a->num_sequences + kShapeWarps - 1) / kShapeWarps;
   shape_pass_kernel<<<grid, 32 * kShapeWarps, shape_smem_bytes(m->num_shape), (cudaStream_t)stream>>>(p);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return K2B_OK;
+}
+
+// ---- general articulated fit (hands / face observations, MANO, FLAME) ---------------------------------------
+struct k2b_artic {
+  ar::ArticModel M{};
+  std::vector<void*> owned;
+  int num_sms = 0;
+};
+
+extern "C" void k2b_artic_destroy(k2b_artic* a) {
+  if (!a) return;
+  for (void* p : a->owned) cudaFree(p);
+  delete a;
+}
+
+extern "C" int k2b_artic_create(const k2b_artic_desc* d, k2b_artic** out) {
+  if (!d || !out) return fail(K2B_EINVAL, "null argument");
+  if (d->num_joints < 1 || d->num_joints > ar::kMaxJoints) return fail(K2B_EUNSUPPORTED, "1 .. 56 joints");
+  if (d->num_shape < 0 || d->num_shape > ar::kMaxShape) return fail(K2B_EUNSUPPORTED, "at most 20 shape coefficients");
+  if (d->num_params < 1 || d->num_params > ar::kMaxParams) return fail(K2B_EUNSUPPORTED, "at most 200 parameters");
+  if (!d->parents || !d->J0 || !d->JS || !d->pose_src || !d->shape_src || !d->reg_w || !d->keep_w)
+    return fail(K2B_EINVAL, "missing required array");
+  if (d->num_picked > 0 && (!d->pv_template || !d->pv_shapedirs || !d->pv_posedirs || !d->pv_skin_idx || !d->pv_skin_w))
+    return fail(K2B_EINVAL, "missing picked-vertex array");
+  if (d->body_off >= 0 && (!d->prior_model || d->body_off + kBodyDim > d->num_params))
+    return fail(K2B_EINVAL, "body priors need prior_model and 69 parameters at body_off");
+  for (int j = 0; j < d->num_joints; ++j)
+    if (d->parents[j] >= j) return fail(K2B_EINVAL, "parents must precede their children");
+  k2b_artic* a = new k2b_artic();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&a->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const int nj = d->num_joints, ns = d->num_shape, n = d->num_params, P = d->num_picked, npf = 9 * (nj - 1);
+  bool ok = true;
+  auto up = [&](const void* src, size_t bytes) -> const void* {
+    if (!ok || bytes == 0 || !src) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+      ok = false;
+      return nullptr;
+    }
+    a->owned.push_back(p);
+    return p;
+  };
+  ar::ArticModel& M = a->M;
+  M.nj = nj; M.ns = ns; M.n = n; M.npick = P; M.npf = npf;
+  M.parents = (const int*)up(d->parents, sizeof(int) * nj);
+  M.J0 = (const float*)up(d->J0, sizeof(float) * nj * 3);
+  M.JS = (const float*)up(d->JS, sizeof(float) * nj * 3 * (ns > 0 ? ns : 1));
+  M.pose_src = (const int*)up(d->pose_src, sizeof(int) * 3 * nj);
+  M.shape_src = (const int*)up(d->shape_src, sizeof(int) * (ns > 0 ? ns : 1));
+  M.transl_src = d->transl_src;
+  M.pv_t = (const float*)up(d->pv_template, sizeof(float) * P * 3);
+  M.pv_S = (const float*)up(d->pv_shapedirs, sizeof(float) * P * 3 * ns);
+  M.pv_P = (const float*)up(d->pv_posedirs, sizeof(float) * (size_t)P * 3 * npf);
+  M.pv_idx = (const int*)up(d->pv_skin_idx, sizeof(int) * P * ar::kMaxSkin);
+  M.pv_w = (const float*)up(d->pv_skin_w, sizeof(float) * P * ar::kMaxSkin);
+  M.reg_w = (const float*)up(d->reg_w, sizeof(float) * n);
+  M.keep_w = (const float*)up(d->keep_w, sizeof(float) * n);
+  M.body_off = d->body_off;
+  if (d->body_off >= 0) {      // the prior tables stay owned by the k2b_model, which must outlive this object
+    M.gmm_P = d->prior_model->prec;
+    M.gmm_mu = d->prior_model->mu;
+    M.gmm_nlw = d->prior_model->nlw;
+  }
+  if (!ok) {
+    k2b_artic_destroy(a);
+    return fail(K2B_ECUDA, "articulated model upload failed");
+  }
+  *out = a;
+  return K2B_OK;
+}
+
+namespace {
+int artic_grid(const k2b_artic* a, long B) {
+  const long blocks = (B + ar::kArticThreads - 1) / ar::kArticThreads;
+  const long cap = (long)a->num_sms * 4;
+  return (int)(blocks < cap ? blocks : cap);
+}
+}  // namespace
+
+extern "C" size_t k2b_artic_workspace_bytes(const k2b_artic* a, int64_t num_frames, int32_t mode, int32_t num_iters) {
+  if (!a || num_frames <= 0 || mode != K2B_ARTIC_LBFGS) return 256;
+  const long slots = (long)artic_grid(a, num_frames) * ar::kArticThreads;
+  return sizeof(float) * (size_t)slots * (size_t)Vecs::floats_per_frame(a->M.n, lbfgs_history_capacity(num_iters));
+}
+
+extern "C" int k2b_artic_fit(const k2b_artic* a, const k2b_artic_fit_args* g, void* stream) {
+  if (!a || !g) return fail(K2B_EINVAL, "null argument");
+  if (g->num_frames <= 0 || g->num_obs <= 0 || g->num_obs > ar::kMaxObs) return fail(K2B_EINVAL, "1 .. 128 observations");
+  if (g->mode < 0 || g->mode > 2) return fail(K2B_EINVAL, "unknown mode");
+  if (!g->obs_idx || !g->targets || !g->init_x || !g->out_x || !g->out_loss) return fail(K2B_EINVAL, "missing required array");
+  if (g->mode == K2B_ARTIC_EVAL && !g->out_grad) return fail(K2B_EINVAL, "evaluation needs out_grad");
+  ar::ArticFitParams p{};
+  p.M = a->M;
+  p.num_frames = g->num_frames;
+  p.K = g->num_obs;
+  p.mode = g->mode;
+  p.iters = g->num_iters;
+  p.conf_per_frame = g->conf_per_frame;
+  p.hmax = lbfgs_history_capacity(g->num_iters);
+  p.lr = g->lr;
+  p.joint_w2 = g->joint_loss_weight * g->joint_loss_weight;
+  p.keep_scale = g->keep_scale;
+  p.obs_idx = g->obs_idx; p.targets = g->targets; p.conf = g->conf; p.init_x = g->init_x; p.keep_x = g->keep_x;
+  p.frozen = g->frozen;
+  p.out_x = g->out_x; p.out_loss = g->out_loss; p.out_grad = g->out_grad; p.out_points = g->out_points;
+  p.out_evals = g->out_evals; p.out_comp = g->out_gmm_component;
+  if (g->mode == K2B_ARTIC_LBFGS) {
+    if (!g->workspace || g->workspace_bytes < k2b_artic_workspace_bytes(a, g->num_frames, g->mode, g->num_iters))
+      return fail(K2B_ENOMEM, "workspace too small");
+    p.ws = (float*)g->workspace;
+  }
+  for (int k = 1; k <= ar::kArticAdamTable; ++k) {
+    p.adam_step[k - 1] = (float)((double)g->lr / (1.0 - std::pow(0.9, (double)k)));
+    p.adam_bc2[k - 1] = (float)std::sqrt(1.0 - std::pow(0.999, (double)k));
+  }
+  ar::artic_fit_kernel<<<artic_grid(a, g->num_frames), ar::kArticThreads, 0, (cudaStream_t)stream>>>(p);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return K2B_OK;

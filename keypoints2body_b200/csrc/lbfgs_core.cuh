@@ -100,11 +100,13 @@ template <int N>
 struct ThreadOps {
   typedef Cols C;
   typedef Vecs V;
+  // N == 0: the vector length is a run-time property of the vectors (the general articulated fit, artic_core.cuh)
+  static K2B_HD int len(const V& v) { return N > 0 ? N : v.n; }
   static K2B_HD float dot_cur_d(const V& v, int cur) {
     const int og = v.gslot(cur), od = v.d();
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < len(v); ++i) {
       if (i & 1) a1 = fmaf(v.at(og + i), v.at(od + i), a1);
       else a0 = fmaf(v.at(og + i), v.at(od + i), a0);
     }
@@ -113,14 +115,14 @@ struct ThreadOps {
   static K2B_HD void set_trial(const C& c, const V& v, float tf) {
     const int od = v.d();
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, v.at(od + i), v.at(i));
+    for (int i = 0; i < len(v); ++i) c.X(i) = fmaf(tf, v.at(od + i), v.at(i));
   }
   // xk = x; returns max |flat_grad| (slot 0)
   static K2B_HD float begin_copy(const C& c, const V& v) {
     float gmax = 0.f;
     const int og = v.gslot(0);
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < len(v); ++i) {
       v.at(i) = c.X(i);
       gmax = fmaxf(gmax, fabsf(v.at(og + i)));
     }
@@ -130,7 +132,7 @@ struct ThreadOps {
   static K2B_HD void neg_grad(const C& c, const V& v, int g0) {
     const int og = v.gslot(g0);
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) c.X(i) = -v.at(og + i);
+    for (int i = 0; i < len(v); ++i) c.X(i) = -v.at(og + i);
   }
   // later outer iterations: history update + two-loop recursion (lbfgs.py:399-442); leaves q in the x column
   static K2B_HD void update_direction(const C& c, const V& v, int g0, int slot_prev_grad, float tf, int& num_old,
@@ -143,7 +145,7 @@ struct ThreadOps {
     const int oy = v.y(h), os = v.s(h);
     float ys0 = 0.f, ys1 = 0.f, yy0 = 0.f, yy1 = 0.f;
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < len(v); ++i) {
       const float gi = v.at(og + i);
       const float yi = gi - v.at(op + i);
       const float si = v.at(od + i) * tf;
@@ -167,30 +169,30 @@ struct ThreadOps {
       const int oyk = v.y(hk), osk = v.s(hk);
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll kVecUnroll
-      for (int i = 0; i < N; ++i) {
+      for (int i = 0; i < len(v); ++i) {
         if (i & 1) a1 = fmaf(v.at(osk + i), c.X(i), a1);
         else a0 = fmaf(v.at(osk + i), c.X(i), a0);
       }
       const float a = (a0 + a1) * v.at(v.ro(hk));
       v.at(v.al(hk)) = a;
 #pragma unroll kVecUnroll
-      for (int i = 0; i < N; ++i) c.X(i) = fmaf(-a, v.at(oyk + i), c.X(i));
+      for (int i = 0; i < len(v); ++i) c.X(i) = fmaf(-a, v.at(oyk + i), c.X(i));
     }
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) c.X(i) *= H_diag;
+    for (int i = 0; i < len(v); ++i) c.X(i) *= H_diag;
 #pragma unroll 1
     for (int k = 0; k < num_old; ++k) {
       const int hk = (head + k) % v.hmax;
       const int oyk = v.y(hk), osk = v.s(hk);
       float b0 = 0.f, b1 = 0.f;
 #pragma unroll kVecUnroll
-      for (int i = 0; i < N; ++i) {
+      for (int i = 0; i < len(v); ++i) {
         if (i & 1) b1 = fmaf(v.at(oyk + i), c.X(i), b1);
         else b0 = fmaf(v.at(oyk + i), c.X(i), b0);
       }
       const float coef = v.at(v.al(hk)) - (b0 + b1) * v.at(v.ro(hk));
 #pragma unroll kVecUnroll
-      for (int i = 0; i < N; ++i) c.X(i) = fmaf(coef, v.at(osk + i), c.X(i));
+      for (int i = 0; i < len(v); ++i) c.X(i) = fmaf(coef, v.at(osk + i), c.X(i));
     }
   }
   // d = q; sum |g|, g.d, max |d|
@@ -200,7 +202,7 @@ struct ThreadOps {
     gsum = 0.f;
     dmax = 0.f;
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < len(v); ++i) {
       const float gi = v.at(og + i), di = c.X(i);
       v.at(od + i) = di;
       gsum += fabsf(gi);
@@ -212,14 +214,14 @@ struct ThreadOps {
   // first trial point: x = xk + t d with d still in the x column
   static K2B_HD void first_trial(const C& c, const V& v, float tf) {
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) c.X(i) = fmaf(tf, c.X(i), v.at(i));
+    for (int i = 0; i < len(v); ++i) c.X(i) = fmaf(tf, c.X(i), v.at(i));
   }
   // xk += t d (_add_grad); returns max |t d|
   static K2B_HD float move_iterate(const C& c, const V& v, float tf) {
     const int od = v.d();
     float dtmax = 0.f;
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < len(v); ++i) {
       const float di = v.at(od + i);
       v.at(i) = fmaf(tf, di, v.at(i));
       dtmax = fmaxf(dtmax, fabsf(di * tf));
@@ -230,7 +232,7 @@ struct ThreadOps {
     float gmax = 0.f;
     const int og = v.gslot(slot);
 #pragma unroll kVecUnroll
-    for (int i = 0; i < N; ++i) gmax = fmaxf(gmax, fabsf(v.at(og + i)));
+    for (int i = 0; i < len(v); ++i) gmax = fmaxf(gmax, fabsf(v.at(og + i)));
     return gmax;
   }
   // line-search replay (1-D surrogate, N == 1): iterate 0, direction 1, flat_grad = g.d

@@ -57,6 +57,11 @@ def _hand_centres(sign: float) -> list[tuple]:
     return out
 
 
+# MANO: wrist + five 3-joint finger chains (16 joints); FLAME: head root, neck, jaw, two eyes (5 joints) [smplx-from-memory]
+MANO_PARENTS = [-1] + _hand_parents(0, 1)
+FLAME_PARENTS = [-1, 0, 1, 1, 1]
+
+
 def skeleton(model_type: str):
     """(parents list, (n_j,3) float64 T-pose joint centres) for a model type."""
     if model_type == "smpl":
@@ -69,14 +74,27 @@ def skeleton(model_type: str):
         face = [(0.00, 0.33, 0.06), (0.03, 0.40, 0.09), (-0.03, 0.40, 0.09)]
         centres = _BODY22_CENTRES + face + _hand_centres(1.0) + _hand_centres(-1.0)
         return SMPLX_PARENTS, np.asarray(centres)
+    if model_type == "mano":
+        centres = [(0.0, 0.0, 0.0)]
+        for f in range(5):
+            for k in range(3):
+                centres.append((0.09 + 0.03 * k, 0.005 * (2 - f), 0.02 * (f - 2)))
+        return MANO_PARENTS, np.asarray(centres)
+    if model_type == "flame":
+        centres = [(0.0, 0.0, 0.0), (0.0, 0.06, -0.01), (0.0, 0.08, 0.05), (0.03, 0.13, 0.07), (-0.03, 0.13, 0.07)]
+        return FLAME_PARENTS, np.asarray(centres)
     raise ValueError(f"no synthetic skeleton for model_type={model_type}")
 
 
-_NUM_VERTS = {"smpl": 6890, "smplh": 6890, "smplx": 10475}
+_NUM_VERTS = {"smpl": 6890, "smplh": 6890, "smplx": 10475, "mano": 778, "flame": 5023}
 _NUM_EXTRA = 21  # vertex-picked extra joints (nose/eyes/ears/feet/finger tips)
+# SMPL-H / SMPL-X carry enough vertex-picked joints for the reference's dict-block indices (hands 25..66, face 67..,
+# constants.py:65-71): 52 + 21 = 73 and 55 + 76 = 131 model joints; MANO: 5 finger tips; FLAME: 51 landmarks
+_NUM_EXTRA_BY_TYPE = {"smpl": 21, "smplh": 21, "smplx": 21, "mano": 5, "flame": 51}
+NUM_EXTRA_SMPLX_BLOCKS = 76     # make_body_model("smplx", num_extra=76): 131 model joints, enough for a 64-landmark face block
 
 
-def make_body_model(model_type: str = "smpl", seed: int = 0, dtype=torch.float32):
+def make_body_model(model_type: str = "smpl", seed: int = 0, dtype=torch.float32, num_extra: Optional[int] = None):
     """Random body-model weights of the official shapes.
 
     Returns a namespace with the smplx buffer names (``v_template (V,3)``,
@@ -89,11 +107,12 @@ def make_body_model(model_type: str = "smpl", seed: int = 0, dtype=torch.float32
     """
     parents, centres = skeleton(model_type)
     n_j, n_v = len(parents), _NUM_VERTS[model_type]
-    n_shape = 20 if model_type == "smplx" else 10
+    n_shape = 20 if model_type in ("smplx", "flame") else 10
+    scale = {"mano": 0.2, "flame": 0.25}.get(model_type, 1.0)      # hand / head sized vertex clouds and blend shapes
     g = torch.Generator().manual_seed(seed)
     owner = torch.arange(n_v) % n_j
     c = torch.as_tensor(centres, dtype=torch.float64)
-    v_template = c[owner] + 0.04 * torch.randn(n_v, 3, generator=g, dtype=torch.float64)
+    v_template = c[owner] + 0.04 * scale * torch.randn(n_v, 3, generator=g, dtype=torch.float64)
     J_regressor = torch.zeros(n_j, n_v, dtype=torch.float64)
     J_regressor[owner, torch.arange(n_v)] = 1.0
     J_regressor /= J_regressor.sum(dim=1, keepdim=True)
@@ -102,9 +121,12 @@ def make_body_model(model_type: str = "smpl", seed: int = 0, dtype=torch.float32
     lbs = torch.zeros(n_v, n_j, dtype=torch.float64)
     lbs[torch.arange(n_v), owner] += 0.7
     lbs[torch.arange(n_v), par_owner] += 0.3
-    shapedirs = 0.01 * torch.randn(n_v, 3, n_shape, generator=g, dtype=torch.float64)
-    posedirs = 0.001 * torch.randn((n_j - 1) * 9, 3 * n_v, generator=g, dtype=torch.float64)
-    extra = torch.randperm(n_v, generator=g)[:_NUM_EXTRA].sort().values
+    shapedirs = 0.01 * scale * torch.randn(n_v, 3, n_shape, generator=g, dtype=torch.float64)
+    posedirs = 0.001 * scale * torch.randn((n_j - 1) * 9, 3 * n_v, generator=g, dtype=torch.float64)
+    perm = torch.randperm(n_v, generator=g)
+    n_extra = _NUM_EXTRA_BY_TYPE[model_type] if num_extra is None else int(num_extra)
+    # the first 21 are the round-1 set (goldens depend on them); further ones are appended
+    extra = torch.cat([perm[:min(n_extra, _NUM_EXTRA)].sort().values, perm[_NUM_EXTRA:n_extra].sort().values])
     m = SimpleNamespace(
         model_type=model_type,
         v_template=v_template.to(dtype),
@@ -116,7 +138,7 @@ def make_body_model(model_type: str = "smpl", seed: int = 0, dtype=torch.float32
         extra_vertex_ids=extra.long(),
         num_betas=10,
         NUM_HAND_JOINTS=15,
-        num_expression_coeffs=10 if model_type == "smplx" else 0,
+        num_expression_coeffs=10 if model_type in ("smplx", "flame") else 0,
         NUM_BODY_JOINTS=21 if model_type != "smpl" else 23,
     )
     return m

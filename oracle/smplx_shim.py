@@ -61,6 +61,15 @@ class BodyModelShim(nn.Module):
 
     def _full_pose(self, global_orient, body_pose, kw):
         B = global_orient.shape[0]
+        if self.model_type in ("mano", "flame"):
+            def need(name, dim):
+                v = kw.get(name)
+                return v if v is not None else torch.zeros(B, dim, dtype=global_orient.dtype, device=global_orient.device)
+            if self.model_type == "mano":          # [go | hand45]
+                return torch.cat([global_orient, need("hand_pose", 45)], dim=1)
+            # FLAME joint order: head root, neck, jaw, left eye, right eye
+            return torch.cat([global_orient, need("neck_pose", 3), need("jaw_pose", 3), need("leye_pose", 3),
+                              need("reye_pose", 3)], dim=1)
 
         def opt(name, dim):
             v = kw.get(name)
@@ -77,13 +86,18 @@ class BodyModelShim(nn.Module):
         face = [opt("jaw_pose", 3), opt("leye_pose", 3), opt("reye_pose", 3)]
         return torch.cat([global_orient, body] + face + hands, dim=1)
 
-    def forward(self, global_orient=None, body_pose=None, betas=None, transl=None,
-                return_full_pose=False, **kw):
+    def forward(self, global_orient=None, body_pose=None, betas=None, transl=None, left_hand_pose=None,
+                right_hand_pose=None, expression=None, jaw_pose=None, leye_pose=None, reye_pose=None,
+                hand_pose=None, neck_pose=None, return_full_pose=False):
+        # every block is a NAMED parameter: the reference's MANO / FLAME fitters keep only the keyword arguments that
+        # inspect.signature(model.forward) lists (core/fitters/misc_models.py:12-15)
+        kw = dict(left_hand_pose=left_hand_pose, right_hand_pose=right_hand_pose, expression=expression,
+                  jaw_pose=jaw_pose, leye_pose=leye_pose, reye_pose=reye_pose, hand_pose=hand_pose, neck_pose=neck_pose)
         B = global_orient.shape[0]
         dt, dev = global_orient.dtype, global_orient.device
         full_pose = self._full_pose(global_orient, body_pose, kw)
         shape = betas
-        if self.model_type == "smplx":
+        if self.model_type in ("smplx", "flame"):
             expr = kw.get("expression")
             if expr is None:
                 expr = torch.zeros(B, self.num_expression_coeffs, dtype=dt, device=dev)

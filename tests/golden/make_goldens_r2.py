@@ -291,8 +291,102 @@ def section_adam_pert():
     save("r2_adam_pert.npz", G)
 
 
+def generic_problem(mt, B, seed):
+    """Ground-truth parameters with articulated hands / face, targets = the model's joints at them + 3 mm noise, and an
+    initialisation a little off.  Shared with the tests (regenerated from the seed)."""
+    from oracle.problems import articulated_problem
+
+    return articulated_problem(mt, B, seed)
+
+
+def section_generic():
+    """Observations of hands / face (dict-block indices: kinematic finger joints and vertex-picked landmarks) through the
+    reference's WorldSpaceFitter GENERIC path (world_space.py:198-201), and its MANO / FLAME fitters
+    (core/fitters/misc_models.py:18-359).  Adam: strict goldens; L-BFGS: losses and evaluation counts."""
+    ref, tmp = setup()
+    from keypoints2body.core.fitters.misc_models import FLAMEFitter, MANOFitter
+    from keypoints2body.core.fitters.world_space import WorldSpaceFitter
+    from keypoints2body.models.smpl_data import FLAMEData, MANOData, SMPLHData, SMPLXData
+
+    from oracle.problems import articulated_problem
+
+    G = {}
+    with ref_loader.reference_cwd(tmp):
+        for mt in ("smplx", "smplh", "mano", "flame"):
+            model, tgt, idx, init, B = articulated_problem(mt, 3, seed=700)
+            cls = {"smplx": SMPLXData, "smplh": SMPLHData, "mano": MANOData, "flame": FLAMEData}[mt]
+            for opt, lbfgs in (("adam", False), ("lbfgs", True)):
+                for seq_ind in (0, 2):
+                    if mt in ("smplx", "smplh"):
+                        fit = WorldSpaceFitter(model, step_size=1e-2, num_iters_first=10, num_iters_followup=10, use_lbfgs=lbfgs,
+                                               joints_category="GENERIC")
+                    else:
+                        fit = (MANOFitter if mt == "mano" else FLAMEFitter)(model, coordinate_mode="world", step_size=1e-2,
+                                                                            num_iters_first=10, num_iters_followup=10,
+                                                                            use_lbfgs=lbfgs)
+                    outs = {}
+                    with LbfgsSpy() as spy:
+                        for b in range(B):
+                            p0 = cls(**{k: (v[b:b + 1] if v is not None else None) for k, v in init.items()})
+                            r = fit.fit_frame(p0, tgt[b:b + 1], torch.ones(len(idx)), seq_ind=seq_ind, target_model_indices=idx)
+                            for k in init:
+                                v = getattr(r.params, k)
+                                if v is not None:
+                                    outs.setdefault(k, []).append(v)
+                            outs.setdefault("joints", []).append(r.joints)
+                            outs.setdefault("loss", []).append(r.loss.reshape(1))
+                            outs.setdefault("verts0", []).append(r.vertices[:, :64])
+                    tag = f"{mt}_{opt}_s{seq_ind}"
+                    for k, v in outs.items():
+                        G[f"{tag}_{k}"] = torch.cat(v)
+                    if lbfgs:
+                        G[f"{tag}_evals"] = np.asarray(spy.evals, np.int32)
+                    print(tag, "loss", [round(float(x), 2) for x in outs["loss"]], flush=True)
+    save("r2_generic.npz", G)
+
+
+def section_generic_api():
+    """The reference's PUBLIC API on the articulated inputs: optimize_params_sequence for MANO / FLAME (raw model joint
+    order, api/sequence.py:155-158, 192-281) and for SMPL-X dict blocks body + both hands + face (adapters.py:224-380),
+    optimize_params_frame for SMPL-H dict blocks; Adam, 4-frame chains from the default initialisation."""
+    ref, tmp = setup()
+    from oracle.problems import articulated_problem
+
+    G = {}
+    with ref_loader.reference_cwd(tmp):
+        for mt in ("mano", "flame"):
+            model, tgt, idx, init, B = articulated_problem(mt, 4, seed=710)
+            res = ref.optimize_params_sequence(tgt.numpy(), body_model=mt, model=model,
+                                               config=dict(frame=dict(use_lbfgs=False)))
+            names = [k for k in init if init[k].shape[-1] > 0]
+            for k in names:
+                G[f"api_{mt}_{k}"] = torch.cat([getattr(r.params, k) for r in res])
+            G[f"api_{mt}_joints"] = torch.cat([r.joints for r in res])
+            G[f"api_{mt}_loss"] = torch.stack([r.loss.reshape(()) for r in res])
+            print(mt, "loss", [round(float(r.loss), 2) for r in res], flush=True)
+        for mt in ("smplx", "smplh"):
+            model, tgt, idx, init, B = articulated_problem(mt, 3, seed=711)
+            blocks = {"body": tgt[:, :22].numpy(), "left_hand": tgt[:, 22:43].numpy(), "right_hand": tgt[:, 43:64].numpy()}
+            if mt == "smplx":
+                blocks["face"] = tgt[:, 64:84].numpy()
+            if mt == "smplx":
+                res = ref.optimize_params_sequence(blocks, body_model=mt, model=model,
+                                                   config=dict(frame=dict(use_lbfgs=False)))
+            else:
+                res = [ref.optimize_params_frame({k: v[0] for k, v in blocks.items()}, body_model=mt, model=model,
+                                                 config=dict(use_lbfgs=False))]
+            for k in init:
+                v0 = getattr(res[0].params, k, None)
+                if v0 is not None:
+                    G[f"api_{mt}_{k}"] = torch.cat([getattr(r.params, k) for r in res])
+            G[f"api_{mt}_joints"] = torch.cat([r.joints for r in res])
+            G[f"api_{mt}_loss"] = torch.stack([r.loss.reshape(()) for r in res])
+            print(mt, "loss", [round(float(r.loss), 2) for r in res], flush=True)
+    save("r2_generic_api.npz", G)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     sys.path.insert(0, HERE)
     {"points": section_points, "dist": section_dist, "dist64": section_dist64, "chains": section_chains,
-     "adam": section_adam, "adam_pert": section_adam_pert}[sys.argv[1]]()
+     "adam": section_adam, "adam_pert": section_adam_pert, "generic": section_generic, "generic_api": section_generic_api}[sys.argv[1]]()

@@ -14,7 +14,7 @@ from keypoints2body_b200 import _native as nat
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 STRUCTS = {"k2b_model_desc": nat.ModelDesc, "k2b_fit_args": nat.FitArgs, "k2b_chain_args": nat.ChainArgs,
            "k2b_eval_args": nat.EvalArgs, "k2b_mesh_args": nat.MeshArgs, "k2b_shape_args": nat.ShapeArgs,
-           "k2b_replay_args": nat.ReplayArgs}
+           "k2b_replay_args": nat.ReplayArgs, "k2b_artic_desc": nat.ArticDesc, "k2b_artic_fit_args": nat.ArticFitArgs}
 
 pytestmark = pytest.mark.skipif(shutil.which("gcc") is None, reason="gcc needed")
 

@@ -232,5 +232,11 @@ def test_explicit_target_model_indices(generic_goldens, weights, gmm):
                       transl=torch.zeros(1, 3), left_hand_pose=torch.zeros(1, 45), right_hand_pose=torch.zeros(1, 45),
                       expression=torch.zeros(1, 10), jaw_pose=torch.zeros(1, 3), leye_pose=torch.zeros(1, 3),
                       reye_pose=torch.zeros(1, 3))
-    with pytest.raises(NotImplementedError):     # a hand joint of SMPL-X
-        fx.fit_frame(xinit, torch.zeros(1, 2, 3), torch.ones(2), target_model_indices=torch.tensor([0, 30]))
+    # a hand joint of SMPL-X: served by the general articulated fit (tests/test_gpu_articulated.py pins it); an index
+    # beyond the model's joints is an error; the batched body-keypoint entry points still refuse hand joints
+    rx = fx.fit_frame(xinit, torch.zeros(1, 2, 3), torch.ones(2), target_model_indices=torch.tensor([0, 30]))
+    assert rx.params.left_hand_pose.shape == (1, 45) and torch.isfinite(rx.loss)
+    with pytest.raises(ValueError):
+        fx.fit_frame(xinit, torch.zeros(1, 2, 3), torch.ones(2), target_model_indices=torch.tensor([0, 4000]))
+    with pytest.raises(NotImplementedError):
+        fx.scatter_observations(torch.zeros(1, 2, 3), torch.ones(2), torch.tensor([0, 30]))

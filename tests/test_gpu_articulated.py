@@ -1,0 +1,194 @@
+"""GPU tests of the general articulated fit (k2b_artic_fit): hand / face observations for SMPL-H / SMPL-X, MANO, FLAME.
+
+Goldens: tests/golden/r2_generic.npz (the reference's WorldSpaceFitter GENERIC path and its MANOFitter / FLAMEFitter,
+called directly) and r2_generic_api.npz (the reference's optimize_params_frame / optimize_params_sequence on the same
+kinds of input), both produced from the unmodified reference by tests/golden/make_goldens_r2.py.  Adam: G2 bars;
+L-BFGS: torch's evaluation budget and the final loss range (see tests/test_gpu_lbfgs_parity.py for why single L-BFGS
+trajectories are not comparable number by number).  The CPU twin on the host emulation is tests/test_artic_emul.py.
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def G():
+    return dict(np.load(os.path.join(HERE, "golden", "r2_generic.npz")))
+
+
+@pytest.fixture(scope="module")
+def A():
+    return dict(np.load(os.path.join(HERE, "golden", "r2_generic_api.npz")))
+
+
+@pytest.fixture()
+def asset_cwd(tmp_path, monkeypatch):
+    from keypoints2body_b200 import synthetic as syn
+
+    syn.write_assets(str(tmp_path / "data" / "models"), seed=0)
+    monkeypatch.chdir(tmp_path)
+    return tmp_path
+
+
+def _model(mt):
+    from keypoints2body_b200 import synthetic as syn
+
+    return syn.make_body_model(mt, seed=0, num_extra=syn.NUM_EXTRA_SMPLX_BLOCKS if mt == "smplx" else None)
+
+
+def _fitter(mt, lbfgs, gmm):
+    from keypoints2body_b200.core.fitters.misc_models import FLAMEFitter, MANOFitter
+    from keypoints2body_b200.core.fitters.world_space import WorldSpaceFitter
+
+    if mt in ("smplx", "smplh"):
+        return WorldSpaceFitter(_model(mt), step_size=1e-2, num_iters_first=10, num_iters_followup=10, use_lbfgs=lbfgs,
+                                joints_category="GENERIC", model_type=mt, gmm=gmm)
+    return (MANOFitter if mt == "mano" else FLAMEFitter)(_model(mt), coordinate_mode="world", step_size=1e-2,
+                                                         num_iters_first=10, num_iters_followup=10, use_lbfgs=lbfgs)
+
+
+def _data_cls(mt):
+    import keypoints2body_b200 as k2b
+
+    return {"smplx": k2b.SMPLXData, "smplh": k2b.SMPLHData, "mano": k2b.MANOData, "flame": k2b.FLAMEData}[mt]
+
+
+@pytest.mark.parametrize("mt", ["smplx", "smplh", "mano", "flame"])
+@pytest.mark.parametrize("seq_ind", [0, 2])
+def test_fit_frame_adam_matches_reference(G, gmm, mt, seq_ind):
+    from oracle.problems import articulated_problem
+
+    _, tgt, idx, init, B = articulated_problem(mt, 3, seed=700)
+    fit, cls = _fitter(mt, False, gmm), _data_cls(mt)
+    tag = f"{mt}_adam_s{seq_ind}"
+    worst = {}
+    for b in range(B):
+        p0 = cls(**{k: v[b:b + 1].cuda() for k, v in init.items()})
+        r = fit.fit_frame(p0, tgt[b:b + 1], torch.ones(len(idx)), seq_ind=seq_ind, target_model_indices=idx)
+        for k in init:
+            if f"{tag}_{k}" not in G or init[k].shape[-1] == 0:
+                continue
+            d = float(np.abs(getattr(r.params, k).cpu().numpy() - G[f"{tag}_{k}"][b]).max())
+            worst[k] = max(worst.get(k, 0.0), d)
+        nj = G[f"{tag}_joints"].shape[1]
+        assert r.joints.shape == (1, nj, 3)
+        worst["joints"] = max(worst.get("joints", 0.0), float(np.abs(r.joints.cpu().numpy() - G[f"{tag}_joints"][b]).max()))
+        worst["verts"] = max(worst.get("verts", 0.0), float(np.abs(r.vertices[:, :64].cpu().numpy() - G[f"{tag}_verts0"][b]).max()))
+        np.testing.assert_allclose(float(r.loss), float(G[f"{tag}_loss"][b]), rtol=1e-4)
+    print(tag, {k: f"{v:.1e}" for k, v in worst.items()})
+    for k, v in worst.items():
+        assert v < (1e-5 if k == "transl" else 1e-4), (k, v)
+
+
+@pytest.mark.parametrize("mt", ["smplx", "smplh", "mano", "flame"])
+def test_fit_frame_lbfgs_budget_and_loss(G, gmm, mt):
+    from oracle.problems import articulated_problem
+
+    _, tgt, idx, init, B = articulated_problem(mt, 3, seed=700)
+    fit, cls = _fitter(mt, True, gmm), _data_cls(mt)
+    for seq_ind in (0, 2):
+        tag = f"{mt}_lbfgs_s{seq_ind}"
+        losses = []
+        for b in range(B):
+            p0 = cls(**{k: v[b:b + 1].cuda() for k, v in init.items()})
+            r = fit.fit_frame(p0, tgt[b:b + 1], torch.ones(len(idx)), seq_ind=seq_ind, target_model_indices=idx)
+            losses.append(float(r.loss))
+        ref = G[f"{tag}_loss"]
+        print(tag, "loss", np.round(losses, 1), "reference", np.round(ref, 1))
+        assert np.all(np.asarray(losses) < 1.25 * ref) and np.median(np.asarray(losses) / ref) < 1.05
+
+
+@pytest.mark.parametrize("mt", ["mano", "flame"])
+def test_sequence_api_mano_flame(A, mt, asset_cwd):
+    """optimize_params_sequence(body_model='mano' | 'flame') against the reference's own call (Adam, 4-frame chain)."""
+    import keypoints2body_b200 as k2b
+    from oracle.problems import articulated_problem
+
+    _, tgt, idx, init, B = articulated_problem(mt, 4, seed=710)
+    res = k2b.optimize_params_sequence(tgt.numpy(), body_model=mt, model=_model(mt), config=dict(frame=dict(use_lbfgs=False)))
+    assert len(res) == B and isinstance(res[0].params, _data_cls(mt))
+    for k in init:
+        if f"api_{mt}_{k}" not in A or init[k].shape[-1] == 0:
+            continue
+        got = torch.cat([getattr(r.params, k) for r in res]).cpu().numpy()
+        assert np.abs(got - A[f"api_{mt}_{k}"]).max() < 1e-4, k
+    joints = torch.cat([r.joints for r in res]).cpu().numpy()
+    assert np.abs(joints - A[f"api_{mt}_joints"]).max() < 1e-4
+    np.testing.assert_allclose([float(r.loss) for r in res], A[f"api_{mt}_loss"], rtol=1e-4)
+    # the single-frame entry point is the sequence's first frame
+    r0 = k2b.optimize_params_frame(tgt[0].numpy(), body_model=mt, model=_model(mt), config=dict(use_lbfgs=False))
+    np.testing.assert_allclose(float(r0.loss), float(A[f"api_{mt}_loss"][0]), rtol=1e-4)
+
+
+def test_sequence_api_smplx_dict_blocks(A, asset_cwd):
+    """Dict input with body + left_hand + right_hand + face blocks through optimize_params_sequence (SMPL-X) and
+    optimize_params_frame (SMPL-H) from the default (mean-pose) initialisation, against the reference's own calls."""
+    import keypoints2body_b200 as k2b
+    from oracle.problems import articulated_problem
+
+    for mt in ("smplx", "smplh"):
+        _, tgt, idx, init, B = articulated_problem(mt, 3, seed=711)
+        blocks = {"body": tgt[:, :22].numpy(), "left_hand": tgt[:, 22:43].numpy(), "right_hand": tgt[:, 43:64].numpy()}
+        if mt == "smplx":
+            blocks["face"] = tgt[:, 64:84].numpy()
+            res = k2b.optimize_params_sequence(blocks, body_model=mt, model=_model(mt), config=dict(frame=dict(use_lbfgs=False)))
+        else:
+            res = [k2b.optimize_params_frame({k: v[0] for k, v in blocks.items()}, body_model=mt, model=_model(mt),
+                                             config=dict(use_lbfgs=False))]
+        worst = {}
+        for k in init:
+            if f"api_{mt}_{k}" not in A:
+                continue
+            got = torch.cat([getattr(r.params, k) for r in res]).cpu().numpy()
+            worst[k] = float(np.abs(got - A[f"api_{mt}_{k}"]).max())
+        worst["joints"] = float(np.abs(torch.cat([r.joints for r in res]).cpu().numpy() - A[f"api_{mt}_joints"]).max())
+        print(mt, {k: f"{v:.1e}" for k, v in worst.items()})
+        for k, v in worst.items():
+            assert v < (1e-5 if k == "transl" else 1e-4), (mt, k, v)
+        np.testing.assert_allclose([float(r.loss) for r in res], A[f"api_{mt}_loss"], rtol=1e-4)
+
+
+def test_articulated_evaluation_gradient_vs_autograd(gmm):
+    """k2b_artic_fit in evaluation mode against torch autograd of the same objective on the oracle's shim: loss rel
+    1e-5, gradient 1e-4 of its max-abs (G1 bars), for every model type incl. the SMPL priors."""
+    from keypoints2body_b200 import _native as nat
+    from keypoints2body_b200.core.fitters import articulated as art
+    from oracle import reference_port as rp
+    from oracle.problems import articulated_problem
+    from oracle.smplx_shim import BodyModelShim
+
+    for mt in ("smplx", "smplh", "mano", "flame"):
+        _, tgt, idx, init, B = articulated_problem(mt, 4, seed=720)
+        fit = _fitter(mt, False, gmm)
+        am = art.get_articulated(fit.native, with_body_priors=True) if mt in ("smplx", "smplh") else fit.artic
+        x0, frozen = am.pack({k: v for k, v in init.items()}, B)
+        out = am.run(nat.ARTIC_EVAL, x0, tgt, torch.ones(len(idx)), idx, keep_on=False, num_iters=0, lr=1e-2,
+                     joint_loss_weight=600.0, pose_preserve_weight=5.0, frozen=frozen)
+        shim = BodyModelShim(_model(mt))
+        p = {k: v.clone().requires_grad_(True) for k, v in init.items() if v.shape[-1] > 0}
+        joints = shim(**p).joints[:, idx]
+        err = joints - tgt
+        loss = (600.0 ** 2) * (1e4 * err ** 2 / (1e4 + err ** 2)).sum(dim=(1, 2))
+        if mt in ("smplx", "smplh"):
+            body = p["body_pose"]
+            loss = rp.body_fitting_loss_3d(body, body.detach(), p["betas"], joints, tgt, rp.GMMPrior(gmm),
+                                           torch.ones(len(idx)), joint_loss_weight=600.0, reduce=False)
+        elif mt == "mano":
+            loss = loss + 1e-2 * (p["hand_pose"] ** 2).sum(dim=-1) + 5.0 * (p["betas"] ** 2).sum(dim=-1)
+        else:
+            loss = loss + 1e-2 * (p["jaw_pose"] ** 2).sum(dim=-1) + 1e-3 * (p["expression"] ** 2).sum(dim=-1) \
+                + 5.0 * (p["betas"] ** 2).sum(dim=-1)
+        loss.sum().backward()
+        np.testing.assert_allclose(out["loss"].cpu().numpy(), loss.detach().numpy(), rtol=1e-5)
+        got = am.unpack(out["grad"])
+        for k in p:
+            gref = p[k].grad.numpy()
+            d = np.abs(got[k].cpu().numpy() - gref).max()
+            assert d < 1e-4 * max(1.0, np.abs(gref).max()), (mt, k, d, np.abs(gref).max())
