@@ -49,7 +49,12 @@ constexpr int kTcN = 128;          // output columns per tile (the MMA's M)
 constexpr int kTcBK = 64;          // K block streamed per TMA copy = one 128-byte swizzle atom of FP16 (4 MMAs of K = 16)
 constexpr int kTcKpadWide = 256;   // SMPL: 207 pose features + 3 x 10 split shape rows, padded to 8 x 32
 constexpr int kTcKpadMax = 576;    // SMPL-X: 486 pose features + 3 x 20 split shape/expression rows, 18 x 32
-constexpr int kTcThreads = 320;    // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+#ifndef K2B_TC_EPI_WARPS
+#define K2B_TC_EPI_WARPS 16
+#endif
+constexpr int kTcEpiWarps = K2B_TC_EPI_WARPS;          // 8 | 16: (lane quarter) x (tile of the pair) x (frame part)
+constexpr int kTcEpiParts = kTcEpiWarps / 8;           // warps sharing one accumulator quarter, each takes FR / parts frames
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 2);     // epilogue warps, then the TMA producer warp, then the MMA issuer
 constexpr int kTcStages = 4;       // ring depth (K blocks of dirs, 16 KB each) of the plain blend
 constexpr int kTcStagesFused = 6;
 constexpr int kTcFusedJoints = 24; // the fused blend + skinning kernel is instantiated for the SMPL skeleton
@@ -196,7 +201,7 @@ __host__ __device__ constexpr int tc_tile_vertex(int tile, int n) {
 template <int FR, int STAGES, int NE, int NJ>
 __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __grid_constant__ BlendParams p) {
   constexpr bool FUSED = NE > 0;   // NE = skinning weights per vertex (ELL width, 1..4); 0 = unfused
-  static_assert(FR % 16 == 0 && FR >= 16 && FR * kTcAccStages <= kTcTmemCols && STAGES <= 6, "tile shape");
+  static_assert(FR % (16 * kTcEpiParts) == 0 && FR >= 16 && FR * kTcAccStages <= kTcTmemCols && STAGES <= 6, "tile shape");
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   const int kpad = p.kpad;
   constexpr int b_bytes = tc_b_bytes();
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
     }
     for (int i = 0; i < kTcAccStages; ++i) {
       tc::mbar_init(BAR(12 + i), 1);     // acc_full: tcgen05.commit
-      tc::mbar_init(BAR(16 + i), 128);   // acc_empty: the four epilogue warps that drained it
+      tc::mbar_init(BAR(16 + i), 128 * kTcEpiParts);   // acc_empty: the epilogue warps that drained it
     }
     tc::fence_barrier_init();
   }
@@ -260,19 +265,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
       sF[(k >> 6) * (FR * 64) + tc_elem_off(r, k & 63)] = x;
     }
     if constexpr (FUSED) {     // this pass's skinning matrices (rows past the last frame are never read)
+      // The frame's translation is folded into the last column of every joint's matrix: the skinning weights of a
+      // vertex sum to one, so sum_k w_k (A_k.w + t) = sum_k w_k A_k.w + t -- one shared-memory read less per output.
       const float4* src = p.skin + f0 * (3L * NJ);
-      for (int i = tid; i < FR * 3 * NJ; i += kTcThreads) sA[i] = src[i];
-      if (tid < FR) {
-        const long f = f0 + tid;
-        const bool ok = p.transl && f < p.num_frames;
-        sT[tid] = ok ? make_float4(p.transl[f * 3], p.transl[f * 3 + 1], p.transl[f * 3 + 2], 0.f)
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < FR * 3 * NJ; i += kTcThreads) {
+        float4 r = src[i];
+        const int fr = i / (3 * NJ), c = i % 3;
+        const long f = f0 + fr;
+        if (p.transl && f < p.num_frames) r.w += p.transl[f * 3 + c];
+        sA[i] = r;
       }
     }
     tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
 
-    if (warp == 8) {
+    if (warp == kTcEpiWarps) {
       // ---- TMA producer: blocks in the order the MMA warp consumes them: (2p,kb), (2p+1,kb) -------
       if (lane == 0) {
         long seq = blk_seq;
@@ -290,7 +297,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
                            BAR(s));
             }
       }
-    } else if (warp == 9) {
+    } else if (warp == kTcEpiWarps + 1) {
       // ---- MMA issuer: one thread; two interleaved accumulation chains per pair -------------------
       if (lane == 0) {
         const uint32_t f_addr = tc::smem_u32(sF);
@@ -334,10 +341,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
         // from its two neighbour lanes, builds row c3 of the vertex's skinning matrix
         // sum_k w_k A[frame][joint_k] and writes verts[frame][vertex][c3] -- v_posed never leaves the SM.
         // All per-frame strides are compile-time (NJ) or running pointers, so a frame costs ~25 instructions.
-        const int q = warp & 3, h = warp >> 2;
+        const int q = warp & 3, h = (warp >> 2) & 1, part = warp >> 3;
+        constexpr int CH = FR / 16 / kTcEpiParts;      // 16-frame chunks per warp
         const int c3 = lane % 3, lbase = lane - c3;
-        const int sx = lbase, sy = lbase + 1 < 32 ? lbase + 1 : 31, sz = lbase + 2 < 32 ? lbase + 2 : 31;
-        const float* sTc = reinterpret_cast<const float*>(sT) + c3;
+        // the two other coordinates of this lane's vertex come from lanes lbase + (c3 + 1) % 3 and lbase + (c3 + 2) % 3
+        // (two shuffles; the matrix row is rotated to match instead of fetching x, y, z with three)
+        const int s1 = lbase + (c3 + 1) % 3 < 32 ? lbase + (c3 + 1) % 3 : 31;
+        const int s2 = lbase + (c3 + 2) % 3 < 32 ? lbase + (c3 + 2) % 3 : 31;
         const long ncols = 3L * p.nv;
         for (int pr = 0; pr < npairs; ++pr) {
           const long pseq = pair_seq + pr;
@@ -363,15 +373,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
             tc::mbar_arrive(BAR(16 + a));
             continue;
           }
-          float* o = p.out + f0 * ncols + col;
+          float* o = p.out + (f0 + part * (CH * 16)) * ncols + col;
           const long left = p.num_frames - f0;
-          int nvalid = (st_ok ? (left < FR ? (int)left : FR) : 0);   // frames of this pass this lane stores
+          int nvalid = (st_ok ? (left < FR ? (int)left : FR) : 0) - part * (CH * 16);   // frames this lane stores
 #pragma unroll 1
-          for (int ch = 0; ch < FR / 16; ++ch) {
+          for (int ch = part * CH; ch < (part + 1) * CH; ++ch) {
             uint32_t acc[16];
             tc::tmem_ld16(taddr + (uint32_t)(ch * 16), acc);
             tc::tmem_ld_wait();
-            if (ch == FR / 16 - 1) {
+            if (ch == (part + 1) * CH - 1) {
               tc::tc_fence_before();
               tc::mbar_arrive(BAR(16 + a));                        // accumulator may be overwritten
             }
@@ -379,16 +389,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
 #pragma unroll
             for (int i = 0; i < 16; ++i) {                         // fully unrolled, branch-free: 16 frames overlap
               const float pc = fmaf(__uint_as_float(acc[i]), p.inv_scale, tv);
-              const float px = __shfl_sync(0xffffffffu, pc, sx), py = __shfl_sync(0xffffffffu, pc, sy),
-                          pz = __shfl_sync(0xffffffffu, pc, sz);
-              float4 T = make_float4(0.f, 0.f, 0.f, sTc[(ch * 16 + i) * 4]);
+              const float p1 = __shfl_sync(0xffffffffu, pc, s1), p2 = __shfl_sync(0xffffffffu, pc, s2);
+              float4 T = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
               for (int k = 0; k < NE; ++k) {
                 const float4 r = Ak[k][(ch * 16 + i) * FS];
                 T.x = fmaf(wk[k], r.x, T.x); T.y = fmaf(wk[k], r.y, T.y);
                 T.z = fmaf(wk[k], r.z, T.z); T.w = fmaf(wk[k], r.w, T.w);
               }
-              const float ov = fmaf(T.x, px, fmaf(T.y, py, fmaf(T.z, pz, T.w)));
+              // row entries for (own, next, next-next) coordinate: c3 = 0 -> (x, y, z), 1 -> (y, z, x), 2 -> (z, x, y)
+              const float t0 = c3 == 0 ? T.x : (c3 == 1 ? T.y : T.z);
+              const float t1 = c3 == 0 ? T.y : (c3 == 1 ? T.z : T.x);
+              const float t2 = c3 == 0 ? T.z : (c3 == 1 ? T.x : T.y);
+              const float ov = fmaf(t0, pc, fmaf(t1, p1, fmaf(t2, p2, T.w)));
               if (i < nvalid) o[0] = ov;
               o += ncols;
             }
@@ -397,7 +410,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
         }
       } else {
         // ---- epilogue warps 0-7: lane quarter q = warp % 4, tile h = warp / 4 of every pair -----------
-        const int q = warp & 3, h = warp >> 2;
+        const int q = warp & 3, h = (warp >> 2) & 1, part = warp >> 3;
+        constexpr int CH = FR / 16 / kTcEpiParts;
         for (int pr = 0; pr < npairs; ++pr) {
           const long pseq = pair_seq + pr;
           const int a = (int)(pseq & 1) * 2 + h;
@@ -416,11 +430,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
             continue;
           }
   #pragma unroll 1
-          for (int ch = 0; ch < FR / 16; ++ch) {
+          for (int ch = part * CH; ch < (part + 1) * CH; ++ch) {
             uint32_t v[16];
             tc::tmem_ld16(taddr + (uint32_t)(ch * 16), v);
             tc::tmem_ld_wait();
-            if (ch == FR / 16 - 1) {
+            if (ch == (part + 1) * CH - 1) {
               tc::tc_fence_before();
               tc::mbar_arrive(BAR(16 + a));                        // accumulator may be overwritten
             }

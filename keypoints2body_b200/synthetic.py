@@ -94,7 +94,8 @@ _NUM_EXTRA_BY_TYPE = {"smpl": 21, "smplh": 21, "smplx": 21, "mano": 5, "flame": 
 NUM_EXTRA_SMPLX_BLOCKS = 76     # make_body_model("smplx", num_extra=76): 131 model joints, enough for a 64-landmark face block
 
 
-def make_body_model(model_type: str = "smpl", seed: int = 0, dtype=torch.float32, num_extra: Optional[int] = None):
+def make_body_model(model_type: str = "smpl", seed: int = 0, dtype=torch.float32, num_extra: Optional[int] = None,
+                    skin_layout: str = "interleaved"):
     """Random body-model weights of the official shapes.
 
     Returns a namespace with the smplx buffer names (``v_template (V,3)``,
@@ -104,13 +105,19 @@ def make_body_model(model_type: str = "smpl", seed: int = 0, dtype=torch.float32
     ``num_expression_coeffs``).  Vertex v is owned by joint ``v mod n_j``; the
     regressor averages the owned vertices and skinning weights are 0.7 owner /
     0.3 parent, so rest joints sit at the skeleton centres (+- noise).
+
+    ``skin_layout="interleaved"`` (default; every golden uses it) is the worst case for the mesh kernels: neighbouring
+    vertices never share a joint.  ``"coherent"`` owns vertices in contiguous runs (joint ``v * n_j // V``), which is
+    how the real models are ordered (a body part's vertices are mostly consecutive); same arithmetic, same sizes.
     """
     parents, centres = skeleton(model_type)
     n_j, n_v = len(parents), _NUM_VERTS[model_type]
     n_shape = 20 if model_type in ("smplx", "flame") else 10
     scale = {"mano": 0.2, "flame": 0.25}.get(model_type, 1.0)      # hand / head sized vertex clouds and blend shapes
     g = torch.Generator().manual_seed(seed)
-    owner = torch.arange(n_v) % n_j
+    if skin_layout not in ("interleaved", "coherent"):
+        raise ValueError(f"skin_layout must be 'interleaved' or 'coherent', got {skin_layout}")
+    owner = torch.arange(n_v) % n_j if skin_layout == "interleaved" else (torch.arange(n_v) * n_j) // n_v
     c = torch.as_tensor(centres, dtype=torch.float64)
     v_template = c[owner] + 0.04 * scale * torch.randn(n_v, 3, generator=g, dtype=torch.float64)
     J_regressor = torch.zeros(n_j, n_v, dtype=torch.float64)

@@ -81,6 +81,7 @@ if what == "mesh":
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
     print(f"mesh B={B}: {dt*1e3:.2f} ms -> {B/dt/1e6:.2f} M frames/s, {B*6890*12/dt/1e9:.0f} GB/s of vertex output")
 if what == "meshprof":
+    w = syn.make_body_model("smpl", skin_layout=os.environ.get("K2B_SKIN_LAYOUT", "interleaved"))
     f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm)
     B = 148 * 128 * 2
     gg = torch.Generator().manual_seed(1)
@@ -199,3 +200,31 @@ if what == "cross":
                         f.fit_batch(init, tgt, None, seq_ind=seq, with_mesh=False, kernel=kern)
                     torch.cuda.synchronize(); row.append((time.perf_counter() - t0) / 3 * 1e3)
                 print(f"cross {opt} B={B} seq_ind={seq}: frame {row[0]:.2f} ms, warp {row[1]:.2f} ms", flush=True)
+
+if what == "meshc":
+    # full-mesh throughput with the interleaved (worst case) and the coherent (realistic) vertex -> joint assignment
+    from oracle.smplx_shim import BodyModelShim
+    for mt, nv in (("smpl", 6890), ("smplh", 6890), ("smplx", 10475)):
+        for layout in ("interleaved", "coherent"):
+            wx = syn.make_body_model(mt, skin_layout=layout)
+            f = WorldSpaceFitter(wx, joints_category="AMASS", model_type=mt, gmm=gmm)
+            B = 1 << 16
+            gg = torch.Generator().manual_seed(1)
+            params = dict(global_orient=0.3 * torch.randn(B, 3, generator=gg), body_pose=0.3 * torch.randn(B, 69, generator=gg),
+                          betas=torch.randn(B, 10, generator=gg), transl=torch.randn(B, 3, generator=gg))
+            if mt != "smpl":
+                params.update(left_hand_pose=0.2 * torch.randn(B, 45, generator=gg), right_hand_pose=0.2 * torch.randn(B, 45, generator=gg))
+            if mt == "smplx":
+                params.update(expression=torch.randn(B, 10, generator=gg), jaw_pose=0.2 * torch.randn(B, 3, generator=gg),
+                              leye_pose=0.2 * torch.randn(B, 3, generator=gg), reye_pose=0.2 * torch.randn(B, 3, generator=gg))
+            ref = BodyModelShim(wx)(**{k: v[:200] for k, v in params.items()})
+            params = {k: v.cuda() for k, v in params.items()}
+            buf = torch.empty(B, nv, 3, device="cuda")
+            for _ in range(2):
+                out = f.forward_batch(params, out_vertices=buf)
+            dv = (out["vertices"][:200].cpu() - ref.vertices).abs().max().item()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(3):
+                f.forward_batch(params, out_vertices=buf)
+            torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
+            print(f"{mt} {layout}: B={B} {dt*1e3:.2f} ms -> {B/dt/1e6:.2f} M frames/s, {B*nv*12/dt/1e9:.0f} GB/s of vertex output, max|verts-shim|={dv:.2e}", flush=True)
