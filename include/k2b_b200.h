@@ -190,6 +190,15 @@ typedef struct k2b_chain_args {
   int32_t final_loss_mode;
   float depth_weight;
   const float* depth_ref;       /* [S][stride][3], required for loss_kind 1 */
+  /* 1: every frame is a whole CameraSpaceFitter.fit_frame (core/fitters/camera_space.py:81-339) inside the launch, so a
+   * camera-space sequence (api/sequence.py:214-281 with coordinate_mode="camera") is ONE launch: forward at the frame's
+   * initial parameters -> camera translation from the four torso joints (guess_init_3d, :16-41), stage 1 over
+   * [global_orient, camera translation] (camera_fitting_loss_3d), stage 2 over the body with the translation acting as
+   * camera translation; the returned loss is stage 2's without the temporal term.  Both stages run num_iters_first
+   * iterations (set num_iters_followup to the same value); init_transl is ignored; freeze_betas bit 0 applies to frames
+   * with seq_ind > 0 only (:219-224); loss_kind / final_loss_mode / depth_ref must be 0 / 0 / NULL, depth_weight is
+   * used; out_joints is required (the per-frame fit joints, camera translation included). */
+  int32_t camera_sequence;
 } k2b_chain_args;
 
 size_t k2b_chain_workspace_bytes(const k2b_model* m, int64_t num_sequences, int32_t optimizer,

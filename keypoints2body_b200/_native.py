@@ -68,7 +68,7 @@ class ChainArgs(C.Structure):
         ("out_loss", C.c_void_p), ("out_joints", C.c_void_p), ("out_evals", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("loss_kind", C.c_int32), ("final_loss_mode", C.c_int32), ("depth_weight", C.c_float),
-        ("depth_ref", C.c_void_p),
+        ("depth_ref", C.c_void_p), ("camera_sequence", C.c_int32),
     ]
 
 

@@ -71,6 +71,11 @@ def fit_sequence_batched(fitter, xyz, conf, init: dict, seq_cfg: SequenceOptimiz
         # the camera translation (camera_space.py:301-306), is produced by one batched pass at the end
         if seq_cfg.schedule == "two_sweep":
             raise NotImplementedError("schedule='two_sweep' is defined for the world-space fitter")
+        if os.environ.get("K2B_CAMERA_LAUNCH_PER_FRAME", "0") != "1":
+            # the whole loop in ONE launch: a warp walks the sequence, both camera stages per frame (camera_sequence)
+            return fitter.fit_sequences({k: v for k, v in init.items() if v is not None and k != "transl"}, xyz[None], conf[None],
+                                        first_seq_ind=first_seq_ind, chain=seq_cfg.use_previous_frame_init, **kw)
+        # diagnostic path: two launches per frame
         prev, rows = init, []
         for t in range(T):
             r = fitter.fit_batch(prev, xyz[t:t + 1], conf[t], seq_ind=first_seq_ind + t, with_mesh=False, **kw)

@@ -92,6 +92,39 @@ class CameraSpaceFitter(WorldSpaceFitter):
             out.update(self.forward_batch({k: v for k, v in params.items() if k != "transl"}))
         return out
 
+    def fit_sequences(self, init: dict, j3d, conf=None, *, first_seq_ind: int = 0, chain: bool = True,
+                      joint_loss_weight=600.0, pose_preserve_weight=5.0, freeze_betas=True, with_mesh=True):
+        """S camera-space sequences of T frames in ONE launch (``k2b_fit_chain`` with ``camera_sequence = 1``): every frame
+        is a whole ``fit_frame`` -- camera translation from the torso joints at the frame's initial parameters, stage 1,
+        stage 2 -- and with ``chain`` frame t starts from frame t-1's result, which is the reference's loop
+        (api/sequence.py:214-281 with ``coordinate_mode="camera"``).  ``init``: (S,dim) blocks; ``j3d`` (S,T,K,3);
+        ``conf`` None | (K,) | (S,T,K).  Returns the batched result dict with rows ordered [sequence][frame]."""
+        dev = self.device
+        targets = _f32(j3d, dev)
+        if targets.dim() != 4:
+            raise ValueError(f"j3d must be (S, T, K, 3), got {tuple(targets.shape)}")
+        S, T = targets.shape[0], targets.shape[1]
+        targets = targets[:, :, : self.num_obs].contiguous()
+        go, bp = _f32(init["global_orient"], dev), _f32(init["body_pose"], dev)
+        betas = _f32(init["betas"], dev)
+        if betas.shape[0] != S:
+            betas = betas.expand(S, -1)
+        conf = _f32(conf, dev)
+        cm = 0 if conf is None else (2 if conf.dim() == 3 else 1)
+        if conf is not None:
+            conf = conf[..., : self.num_obs].contiguous()
+        pose = torch.cat([go, bp], dim=1).expand(S, -1).contiguous()
+        opt = nat.OPT_LBFGS if self.use_lbfgs else nat.OPT_ADAM
+        s2 = self._run_chain(S, T, targets, conf, cm, pose, betas.contiguous(), torch.zeros(S, 3, device=dev), None, None,
+                             int(first_seq_ind), chain, self.num_iters, self.num_iters, opt, joint_loss_weight,
+                             pose_preserve_weight, bool(freeze_betas), camera_sequence=True)
+        params = {"global_orient": s2["pose"][:, :3], "body_pose": s2["pose"][:, 3:], "betas": s2["betas"],
+                  "transl": s2["transl"]}
+        out = {"params": params, "loss": s2["loss"], "evals": s2["evals"], "fit_joints": s2["fit_joints"]}
+        if with_mesh:
+            out.update(self.forward_batch({k: v for k, v in params.items() if k != "transl"}))
+        return out
+
     def _fit_two_stage_frames(self, B, targets, conf, conf_pf, pose, betas, cam_t0, bp, seq_ind, opt, joint_loss_weight,
                               pose_preserve_weight, move_betas):
         """Both stages on the one-thread-per-frame kernel (large batches)."""

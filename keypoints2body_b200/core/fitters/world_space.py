@@ -172,7 +172,7 @@ class WorldSpaceFitter:
     def _run_chain(self, S, T, targets, conf, conf_mode, pose, betas, transl, expr, preserve, first_seq_ind, chain,
                    iters_first, iters_follow, optimizer, joint_loss_weight, pose_preserve_weight, freeze_betas,
                    want_joints=True, outs=None, window=None, time_major=False, seq_first=None, loss_kind=0,
-                   final_loss_mode=0, depth_ref=None, depth_weight=100.0):
+                   final_loss_mode=0, depth_ref=None, depth_weight=100.0, camera_sequence=False):
         """One launch of the warp-per-sequence kernel (``k2b_fit_chain``): S sequences x T frames, serial in t.
 
         ``outs``: preallocated output dict (rows of this launch), else allocated here.  ``window = (a, b, T_total)``:
@@ -209,7 +209,7 @@ class WorldSpaceFitter:
             out_expr=nat.ptr(outs["expression"]), out_loss=nat.ptr(outs["loss"]),
             out_joints=nat.ptr(outs["fit_joints"]), out_evals=nat.ptr(outs["evals"]), workspace=nat.ptr(ws),
             workspace_bytes=ws.numel(), loss_kind=int(loss_kind), final_loss_mode=int(final_loss_mode),
-            depth_weight=float(depth_weight), depth_ref=nat.ptr(depth_ref),
+            depth_weight=float(depth_weight), depth_ref=nat.ptr(depth_ref), camera_sequence=int(bool(camera_sequence)),
         )
         with torch.cuda.device(dev):
             nat.check(lib.k2b_fit_chain(self.native.handle, C.byref(a), nat.current_stream()))

@@ -300,7 +300,8 @@ extern "C" int k2b_evaluate_batch(const k2b_model* m, const k2b_eval_args* a, vo
 namespace {
 // Launch geometry of the warp-per-sequence kernel.  teams = sequences walked concurrently by one CTA; a team is
 // `evals` evaluator warps (> 1: speculative line-search evaluation, L-BFGS only) x (1 + helpers) warps.
-void chain_geometry(const k2b_model* m, long S, bool lbfgs, int hmax, int& grid, int& teams, int& helpers, int& evals) {
+void chain_geometry(const k2b_model* m, long S, bool lbfgs, int hmax, int& grid, int& teams, int& helpers, int& evals,
+                    bool single = false) {
   // Few sequences: the launch is latency-bound and most schedulers idle.  Helper warps take the mixture prior off the
   // evaluator (measured on B200, L-BFGS, us per frame: 1 sequence 106 / 80 / 66 with 0 / 1 / 2 helpers; 256 sequences
   // 113 / 86 / 80; 512 sequences 128 / 110 / 114), and with L-BFGS further evaluators try the line search's next
@@ -315,6 +316,7 @@ void chain_geometry(const k2b_model* m, long S, bool lbfgs, int hmax, int& grid,
   // L-BFGS evaluates the mixture prior in line form (chain_core.cuh, LineEval): the evaluators share the matrix
   // products, there is nothing for helper warps to do; Adam has no line search to speculate on
   if (lbfgs) helpers = 0; else evals = 1;
+  if (single) evals = 1;      // camera sequences: the stage is a state of the leading evaluator only
   helpers = helpers < 0 ? 0 : (helpers > 3 ? 3 : helpers);
   evals = evals < 1 ? 1 : (evals > wc::kMaxCand ? wc::kMaxCand : evals);
   while (evals * (1 + helpers) > kChainMaxWarps) {
@@ -344,7 +346,10 @@ extern "C" size_t k2b_chain_workspace_bytes(const k2b_model* m, int64_t num_sequ
   int grid, teams, helpers, evals;
   const int hmax = lbfgs_history_capacity(max_iters);
   chain_geometry(m, num_sequences, true, hmax, grid, teams, helpers, evals);
-  return sizeof(float) * (size_t)grid * teams * (size_t)wc::hist_floats(hmax);
+  size_t need = (size_t)grid * teams;
+  chain_geometry(m, num_sequences, true, hmax, grid, teams, helpers, evals, true);      // camera_sequence launches
+  if ((size_t)grid * teams > need) need = (size_t)grid * teams;
+  return sizeof(float) * need * (size_t)wc::hist_floats(hmax);
 }
 
 extern "C" int k2b_chain_geometry(const k2b_model* m, int64_t num_sequences, int32_t* out_ctas, int32_t* out_warps) {
@@ -369,10 +374,19 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   if (a->conf_mode < 0 || a->conf_mode > 2) return fail(K2B_EINVAL, "conf_mode must be 0, 1 or 2");
   const int hmax = chain_hmax(a);
   int grid, teams, helpers, evals;
-  chain_geometry(m, a->num_sequences, a->optimizer == K2B_OPT_LBFGS, hmax, grid, teams, helpers, evals);
+  const bool camera_seq = a->camera_sequence != 0;
+  if (camera_seq) {
+    if (a->loss_kind != 0 || a->final_loss_mode != 0 || a->depth_ref)
+      return fail(K2B_EINVAL, "camera_sequence runs both stages itself: loss_kind, final_loss_mode, depth_ref must be 0");
+    if (!a->out_joints) return fail(K2B_EINVAL, "camera_sequence needs out_joints");
+    if (m->num_shape != 10) return fail(K2B_EUNSUPPORTED, "the camera-space fitter takes SMPL parameters (camera_space.py:83)");
+    if (a->preserve_pose) return fail(K2B_EINVAL, "camera_sequence anchors every frame at its own initial body pose");
+  }
+  chain_geometry(m, a->num_sequences, a->optimizer == K2B_OPT_LBFGS, hmax, grid, teams, helpers, evals, camera_seq);
   if (chain_smem_bytes(m->num_shape, teams, evals, helpers, hmax) > 227 * 1024)
     return fail(K2B_EUNSUPPORTED, "iteration budget too large");
   wc::ChainParams p{};
+  p.camera_seq = camera_seq ? 1 : 0;
   p.num_seq = a->num_sequences;
   p.frames = a->frames_per_sequence;
   p.in_seq_stride = a->in_sequence_stride > 0 ? a->in_sequence_stride : a->frames_per_sequence;
@@ -398,7 +412,7 @@ extern "C" int k2b_fit_chain(const k2b_model* m, const k2b_chain_args* a, void* 
   if (a->loss_kind != 0 && a->loss_kind != 1) return fail(K2B_EINVAL, "unknown loss_kind");
   if (a->loss_kind == 1 && !a->depth_ref) return fail(K2B_EINVAL, "loss_kind 1 needs depth_ref");
   p.loss_kind = a->loss_kind;
-  p.final_mode = a->final_loss_mode;
+  p.final_mode = camera_seq ? 1 : a->final_loss_mode;
   p.depth_w2 = 4.f * a->depth_weight * a->depth_weight;   // added to each of the 4 joint rows by the reference's broadcast
   p.depth_ref = a->depth_ref;
   p.hmax = hmax;

@@ -952,6 +952,11 @@ struct ChainParams {
   int loss_kind, final_mode;
   float depth_w2;
   const float* depth_ref;  // [S][stride][3] initial camera translation (loss_kind 1)
+  int camera_seq;          // 1: CameraSpaceFitter.fit_frame per frame inside the launch (camera_space.py:81-339): forward at
+                           // the frame's initial parameters -> camera translation from the four torso joints (:16-41),
+                           // stage 1 over [global_orient, camera translation], stage 2 over the body (final_mode 1
+                           // semantics); iters_first = iters_follow = num_iters; freeze_betas bit 0 holds for seq_ind > 0
+                           // only (:219-224).  Needs out_joints and team == 1.
   int eval_only;           // 1: no fit -- one evaluation at the initial parameters per frame; out_pose / out_betas / out_transl /
                            // out_expr receive the GRADIENT, out_evals the arg-min mixture component (k2b_evaluate_batch, warp evaluator)
   float adam_step[kAdamTableW], adam_bc2[kAdamTableW];
@@ -991,7 +996,7 @@ K2B_HD void load_frame_obs(const ChainParams& p, long f, bool stage1, FrameObs& 
   ob.plain_sq = stage1;
   ob.depth_w2 = stage1 ? p.depth_w2 : 0.f;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) ob.dref[c] = (stage1 && lane == 24) ? p.depth_ref[f * 3 + c] : 0.f;
+  for (int c = 0; c < 3; ++c) ob.dref[c] = (stage1 && lane == 24 && p.depth_ref) ? p.depth_ref[f * 3 + c] : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1007,19 +1012,26 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
   const int lane = lane_id();
   const bool leader = idx == 0;
   const bool teamed = tm.E > 1;
-  const bool stage1 = p.loss_kind == 1;       // camera-space stage 1: only global_orient and the translation move, no priors
-  const bool priors_on = !stage1;
+  // camera-space stage 1: only global_orient and the translation move, no priors.  A launch constant for the two-launch
+  // camera fit (loss_kind), a per-frame state of the leader when both stages run inside the launch (camera_seq).
+  bool stage1 = p.loss_kind == 1;
+  bool priors_on = !stage1;
   constexpr bool lbfgs = LB;
   const bool body_owner = lane >= 1 && lane < 24;
   bool frozen[3];
+  auto set_frozen = [&](bool s1, bool betas_fixed) {
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int e = 3 * lane + c;
-    frozen[c] = e >= 75 + NS || ((p.freeze_betas & 1) && e >= kShapeOff && e < kShapeOff + 10) ||
-                ((p.freeze_betas & 2) && e >= kShapeOff + 10) ||
-                (stage1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
-  }
-  enum { kNewFrame, kAdam, kAdamFinal, kRound, kFinal, kEvalOnly };
+    for (int c = 0; c < 3; ++c) {
+      const int e = 3 * lane + c;
+      frozen[c] = e >= 75 + NS || (betas_fixed && e >= kShapeOff && e < kShapeOff + 10) ||
+                  ((p.freeze_betas & 2) && e >= kShapeOff + 10) || (s1 && !(e < 3 || (e >= kTranslOff && e < kShapeOff)));
+    }
+  };
+  set_frozen(stage1, (p.freeze_betas & 1) != 0);
+  int cstage = 0;            // camera_seq: 1 forward at the initial parameters, 2 stage 1, 3 stage 2
+  int evals_prev = 0;        // camera_seq: evaluations of stage 1
+  bool first_frame = false;
+  enum { kNewFrame, kAdam, kAdamFinal, kRound, kFinal, kEvalOnly, kCamGuess };
   // ---- leader state ------------------------------------------------------------------------------------------
   long seq = first_seq, f = 0, frow = 0;
   int t = -1, phase = kNewFrame, iters = 0, evals = 0, k = 1;
@@ -1056,6 +1068,35 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
 #pragma unroll
     for (int c = 0; c < 3; ++c) xr[c] = x0[c] = load_elem<NS>(p, seq, 3 * lane + c);
   }
+  // camera_seq: (re)start the optimiser on the current xr for camera stage 1 (s1) or stage 2
+  auto begin_camera_stage = [&](bool s1) {
+    stage1 = s1;
+    priors_on = !s1;
+    set_frozen(s1, (p.freeze_betas & 1) != 0 && !first_frame);      // betas move on the first frame (camera_space.py:219-224)
+    float dref[3] = {ob.dref[0], ob.dref[1], ob.dref[2]};
+    load_frame_obs<K>(p, f, s1, ob);                                 // joint weights of the stage; keeps ob.keep
+    if (s1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ob.dref[c] = dref[c];
+    }
+    ob.keep_w2 = (s1 || first_frame) ? 0.f : p.keep_w2;
+    cstage = s1 ? 2 : 3;
+    evals = 0;
+    if (lbfgs) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { v.x[c] = xr[c]; v.xk[c] = xr[c]; v.d[c] = 0.f; }
+      st.init();
+      lfirst = true;
+      tab_next = kTabRefresh;
+      t_pending = 0.f;
+      phase = kRound;
+    } else {
+      k = 1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) m1[c] = m2[c] = 0.f;
+      phase = iters > 0 ? kAdam : kAdamFinal;
+    }
+  };
 #pragma unroll 1
   while (true) {
     // ===== 1. the next point ======================================================================================
@@ -1093,11 +1134,18 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         for (int c = 0; c < 3; ++c)
           ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[f * kBodyDim + 3 * lane - 3 + c] : xr[c];
         const bool first = (p.seq_first ? (long)p.seq_first[seq] : p.first_seq_ind) + t == 0;
+        first_frame = first;
         ob.keep_w2 = first ? 0.f : p.keep_w2;      // the temporal term is on for seq_ind > 0 (world_space.py:211)
         iters = first ? p.iters_first : p.iters_follow;
         evals = 0;
+        evals_prev = 0;
         out_loss = 0.f;
-        if (p.eval_only) {
+        if (p.camera_seq) {
+          cstage = 1;
+          stage1 = false;
+          priors_on = false;
+          phase = kCamGuess;
+        } else if (p.eval_only) {
           phase = kEvalOnly;
         } else if (lbfgs) {
 #pragma unroll
@@ -1118,6 +1166,11 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       if (phase == kEvalOnly) {
         jout = jframe;
         want_comp = true;
+      } else if (phase == kCamGuess) {
+        // model joints at the frame's initial parameters, without a translation (camera_space.py:113-117)
+        with_grad = false;
+        with_priors = false;
+        jout = jframe;
       } else if (!LB && phase == kAdamFinal) {
         // joints at the final parameters (world_space.py:258-278); camera stage 2 also re-evaluates the loss there
         do_eval = jframe != nullptr || p.final_mode != 0;
@@ -1158,6 +1211,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) x[c] = (LB && phase == kRound) ? v.x[c] : xr[c];
+      if (phase == kCamGuess && lane == 24) x[0] = x[1] = x[2] = 0.f;
     } else {
       bar_sync(tm.bar_go, 32 * tm.E);
       if (*reinterpret_cast<const volatile int*>(tm.cmd) == kCmdExit) break;
@@ -1220,7 +1274,25 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       continue;
     }
     bool frame_done = false;
-    if (phase == kEvalOnly) {
+    if (phase == kCamGuess) {
+      // initial camera translation: mean offset of RHip, LHip, RShoulder, LShoulder (guess_init_3d, camera_space.py:16-41)
+      wsync();
+      const float* jg = p.out_joints + frow * K * 3;
+      const float* tg = p.targets + f * K * 3;
+      float ct[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float d2 = tg[2 * 3 + c] - jg[2 * 3 + c], d1 = tg[1 * 3 + c] - jg[1 * 3 + c];
+        const float d17 = tg[17 * 3 + c] - jg[17 * 3 + c], d16 = tg[16 * 3 + c] - jg[16 * 3 + c];
+        ct[c] = (((d2 + d1) + d17) + d16) / 4.f;
+      }
+      wsync();
+      if (lane == 24) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { xr[c] = ct[c]; ob.dref[c] = ct[c]; }
+      }
+      begin_camera_stage(true);
+    } else if (phase == kEvalOnly) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, gr[c]);
       if (lane == 0) {
@@ -1242,7 +1314,14 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         if (!frozen[c]) adam_update(xr[c], m1[c], m2[c], gr[c], step_k, bc2_k);
-      if (++k > iters) phase = kAdamFinal;
+      if (++k > iters) {
+        if (cstage == 2) {          // camera stage 1 is over: stage 2 starts from its result
+          evals_prev = evals;
+          begin_camera_stage(false);
+        } else {
+          phase = kAdamFinal;
+        }
+      }
     } else if (!LB && phase == kAdamFinal) {
       if (do_eval && p.final_mode) out_loss = loss;
       frame_done = true;
@@ -1294,7 +1373,10 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         // ARE the accepted trial point (lbfgs.py:488-493 adds t d to the iterate the same way the trial was formed), so
         // the loss is the machine's own, bit for bit; the extra forward pass is only run when joints are wanted or the
         // camera stage re-evaluates without the temporal term.
-        if (p.out_joints || p.final_mode) {
+        if (cstage == 2) {          // camera stage 1 is over: stage 2 starts from its result
+          evals_prev = st.evals;
+          begin_camera_stage(false);
+        } else if (p.out_joints || p.final_mode) {
           phase = kFinal;
         } else {
           out_loss = (float)st.loss;
@@ -1313,7 +1395,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, xr[c]);
       if (lane == 0) {
         p.out_loss[frow] = out_loss;
-        if (p.out_evals) p.out_evals[frow] = evals;
+        if (p.out_evals) p.out_evals[frow] = evals + evals_prev;
       }
       phase = kNewFrame;
     }

@@ -385,8 +385,33 @@ def section_generic_api():
     save("r2_generic_api.npz", G)
 
 
+def section_camera_seq():
+    """optimize_params_sequence(coordinate_mode="camera") of the unmodified reference on a smooth 12-frame sequence
+    (Adam and L-BFGS, 15 iterations per stage): the loop api/sequence.py:214-281 over CameraSpaceFitter.fit_frame."""
+    ref, tmp = setup()
+    G = {}
+    weights = syn.make_body_model("smpl", seed=0)
+    model = BodyModelShim(weights)
+    from oracle.problems import chain_problem
+
+    tgt = chain_problem(weights, 1, 12, seed=77)[0]
+    G["camseq_in_target"] = tgt
+    with ref_loader.reference_cwd(tmp):
+        for name, lb in (("camseq_adam", False), ("camseq_lbfgs", True)):
+            res = ref.optimize_params_sequence(tgt.numpy(), body_model="smpl", joint_layout="AMASS", model=model,
+                                               config=dict(frame=dict(use_lbfgs=lb, coordinate_mode="camera", num_iters=15),
+                                                           use_shape_optimization=False))
+            G[name + "_pose"] = torch.cat([r.params.pose for r in res])
+            G[name + "_transl"] = torch.cat([r.params.transl for r in res])
+            G[name + "_betas"] = torch.cat([r.params.betas for r in res])
+            G[name + "_joints"] = torch.cat([r.joints for r in res])
+            G[name + "_loss"] = torch.stack([r.loss.reshape(()) for r in res])
+            print(name, "loss", [round(float(r.loss), 1) for r in res], flush=True)
+    save("r2_camera_seq.npz", G)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     sys.path.insert(0, HERE)
     {"points": section_points, "dist": section_dist, "dist64": section_dist64, "chains": section_chains,
-     "adam": section_adam, "adam_pert": section_adam_pert, "generic": section_generic, "generic_api": section_generic_api}[sys.argv[1]]()
+     "adam": section_adam, "adam_pert": section_adam_pert, "generic": section_generic, "generic_api": section_generic_api, "camera_seq": section_camera_seq}[sys.argv[1]]()

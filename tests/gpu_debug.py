@@ -228,3 +228,20 @@ if what == "meshc":
                 f.forward_batch(params, out_vertices=buf)
             torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
             print(f"{mt} {layout}: B={B} {dt*1e3:.2f} ms -> {B/dt/1e6:.2f} M frames/s, {B*nv*12/dt/1e9:.0f} GB/s of vertex output, max|verts-shim|={dv:.2e}", flush=True)
+if what == "camseq":
+    # a lone 128-frame camera-space sequence through the public API: one launch vs two launches per frame
+    import keypoints2body_b200 as k2b
+    import tempfile
+    from oracle.problems import chain_problem
+    tmp = tempfile.mkdtemp(); syn.write_assets(os.path.join(tmp, "data/models"), seed=0); os.chdir(tmp)
+    tgt = chain_problem(w, 1, 128, seed=5)[0].numpy()
+    for opt in ("adam", "lbfgs"):
+        cfg = dict(frame=dict(use_lbfgs=opt == "lbfgs", coordinate_mode="camera", num_iters=10), use_shape_optimization=False)
+        for mode in ("0", "1"):
+            os.environ["K2B_CAMERA_LAUNCH_PER_FRAME"] = mode
+            k2b.optimize_params_sequence(tgt, body_model="smpl", joint_layout="AMASS", model=w, config=cfg)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            res = k2b.optimize_params_sequence(tgt, body_model="smpl", joint_layout="AMASS", model=w, config=cfg)
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            print(f"camera sequence {opt} 128 frames, {'launch per frame' if mode == '1' else 'one launch'}: {dt*1e3:.1f} ms, "
+                  f"{128/dt:.0f} frames/s, median loss {np.median([float(r.loss) for r in res]):.1f}", flush=True)

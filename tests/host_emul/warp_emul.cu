@@ -243,6 +243,10 @@ extern "C" int wemu_eval(void* model, int K, float joint_w, float keep_w, const 
 
 // Team of the following wemu_eval / wemu_chain calls: E evaluator warps (> 1: speculative line-search evaluation,
 // L-BFGS chains only) and H helper warps per evaluator (mixture prior scanned by other warps).
+// 1: the next wemu_chain calls run whole camera-space fits per frame (ChainParams::camera_seq)
+static int g_camera_seq = 0;
+extern "C" void wemu_set_camera_seq(int on) { g_camera_seq = on; }
+
 extern "C" void wemu_set_team(int evaluators, int helpers) {
   g.E = evaluators < 1 ? 1 : evaluators;
   g.H = helpers < 0 ? 0 : helpers;
@@ -279,7 +283,9 @@ extern "C" int wemu_chain(void* model, int K, int S, int T, long first_seq_ind, 
     p.adam_step[k - 1] = (float)((double)lr / (1.0 - std::pow(0.9, (double)k)));
     p.adam_bc2[k - 1] = (float)std::sqrt(1.0 - std::pow(0.999, (double)k));
   }
-  const int E = lbfgs ? g.E : 1;
+  p.camera_seq = g_camera_seq;
+  if (p.camera_seq) p.final_mode = 1;
+  const int E = (lbfgs && !p.camera_seq) ? g.E : 1;
   p.team = E;
   p.helpers = g.H;
   const int keepE = g.E;

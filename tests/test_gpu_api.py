@@ -240,3 +240,38 @@ def test_explicit_target_model_indices(generic_goldens, weights, gmm):
         fx.fit_frame(xinit, torch.zeros(1, 2, 3), torch.ones(2), target_model_indices=torch.tensor([0, 4000]))
     with pytest.raises(NotImplementedError):
         fx.scatter_observations(torch.zeros(1, 2, 3), torch.ones(2), torch.tensor([0, 30]))
+
+
+@pytest.mark.parametrize("opt", ["adam", "lbfgs"])
+def test_sequence_api_camera_mode_one_launch(opt, weights, asset_cwd, monkeypatch):
+    """optimize_params_sequence(coordinate_mode="camera"): the reference's loop over CameraSpaceFitter.fit_frame
+    (api/sequence.py:214-281, core/fitters/camera_space.py:81-339) runs inside ONE launch (k2b_fit_chain,
+    camera_sequence).  Against the unmodified reference's own call on a smooth 12-frame sequence (outcome level, like
+    every camera fit from the default start: DESIGN.md section 3, note on G6'), and against the launch-per-frame path."""
+    import keypoints2body_b200 as k2b
+    from keypoints2body_b200 import _native as nat
+
+    G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "r2_camera_seq.npz")))
+    tgt = G["camseq_in_target"]
+    cfg = dict(frame=dict(use_lbfgs=opt == "lbfgs", coordinate_mode="camera", num_iters=15), use_shape_optimization=False)
+    lib = nat.load_library()
+    n0 = lib.k2b_launch_count()
+    res = k2b.optimize_params_sequence(tgt, body_model="smpl", joint_layout="AMASS", model=weights("smpl"), config=cfg)
+    launches = lib.k2b_launch_count() - n0
+    assert launches <= 8, launches                      # shape pass off: root alignment + ONE chain launch + the mesh pass
+    monkeypatch.setenv("K2B_CAMERA_LAUNCH_PER_FRAME", "1")
+    per_frame = k2b.optimize_params_sequence(tgt, body_model="smpl", joint_layout="AMASS", model=weights("smpl"), config=cfg)
+    loss = np.array([float(r.loss) for r in res])
+    loss_pf = np.array([float(r.loss) for r in per_frame])
+    ref_loss = G[f"camseq_{opt}_loss"]
+    print(opt, "loss ours", np.round(loss, 1), "per-frame path", np.round(loss_pf, 1), "reference", np.round(ref_loss, 1))
+    assert len(res) == 12 and res[0].vertices.shape == (1, 6890, 3)
+    # settled part of the chain (frames 4..): within 25 % of the reference and of the launch-per-frame path, per frame
+    assert np.all(np.abs(loss[4:] - ref_loss[4:]) < 0.25 * ref_loss[4:])
+    assert np.all(np.abs(loss[4:] - loss_pf[4:]) < 0.25 * loss_pf[4:])
+    assert abs(np.median(loss / ref_loss) - 1.0) < 0.1
+    pose = torch.cat([r.params.pose for r in res]).cpu().numpy()
+    # (L-BFGS trajectories separate at the first accept test decided by rounding noise: tests/test_gpu_lbfgs_parity.py)
+    assert np.abs(pose[4:] - G[f"camseq_{opt}_pose"][4:]).max() < (0.1 if opt == "adam" else 0.25)
+    joints = torch.cat([r.joints for r in res]).cpu().numpy()           # camera translation excluded (camera_space.py:301-306)
+    assert np.abs(joints[4:] - G[f"camseq_{opt}_joints"][4:]).max() < 0.05

@@ -249,3 +249,47 @@ def test_team_is_bit_identical_to_one_warp(goldens, wemu, wmodels, shims, E, H):
             assert np.array_equal(a[k], b[k]), (E, H, k)
     assert np.abs(adam["pose"][0] - g["seq_adam_chain_pose"]).max() < 1e-4
     print("evaluations per frame", ref["evals"].ravel())
+
+
+@pytest.mark.parametrize("lbfgs,iters", [(False, 15), (True, 20)])
+def test_camera_sequence_in_one_launch(goldens, wemu, wmodels, lbfgs, iters):
+    """``camera_sequence``: every frame a whole CameraSpaceFitter.fit_frame inside the launch (camera translation from
+    the torso joints at the frame's initial parameters, stage 1, stage 2; camera_space.py:81-339), frames chained like
+    the reference's loop (api/sequence.py:214-281).  (a) Bit-identical to the same fit done as separate stage launches
+    chained by hand; (b) the first frame lands where the reference's fit from its default start lands (outcome level:
+    the reference's first stage-1 step is decided by rounding noise, DESIGN.md section 3, note on G6')."""
+    g = goldens
+    m = wmodels("smpl")
+    wemu.wemu_set_camera_seq.argtypes = [C.c_int]
+    pose, tgt = g["cam_in_pose"], g["cam_in_target"]
+    T = tgt.shape[0]
+    x0 = pack_x(pose[:1], np.zeros((1, 3), np.float32), np.zeros((1, 10), np.float32))
+    wemu.wemu_set_camera_seq(1)
+    try:
+        one = m.chain(x0, tgt[None], np.ones(22), first_seq_ind=0, chain=True, lbfgs=lbfgs, iters_first=iters,
+                      iters_follow=iters, freeze=True)
+    finally:
+        wemu.wemu_set_camera_seq(0)
+    # the same, stage by stage and frame by frame
+    prev = x0.copy()
+    for t in range(T):
+        z = prev.copy()
+        z[:, 72:75] = 0
+        j0 = m.evaluate(z[0], tgt[t], np.ones(22), z[0, 3:72], 0.0)["joints"]
+        d = tgt[t] - j0
+        cam0 = ((((d[2] + d[1]) + d[17]) + d[16]) / np.float32(4.0)).astype(np.float32)[None]
+        x1 = prev.copy()
+        x1[:, 72:75] = cam0
+        s1 = m.chain(x1, tgt[t][None, None], np.ones(22), first_seq_ind=0, lbfgs=lbfgs, iters_first=iters, iters_follow=iters,
+                     freeze=True, loss_kind=1, depth_ref=cam0)
+        x2 = pack_x(s1["pose"][:, 0], s1["transl"][:, 0], s1["betas"][:, 0])
+        s2 = m.chain(x2, tgt[t][None, None], np.ones(22), first_seq_ind=1 if t > 0 else 0, lbfgs=lbfgs, iters_first=iters,
+                     iters_follow=iters, freeze=t > 0, keep=prev[:, None, 3:72], final_mode=1)
+        for k in ("pose", "transl", "betas", "loss"):
+            assert np.array_equal(one[k][0, t], s2[k][0, 0]), (t, k)
+        assert one["evals"][0, t] == s1["evals"][0, 0] + s2["evals"][0, 0]
+        prev = pack_x(s2["pose"][:, 0], s2["transl"][:, 0], s2["betas"][:, 0])
+    tag = "cam_lbfgs" if lbfgs else "cam_adam"
+    ref_loss = float(g[tag + "_loss"][0])
+    assert one["loss"][0, 0] < 1.25 * ref_loss, (one["loss"][0, 0], ref_loss)
+    assert np.abs(one["pose"][0, 0] - g[tag + "_pose"][0]).max() < 0.1
