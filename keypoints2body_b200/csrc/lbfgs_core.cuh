@@ -393,6 +393,10 @@ struct Lbfgs {
     d_norm = (double)dmax;
     f0 = loss;
     gtd0 = gtd;
+    // torch 2.11's step() calls _strong_wolfe(..., max_ls=max_eval - current_evals) (torch/optim/lbfgs.py, the call in
+    // LBFGS.step; the function's own default of 25 is not used): a line search that starts near the end of the
+    // budget is cut short, which is why the reference's evaluation counts are always max_eval or max_eval + 1
+    // (tests/golden/r2_dist.npz: 37 | 38 and 12 | 13 over 1 024 fits)
     max_ls = max_eval - evals;
     ls_evals = 0;
     t_prev = 0.0;

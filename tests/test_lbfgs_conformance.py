@@ -16,6 +16,7 @@ SURVEY.md section 8(c):
 
 import ctypes as C
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -222,3 +223,17 @@ def test_first_divergence_is_a_noise_level_decision_warp_policy(goldens, emu, we
         n, why = _first_divergence_is_noise(emu.emu_linesearch_replay, g[tag + "_linesearch"][b], g[tag + "_trace"][b],
                                             rows[: int(cnt[0])], n_ref)
         print(tag, "frame", b, "warp policy: agrees for", n, "of", n_ref, "trials;", why)
+
+
+def test_line_search_budget_is_torchs():
+    """lbfgs_core.cuh caps a line search at ``max_eval - evals`` iterations.  That is what the torch this reference runs
+    on does (``LBFGS.step`` passes ``max_ls=max_eval - current_evals`` to ``_strong_wolfe``, whose own default of 25 is
+    not used), and it shows in the reference's evaluation counts: always ``max_eval`` or ``max_eval + 1``."""
+    import inspect
+
+    from torch.optim import lbfgs
+
+    assert "max_ls=max_eval - current_evals" in inspect.getsource(lbfgs.LBFGS.step)
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "r2_dist.npz"))
+    assert set(np.unique(d["s0_evals"]).tolist()) <= {37, 38}          # max_iter 30 -> max_eval 37
+    assert set(np.unique(d["s1_evals"]).tolist()) <= {12, 13}          # max_iter 10 -> max_eval 12
