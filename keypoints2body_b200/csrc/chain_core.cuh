@@ -1006,7 +1006,10 @@ K2B_HD void load_frame_obs(const ChainParams& p, long f, bool stage1, FrameObs& 
 // leader posts.  All of them pass through the same evaluation call; see the note on code size at the top.
 // ---------------------------------------------------------------------------------------------
 // LB: the optimiser is a compile-time choice, so that the other optimiser's state does not occupy registers.
-template <int NS, int K, bool LB>
+// CAM: camera sequences (ChainParams::camera_seq) -- a separate instantiation, because the per-frame stage state costs the
+// world-space kernel registers it does not have (168 of 168 used: the L-BFGS build went from 36 to 130 bytes of spills
+// and 16 % slower with the stage as run-time state).
+template <int NS, int K, bool LB, bool CAM = false>
 K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, int idx,
                           long first_seq, long seq_stride, float* hist) {
   const int lane = lane_id();
@@ -1134,13 +1137,13 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         for (int c = 0; c < 3; ++c)
           ob.keep[c] = (p.preserve_pose && body_owner) ? p.preserve_pose[f * kBodyDim + 3 * lane - 3 + c] : xr[c];
         const bool first = (p.seq_first ? (long)p.seq_first[seq] : p.first_seq_ind) + t == 0;
-        first_frame = first;
+        if (CAM) first_frame = first;
         ob.keep_w2 = first ? 0.f : p.keep_w2;      // the temporal term is on for seq_ind > 0 (world_space.py:211)
         iters = first ? p.iters_first : p.iters_follow;
         evals = 0;
-        evals_prev = 0;
+        if (CAM) evals_prev = 0;
         out_loss = 0.f;
-        if (p.camera_seq) {
+        if (CAM) {
           cstage = 1;
           stage1 = false;
           priors_on = false;
@@ -1166,7 +1169,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       if (phase == kEvalOnly) {
         jout = jframe;
         want_comp = true;
-      } else if (phase == kCamGuess) {
+      } else if (CAM && phase == kCamGuess) {
         // model joints at the frame's initial parameters, without a translation (camera_space.py:113-117)
         with_grad = false;
         with_priors = false;
@@ -1211,7 +1214,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) x[c] = (LB && phase == kRound) ? v.x[c] : xr[c];
-      if (phase == kCamGuess && lane == 24) x[0] = x[1] = x[2] = 0.f;
+      if (CAM && phase == kCamGuess && lane == 24) x[0] = x[1] = x[2] = 0.f;
     } else {
       bar_sync(tm.bar_go, 32 * tm.E);
       if (*reinterpret_cast<const volatile int*>(tm.cmd) == kCmdExit) break;
@@ -1274,7 +1277,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       continue;
     }
     bool frame_done = false;
-    if (phase == kCamGuess) {
+    if (CAM && phase == kCamGuess) {
       // initial camera translation: mean offset of RHip, LHip, RShoulder, LShoulder (guess_init_3d, camera_space.py:16-41)
       wsync();
       const float* jg = p.out_joints + frow * K * 3;
@@ -1291,7 +1294,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
 #pragma unroll
         for (int c = 0; c < 3; ++c) { xr[c] = ct[c]; ob.dref[c] = ct[c]; }
       }
-      begin_camera_stage(true);
+      if constexpr (CAM) begin_camera_stage(true);
     } else if (phase == kEvalOnly) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, gr[c]);
@@ -1315,9 +1318,9 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       for (int c = 0; c < 3; ++c)
         if (!frozen[c]) adam_update(xr[c], m1[c], m2[c], gr[c], step_k, bc2_k);
       if (++k > iters) {
-        if (cstage == 2) {          // camera stage 1 is over: stage 2 starts from its result
+        if (CAM && cstage == 2) {          // camera stage 1 is over: stage 2 starts from its result
           evals_prev = evals;
-          begin_camera_stage(false);
+          if constexpr (CAM) begin_camera_stage(false);
         } else {
           phase = kAdamFinal;
         }
@@ -1373,9 +1376,9 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         // ARE the accepted trial point (lbfgs.py:488-493 adds t d to the iterate the same way the trial was formed), so
         // the loss is the machine's own, bit for bit; the extra forward pass is only run when joints are wanted or the
         // camera stage re-evaluates without the temporal term.
-        if (cstage == 2) {          // camera stage 1 is over: stage 2 starts from its result
+        if (CAM && cstage == 2) {          // camera stage 1 is over: stage 2 starts from its result
           evals_prev = st.evals;
-          begin_camera_stage(false);
+          if constexpr (CAM) begin_camera_stage(false);
         } else if (p.out_joints || p.final_mode) {
           phase = kFinal;
         } else {
@@ -1395,7 +1398,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, xr[c]);
       if (lane == 0) {
         p.out_loss[frow] = out_loss;
-        if (p.out_evals) p.out_evals[frow] = evals + evals_prev;
+        if (p.out_evals) p.out_evals[frow] = CAM ? evals + evals_prev : evals;
       }
       phase = kNewFrame;
     }

@@ -13,14 +13,21 @@ cudaError_t launch_chain<K2B_NS, K2B_K>(const wc::ChainParams& p, const ChainTab
                                         cudaStream_t st) {
   // the optimiser is a template parameter of the kernel (the other optimiser's state would only cost registers)
   const bool lb = p.lbfgs != 0 && !p.eval_only;
-  auto kern = lb ? chain_kernel<K2B_NS, K2B_K, true> : chain_kernel<K2B_NS, K2B_K, false>;
+  auto kern = lb ? chain_kernel<K2B_NS, K2B_K, true, false> : chain_kernel<K2B_NS, K2B_K, false, false>;
+#if K2B_NS == 10
+  // camera sequences (SMPL only, like the reference's CameraSpaceFitter) are their own instantiation
+  if (p.camera_seq) kern = lb ? chain_kernel<K2B_NS, K2B_K, true, true> : chain_kernel<K2B_NS, K2B_K, false, true>;
+#else
+  if (p.camera_seq) return cudaErrorInvalidValue;
+#endif
   const int warps = teams * p.team * (1 + p.helpers);
   const size_t smem = chain_smem_bytes(K2B_NS, teams, p.team, p.helpers, p.hmax);
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[lb]) {
+  static size_t configured[4] = {0, 0, 0, 0};
+  const int variant = (lb ? 1 : 0) + (p.camera_seq ? 2 : 0);
+  if (smem > configured[variant]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[lb] = smem;
+    configured[variant] = smem;
   }
   kern<<<grid, 32 * warps, smem, st>>>(p, tab);
   return cudaGetLastError();

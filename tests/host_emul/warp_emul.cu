@@ -208,7 +208,10 @@ void lane_job() {
     wc::team_release_helpers(wm);
     return;
   }
-  if (g.p.lbfgs) wc::run_evaluator<NS, K, true>(g.p, tb, wm, tm, member, g.seq, g.p.num_seq, g.hist.data());      // one sequence per run
+  if (g.p.camera_seq) {
+    if (g.p.lbfgs) wc::run_evaluator<NS, K, true, true>(g.p, tb, wm, tm, member, g.seq, g.p.num_seq, g.hist.data());
+    else wc::run_evaluator<NS, K, false, true>(g.p, tb, wm, tm, member, g.seq, g.p.num_seq, g.hist.data());
+  } else if (g.p.lbfgs) wc::run_evaluator<NS, K, true>(g.p, tb, wm, tm, member, g.seq, g.p.num_seq, g.hist.data());      // one sequence per run
   else wc::run_evaluator<NS, K, false>(g.p, tb, wm, tm, member, g.seq, g.p.num_seq, g.hist.data());
 }
 
