@@ -922,6 +922,24 @@ K2B_HD int team_candidates(const Machine& st, int E, float (&tc)[kMaxCand]) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kAdamTableW = 64;
 
+// Cycle accounting of the leading evaluator (diagnostic builds only: make EXTRA=-DK2B_CHAIN_PROF; read with
+// k2b_chain_prof).  Slots: 0 rounds, 1 next point + post, 2 line tables, 3 evaluation, 4 wait for the team, 5 machine
+// (advance + candidates), 6 outer update (two-loop recursion), 7 rest of the round, 8 frames.
+#if defined(K2B_CHAIN_PROF) && defined(__CUDACC__)
+__device__ unsigned long long k2b_chain_prof_slots[16];
+#endif
+#if defined(K2B_CHAIN_PROF) && defined(__CUDA_ARCH__)
+#define K2B_PROF_DECL long long pf_t = clock64(); unsigned long long pf_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define K2B_PROF_MARK(slot) { const long long pf_n = clock64(); pf_acc[slot] += (unsigned long long)(pf_n - pf_t); pf_t = pf_n; }
+#define K2B_PROF_COUNT(slot) { ++pf_acc[slot]; }
+#define K2B_PROF_FLUSH if (leader && lane == 0) { for (int i = 0; i < 9; ++i) atomicAdd(&k2b_chain_prof_slots[i], pf_acc[i]); }
+#else
+#define K2B_PROF_DECL
+#define K2B_PROF_MARK(slot)
+#define K2B_PROF_COUNT(slot)
+#define K2B_PROF_FLUSH
+#endif
+
 struct ChainParams {
   long num_seq;            // S sequences, one warp each
   int frames;              // T frames per sequence, walked serially
@@ -1100,8 +1118,11 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       phase = iters > 0 ? kAdam : kAdamFinal;
     }
   };
+  K2B_PROF_DECL
 #pragma unroll 1
   while (true) {
+    K2B_PROF_MARK(7)
+    K2B_PROF_COUNT(0)
     // ===== 1. the next point ======================================================================================
     float x[3] = {0.f, 0.f, 0.f};
     bool with_grad = true, with_priors = priors_on, final_obs = false, do_eval = true, use_line = false, want_comp = false;
@@ -1249,11 +1270,13 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         le_t = base ? 0.f : ti;
       }
     }
+    K2B_PROF_MARK(1)
     // ===== 2. line tables: every evaluator of the team takes its share of the mixture components ====================
     if (tab_mode != kTabKeep) {
       line_tables_update(tb, wm.dbuf, tm, tab_mode, t_step, idx);
       if (teamed) bar_sync(tm.bar_tab, 32 * tm.E);
     }
+    K2B_PROF_MARK(2)
     // ===== 3. the evaluation (the kernel's only call site of eval_warp) =============================================
     float gr[3] = {0.f, 0.f, 0.f};
     float loss = 0.f;
@@ -1265,6 +1288,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       loss = eval_warp<NS, K>(tb, wm, oe, x, with_grad, with_priors, gr, jout, want_comp ? &comp : nullptr,
                               use_line ? &le : nullptr);
     }
+    K2B_PROF_MARK(3)
     // ===== 4. where the result goes ==================================================================================
     if (!leader) {
       if (do_eval) {
@@ -1333,6 +1357,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       for (int c = 0; c < 3; ++c) v.G(st.cur, c) = frozen[c] ? 0.f : gr[c];
       wsync();
       if (teamed) bar_sync(tm.bar_done, 32 * tm.E);
+      K2B_PROF_MARK(4)
       // feed the machine: own result, then every published result it asks for
       unsigned used = 1u;
       float next_loss = loss;
@@ -1353,7 +1378,9 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
           t_pending = (float)st.t;
           tab_next = kTabPoint;
           if (st.need_outer && !st.done) {
+            K2B_PROF_MARK(5)
             st.start_outer(v, v);
+            K2B_PROF_MARK(6)
             if (!st.done) tab_next = kTabLine;
           }
           break;
@@ -1369,6 +1396,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         next_loss = tm.res_f[j];
         wsync();
       }
+      K2B_PROF_MARK(5)
       if (st.done) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) xr[c] = v.xk[c];
@@ -1394,6 +1422,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       frame_done = true;
     }
     if (frame_done) {
+      K2B_PROF_COUNT(8)
 #pragma unroll
       for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, xr[c]);
       if (lane == 0) {
@@ -1403,6 +1432,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       phase = kNewFrame;
     }
   }
+  K2B_PROF_FLUSH
   team_release_helpers(wm);
 }
 

@@ -33,4 +33,16 @@ cudaError_t launch_chain<K2B_NS, K2B_K>(const wc::ChainParams& p, const ChainTab
   return cudaGetLastError();
 }
 
+#if defined(K2B_CHAIN_PROF) && K2B_NS == 10 && K2B_K == 22
+// diagnostic builds only: read (and optionally clear) the leader's cycle accounting of the <10, 22> instantiation
+extern "C" int k2b_chain_prof(unsigned long long* out16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, wc::k2b_chain_prof_slots, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[16] = {0};
+    e = cudaMemcpyToSymbol(wc::k2b_chain_prof_slots, z, sizeof(z));
+  }
+  return e == cudaSuccess ? 0 : -1;
+}
+#endif
+
 }  // namespace k2b

@@ -245,3 +245,33 @@ if what == "camseq":
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
             print(f"camera sequence {opt} 128 frames, {'launch per frame' if mode == '1' else 'one launch'}: {dt*1e3:.1f} ms, "
                   f"{128/dt:.0f} frames/s, median loss {np.median([float(r.loss) for r in res]):.1f}", flush=True)
+if what == "chaincycles":
+    # cycle accounting of the leading evaluator (library built with EXTRA=-DK2B_CHAIN_PROF)
+    import ctypes as C
+    from keypoints2body_b200 import _native as nat
+    lib = nat.load_library()
+    names = ["rounds", "next point + post", "line tables", "evaluation", "wait for the team", "machine", "outer update",
+             "rest of the round", "frames"]
+    for cfg in sys.argv[2:] or ["256x64"]:
+        S, Tn = (int(v) for v in cfg.split("x"))
+        f = WorldSpaceFitter(w, joints_category="AMASS", model_type="smpl", gmm=gmm, use_lbfgs=True)
+        mo = syn.make_motion(S * Tn, seed=3)
+        tgt = syn.kinematic_joints(w, mo["pose"][:, :66], mo["betas"], mo["transl"], 22).reshape(S, Tn, 22, 3).cuda()
+        init = dict(global_orient=torch.zeros(S, 3), body_pose=torch.zeros(S, 69), betas=torch.zeros(S, 10),
+                    transl=mo["transl"].reshape(S, Tn, 3)[:, 0].contiguous())
+        init = {k: v.cuda() for k, v in init.items()}
+        f.fit_chain(init, tgt, None, with_mesh=False)
+        torch.cuda.synchronize()
+        buf = (C.c_ulonglong * 16)()
+        lib.k2b_chain_prof(buf, 1)
+        t0 = time.perf_counter()
+        f.fit_chain(init, tgt, None, with_mesh=False)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        lib.k2b_chain_prof(buf, 1)
+        v = list(buf)
+        rounds, frames = v[0], v[8]
+        cyc = sum(v[1:8])
+        print(f"S={S} T={Tn}: {dt*1e3:.2f} ms, {dt/Tn*1e6:.1f} us per frame-step; {rounds/frames:.2f} rounds per frame, "
+              f"{cyc/frames/1.965e3:.1f} us of leader cycles per frame")
+        for i in range(1, 8):
+            print(f"   {names[i]:20s} {v[i]/frames/1.965e3:7.2f} us per frame  {100*v[i]/cyc:5.1f} %  ({v[i]/rounds:7.0f} cycles per round)")
