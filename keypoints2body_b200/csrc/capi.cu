@@ -317,7 +317,7 @@ void chain_geometry(const k2b_model* m, long S, bool lbfgs, int hmax, int& grid,
   // products, there is nothing for helper warps to do; Adam has no line search to speculate on
   if (lbfgs) helpers = 0; else evals = 1;
   if (single) evals = 1;      // camera sequences: the stage is a state of the leading evaluator only
-  helpers = helpers < 0 ? 0 : (helpers > 3 ? 3 : helpers);
+  helpers = helpers < 0 ? 0 : (helpers > 5 ? 5 : helpers);
   evals = evals < 1 ? 1 : (evals > wc::kMaxCand ? wc::kMaxCand : evals);
   while (evals * (1 + helpers) > kChainMaxWarps) {
     if (helpers > 0) --helpers; else --evals;

@@ -799,59 +799,109 @@ K2B_HD void team_post(const TeamMem& tm, int kind, int n_c, int flags, long row,
 }
 
 // This warp's share (components idx, idx + E, ..) of a line-table update; every evaluator of the team calls it in the
-// same round, then the team meets at bar_tab.  dbuf: 72+ floats of this warp's scratch.
+// same round, then the team meets at bar_tab.  dbuf: this warp's two staging buffers ([2][kDbufStride]).
+// Components are taken two at a time and walked in lockstep: an update is a chain of dependent shared-memory round trips
+// (stage, product, dot products, butterfly), ~2 300 cycles per component at IPC 0.2 when done one after the other
+// (measured with K2B_CHAIN_PROF); two independent chains interleave.  Per component the arithmetic and its order are
+// unchanged, so results are bit-identical to the one-at-a-time version.
 K2B_HD void line_tables_update(const WarpTables& tb, float* dbuf, const TeamMem& tm, int mode, float t_step, int idx) {
   const int lane = lane_id();
+  const bool refresh = mode == kTabRefresh, line = mode == kTabLine;
+  const int rg = lane < 24 ? lane >> 3 : lane - 24;
+  const int cc = lane < 24 ? lane & 7 : 8;
+  const bool act = lane < 27;
+  const int p1 = lane < 24 ? (lane + 8) % 24 : 24 + (lane - 23) % 3;
+  const int p2 = lane < 24 ? (lane + 16) % 24 : 24 + (lane - 22) % 3;
 #pragma unroll 1
-  for (int m = idx; m < kGmmM; m += tm.E) {
-    float* u = tm.lu + m * kPStride;
-    float* w = tm.lw + m * kPStride;
-    float* abc = tm.labc + 4 * m;
-    float A = abc[0];
-    const float B = abc[1], Cc = abc[2];
+  for (int m0 = idx; m0 < kGmmM; m0 += 2 * tm.E) {
+    const int m1 = m0 + tm.E;
+    const bool two = m1 < kGmmM;
+    const int ms[2] = {m0, two ? m1 : m0};
+    float* u[2] = {tm.lu + ms[0] * kPStride, tm.lu + ms[1] * kPStride};
+    float* w[2] = {tm.lw + ms[0] * kPStride, tm.lw + ms[1] * kPStride};
+    float* abc[2] = {tm.labc + 4 * ms[0], tm.labc + 4 * ms[1]};
+    float* db[2] = {dbuf, dbuf + kDbufStride};
+    float A[2], pa[2] = {0.f, 0.f}, pb[2] = {0.f, 0.f}, pc[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      A[k] = abc[k][0];
+      const float B = abc[k][1], Cc = abc[k][2];
+      if (!refresh) A[k] = fmaf(t_step, fmaf(t_step, Cc, 2.f * B), A[k]);   // follow the iterate: xk moved by t_step along d
+    }
     wsync();
-    float pa = 0.f, pb = 0.f, pc = 0.f;
-    const bool refresh = mode == kTabRefresh, line = mode == kTabLine;
-    if (!refresh) {
-      // follow the iterate: xk moved by t_step along the previous direction
-      A = fmaf(t_step, fmaf(t_step, Cc, 2.f * B), A);
-      if (lane < 24) {
+    if (lane < 24) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !two) break;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const int i = 3 * lane + c;
-          u[i] = fmaf(t_step, w[i], u[i]);
+          if (!refresh) u[k][i] = fmaf(t_step, w[k][i], u[k][i]);
+          float dv = 0.f;
+          if (i < kBodyDim) dv = refresh ? tm.xk[3 + i] - tb.mu[ms[k] * kMuStride + i] : tm.d[3 + i];
+          db[k][i] = dv;
+          if (!line) w[k][i] = 0.f;
         }
-      }
-    }
-    if (lane < 24) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int i = 3 * lane + c;
-        float dv = 0.f;
-        if (i < kBodyDim) dv = refresh ? tm.xk[3 + i] - tb.mu[m * kMuStride + i] : tm.d[3 + i];
-        dbuf[i] = dv;
-        if (!line) w[i] = 0.f;
       }
     }
     wsync();
-    if (refresh || line) gmm_matvec(tb, dbuf, m, refresh ? u : w);      // the one precision-matrix product
+    if (refresh || line) {        // the precision-matrix products of the pair
+      float2 acc[2][4];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (act && (k == 0 || two)) gmm_rows(tb, db[k], ms[k], rg, cc, acc[k]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[k][j] = make_float2(0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float y[8] = {acc[k][0].x, acc[k][0].y, acc[k][1].x, acc[k][1].y, acc[k][2].x, acc[k][2].y, acc[k][3].x, acc[k][3].y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (y[j] + shfl(y[j], p1)) + shfl(y[j], p2);
+        if (act && rg == 0 && (k == 0 || two)) {
+          float* out = refresh ? u[k] : w[k];
+          *reinterpret_cast<float4*>(out + 4 * cc) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(out + 36 + 4 * cc) = make_float4(y[4], y[5], y[6], y[7]);
+        }
+      }
+      wsync();
+    }
     if (lane < 24) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int i = 3 * lane + c;
-        if (refresh) pa = fmaf(dbuf[i], u[i], pa);
-        if (line) {
-          pb = fmaf(dbuf[i], u[i], pb);
-          pc = fmaf(dbuf[i], w[i], pc);
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int i = 3 * lane + c;
+          if (refresh) pa[k] = fmaf(db[k][i], u[k][i], pa[k]);
+          if (line) {
+            pb[k] = fmaf(db[k][i], u[k][i], pb[k]);
+            pc[k] = fmaf(db[k][i], w[k][i], pc[k]);
+          }
         }
       }
     }
-    if (refresh) A = wsum(pa);
-    if (line) {
-      pb = wsum(pb);
-      pc = wsum(pc);
+    if (refresh) {
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const float a0 = shfl(pa[0], lane ^ s), a1 = shfl(pa[1], lane ^ s);
+        pa[0] += a0; pa[1] += a1;
+      }
+      A[0] = pa[0]; A[1] = pa[1];
     }
-    if (lane == 0) { abc[0] = A; abc[1] = pb; abc[2] = pc; }
+    if (line) {
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const float b0 = shfl(pb[0], lane ^ s), c0 = shfl(pc[0], lane ^ s);
+        const float b1 = shfl(pb[1], lane ^ s), c1 = shfl(pc[1], lane ^ s);
+        pb[0] += b0; pc[0] += c0; pb[1] += b1; pc[1] += c1;
+      }
+    }
+    if (lane == 0) {
+      abc[0][0] = A[0]; abc[0][1] = pb[0]; abc[0][2] = pc[0];
+      if (two) { abc[1][0] = A[1]; abc[1][1] = pb[1]; abc[1][2] = pc[1]; }
+    }
   }
   wsync();
 }
@@ -929,10 +979,12 @@ constexpr int kAdamTableW = 64;
 __device__ unsigned long long k2b_chain_prof_slots[16];
 #endif
 #if defined(K2B_CHAIN_PROF) && defined(__CUDA_ARCH__)
-#define K2B_PROF_DECL long long pf_t = clock64(); unsigned long long pf_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#define K2B_PROF_MARK(slot) { const long long pf_n = clock64(); pf_acc[slot] += (unsigned long long)(pf_n - pf_t); pf_t = pf_n; }
-#define K2B_PROF_COUNT(slot) { ++pf_acc[slot]; }
-#define K2B_PROF_FLUSH if (leader && lane == 0) { for (int i = 0; i < 9; ++i) atomicAdd(&k2b_chain_prof_slots[i], pf_acc[i]); }
+// accumulators live in shared memory (the kernel has no registers to spare), one row per warp of the CTA
+#define K2B_PROF_DECL __shared__ unsigned long long pf_sh[12][16]; long long pf_t = clock64(); \
+  unsigned long long* pf_acc = pf_sh[threadIdx.x >> 5]; if ((threadIdx.x & 31) < 16) pf_acc[threadIdx.x & 31] = 0ull; __syncwarp();
+#define K2B_PROF_MARK(slot) { const long long pf_n = clock64(); if ((threadIdx.x & 31) == 0) pf_acc[slot] += (unsigned long long)(pf_n - pf_t); pf_t = pf_n; }
+#define K2B_PROF_COUNT(slot) { if ((threadIdx.x & 31) == 0) ++pf_acc[slot]; }
+#define K2B_PROF_FLUSH __syncwarp(); if (leader && lane == 0) { for (int i = 0; i < 14; ++i) atomicAdd(&k2b_chain_prof_slots[i], pf_acc[i]); }
 #else
 #define K2B_PROF_DECL
 #define K2B_PROF_MARK(slot)
@@ -1273,8 +1325,11 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
     K2B_PROF_MARK(1)
     // ===== 2. line tables: every evaluator of the team takes its share of the mixture components ====================
     if (tab_mode != kTabKeep) {
+      K2B_PROF_COUNT(9)
       line_tables_update(tb, wm.dbuf, tm, tab_mode, t_step, idx);
+      K2B_PROF_MARK(10)
       if (teamed) bar_sync(tm.bar_tab, 32 * tm.E);
+      K2B_PROF_MARK(11)
     }
     K2B_PROF_MARK(2)
     // ===== 3. the evaluation (the kernel's only call site of eval_warp) =============================================

@@ -275,3 +275,5 @@ if what == "chaincycles":
               f"{cyc/frames/1.965e3:.1f} us of leader cycles per frame")
         for i in range(1, 8):
             print(f"   {names[i]:20s} {v[i]/frames/1.965e3:7.2f} us per frame  {100*v[i]/cyc:5.1f} %  ({v[i]/rounds:7.0f} cycles per round)")
+        if v[9]:
+            print(f"   table updates per frame {v[9]/frames:.2f}: own share {v[10]/v[9]:.0f} cycles, wait for the team {v[11]/v[9]:.0f} cycles per update")

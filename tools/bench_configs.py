@@ -93,7 +93,7 @@ def main():
                                       use_shape_optimization=False)
         ms = wall_ms(lambda: k2b.optimize_params_sequence(tgt[:Tc], body_model="smpl", joint_layout="AMASS", model=w,
                                                           config=scfg), warm=1, reps=2)
-        emit(config=f"f1 camera-space optimize_params_sequence SMPL T={Tc} (serial, 2 launches per frame)",
+        emit(config=f"f1 camera-space optimize_params_sequence SMPL T={Tc} (one launch: k2b_fit_chain camera_sequence)",
              optimizer="lbfgs" if lb else "adam", ms_per_call=ms, frames_per_s=Tc * 1e3 / ms,
              timing="wall clock through the public API")
 
@@ -137,6 +137,37 @@ def main():
         emit(config=f"config5 {mt} full mesh of {B} parameter sets ({nv} vertices)", ms=ms, frames_per_s=B * 1e3 / ms,
              vertex_output_GBps=B * nv * 12 / ms / 1e6, hbm_frac_of_measured=B * nv * 12 / ms / 1e6 / 6551.7,
              timing="CUDA events, chunk of 131072 frames (1M frames = 8 such chunks)")
+        if mt == "smplx":       # BASELINE configs[4] as written: 1 M fitted SMPL-X frames (8 chunks into one 15.7 GB window)
+            def million():
+                for _ in range(8):
+                    f.forward_batch(p, out_vertices=buf)
+            ms = cuda_ms(million, warm=1, reps=2)
+            emit(config=f"config5 smplx full mesh of {8 * B} parameter sets (8 chunks of {B})", ms=ms, frames_per_s=8 * B * 1e3 / ms,
+                 vertex_output_GBps=8 * B * nv * 12 / ms / 1e6, hbm_frac_of_measured=8 * B * nv * 12 / ms / 1e6 / 6551.7,
+                 timing="CUDA events")
+        wc_ = syn.make_body_model(mt, skin_layout="coherent")
+        fc_ = WorldSpaceFitter(wc_, joints_category="AMASS", model_type=mt, gmm=gmm, device=dev)
+        ms = cuda_ms(lambda: fc_.forward_batch(p, out_vertices=buf))
+        emit(config=f"config5 {mt} full mesh of {B} parameter sets, coherent vertex -> joint assignment", ms=ms,
+             frames_per_s=B * 1e3 / ms, vertex_output_GBps=B * nv * 12 / ms / 1e6,
+             hbm_frac_of_measured=B * nv * 12 / ms / 1e6 / 6551.7, timing="CUDA events")
+
+    # ---- rows f2 / f4: the general articulated fit through its fitters (B = 1 per call, like the reference) ----------
+    from keypoints2body_b200.core.fitters.misc_models import FLAMEFitter, MANOFitter
+    from keypoints2body_b200.models.smpl_data import FLAMEData, MANOData, SMPLHData, SMPLXData
+    from oracle_free_problem import articulated_problem
+    for mt in ("smplx", "smplh", "mano", "flame"):
+        wmod, tgt_a, idx_a, init_a = articulated_problem(mt, 1, seed=700)
+        cls = {"smplx": SMPLXData, "smplh": SMPLHData, "mano": MANOData, "flame": FLAMEData}[mt]
+        for lb in (True, False):
+            if mt in ("smplx", "smplh"):
+                fit = WorldSpaceFitter(wmod, joints_category="GENERIC", model_type=mt, gmm=gmm, use_lbfgs=lb, device=dev)
+            else:
+                fit = (MANOFitter if mt == "mano" else FLAMEFitter)(wmod, coordinate_mode="world", use_lbfgs=lb, device=dev)
+            p0 = cls(**{k: v.to(dev) for k, v in init_a.items()})
+            ms = wall_ms(lambda: fit.fit_frame(p0, tgt_a, torch.ones(len(idx_a)), seq_ind=0, target_model_indices=idx_a), warm=2, reps=10)
+            emit(config=f"f2/f4 {mt} fit_frame, {len(idx_a)} observed model points (30 its, full mesh), general articulated fit",
+                 optimizer="lbfgs" if lb else "adam", ms_per_call=ms, frames_per_s=1e3 / ms, timing="wall clock incl. Python")
 
 
 if __name__ == "__main__":
