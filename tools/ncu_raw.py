@@ -23,10 +23,10 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
-    for r in rows[2:]:
+    for n, r in enumerate(rows[2:]):
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
-        print("##", d.get("Kernel Name", "")[:90])
+        print(f"## launch {n}:", d.get("Kernel Name", "")[:90])
         for k in KEYS:
             if k in d:
                 print(f"{k} = {d[k]} {u[k]}")
