@@ -457,6 +457,221 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_tc_kernel(const __gr
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_base, kTcTmemCols);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused blend + skinning with lane = VERTEX (round 2).  A column tile is 128 vertices; it has THREE accumulators
+// D_c[vertex lane][frame], c = x, y, z (three MMA chains over the same frame operand, 3 x FR TMEM columns), so a lane
+// reads its vertex's three coordinates straight from tensor memory: no shuffles, every lane useful (the
+// lane = coordinate layout above uses 30 of 32 and needs two shuffles per output), and the three rows of a joint's
+// skinning matrix are loaded once per vertex instead of once per coordinate lane: 2 NE x 3 LDS.128 per 96 outputs
+// = 0.25 shared-memory wavefronts per output instead of 0.43 -- the shared-memory pipe is what bounds the kernel
+// (profiles/r02_blend_skin_ncu_metrics.txt: 81 % of peak).  Price: a lane stores x, y, z of its vertex (12 bytes), so a
+// store instruction writes 4 bytes every 12 (three instructions fill the 384-byte run).  Two tiles are in flight (two
+// accumulator stages of 3 x FR columns); dirs blocks stream through the same TMA ring, three per K block.
+// b_tiles layout: [tile][coordinate][K block][128 rows x 128 B swizzled image], row n = vertex 128 tile + n.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kTcVtVerts = 128;      // vertices per tile of the lane = vertex kernel
+constexpr int kTcVtAccStages = 2;
+
+template <int FR, int STAGES, int NE, int NJ>
+__global__ void __launch_bounds__(kTcThreads, 1) blend_skin_vt_kernel(const __grid_constant__ BlendParams p) {
+  static_assert(FR % (16 * kTcEpiParts) == 0 && 3 * FR * kTcVtAccStages <= kTcTmemCols && STAGES <= 6 && STAGES % 3 == 0,
+                "tile shape");
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  const int kpad = p.kpad;
+  constexpr int b_bytes = tc_b_bytes();
+  const int f_bytes = tc_f_bytes(kpad, FR);
+  __half* sF = reinterpret_cast<__half*>(tc_smem);
+  unsigned char* sR = tc_smem + f_bytes;
+  float4* sA = reinterpret_cast<float4*>(tc_smem + f_bytes + (size_t)STAGES * b_bytes);   // [FR][NJ][3] rows, translation folded in
+  const size_t a_bytes = (size_t)FR * NJ * 48 + (size_t)FR * 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + f_bytes + (size_t)STAGES * b_bytes + a_bytes);
+  // bars: [0,6) ring_full; [6,12) ring_empty; [12,14) acc_full; [16,18) acc_empty; then the TMEM base word
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = tc::smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      tc::mbar_init(BAR(i), 1);
+      tc::mbar_init(BAR(6 + i), 1);
+    }
+    for (int i = 0; i < kTcVtAccStages; ++i) {
+      tc::mbar_init(BAR(12 + i), 1);                       // acc_full: tcgen05.commit
+      tc::mbar_init(BAR(16 + i), 128 * kTcEpiParts);       // acc_empty: the epilogue warps that drained the stage
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_word), kTcTmemCols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_word;
+
+  const long num_passes = (p.num_frames + FR - 1) / FR;
+  const uint32_t idesc = tc::make_idesc(kTcN, FR);
+  const int kblocks = kpad / kTcBK;
+  const int ntiles = p.n_tiles;
+  uint32_t ph_rfull = 0, ph_rempty = 0, ph_afull = 0, ph_aempty = 0;
+  long tile_seq = 0;   // running tile counter across passes (accumulator stage = tile_seq & 1)
+  long blk_seq = 0;    // running dirs-block counter across passes (ring position)
+
+  for (long ps = blockIdx.x; ps < num_passes; ps += gridDim.x) {
+    const long f0 = ps * FR;
+    __syncthreads();      // every MMA of the previous pass has retired before the features are overwritten
+    for (int i = tid; i < FR * kpad; i += kTcThreads) {
+      const int r = i / kpad, k = i - r * kpad;
+      const long f = f0 + r;
+      __half x = __float2half_rn(0.f);
+      if (k < p.npose) {
+        x = __float2half_rn(p.feat[f * p.npose + k]);
+      } else if (k < p.npose + 3 * p.ns && f < p.num_frames) {
+        const int part = (k - p.npose) / p.ns, s = (k - p.npose) - part * p.ns;
+        const float b = p.shape[f * p.ns + s];
+        const __half hi = __float2half_rn(b);
+        x = part == 1 ? __float2half_rn(b - __half2float(hi)) : hi;   // [hi | lo | hi]
+      }
+      sF[(k >> 6) * (FR * 64) + tc_elem_off(r, k & 63)] = x;
+    }
+    {
+      const float4* src = p.skin + f0 * (3L * NJ);
+      for (int i = tid; i < FR * 3 * NJ; i += kTcThreads) {
+        float4 r = src[i];
+        const int fr = i / (3 * NJ), c = i % 3;
+        const long f = f0 + fr;
+        if (p.transl && f < p.num_frames) r.w += p.transl[f * 3 + c];    // sum_k w_k = 1: the translation rides along
+        sA[i] = r;
+      }
+    }
+    tc::fence_proxy_async();
+    __syncthreads();
+
+    if (warp == kTcEpiWarps) {
+      // ---- TMA producer: blocks in the order the MMA warp consumes them: (tile, kb, coordinate) -----------------
+      if (lane == 0) {
+        long seq = blk_seq;
+        for (int t = 0; t < ntiles; ++t)
+          for (int kb = 0; kb < kblocks; ++kb)
+            for (int c = 0; c < 3; ++c, ++seq) {
+              const int s = (int)(seq % STAGES);
+              if (seq >= STAGES) {
+                tc::mbar_wait(BAR(6 + s), (ph_rempty >> s) & 1u);
+                ph_rempty ^= 1u << s;
+              }
+              const size_t blk = ((size_t)t * 3 + c) * kblocks + kb;
+              tc::mbar_expect_tx(BAR(s), (uint32_t)b_bytes);
+              tc::bulk_g2s(tc::smem_u32(sR + (size_t)s * b_bytes), p.b_tiles + blk * (b_bytes / 2), (uint32_t)b_bytes, BAR(s));
+            }
+      }
+    } else if (warp == kTcEpiWarps + 1) {
+      // ---- MMA issuer: three interleaved accumulation chains (x, y, z) per tile ------------------------------------
+      if (lane == 0) {
+        const uint32_t f_addr = tc::smem_u32(sF);
+        long seq = blk_seq;
+        for (int t = 0; t < ntiles; ++t) {
+          const long ts = tile_seq + t;
+          const int a = (int)(ts & 1);
+          if (ts >= kTcVtAccStages) {
+            tc::mbar_wait(BAR(16 + a), (ph_aempty >> a) & 1u);
+            ph_aempty ^= 1u << a;
+          }
+          const uint32_t d0 = tmem_base + (uint32_t)(a * 3 * FR);
+          for (int kb = 0; kb < kblocks; ++kb, seq += 3) {
+            uint32_t rr[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const int s = (int)((seq + c) % STAGES);
+              tc::mbar_wait(BAR(s), (ph_rfull >> s) & 1u);
+              ph_rfull ^= 1u << s;
+              rr[c] = tc::smem_u32(sR + (size_t)s * b_bytes);
+            }
+            tc::tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < kTcBK / 16; ++j) {
+              const uint64_t fdesc = tc::make_desc(f_addr + (uint32_t)(kb * (FR * 128) + j * 32));
+              const uint32_t acc = (kb | j) ? 1u : 0u;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) tc::mma_f16(d0 + (uint32_t)(c * FR), tc::make_desc(rr[c] + j * 32), fdesc, idesc, acc);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tc::mma_commit(BAR(6 + (int)((seq + c) % STAGES)));
+          }
+          tc::mma_commit(BAR(12 + a));
+        }
+      }
+    } else {
+      // ---- epilogue warps: lane quarter q = warp % 4, accumulator stage h = tile parity, frame part ----------------
+      const int q = warp & 3, h = (warp >> 2) & 1, part = warp >> 3;
+      constexpr int CH = FR / 16 / kTcEpiParts;
+      constexpr int FS = 3 * NJ;                              // float4 rows per frame
+      const long ncols = 3L * p.nv;
+      for (int t = 0; t < ntiles; ++t) {
+        const long ts = tile_seq + t;
+        if ((int)(ts & 1) != h) continue;
+        const int v = t * kTcVtVerts + q * 32 + lane;
+        const bool v_ok = v < p.nv;
+        float tv[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tv[c] = v_ok ? __ldg(p.v_template + 3 * v + c) : 0.f;
+        const float4* Ak[NE];
+        float wk[NE];
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+          Ak[k] = sA + 3 * (v_ok ? __ldg(p.ell_idx + (long)k * p.nv + v) : 0);
+          wk[k] = v_ok ? __ldg(p.ell_w + (long)k * p.nv + v) : 0.f;
+        }
+        tc::mbar_wait(BAR(12 + h), (ph_afull >> h) & 1u);
+        ph_afull ^= 1u << h;
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 3 * FR);
+        float* o = p.out + (f0 + part * (CH * 16)) * ncols + 3L * v;
+        const long left = p.num_frames - f0;
+        int nvalid = (v_ok ? (left < FR ? (int)left : FR) : 0) - part * (CH * 16);
+#pragma unroll 1
+        for (int ch = part * CH; ch < (part + 1) * CH; ++ch) {
+          uint32_t ax[16], ay[16], az[16];
+          tc::tmem_ld16(taddr + (uint32_t)(ch * 16), ax);
+          tc::tmem_ld16(taddr + (uint32_t)(FR + ch * 16), ay);
+          tc::tmem_ld16(taddr + (uint32_t)(2 * FR + ch * 16), az);
+          tc::tmem_ld_wait();
+          if (ch == (part + 1) * CH - 1) {
+            tc::tc_fence_before();
+            tc::mbar_arrive(BAR(16 + h));                      // the stage may be overwritten
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float px = fmaf(__uint_as_float(ax[i]), p.inv_scale, tv[0]);
+            const float py = fmaf(__uint_as_float(ay[i]), p.inv_scale, tv[1]);
+            const float pz = fmaf(__uint_as_float(az[i]), p.inv_scale, tv[2]);
+            float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
+#pragma unroll
+            for (int k = 0; k < NE; ++k) {
+              const float4* r = Ak[k] + (ch * 16 + i) * FS;
+              const float4 r0 = r[0], r1 = r[1], r2 = r[2];
+              T0.x = fmaf(wk[k], r0.x, T0.x); T0.y = fmaf(wk[k], r0.y, T0.y); T0.z = fmaf(wk[k], r0.z, T0.z); T0.w = fmaf(wk[k], r0.w, T0.w);
+              T1.x = fmaf(wk[k], r1.x, T1.x); T1.y = fmaf(wk[k], r1.y, T1.y); T1.z = fmaf(wk[k], r1.z, T1.z); T1.w = fmaf(wk[k], r1.w, T1.w);
+              T2.x = fmaf(wk[k], r2.x, T2.x); T2.y = fmaf(wk[k], r2.y, T2.y); T2.z = fmaf(wk[k], r2.z, T2.z); T2.w = fmaf(wk[k], r2.w, T2.w);
+            }
+            if (i < nvalid) {
+              o[0] = fmaf(T0.x, px, fmaf(T0.y, py, fmaf(T0.z, pz, T0.w)));
+              o[1] = fmaf(T1.x, px, fmaf(T1.y, py, fmaf(T1.z, pz, T1.w)));
+              o[2] = fmaf(T2.x, px, fmaf(T2.y, py, fmaf(T2.z, pz, T2.w)));
+            }
+            o += ncols;
+          }
+          nvalid -= 16;
+        }
+      }
+    }
+    tile_seq += ntiles;
+    blk_seq += (long)ntiles * 3 * kblocks;
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, kTcTmemCols);
+}
 #endif  // __CUDACC__
 
 }  // namespace k2b

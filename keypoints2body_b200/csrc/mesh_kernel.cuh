@@ -47,6 +47,7 @@ struct MeshModel {
   // tensor-core blend (blend_tc.cuh)
   bool tc = false;
   bool fused = false;          // skinning fused into the blend epilogue (needs features + skinning rows in smem)
+  bool vt = false;             // fused with lane = vertex tiles (blend_skin_vt_kernel); false: lane = coordinate tiles
   int kpad = 0, n_tiles = 0;
   __half* b_tiles = nullptr;   // [n_tiles][kpad/64][tc_b_bytes/2] pre-tiled FP16 image of dir_scale * [posedirs ; shapedirs]
   float dir_scale = 1.f;       // power of two that lifts the dirs into FP16's normal range
@@ -154,8 +155,14 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
     // SMPL: 64 frames of features (64 KB) + their skinning rows (72 KB) + the ring fit one SM -> fused epilogue
     m.fused = nj == kTcFusedJoints && ell <= 4 && m.kpad <= kTcKpadWide &&
               tc_smem_bytes(m.kpad, kTcMFused, kTcStagesFused, nj) <= 227 * 1024;
+    // fused: lane = vertex tiles (128 vertices, three coordinate blocks each) unless K2B_MESH_LAYOUT=coord asks for the
+    // round-1 lane = coordinate tiles (40 vertices x 3 coordinates per 128-row block; kept for A/B runs)
+    const char* lay = getenv("K2B_MESH_LAYOUT");
+    m.vt = m.fused && !(lay && std::string(lay) == "coord");
     const int per_tile = m.fused ? kTcVertsPerTile * 3 : kTcN;
-    m.n_tiles = ((ncols + per_tile - 1) / per_tile + 1) / 2 * 2;   // tiles are consumed in pairs
+    m.n_tiles = m.vt ? (nv + kTcVtVerts - 1) / kTcVtVerts
+                     : ((ncols + per_tile - 1) / per_tile + 1) / 2 * 2;   // lane = coordinate tiles are consumed in pairs
+    const int blocks_per_tile = m.vt ? 3 : 1;
     const size_t blk_halfs = (size_t)tc_b_bytes() / 2;
     // FP16 keeps TF32's 10 mantissa bits only in its normal range (>= 6.1e-5): scale the dirs by a power of two
     // so their largest entry sits near 2^10; the epilogue multiplies the accumulator by 1 / scale (exact).
@@ -166,12 +173,16 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
     if (dmax > 0.f) frexpf(dmax, &e);                 // dmax = f * 2^e, f in [0.5, 1)
     m.dir_scale = ldexpf(1.f, 10 - e);
     const float S = m.dir_scale;
-    std::vector<__half> bt((size_t)m.n_tiles * kblocks * blk_halfs, __float2half_rn(0.f));
-    for (int nt = 0; nt < m.n_tiles; ++nt)
+    std::vector<__half> bt((size_t)m.n_tiles * blocks_per_tile * kblocks * blk_halfs, __float2half_rn(0.f));
+    for (int nb = 0; nb < m.n_tiles * blocks_per_tile; ++nb)
       for (int n = 0; n < kTcN; ++n) {
-        int col = nt * kTcN + n;
-        if (m.fused) {
-          const int vert = tc_tile_vertex(nt, n);
+        const int nt = nb;      // block index in the image ([tile][coordinate] for lane = vertex tiles)
+        int col = nb * kTcN + n;
+        if (m.vt) {
+          const int vert = (nb / 3) * kTcVtVerts + n;
+          col = vert < nv ? 3 * vert + nb % 3 : ncols;
+        } else if (m.fused) {
+          const int vert = tc_tile_vertex(nb, n);
           col = vert < 0 ? ncols : 3 * vert + (n % 32) % 3;
         }
         if (col >= ncols) continue;
@@ -459,14 +470,19 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
     const int fr = m.fused ? kTcMFused : kTcM;
     const size_t tsm = tc_smem_bytes(m.kpad, fr, m.fused ? kTcStagesFused : kTcStages, m.fused ? m.nj : 0);
     auto* kern = blend_skin_tc_kernel<kTcM, kTcStages, 0, 0>;
-    if (m.fused) {
+    if (m.fused && m.vt) {
+      kern = m.ell == 1 ? blend_skin_vt_kernel<kTcMFused, kTcStagesFused, 1, kTcFusedJoints>
+           : m.ell == 2 ? blend_skin_vt_kernel<kTcMFused, kTcStagesFused, 2, kTcFusedJoints>
+           : m.ell == 3 ? blend_skin_vt_kernel<kTcMFused, kTcStagesFused, 3, kTcFusedJoints>
+                        : blend_skin_vt_kernel<kTcMFused, kTcStagesFused, 4, kTcFusedJoints>;
+    } else if (m.fused) {
       kern = m.ell == 1 ? blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 1, kTcFusedJoints>
            : m.ell == 2 ? blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 2, kTcFusedJoints>
            : m.ell == 3 ? blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 3, kTcFusedJoints>
                         : blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 4, kTcFusedJoints>;
     }
-    static size_t tc_configured[5] = {0, 0, 0, 0, 0};
-    const int variant = m.fused ? m.ell : 0;
+    static size_t tc_configured[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int variant = m.fused ? m.ell + (m.vt ? 4 : 0) : 0;
     if (tsm > tc_configured[variant]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
       if (e != cudaSuccess) {
