@@ -291,6 +291,109 @@ mesh_pose_kernel(int nj, int ns, const int* __restrict__ parents, const float4* 
   }
 }
 
+// ---- kernel A': the same, staged through shared memory (round 2) -----------------------------------------------------
+// Kernel A gives every thread its own 0.8 + 1.2 KB rows of the two output arrays, so a warp's store instruction touches
+// 32 sectors, and it walks the kinematic chain through global memory (the parent's transform is read back).  Here a
+// block of kPoseStagedThreads frames builds its rows in shared memory (row strides padded to an odd number of words:
+// conflict-free) and copies them out as one contiguous, coalesced run per array.  Used when the rows of 32 frames fit in
+// 64 KB (SMPL, MANO, FLAME); same arithmetic in the same order as kernel A.
+constexpr int kPoseStagedThreads = 32;
+inline size_t mesh_pose_staged_smem(int nj) {
+  const int npose = 9 * (nj - 1);
+  return sizeof(float) * (size_t)kPoseStagedThreads * (size_t)((npose | 1) + ((nj * 12) | 1));
+}
+__global__ void __launch_bounds__(kPoseStagedThreads)
+mesh_pose_staged_kernel(int nj, int ns, const int* __restrict__ parents, const float4* __restrict__ rel,
+                        const float4* __restrict__ J0S, const float* __restrict__ full_pose,
+                        const float* __restrict__ shape, const float* __restrict__ transl, long B, long Bp,
+                        float* __restrict__ posefeat, float* __restrict__ skin, float* __restrict__ out_joints,
+                        int njout) {
+  extern __shared__ __align__(16) float ps_sm[];
+  const int npose = 9 * (nj - 1), na = nj * 12;
+  const int spf = npose | 1, sa = na | 1;          // odd row strides
+  float* s_pf = ps_sm;
+  float* s_A = ps_sm + (size_t)kPoseStagedThreads * spf;
+  const int tid = threadIdx.x;
+  const long f0 = (long)blockIdx.x * kPoseStagedThreads;
+  const long f = f0 + tid;
+  float* pf = s_pf + (size_t)tid * spf;
+  float* A = s_A + (size_t)tid * sa;
+  if (f >= B) {  // zero the padding frames so the tile kernels read finite values
+    for (int i = 0; i < npose; ++i) pf[i] = 0.f;
+    for (int i = 0; i < na; ++i) A[i] = 0.f;
+  } else {
+    float sh[20];
+    for (int s = 0; s < ns; ++s) sh[s] = shape[f * ns + s];
+    const V3 tr = transl ? v3(transl[f * 3], transl[f * 3 + 1], transl[f * 3 + 2]) : v3(0.f, 0.f, 0.f);
+    for (int j = 0; j < nj; ++j) {
+      const float* r = full_pose + (f * nj + j) * 3;
+      Rod o;
+      const M3 R = rodrigues(v3(r[0], r[1], r[2]), o);
+      if (j > 0) {
+        float* q = pf + (j - 1) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) q[i] = R.m[i] - ((i == 0 || i == 4 || i == 8) ? 1.f : 0.f);
+      }
+      const float4* e = rel + (long)j * (1 + ns);
+      float4 r0 = e[0];
+      V3 off = v3(r0.x, r0.y, r0.z);
+      for (int s = 0; s < ns; ++s) {
+        const float4 d = e[1 + s];
+        off.x = fmaf(d.x, sh[s], off.x); off.y = fmaf(d.y, sh[s], off.y); off.z = fmaf(d.z, sh[s], off.z);
+      }
+      M3 Rw;
+      V3 t;
+      const int pj = parents[j];
+      if (pj < 0) {
+        Rw = R;
+        t = off;
+      } else {
+        const float* P = A + pj * 12;
+        M3 Rp;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          Rp.m[3 * i] = P[4 * i]; Rp.m[3 * i + 1] = P[4 * i + 1]; Rp.m[3 * i + 2] = P[4 * i + 2];
+        }
+        Rw = matmul(Rp, R);
+        t = matvec(Rp, off) + v3(P[3], P[7], P[11]);
+      }
+      float* Q = A + j * 12;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        Q[4 * i] = Rw.m[3 * i]; Q[4 * i + 1] = Rw.m[3 * i + 1]; Q[4 * i + 2] = Rw.m[3 * i + 2];
+      }
+      Q[3] = t.x; Q[7] = t.y; Q[11] = t.z;
+      float* oj = out_joints + (f * njout + j) * 3;
+      oj[0] = t.x + tr.x; oj[1] = t.y + tr.y; oj[2] = t.z + tr.z;
+    }
+    for (int j = 0; j < nj; ++j) {
+      const float4* e = J0S + (long)j * (1 + ns);
+      float4 r0 = e[0];
+      V3 J = v3(r0.x, r0.y, r0.z);
+      for (int s = 0; s < ns; ++s) {
+        const float4 d = e[1 + s];
+        J.x = fmaf(d.x, sh[s], J.x); J.y = fmaf(d.y, sh[s], J.y); J.z = fmaf(d.z, sh[s], J.z);
+      }
+      float* Q = A + j * 12;
+      Q[3] -= fmaf(Q[0], J.x, fmaf(Q[1], J.y, Q[2] * J.z));
+      Q[7] -= fmaf(Q[4], J.x, fmaf(Q[5], J.y, Q[6] * J.z));
+      Q[11] -= fmaf(Q[8], J.x, fmaf(Q[9], J.y, Q[10] * J.z));
+    }
+  }
+  __syncwarp();
+  // coalesced copy-out: the block's rows are one contiguous run in each global array (Bp is a multiple of 128)
+  float* gp = posefeat + f0 * npose;
+  for (int i = tid; i < kPoseStagedThreads * npose; i += kPoseStagedThreads) {
+    const int fr = i / npose, e = i - fr * npose;
+    gp[i] = s_pf[(size_t)fr * spf + e];
+  }
+  float* ga = skin + f0 * (long)na;
+  for (int i = tid; i < kPoseStagedThreads * na; i += kPoseStagedThreads) {
+    const int fr = i / na, e = i - fr * na;
+    ga[i] = s_A[(size_t)fr * sa + e];
+  }
+}
+
 // ---- kernel B: blend + skin a (vertex tile x frame tile) -------------------------------------
 // thread = vertex; 16 frames per thread in registers; posefeat / shape / skin tiles in smem.
 __global__ void __launch_bounds__(kMeshVT)
@@ -459,9 +562,25 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
   float* posefeat = (float*)a.workspace;
   float* skin = posefeat + Bp * m.npose;
   const int njout = m.nj + m.nextra;
-  mesh_pose_kernel<<<(unsigned)((Bp + 127) / 128), 128, 0, st>>>(
-      m.nj, m.ns, m.parents, (const float4*)m.rel, (const float4*)m.J0S, a.full_pose, a.shape, a.transl, B, Bp,
-      posefeat, skin, a.out_joints, njout);
+  const size_t psm = mesh_pose_staged_smem(m.nj);
+  if (psm <= 64 * 1024) {
+    static size_t pose_configured = 0;
+    if (psm > pose_configured) {
+      cudaError_t e = cudaFuncSetAttribute(mesh_pose_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+      if (e != cudaSuccess) {
+        err = cudaGetErrorString(e);
+        return false;
+      }
+      pose_configured = psm;
+    }
+    mesh_pose_staged_kernel<<<(unsigned)(Bp / kPoseStagedThreads), kPoseStagedThreads, psm, st>>>(
+        m.nj, m.ns, m.parents, (const float4*)m.rel, (const float4*)m.J0S, a.full_pose, a.shape, a.transl, B, Bp,
+        posefeat, skin, a.out_joints, njout);
+  } else {
+    mesh_pose_kernel<<<(unsigned)((Bp + 127) / 128), 128, 0, st>>>(
+        m.nj, m.ns, m.parents, (const float4*)m.rel, (const float4*)m.J0S, a.full_pose, a.shape, a.transl, B, Bp,
+        posefeat, skin, a.out_joints, njout);
+  }
   ++launches;
   const char* force_fp32 = getenv("K2B_MESH_FP32");   // diagnostics / tests: take the CUDA-core path
   if (m.tc && a.out_vertices && !(force_fp32 && atoi(force_fp32))) {
