@@ -48,6 +48,7 @@ struct MeshModel {
   bool tc = false;
   bool fused = false;          // skinning fused into the blend epilogue (needs features + skinning rows in smem)
   bool vt = false;             // fused with lane = vertex tiles (blend_skin_vt_kernel); false: lane = coordinate tiles
+  int fused_fr = 0;            // frames per pass of the fused kernel (64: SMPL; 32: SMPL-H / SMPL-X, whose skinning rows are larger)
   int kpad = 0, n_tiles = 0;
   __half* b_tiles = nullptr;   // [n_tiles][kpad/64][tc_b_bytes/2] pre-tiled FP16 image of dir_scale * [posedirs ; shapedirs]
   float dir_scale = 1.f;       // power of two that lifts the dirs into FP16's normal range
@@ -153,12 +154,23 @@ inline bool mesh_model_build(const k2b_model_desc& d, const std::vector<double>&
     m.kpad = tc_kpad(kdepth);
     const int ncols = nv * 3, kblocks = m.kpad / kTcBK;
     // SMPL: 64 frames of features (64 KB) + their skinning rows (72 KB) + the ring fit one SM -> fused epilogue
-    m.fused = nj == kTcFusedJoints && ell <= 4 && m.kpad <= kTcKpadWide &&
-              tc_smem_bytes(m.kpad, kTcMFused, kTcStagesFused, nj) <= 227 * 1024;
+    // SMPL-H / SMPL-X (round 2): the lane = vertex kernel at 32 frames per pass (features 33 / 37 KB + ring 96 KB + the
+    // skinning rows of 52 / 55 joints 80 / 84 KB = 211 / 216 KB), so that v_posed never reaches HBM there either
+    const char* lay = getenv("K2B_MESH_LAYOUT");
+    const bool coord = lay && std::string(lay) == "coord";       // round-1 lane = coordinate tiles, kept for A/B runs
+    const char* unf = getenv("K2B_MESH_UNFUSED");                // A/B: blend + in-place skinning for SMPL-H / SMPL-X
+    m.fused = false;
+    if (ell <= 4 && nj == kTcFusedJoints && tc_smem_bytes(m.kpad, kTcMFused, kTcStagesFused, nj) <= 227 * 1024) {
+      m.fused = true;
+      m.fused_fr = kTcMFused;
+    } else if (ell <= 4 && (nj == 52 || nj == 55) && !coord && !(unf && atoi(unf)) &&
+               tc_smem_bytes(m.kpad, 32, kTcStagesFused, nj) <= 227 * 1024) {
+      m.fused = true;
+      m.fused_fr = 32;
+    }
     // fused: lane = vertex tiles (128 vertices, three coordinate blocks each) unless K2B_MESH_LAYOUT=coord asks for the
     // round-1 lane = coordinate tiles (40 vertices x 3 coordinates per 128-row block; kept for A/B runs)
-    const char* lay = getenv("K2B_MESH_LAYOUT");
-    m.vt = m.fused && !(lay && std::string(lay) == "coord");
+    m.vt = m.fused && !coord;
     const int per_tile = m.fused ? kTcVertsPerTile * 3 : kTcN;
     m.n_tiles = m.vt ? (nv + kTcVtVerts - 1) / kTcVtVerts
                      : ((ncols + per_tile - 1) / per_tile + 1) / 2 * 2;   // lane = coordinate tiles are consumed in pairs
@@ -586,22 +598,22 @@ inline bool mesh_forward(const MeshModel& m, const k2b_mesh_args& a, cudaStream_
   if (m.tc && a.out_vertices && !(force_fp32 && atoi(force_fp32))) {
     // ---- tensor-core path: blend (tcgen05) -> in-place skinning -> extra-joint gather ----------
     // SMPL: fused blend + skinning, 64 frames per pass.  SMPL-H / SMPL-X: 128-frame blend, then in-place skinning.
-    const int fr = m.fused ? kTcMFused : kTcM;
+    const int fr = m.fused ? m.fused_fr : kTcM;
     const size_t tsm = tc_smem_bytes(m.kpad, fr, m.fused ? kTcStagesFused : kTcStages, m.fused ? m.nj : 0);
     auto* kern = blend_skin_tc_kernel<kTcM, kTcStages, 0, 0>;
+#define K2B_PICK_NE(KERN, FRV, NJV)                                                   \
+  (m.ell == 1 ? KERN<FRV, kTcStagesFused, 1, NJV> : m.ell == 2 ? KERN<FRV, kTcStagesFused, 2, NJV> \
+   : m.ell == 3 ? KERN<FRV, kTcStagesFused, 3, NJV> : KERN<FRV, kTcStagesFused, 4, NJV>)
     if (m.fused && m.vt) {
-      kern = m.ell == 1 ? blend_skin_vt_kernel<kTcMFused, kTcStagesFused, 1, kTcFusedJoints>
-           : m.ell == 2 ? blend_skin_vt_kernel<kTcMFused, kTcStagesFused, 2, kTcFusedJoints>
-           : m.ell == 3 ? blend_skin_vt_kernel<kTcMFused, kTcStagesFused, 3, kTcFusedJoints>
-                        : blend_skin_vt_kernel<kTcMFused, kTcStagesFused, 4, kTcFusedJoints>;
+      kern = m.nj == 52 ? K2B_PICK_NE(blend_skin_vt_kernel, 32, 52)
+           : m.nj == 55 ? K2B_PICK_NE(blend_skin_vt_kernel, 32, 55)
+                        : K2B_PICK_NE(blend_skin_vt_kernel, kTcMFused, kTcFusedJoints);
     } else if (m.fused) {
-      kern = m.ell == 1 ? blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 1, kTcFusedJoints>
-           : m.ell == 2 ? blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 2, kTcFusedJoints>
-           : m.ell == 3 ? blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 3, kTcFusedJoints>
-                        : blend_skin_tc_kernel<kTcMFused, kTcStagesFused, 4, kTcFusedJoints>;
+      kern = K2B_PICK_NE(blend_skin_tc_kernel, kTcMFused, kTcFusedJoints);
     }
-    static size_t tc_configured[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const int variant = m.fused ? m.ell + (m.vt ? 4 : 0) : 0;
+#undef K2B_PICK_NE
+    static size_t tc_configured[17] = {0};
+    const int variant = m.fused ? m.ell + (m.vt ? 4 : 0) + (m.nj == 52 ? 4 : (m.nj == 55 ? 8 : 0)) : 0;
     if (tsm > tc_configured[variant]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
       if (e != cudaSuccess) {
