@@ -511,7 +511,7 @@ class WorldSpaceFitter:
         while the next window is being fitted -- the fit leaves most of every SM idle when there are few
         sequences.  ``params_ready``: optional event recorded when the fitted parameters are final.
         ``mesh_capped_fraction``: share of the windows whose mesh pass is held to the SMs the fit leaves free
-        (the rest, at the end, run on all SMs); default 0.7 for L-BFGS, 0.45 for Adam, whose fit is shorter
+        (the rest, at the end, run on all SMs); default 0.9 for L-BFGS, 0.55 for Adam, whose fit is shorter
         relative to the mesh.  ``fit_joints=False``: the fit kernel does not return the posed kinematic joints
         (``out["fit_joints"]`` is None; the mesh pass returns all joints anyway), which also spares the L-BFGS fit its
         extra forward pass at the returned parameters -- the returned loss is the accepted trial's, bit for bit.
@@ -605,7 +605,9 @@ class WorldSpaceFitter:
         free_sms = n_sms - ctas.value
         frac = mesh_capped_fraction
         if frac is None:
-            frac = float(os.environ.get("K2B_MESH_CAPPED_FRACTION", "0.7" if lbfgs else "0.45"))
+            # swept on B200 with the round-2 mesh kernels (profiles/r02_mesh_overlap_sweep.txt): L-BFGS 0.7 / 0.8 / 0.9 / 1.0
+            # -> 314.5 / 311.1 / 309.3 / 321.8 ms per step, Adam 0.45 / 0.6 / 0.75 -> 235.4 / 235.0 / 262.3
+            frac = float(os.environ.get("K2B_MESH_CAPPED_FRACTION", "0.9" if lbfgs else "0.55"))
         capped = min(chunks - 1, int(round(chunks * frac))) if free_sms >= 8 else 0
         bounds = [(T * c) // chunks for c in range(chunks + 1)]
         init_c = (pose, betas, transl, expr if self.has_expr else None)
