@@ -78,10 +78,37 @@ K2B_HD void m3_store(float* p, const M3& r) {
 // One evaluation for one frame.  x [n]; obs_idx [K] model-point indices (j < nj kinematic joint, nj + p picked vertex);
 // tgt [K][3]; wgt [K] = joint_w^2 conf^2; keep [n] (temporal anchor) with keep_scale = pose_preserve_weight^2 or 0.
 // with_grad fills g [n].  pts_out [K][3] (optional) receives the model points incl. the translation.
+// WARP: the 32 lanes of a warp work on ONE frame (small batches: a lone frame on one thread leaves the GPU idle for
+// 75 ms).  Every lane runs the whole evaluation redundantly -- identical values in every lane -- except the three loops
+// that carry the work, which are dealt out by lane and combined with shuffles: the pose blend of the picked vertices
+// (forward: lane-strided partial sums + butterfly; backward: each lane accumulates its own entries of dL/dR_local, one
+// all-gather after the observation loop) and the scan of the mixture prior (rows by lane + butterfly).
+K2B_AR_FN float ar_wsum(float v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+#endif
+  return v;
+}
+K2B_AR_FN float ar_bcast(float v, int src) {
+#if defined(__CUDA_ARCH__)
+  return __shfl_sync(0xffffffffu, v, src);
+#else
+  return v;
+#endif
+}
+
+template <bool WARP>
 K2B_AR_FN float artic_eval(const ArticModel& M, const float* x, const int* obs_idx, int K, const float* tgt,
                            const float* wgt, const float* keep, float keep_scale, bool with_grad, float* g,
                            float* pts_out, int* comp_out) {
   const int nj = M.nj, ns = M.ns, n = M.n;
+#if defined(__CUDA_ARCH__)
+  const int lane = WARP ? (int)(threadIdx.x & 31) : 0;
+#else
+  const int lane = 0;
+#endif
+  constexpr int NL = WARP ? 32 : 1;
   float shape[kMaxShape];
   for (int s = 0; s < ns; ++s) shape[s] = M.shape_src[s] >= 0 ? x[M.shape_src[s]] : 0.f;
   float J[kMaxJoints][3], rv[kMaxJoints][3], Rl[kMaxJoints][9], Rw[kMaxJoints][9], tw[kMaxJoints][3];
@@ -131,18 +158,41 @@ K2B_AR_FN float artic_eval(const ArticModel& M, const float* x, const int* obs_i
       p = v3(tw[idx][0], tw[idx][1], tw[idx][2]) + transl;
     } else {
       float vpa[3];
-      for (int c = 0; c < 3; ++c) {
-        float v = M.pv_t[3 * pi + c];
-        const float* sd = M.pv_S + (size_t)(3 * pi + c) * ns;
-        for (int s = 0; s < ns; ++s) v = fmaf(sd[s], shape[s], v);
-        const float* pd = M.pv_P + (size_t)(3 * pi + c) * M.npf;
-        for (int j = 1; j < nj; ++j) {
-          const float* r = Rl[j];
-          const float* q = pd + 9 * (j - 1);
-          v = fmaf(q[0], r[0] - 1.f, fmaf(q[1], r[1], fmaf(q[2], r[2], fmaf(q[3], r[3], fmaf(q[4], r[4] - 1.f,
-              fmaf(q[5], r[5], fmaf(q[6], r[6], fmaf(q[7], r[7], fmaf(q[8], r[8] - 1.f, v)))))))));
+      {
+        // pose blend: sum over the 9 (nj - 1) pose features, entries dealt by lane (three independent chains)
+        const float* pd0 = M.pv_P + (size_t)(3 * pi) * M.npf;
+        const float* pd1 = pd0 + M.npf;
+        const float* pd2 = pd1 + M.npf;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (WARP) {
+          for (int je = lane; je < M.npf; je += NL) {
+            const int j = 1 + je / 9, e = je - 9 * (j - 1);
+            const float feat = Rl[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+            a0 = fmaf(pd0[je], feat, a0);
+            a1 = fmaf(pd1[je], feat, a1);
+            a2 = fmaf(pd2[je], feat, a2);
+          }
+          a0 = ar_wsum(a0); a1 = ar_wsum(a1); a2 = ar_wsum(a2);
+        } else {
+          for (int j = 1; j < nj; ++j) {
+            const float* r = Rl[j];
+            const int o = 9 * (j - 1);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) {
+              const float feat = r[e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+              a0 = fmaf(pd0[o + e], feat, a0);
+              a1 = fmaf(pd1[o + e], feat, a1);
+              a2 = fmaf(pd2[o + e], feat, a2);
+            }
+          }
         }
-        vpa[c] = v;
+        const float ap[3] = {a0, a1, a2};
+        for (int c = 0; c < 3; ++c) {
+          float v = M.pv_t[3 * pi + c];
+          const float* sd = M.pv_S + (size_t)(3 * pi + c) * ns;
+          for (int s = 0; s < ns; ++s) v = fmaf(sd[s], shape[s], v);
+          vpa[c] = v + ap[c];
+        }
       }
       vp = v3(vpa[0], vpa[1], vpa[2]);
       p = transl;
@@ -182,9 +232,31 @@ K2B_AR_FN float artic_eval(const ArticModel& M, const float* x, const int* obs_i
     for (int c = 0; c < 3; ++c) {
       const float* sd = M.pv_S + (size_t)(3 * pi + c) * ns;
       for (int s = 0; s < ns; ++s) gshape[s] = fmaf(sd[s], gv[c], gshape[s]);
-      const float* pd = M.pv_P + (size_t)(3 * pi + c) * M.npf;
-      for (int j = 1; j < nj; ++j)
-        for (int e = 0; e < 9; ++e) gRl[j][e] = fmaf(pd[9 * (j - 1) + e], gv[c], gRl[j][e]);
+    }
+    {
+      // WARP: a lane accumulates only its own entries of dL/dR_local here; they are gathered after the loop
+      const float* pd0 = M.pv_P + (size_t)(3 * pi) * M.npf;
+      const float* pd1 = pd0 + M.npf;
+      const float* pd2 = pd1 + M.npf;
+      if (WARP) {
+        for (int je = lane; je < M.npf; je += NL) {
+          const int j = 1 + je / 9, e = je - 9 * (j - 1);
+          gRl[j][e] = fmaf(pd0[je], gv[0], fmaf(pd1[je], gv[1], fmaf(pd2[je], gv[2], gRl[j][e])));
+        }
+      } else {
+        for (int j = 1; j < nj; ++j) {
+          const int o = 9 * (j - 1);
+#pragma unroll
+          for (int e = 0; e < 9; ++e)
+            gRl[j][e] = fmaf(pd0[o + e], gv[0], fmaf(pd1[o + e], gv[1], fmaf(pd2[o + e], gv[2], gRl[j][e])));
+        }
+      }
+    }
+  }
+  if (WARP && with_grad && M.npick > 0) {      // all-gather of the lane-owned entries (entry je lives in lane je % 32)
+    for (int je = 0; je < M.npf; ++je) {
+      const int j = 1 + je / 9, e = je - 9 * (j - 1);
+      gRl[j][e] = ar_bcast(gRl[j][e], je & 31);
     }
   }
   if (with_grad) {
@@ -245,11 +317,12 @@ K2B_AR_FN float artic_eval(const ArticModel& M, const float* x, const int* obs_i
       const float* P = M.gmm_P + (size_t)m * kBodyDim * 72;
       const float* mu = M.gmm_mu + m * kMuStride;
       float q = 0.f;
-      for (int i = 0; i < kBodyDim; ++i) {
+      for (int i = lane; i < kBodyDim; i += NL) {
         float y = 0.f;
         for (int j = 0; j < kBodyDim; ++j) y = fmaf(P[i * 72 + j], xb[j] - mu[j], y);
         q = fmaf(y, xb[i] - mu[i], q);
       }
+      if (WARP) q = ar_wsum(q);
       const float ll = fmaf(0.5f, q, M.gmm_nlw[m]);
       if (ll < best) { best = ll; bm = m; }
     }

@@ -32,6 +32,7 @@ struct ArticFitParams {
 // The fit of one frame: WorldSpaceFitter.fit_frame / MANOFitter.fit_frame / FLAMEFitter.fit_frame semantics --
 // Adam: torch single-tensor steps, returned loss = the last iteration's, before its step; L-BFGS: torch's machine
 // (lbfgs_core.cuh), returned loss re-evaluated at the returned parameters.
+template <bool WARP>
 K2B_AR_FN void artic_fit_frame(const ArticFitParams& p, long f, float* lb_base, long lb_stride) {
   const ArticModel& M = p.M;
   const int n = M.n, K = p.K;
@@ -49,7 +50,7 @@ K2B_AR_FN void artic_fit_frame(const ArticFitParams& p, long f, float* lb_base, 
   float loss = 0.f;
   int evals = 0, comp = 0;
   if (p.mode == kArticEval) {
-    loss = artic_eval(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, true, g, pts, &comp);
+    loss = artic_eval<WARP>(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, true, g, pts, &comp);
     for (int i = 0; i < n; ++i) p.out_grad[f * n + i] = g[i];
     if (p.out_comp) p.out_comp[f] = comp;
   } else if (p.mode == kArticAdam) {
@@ -64,12 +65,12 @@ K2B_AR_FN void artic_fit_frame(const ArticFitParams& p, long f, float* lb_base, 
         step_k = (float)((double)p.lr / (1.0 - pow(0.9, (double)k)));
         bc2_k = (float)sqrt(1.0 - pow(0.999, (double)k));
       }
-      loss = artic_eval(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, true, g, nullptr, nullptr);
+      loss = artic_eval<WARP>(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, true, g, nullptr, nullptr);
       ++evals;
       for (int i = 0; i < n; ++i)
         if (!(p.frozen && p.frozen[i])) adam_update(x[i], m1[i], m2[i], g[i], step_k, bc2_k);
     }
-    if (pts) artic_eval(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, false, g, pts, nullptr);
+    if (pts) artic_eval<WARP>(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, false, g, pts, nullptr);
   } else {
     Vecs v{lb_base, lb_stride, n, p.hmax};
     Cols c{x, g, 1, 1};
@@ -77,7 +78,7 @@ K2B_AR_FN void artic_fit_frame(const ArticFitParams& p, long f, float* lb_base, 
     st.init();
     bool first = true;
     while (true) {
-      const float l = artic_eval(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, true, g, nullptr, nullptr);
+      const float l = artic_eval<WARP>(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, true, g, nullptr, nullptr);
       const Cols ce = st.eval_cols(c, v);
       for (int i = 0; i < n; ++i) ce.G(i) = (p.frozen && p.frozen[i]) ? 0.f : g[i];
       st.advance_now(c, v, l, first, p.iters, p.lr);
@@ -86,7 +87,7 @@ K2B_AR_FN void artic_fit_frame(const ArticFitParams& p, long f, float* lb_base, 
     }
     evals = st.evals;
     for (int i = 0; i < n; ++i) x[i] = v.at(i);
-    loss = artic_eval(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, false, g, pts, nullptr);
+    loss = artic_eval<WARP>(M, x, p.obs_idx, K, tgt, wgt, keepv, p.keep_scale, false, g, pts, nullptr);
   }
   for (int i = 0; i < n; ++i) p.out_x[f * n + i] = x[i];
   p.out_loss[f] = loss;
@@ -94,10 +95,17 @@ K2B_AR_FN void artic_fit_frame(const ArticFitParams& p, long f, float* lb_base, 
 }
 
 #if defined(__CUDACC__)
+// one thread per frame (throughput: large batches)
 __global__ void __launch_bounds__(kArticThreads) artic_fit_kernel(const __grid_constant__ ArticFitParams p) {
   const long slots = (long)gridDim.x * blockDim.x;
   const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (long f = slot; f < p.num_frames; f += slots) artic_fit_frame(p, f, p.ws ? p.ws + slot : nullptr, slots);
+  for (long f = slot; f < p.num_frames; f += slots) artic_fit_frame<false>(p, f, p.ws ? p.ws + slot : nullptr, slots);
+}
+// one warp per frame (latency: the reference's B = 1 calls); every lane keeps its own L-BFGS scratch column
+__global__ void __launch_bounds__(kArticThreads) artic_fit_warp_kernel(const __grid_constant__ ArticFitParams p) {
+  const long slots = (long)gridDim.x * blockDim.x;
+  const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long f = slot >> 5; f < p.num_frames; f += slots >> 5) artic_fit_frame<true>(p, f, p.ws ? p.ws + slot : nullptr, slots);
 }
 #endif
 

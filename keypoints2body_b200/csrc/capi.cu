@@ -710,8 +710,15 @@ extern "C" int k2b_artic_create(const k2b_artic_desc* d, k2b_artic** out) {
 }
 
 namespace {
+// Few frames (the reference's B = 1 calls, short sequences): one WARP per frame, a single wave of warps; otherwise one
+// thread per frame.  K2B_ARTIC_WARP=0 / 1 forces either (A/B runs).
+bool artic_warp_mode(const k2b_artic* a, long B) {
+  if (const char* e = getenv("K2B_ARTIC_WARP")) return atoi(e) != 0;
+  return B * 32 <= (long)a->num_sms * 4 * ar::kArticThreads;
+}
 int artic_grid(const k2b_artic* a, long B) {
-  const long blocks = (B + ar::kArticThreads - 1) / ar::kArticThreads;
+  const long threads = artic_warp_mode(a, B) ? B * 32 : B;
+  const long blocks = (threads + ar::kArticThreads - 1) / ar::kArticThreads;
   const long cap = (long)a->num_sms * 4;
   return (int)(blocks < cap ? blocks : cap);
 }
@@ -753,7 +760,10 @@ extern "C" int k2b_artic_fit(const k2b_artic* a, const k2b_artic_fit_args* g, vo
     p.adam_step[k - 1] = (float)((double)g->lr / (1.0 - std::pow(0.9, (double)k)));
     p.adam_bc2[k - 1] = (float)std::sqrt(1.0 - std::pow(0.999, (double)k));
   }
-  ar::artic_fit_kernel<<<artic_grid(a, g->num_frames), ar::kArticThreads, 0, (cudaStream_t)stream>>>(p);
+  if (artic_warp_mode(a, g->num_frames))
+    ar::artic_fit_warp_kernel<<<artic_grid(a, g->num_frames), ar::kArticThreads, 0, (cudaStream_t)stream>>>(p);
+  else
+    ar::artic_fit_kernel<<<artic_grid(a, g->num_frames), ar::kArticThreads, 0, (cudaStream_t)stream>>>(p);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return K2B_OK;

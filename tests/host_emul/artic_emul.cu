@@ -52,7 +52,7 @@ extern "C" int emu_artic_fit(const k2b_artic_desc* d, const float* gmm_P, const 
   if (g->mode == K2B_ARTIC_LBFGS) ws.assign((size_t)Vecs::floats_per_frame(M.n, p.hmax), 0.f);
   for (long f = 0; f < p.num_frames; ++f) {
     if (!ws.empty()) std::fill(ws.begin(), ws.end(), 0.f);
-    ar::artic_fit_frame(p, f, ws.empty() ? nullptr : ws.data(), 1);
+    ar::artic_fit_frame<false>(p, f, ws.empty() ? nullptr : ws.data(), 1);
   }
   return 0;
 }

@@ -13,3 +13,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"chain_kernel
 ncu --set full --clock-control none --import-source on -k regex:chain_kernel -s 20 -c 1 -o $O/r02_chain_bench -f python bench.py --skip-cpu-baseline --no-e2e-vertices --no-frame-parallel --steps 1 --warmup 1 > $O/ncu_chain.log 2>&1; echo "chain rc=$?" >> $O/log.txt
 ncu --set full --clock-control none --import-source on -k regex:fit_kernel -c 2 -o $O/r02_fit_bench -f python bench.py --skip-cpu-baseline --no-e2e-vertices --steps 1 --warmup 1 --fp-steps 1 > $O/ncu_fit.log 2>&1; echo "fit rc=$?" >> $O/log.txt
 for L in interleaved coherent; do K2B_SKIN_LAYOUT=$L ncu --set full --clock-control none --import-source on -k regex:blend_skin -s 1 -c 1 -o $O/r02_blend_$L -f python tests/gpu_debug.py meshprof > $O/ncu_blend_$L.log 2>&1; done; echo "blend rc=$?" >> $O/log.txt
+python -c "import __graft_entry__ as g; g.smoke()" > $O/r02_smoke.txt 2>&1; echo "smoke rc=$?" >> $O/log.txt
