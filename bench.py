@@ -512,20 +512,31 @@ def run_ours(args):
     d2h = 4 * (h_pose.numel() + h_betas.numel() + h_transl.numel() + h_loss.numel() + h_joints.numel())
 
     # ---- frame-parallel schedule S2 beside it: frames sharded across the ranks, one-frame NCCL halo ------------
-    fp = None
-    if sf2 is not None:
-        sf2.run(targets, seq_ind)
-        sf2.kernel_events, sf2.halo_events = [], []
-        ms_fp = timed(lambda: sf2.run(targets, seq_ind), args.fp_steps)
+    def measure_fp(sfx):
+        sfx.run(targets, seq_ind)
+        sfx.kernel_events, sfx.halo_events = [], []
+        ms_fp = timed(lambda: sfx.run(targets, seq_ind), args.fp_steps)
         torch.cuda.synchronize()
-        fp_fit_ms = sum(a.elapsed_time(b) for a, b in sf2.kernel_events) / args.fp_steps
-        halo_ms = sum(a.elapsed_time(b) for a, b in sf2.halo_events) / max(1, args.fp_steps)
-        sf2.kernel_events = sf2.halo_events = None
-        o2 = sf2.run(targets, seq_ind)
-        fp = {"ms_per_step": ms_fp, "fit_ms": fp_fit_ms, "halo_ms": halo_ms,
-              "evals": float(sf2.evals0.sum()) + float(sf2.evals1.sum()),
-              "mean_err": float((o2["joints"][:, :22] - targets).norm(dim=-1).mean())}
+        fp_fit_ms = sum(a.elapsed_time(b) for a, b in sfx.kernel_events) / args.fp_steps
+        halo_ms = sum(a.elapsed_time(b) for a, b in sfx.halo_events) / max(1, args.fp_steps)
+        sfx.kernel_events = sfx.halo_events = None
+        o2 = sfx.run(targets, seq_ind)
+        res = {"ms_per_step": ms_fp, "fit_ms": fp_fit_ms, "halo_ms": halo_ms,
+               "evals": float(sfx.evals0.sum()) + float(sfx.evals1.sum()),
+               "mean_err": float((o2["joints"][:, :22] - targets).norm(dim=-1).mean())}
         del o2
+        return res
+
+    fp = measure_fp(sf2) if sf2 is not None else None
+    # ... and with Adam (the strict-parity optimiser), so that the default line carries K1's Adam roofline too
+    fp_adam = None
+    if sf2 is not None and args.optimizer == "lbfgs":
+        fitter_a = WorldSpaceFitter(weights, joints_category="AMASS", use_lbfgs=False, model_type="smpl",
+                                    gmm=syn.make_gmm(seed=0), device=dev)
+        sf2a = SequenceBatchFitter(fitter_a, F, cfg, with_vertices=False)
+        sf2a.vertices = sf.vertices
+        fp_adam = measure_fp(sf2a)
+        del sf2a, fitter_a
 
     if rank != 0:
         if world > 1:
@@ -608,6 +619,17 @@ def run_ours(args):
                          "frac": fp_ach / peak_tflops if peak_tflops else None, "flop_per_eval": EVAL_FLOP["smpl"],
                          "ms_per_step_in_kernel": fp["fit_ms"], "share_of_step": fp["fit_ms"] / fp["ms_per_step"],
                          "traffic": t2, "traffic_note": n2},
+        }
+    if fp_adam is not None:
+        fa_ach = (fp_adam["evals"] + 2 * F) * EVAL_FLOP["smpl"] / (fp_adam["fit_ms"] * 1e-3) / 1e12
+        line["frame_parallel_adam"] = {
+            "what": "the same frame-parallel schedule with Adam (the strict-parity optimiser): fit_kernel<10,22,adam>",
+            "value": world * F / (fp_adam["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": fp_adam["ms_per_step"],
+            "steps": args.fp_steps, "evals_per_frame": fp_adam["evals"] / F, "mean_joint_error_m": fp_adam["mean_err"],
+            "halo_ms_per_step": fp_adam["halo_ms"],
+            "roofline": {"kernel": "fit_kernel<10,22,adam> (sweep 0 + sweep 1)", "bound": "fp32_fma", "achieved": fa_ach,
+                         "peak": peak_tflops, "unit": "TFLOP/s", "frac": fa_ach / peak_tflops if peak_tflops else None,
+                         "flop_per_eval": EVAL_FLOP["smpl"], "ms_per_step_in_kernel": fp_adam["fit_ms"]},
         }
     # ---- the vertices were written: a sample re-evaluated by the FP32 CUDA-core mesh path ---------------------------
     if with_verts:
