@@ -377,13 +377,14 @@ class ChainRunner:
         self.kernel_events = None
         self.evals0 = self.evals1 = torch.zeros(1, device=dev)
 
-    def run(self, targets, seq_ind=None, params_ready=None):
+    def run(self, targets, seq_ind=None, params_ready=None, window_done=None, window_ready=None):
         f = self.f
         tg = targets.view(self.S, SEQ_LEN, 22, 3)
         init = dict(self.init, transl=tg[:, 0, 0] - self.root0)     # root alignment of frame 0 (engine.py:89-128)
         f.chain_events = self.kernel_events                          # (start, end) of the fit on its own stream
         out = f.fit_chain(init, tg, None, with_mesh=True, out_vertices=self.vertices, time_major=True,
-                          chunks=self.chunks, params_ready=params_ready, fit_joints=False)
+                          chunks=self.chunks, params_ready=params_ready, fit_joints=False, window_done=window_done,
+                          window_ready=window_ready)
         f.chain_events = None
         p = out["params"]
         out["pose"] = torch.cat([p["global_orient"], p["body_pose"]], dim=1)
@@ -492,7 +493,63 @@ def run_ours(args):
     side = torch.cuda.Stream(device=dev)
     fitted = torch.cuda.Event()
 
+    def window_home(c, rows, fit_done, outs, joints):
+        """A time window's results go home while the later windows are fitted (schedule S1: outputs are time-major, so a
+        window is one contiguous run of rows in every output array)."""
+        meshed = torch.cuda.Event()
+        meshed.record()                          # this window's mesh pass has been enqueued on the current stream
+        with torch.cuda.stream(side):
+            side.wait_event(fit_done)
+            h_pose[rows].copy_(outs["pose"][rows], non_blocking=True)
+            h_betas[rows].copy_(outs["betas"][rows], non_blocking=True)
+            h_transl[rows].copy_(outs["transl"][rows], non_blocking=True)
+            h_loss[rows].copy_(outs["loss"][rows], non_blocking=True)
+            side.wait_event(meshed)
+            h_joints[rows].copy_(joints[rows], non_blocking=True)
+
+    # keypoints of time window c go up while window c-1 is fitted: the device layout is [sequence][frame], so a window is
+    # a 2-D region (rows = sequences) -- one cudaMemcpy2DAsync per window on a copy stream
+    up, memcpy2d = torch.cuda.Stream(device=dev), None
+    if chain:
+        try:
+            import ctypes
+
+            rt = ctypes.CDLL("libcudart.so.12")
+            memcpy2d = rt.cudaMemcpy2DAsync
+            memcpy2d.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                 ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+            memcpy2d.restype = ctypes.c_int
+        except Exception:
+            memcpy2d = None
+
+    def upload_windows():
+        S_, row = F // SEQ_LEN, 22 * 3 * 4
+        bounds = [(SEQ_LEN * c) // args.chunks for c in range(args.chunks + 1)]
+        events = []
+        up.wait_stream(torch.cuda.current_stream())
+        for c in range(args.chunks):
+            a0, b0 = bounds[c], bounds[c + 1]
+            rc = memcpy2d(d_targets.data_ptr() + a0 * row, SEQ_LEN * row, h_targets.data_ptr() + a0 * row, SEQ_LEN * row,
+                          (b0 - a0) * row, S_, 1, up.cuda_stream)        # 1 = cudaMemcpyHostToDevice
+            if rc != 0:
+                raise RuntimeError(f"cudaMemcpy2DAsync failed: {rc}")
+            ev = torch.cuda.Event()
+            ev.record(up)
+            events.append(ev)
+        return events
+
     def step_host():
+        if chain:
+            if memcpy2d is not None:
+                ready = upload_windows()
+            else:
+                d_targets.copy_(h_targets, non_blocking=True)
+                ready = None
+            if ready is not None:       # frame 0's root alignment reads the first window's keypoints on the current stream
+                torch.cuda.current_stream().wait_event(ready[0])
+            o = sf.run(d_targets, seq_ind, window_done=window_home, window_ready=ready)
+            torch.cuda.current_stream().wait_stream(side)
+            return o
         d_targets.copy_(h_targets, non_blocking=True)
         o = sf.run(d_targets, seq_ind, params_ready=fitted)
         with torch.cuda.stream(side):          # parameters and losses go home while the mesh pass runs
@@ -510,6 +567,15 @@ def run_ours(args):
     ms_e2e = timed(step_host, args.steps)
     h2d = h_targets.numel() * 4
     d2h = 4 * (h_pose.numel() + h_betas.numel() + h_transl.numel() + h_loss.numel() + h_joints.numel())
+    # what arrived in host memory is what the device holds (one more step, untimed)
+    h_joints.fill_(float("nan")); h_pose.fill_(float("nan")); h_loss.fill_(float("nan"))
+    o_chk = step_host()
+    torch.cuda.synchronize()
+    e2e_check = {"joints_max_abs_diff": float((h_joints.to(dev) - o_chk["joints"]).abs().max()),
+                 "pose_max_abs_diff": float((h_pose.to(dev) - o_chk["pose"]).abs().max()),
+                 "loss_max_abs_diff": float((h_loss.to(dev) - o_chk["loss"]).abs().max()),
+                 "targets_max_abs_diff": float((d_targets - targets).abs().max())}
+    del o_chk
 
     # ---- frame-parallel schedule S2 beside it: frames sharded across the ranks, one-frame NCCL halo ------------
     def measure_fp(sfx):
@@ -578,8 +644,11 @@ def run_ours(args):
         "fit_quality": {"evals_per_frame": evals_total / F, "mean_joint_error_m": mean_err},
         "e2e": {"value": world * F / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                "host_copy_check": e2e_check,
                 "note": "vertices stay in HBM (%.1f GB/GPU); params, loss and 45 joints are copied back; see "
-                        "e2e_with_vertices" % (mesh_bytes / 1e9)},
+                        "e2e_with_vertices.%s" % (mesh_bytes / 1e9, " Keypoints go up and results come home one time window "
+                        "at a time (cudaMemcpy2DAsync / pinned copies on side streams) while the other windows are fitted."
+                        if chain else "")},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
         "roofline": {

@@ -496,7 +496,8 @@ class WorldSpaceFitter:
 
     def fit_chain(self, init: dict, j3d, conf=None, *, first_seq_ind=0, chain=True, joint_loss_weight=600.0,
                   pose_preserve_weight=5.0, freeze_betas=False, use_lbfgs=None, with_mesh=True, out_vertices=None,
-                  time_major=False, chunks=1, params_ready=None, mesh_capped_fraction=None, fit_joints=True):
+                  time_major=False, chunks=1, params_ready=None, mesh_capped_fraction=None, fit_joints=True,
+                  window_done=None, window_ready=None):
         """Fit S sequences of T frames each the way the reference's sequence loop does (api/sequence.py:214-281):
         serially in t, frame t starting from frame t-1's result (``chain=True``) or from the sequence's
         initialisation (``chain=False``) -- one warp per sequence, all frames inside one launch.
@@ -515,6 +516,11 @@ class WorldSpaceFitter:
         relative to the mesh.  ``fit_joints=False``: the fit kernel does not return the posed kinematic joints
         (``out["fit_joints"]`` is None; the mesh pass returns all joints anyway), which also spares the L-BFGS fit its
         extra forward pass at the returned parameters -- the returned loss is the accepted trial's, bit for bit.
+        ``window_done(c, rows, fit_done, outs, joints)``: called after window c's launches have been enqueued -- ``rows`` of
+        the raw output buffers ``outs`` (pose / betas / transl / loss / evals) are final once the event ``fit_done`` has
+        passed, ``joints[rows]`` (and the vertices) once everything enqueued so far on the current stream has run; a caller
+        can stream a window's results to the host while later windows are fitted.  ``window_ready``: optional list of
+        ``chunks`` events; the fit of window c waits for event c (its keypoints may still be on their way to the device).
         """
         dev = self.device
         targets = _f32(j3d, dev)
@@ -616,6 +622,8 @@ class WorldSpaceFitter:
             rows = slice(a0 * S, b0 * S)
             o = {k: (v[rows] if v is not None else None) for k, v in outs.items()}
             with torch.cuda.stream(hp):
+                if window_ready is not None:
+                    hp.wait_event(window_ready[c])
                 self._run_chain(S, T, targets, conf, conf_mode, *init_c, None, first_seq_ind, True, *common, outs=o,
                                 window=(a0, b0, T), time_major=tm)
                 done = torch.cuda.Event()
@@ -633,6 +641,8 @@ class WorldSpaceFitter:
             if with_mesh:
                 self.forward_batch(params_of(rows), with_vertices=True, out_vertices=verts[rows], out_joints=joints[rows],
                                    max_ctas=free_sms if c < capped else 0)
+            if window_done is not None:
+                window_done(c, rows, done, outs, joints if with_mesh else None)
         out["params"] = params_of(slice(0, F))
         if with_mesh:
             out["joints"], out["vertices"] = joints, verts
