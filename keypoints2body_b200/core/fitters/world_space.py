@@ -72,6 +72,53 @@ def guess_init_transl_from_root(fitter_or_model, pose_aa, betas, j3d_world_frame
     return (_f32(j3d_world_frame, fitter.device)[:, root, :] - out["joints"][:, root, :]).detach()
 
 
+class _OverlapTuner:
+    """Chooses ``mesh_capped_fraction`` of ``fit_chain`` by measurement.  While windows are being fitted the mesh pass
+    of the finished ones can either be held to the SMs the fit leaves free (slower mesh, undisturbed fit) or run
+    everywhere (its long-lived CTAs delay the next window's fit); which share of the windows to hold back depends on
+    how long a window's fit takes relative to its mesh pass (optimiser, iteration budgets, model).  Each candidate share
+    is tried on one call (after a first, cold call that is not measured), timed by two events on the caller's stream; the timing is read at the start of the next call
+    (by then the work has long finished), so the policy adds no synchronisation to the call it measures."""
+
+    CANDIDATES = (0.55, 0.75, 0.9)
+
+    def __init__(self):
+        self.times = {}
+        self.best = None
+        self.pending = None
+        self.calls = 0          # the first call of a problem shape is cold (allocations, first launches): not measured
+
+    def collect(self):
+        if self.pending is not None:
+            frac, e0, e1 = self.pending
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            self.times[frac] = min(ms, self.times.get(frac, ms))
+            self.pending = None
+            if self.best is None and all(c in self.times for c in self.CANDIDATES):
+                self.best = min(self.CANDIDATES, key=lambda c: self.times[c])
+
+    def next_fraction(self):
+        self.collect()
+        self.calls += 1
+        if self.best is not None:
+            return self.best
+        if self.calls == 1:
+            return self.CANDIDATES[-1]
+        return next(c for c in self.CANDIDATES if c not in self.times)
+
+    def begin(self, stream):
+        self._frac_e0 = torch.cuda.Event(enable_timing=True)
+        self._frac_e0.record(stream)
+
+    def end(self, stream):
+        if self.best is None and self.calls > 1:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(stream)
+            frac = next(c for c in self.CANDIDATES if c not in self.times)
+            self.pending = (frac, self._frac_e0, e1)
+
+
 class WorldSpaceFitter:
     """Per-frame optimiser in world coordinates, B frames per kernel launch."""
 
@@ -512,8 +559,10 @@ class WorldSpaceFitter:
         while the next window is being fitted -- the fit leaves most of every SM idle when there are few
         sequences.  ``params_ready``: optional event recorded when the fitted parameters are final.
         ``mesh_capped_fraction``: share of the windows whose mesh pass is held to the SMs the fit leaves free
-        (the rest, at the end, run on all SMs); default 0.9 for L-BFGS, 0.55 for Adam, whose fit is shorter
-        relative to the mesh.  ``fit_joints=False``: the fit kernel does not return the posed kinematic joints
+        (the rest, at the end, run on all SMs).  Default (None): chosen by measurement -- the first calls of a
+        problem shape (S, T, chunks, optimiser) each run with one candidate share and are timed with CUDA events
+        on the caller's stream (four calls: a cold one and three candidates), later calls use the fastest (``overlap_policy()`` reports what was measured);
+        a number, or the environment variable K2B_MESH_CAPPED_FRACTION, pins it.  ``fit_joints=False``: the fit kernel does not return the posed kinematic joints
         (``out["fit_joints"]`` is None; the mesh pass returns all joints anyway), which also spares the L-BFGS fit its
         extra forward pass at the returned parameters -- the returned loss is the accepted trial's, bit for bit.
         ``window_done(c, rows, fit_done, outs, joints)``: called after window c's launches have been enqueued -- ``rows`` of
@@ -610,10 +659,16 @@ class WorldSpaceFitter:
         n_sms = self.native.lib.k2b_chain_geometry(self.native.handle, S, C.byref(ctas), C.byref(warps))
         free_sms = n_sms - ctas.value
         frac = mesh_capped_fraction
+        if frac is None and os.environ.get("K2B_MESH_CAPPED_FRACTION"):
+            frac = float(os.environ["K2B_MESH_CAPPED_FRACTION"])
+        tuner = None
         if frac is None:
-            # swept on B200 with the round-2 mesh kernels (profiles/r02_mesh_overlap_sweep.txt): L-BFGS 0.7 / 0.8 / 0.9 / 1.0
-            # -> 314.5 / 311.1 / 309.3 / 321.8 ms per step, Adam 0.45 / 0.6 / 0.75 -> 235.4 / 235.0 / 262.3
-            frac = float(os.environ.get("K2B_MESH_CAPPED_FRACTION", "0.9" if lbfgs else "0.55"))
+            if with_mesh and free_sms >= 8:
+                tuner = self._overlap_tuner((S, T, chunks, bool(lbfgs)))
+                frac = tuner.next_fraction()
+                tuner.begin(cur)
+            else:
+                frac = 0.0
         capped = min(chunks - 1, int(round(chunks * frac))) if free_sms >= 8 else 0
         bounds = [(T * c) // chunks for c in range(chunks + 1)]
         init_c = (pose, betas, transl, expr if self.has_expr else None)
@@ -643,9 +698,26 @@ class WorldSpaceFitter:
                                    max_ctas=free_sms if c < capped else 0)
             if window_done is not None:
                 window_done(c, rows, done, outs, joints if with_mesh else None)
+        if tuner is not None:
+            tuner.end(cur)
         out["params"] = params_of(slice(0, F))
         if with_mesh:
             out["joints"], out["vertices"] = joints, verts
+        return out
+
+    def _overlap_tuner(self, key):
+        tuners = self.__dict__.setdefault("_overlap_tuners", {})
+        if key not in tuners:
+            tuners[key] = _OverlapTuner()
+        return tuners[key]
+
+    def overlap_policy(self) -> dict:
+        """What the mesh-overlap policy of ``fit_chain(chunks > 1)`` has measured so far:
+        ``{(S, T, chunks, lbfgs): {"fraction": chosen or None, "ms": {candidate: milliseconds}}}``."""
+        out = {}
+        for key, t in self.__dict__.get("_overlap_tuners", {}).items():
+            t.collect()
+            out[key] = {"fraction": t.best, "ms": dict(t.times)}
         return out
 
     def fit_frame(

@@ -435,6 +435,26 @@ def test_chain_windows_time_major_identical_to_one_launch(goldens, fitters, shim
         assert np.array_equal(a, b), k
 
 
+def test_mesh_overlap_policy_measures_then_settles(goldens, fitters, shims):
+    """fit_chain's share of mesh passes held to the free SMs is chosen by event timing: one candidate per call, then the
+    fastest; whichever share a call runs with, the results are the same bits.  A pinned share is not tuned."""
+    S = 4
+    init, tgt = _chain_init(goldens, shims, S)
+    tgt = tgt[None].expand(S, -1, -1, -1) + 0.01 * torch.arange(S).view(S, 1, 1, 1)
+    f = fitters("smpl", use_lbfgs=False)
+    f.__dict__.pop("_overlap_tuners", None)
+    runs = [f.fit_chain(init, tgt, None, time_major=True, chunks=3) for _ in range(6)]
+    (key, pol), = f.overlap_policy().items()
+    assert key == (S, tgt.shape[1], 3, False)
+    assert sorted(pol["ms"]) == [0.55, 0.75, 0.9] and all(v > 0 for v in pol["ms"].values())
+    assert pol["fraction"] == min(pol["ms"], key=pol["ms"].get)
+    for r in runs[1:]:
+        for k in ("loss", "joints", "vertices"):
+            assert torch.equal(r[k], runs[0][k]), k
+    f.fit_chain(init, tgt, None, time_major=True, chunks=3, mesh_capped_fraction=0.3)
+    assert f.overlap_policy()[key]["ms"] == pol["ms"]
+
+
 @pytest.mark.parametrize("lbfgs", [False, True])
 def test_warp_kernel_edge_cases(fitters, weights, lbfgs):
     """Zero iterations pass the parameters through; a zero-confidence joint does not influence the fit; an explicit

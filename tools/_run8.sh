@@ -1,6 +1,15 @@
 cd $GRAFT_REPO_ROOT
-for sp in 0 2 3 4 5; do
-  echo "== K2B_CHAIN_SPEC=$sp"
-  K2B_CHAIN_SPEC=$sp timeout 300 python tests/gpu_debug.py chain 1x256 148x64 256x64 2>&1 | grep "chain lbfgs"
-done > gpurun_out/r2_spec.log 2>&1
-cat gpurun_out/r2_spec.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "overlap or windows" 2>&1 | tail -5
+timeout 600 python bench.py --skip-cpu-baseline --no-e2e-vertices > gpurun_out/r2_bench_tuner.json 2> gpurun_out/r2_bench_tuner.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2_bench_tuner.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['mesh_overlap'])
+PY
+timeout 600 python bench.py --optimizer adam --skip-cpu-baseline --no-e2e-vertices --no-frame-parallel > gpurun_out/r2_bench_tuner_adam.json 2> gpurun_out/r2_bench_tuner_adam.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2_bench_tuner_adam.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['mesh_overlap'])
+PY
+
