@@ -1083,8 +1083,10 @@ template <int NS, int K, bool LB, bool CAM = false>
 K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, int idx,
                           long first_seq, long seq_stride, float* hist) {
   const int lane = lane_id();
-  const bool leader = idx == 0;
-  const bool teamed = tm.E > 1;
+  // teams of several evaluators exist for L-BFGS only (k2b_fit_chain never combines them with Adam): for the Adam
+  // instantiation the team protocol and the line form of the prior are compile-time dead
+  const bool leader = LB ? idx == 0 : true;
+  const bool teamed = LB && tm.E > 1;
   // camera-space stage 1: only global_orient and the translation move, no priors.  A launch constant for the two-launch
   // camera fit (loss_kind), a per-frame state of the leader when both stages run inside the launch (camera_seq).
   bool stage1 = p.loss_kind == 1;
@@ -1324,7 +1326,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
     }
     K2B_PROF_MARK(1)
     // ===== 2. line tables: every evaluator of the team takes its share of the mixture components ====================
-    if (tab_mode != kTabKeep) {
+    if (LB && tab_mode != kTabKeep) {
       K2B_PROF_COUNT(9)
       line_tables_update(tb, wm.dbuf, tm, tab_mode, t_step, idx);
       K2B_PROF_MARK(10)
@@ -1341,7 +1343,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       if (final_obs && p.final_mode) oe.keep_w2 = 0.f;      // camera_space.py:316-326
       const LineEval le{tm.lu, tm.lw, tm.labc, le_t};
       loss = eval_warp<NS, K>(tb, wm, oe, x, with_grad, with_priors, gr, jout, want_comp ? &comp : nullptr,
-                              use_line ? &le : nullptr);
+                              (LB && use_line) ? &le : nullptr);
     }
     K2B_PROF_MARK(3)
     // ===== 4. where the result goes ==================================================================================

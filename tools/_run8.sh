@@ -1,15 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "overlap or windows" 2>&1 | tail -5
-timeout 600 python bench.py --skip-cpu-baseline --no-e2e-vertices > gpurun_out/r2_bench_tuner.json 2> gpurun_out/r2_bench_tuner.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r2_bench_tuner.json'))
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['mesh_overlap'])
-PY
-timeout 600 python bench.py --optimizer adam --skip-cpu-baseline --no-e2e-vertices --no-frame-parallel > gpurun_out/r2_bench_tuner_adam.json 2> gpurun_out/r2_bench_tuner_adam.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r2_bench_tuner_adam.json'))
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['mesh_overlap'])
-PY
-
+timeout 300 python tests/gpu_debug.py chain 1x256 148x64 256x64 2>&1 | grep "chain " > gpurun_out/r2_adam_guard.log
+cat gpurun_out/r2_adam_guard.log
+timeout 600 python tools/window_tail.py 256 4096 1 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_api.py -q -x 2>&1 | tail -3
