@@ -381,7 +381,9 @@ K2B_HD Acc shfl_acc(const Acc& a, int src) {
 // One function evaluation of one frame by the whole warp.  xr: owned elements of the evaluation point
 // (zero where 3*lane + c >= 75 + NS).  Returns the total loss in every lane; with_grad fills gr with the
 // gradient of the owned elements (zero for unowned ones).  joints_out: global [K][3] or null.
-template <int NS, int K>
+// LINE: the caller always evaluates the mixture prior in line form (`le` is set whenever with_priors is: the L-BFGS
+// instantiation of the kernel), so the component scan and the helper-warp handshake are compiled out.
+template <int NS, int K, bool LINE = false>
 K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& ob, const float (&xr)[3],
                        bool with_grad, bool with_priors, float (&gr)[3], float* joints_out, int* gmm_component,
                        const LineEval* le = nullptr) {
@@ -390,7 +392,7 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
   const int lane = lane_id();
 #pragma unroll
   for (int c = 0; c < 3; ++c) wm.xs[3 * lane + c] = xr[c];
-  if (with_priors && wm.helpers > 0 && !le) {   // hand the point to the helper warps (they read xs and dbuf[0])
+  if (!LINE && with_priors && wm.helpers > 0 && !le) {   // hand the point to the helper warps (they read xs and dbuf[0])
     if (lane == 0) wm.dbuf[0] = with_grad ? 2.f : 1.f;
     bar_arrive(wm.bar_id, wm.bar_threads);
   }
@@ -559,7 +561,7 @@ K2B_HD float eval_warp(const WarpTables& tb, const WarpMem& wm, const FrameObs& 
     int bm = 0;
     const float* ysrc = wm.ybuf;
     const float* yw = nullptr;          // line form: gradient = ysrc + t yw
-    if (le) {
+    if (LINE || le) {
       // every lane evaluates the eight quadratics (first minimum wins, like torch.min)
 #pragma unroll
       for (int m = 0; m < kGmmM; ++m) {
@@ -1223,7 +1225,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
           stage1 = false;
           priors_on = false;
           phase = kCamGuess;
-        } else if (p.eval_only) {
+        } else if (!LB && p.eval_only) {      // evaluation-only launches use the Adam instantiation (chain_inst.cu)
           phase = kEvalOnly;
         } else if (lbfgs) {
 #pragma unroll
@@ -1241,7 +1243,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         }
       }
       float* jframe = p.out_joints ? p.out_joints + frow * K * 3 : nullptr;
-      if (phase == kEvalOnly) {
+      if (!LB && phase == kEvalOnly) {
         jout = jframe;
         want_comp = true;
       } else if (CAM && phase == kCamGuess) {
@@ -1342,8 +1344,8 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       FrameObs oe = ob;
       if (final_obs && p.final_mode) oe.keep_w2 = 0.f;      // camera_space.py:316-326
       const LineEval le{tm.lu, tm.lw, tm.labc, le_t};
-      loss = eval_warp<NS, K>(tb, wm, oe, x, with_grad, with_priors, gr, jout, want_comp ? &comp : nullptr,
-                              (LB && use_line) ? &le : nullptr);
+      loss = eval_warp<NS, K, LB>(tb, wm, oe, x, with_grad, with_priors && (!LB || use_line), gr, jout,
+                                  want_comp ? &comp : nullptr, (LB && use_line) ? &le : nullptr);
     }
     K2B_PROF_MARK(3)
     // ===== 4. where the result goes ==================================================================================
@@ -1376,7 +1378,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         for (int c = 0; c < 3; ++c) { xr[c] = ct[c]; ob.dref[c] = ct[c]; }
       }
       if constexpr (CAM) begin_camera_stage(true);
-    } else if (phase == kEvalOnly) {
+    } else if (!LB && phase == kEvalOnly) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, gr[c]);
       if (lane == 0) {
