@@ -77,7 +77,7 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
   tm.bar_go = 1 + 3 * team;
   tm.bar_tab = 2 + 3 * team;
   tm.bar_done = 3 + 3 * team;
-  if (member < E) {
+  if (LB || member < E) {      // helper warps exist for Adam only (capi.cu, chain_geometry)
     wc::WarpMem wm = wc::make_warp_mem(base + (size_t)member * wc::kEvalMemFloats, tm.gs);
     wm.helpers = H;
     wm.bar_id = bar_b;
