@@ -447,8 +447,11 @@ class WorldSpaceFitter:
     # ------------------------------------------------------------------ public
     def fit_batch(self, init: dict, j3d, conf=None, *, seq_ind=0, preserve_pose=None, num_iters=None,
                   joint_loss_weight=600.0, pose_preserve_weight=5.0, freeze_betas=False, use_lbfgs=None,
-                  with_mesh=True, out_vertices=None, kernel="auto"):
+                  with_mesh=True, out_vertices=None, kernel="auto", fit_joints=True):
         """Fit B independent frames in one launch.
+
+        ``fit_joints=False``: the fit kernel does not return the posed kinematic joints (the mesh pass returns all
+        joints anyway), which spares an L-BFGS fit its extra forward pass at the returned parameters.
 
         ``kernel``: "frame" = one thread per frame (``k2b_fit_batch``, throughput), "warp" = one warp per frame
         (``k2b_fit_chain``, latency), "auto" = warp for small batches.
@@ -523,12 +526,12 @@ class WorldSpaceFitter:
                                   0 if conf is None else (2 if conf_pf else 1), pose, betas, transl,
                                   expr if self.has_expr else None, keep_pose, s0, True, i_first, i_follow,
                                   nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight,
-                                  pose_preserve_weight, freeze, seq_first=seq_first)
+                                  pose_preserve_weight, freeze, seq_first=seq_first, want_joints=fit_joints)
         else:
             res = self._run_fit(B, targets, conf, conf_pf, pose, betas, transl, expr if self.has_expr else None,
                                 keep_pose, frame_iters, frame_preserve, preserve_all, budget,
                                 nat.OPT_LBFGS if lbfgs else nat.OPT_ADAM, joint_loss_weight, pose_preserve_weight,
-                                freeze)
+                                freeze, want_joints=fit_joints)
         params = {"global_orient": res["pose"][:, :3], "body_pose": res["pose"][:, 3:], "betas": res["betas"],
                   "transl": res["transl"]}
         for k in _EXTRA_BLOCKS:

@@ -314,6 +314,13 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
           stage = 2;
 #pragma unroll kVecUnroll
           for (int i = 0; i < NX; ++i) c.X(i) = v.at(i);
+          // The returned parameters ARE the accepted trial point (lbfgs.py:488-493 adds t d to the iterate the way the
+          // trial was formed), so the loss re-evaluated there (world_space.py:246-247) is the machine's own, bit for bit;
+          // the extra forward pass is only run for its joints or for the camera stage's loss without the temporal term.
+          if (!p.out_joints && !p.final_mode) {
+            out_loss = (float)st.loss;
+            break;
+          }
         }
       }
       evals = st.evals;
