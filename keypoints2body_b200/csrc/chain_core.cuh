@@ -962,8 +962,14 @@ K2B_HD int team_candidates(const Machine& st, int E, float (&tc)[kMaxCand]) {
     for (int k = 0; k < 5; ++k) {
       const float f = (float)order[k];
       bool dup = !(fabsf(f) <= 3.0e38f);
-      for (int i = 0; i < n; ++i) dup = dup || tc[i] == f;
-      if (!dup && n < E && n < kMaxCand) tc[n++] = f;
+#pragma unroll
+      for (int i = 0; i < kMaxCand; ++i) dup = dup || (i < n && tc[i] == f);
+      if (!dup && n < E && n < kMaxCand) {
+#pragma unroll
+        for (int i = 0; i < kMaxCand; ++i)       // tc[n] = f without a run-time index (tc stays in registers)
+          if (i == n) tc[i] = f;
+        ++n;
+      }
     }
   }
   return n;
@@ -1275,7 +1281,13 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
             tm.d[3 * lane + c] = v.d[c];
           }
         }
-        if (lane < kMaxCand) tm.tval[lane] = lane < n_c ? tc[lane] : 0.f;
+        {
+          float tl = 0.f;
+#pragma unroll
+          for (int i = 0; i < kMaxCand; ++i)
+            if (i == lane && i < n_c) tl = tc[i];
+          if (lane < kMaxCand) tm.tval[lane] = tl;
+        }
         const bool keep_on = (fin && p.final_mode ? 0.f : ob.keep_w2) != 0.f;
         team_post(tm, kCmdEval, n_c, (fin ? 0 : kFlagGrad) | (priors_on ? kFlagPriors : 0) | (keep_on ? kFlagKeep : 0) |
                                          ((fin || lfirst) ? kFlagBase : 0), f, tab_mode, t_step);
@@ -1446,8 +1458,9 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         }
         const float want = (float)st.t;
         int j = -1;
-        for (int i = 1; i < n_c; ++i)
-          if (!((used >> i) & 1u) && tc[i] == want) j = i;
+#pragma unroll
+        for (int i = 1; i < kMaxCand; ++i)
+          if (i < n_c && !((used >> i) & 1u) && tc[i] == want) j = i;
         if (j < 0) break;
         used |= 1u << j;
 #pragma unroll

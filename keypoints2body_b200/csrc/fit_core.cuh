@@ -158,6 +158,24 @@ K2B_HD void k2b_sincos(float x, float* sn, float* cs) {
   *cs = ((n + 1) & 2) ? -c1 : c1;
 }
 
+// one rounding each, never contracted into a neighbouring operation
+K2B_HD float mul_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  volatile float p = a * b;
+  return p;
+#endif
+}
+K2B_HD float add_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(a, b);
+#else
+  volatile float p = a + b;
+  return p;
+#endif
+}
+
 K2B_HD M3 rodrigues(V3 r, Rod& o) {
   const V3 a = v3(r.x + 1e-8f, r.y + 1e-8f, r.z + 1e-8f);
   const float theta = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
@@ -165,12 +183,17 @@ K2B_HD M3 rodrigues(V3 r, Rod& o) {
   k2b_sincos(theta, &o.s, &o.c);
   const float oc = 1.f - o.c;
   const V3 k = v3(r.x * o.inv, r.y * o.inv, r.z * o.inv);
-  const float xx = k.x * k.x, yy = k.y * k.y, zz = k.z * k.z;
+  // The diagonal is written with explicit roundings: left to the compiler, `1 - oc (yy + zz)` was contracted one way
+  // in one build of a kernel and another way in the next (fma(k.y, k.y, zz) or not, depending on unrelated code around
+  // it), which moves every fit by an ulp and, along a chain of warm-started L-BFGS fits, by millimetres.
+  // (the form below is the one the shipped warp-per-sequence kernel had: yy + zz in two roundings, xx + zz and xx + yy
+  // as fma(k.x, k.x, .))
+  const float yy = mul_rn(k.y, k.y), zz = mul_rn(k.z, k.z);
   const float xy = k.x * k.y, xz = k.x * k.z, yz = k.y * k.z;
   M3 R;
-  R.m[0] = 1.f - oc * (yy + zz); R.m[1] = fmaf(oc, xy, -o.s * k.z); R.m[2] = fmaf(oc, xz, o.s * k.y);
-  R.m[3] = fmaf(oc, xy, o.s * k.z); R.m[4] = 1.f - oc * (xx + zz); R.m[5] = fmaf(oc, yz, -o.s * k.x);
-  R.m[6] = fmaf(oc, xz, -o.s * k.y); R.m[7] = fmaf(oc, yz, o.s * k.x); R.m[8] = 1.f - oc * (xx + yy);
+  R.m[0] = fmaf(-oc, add_rn(yy, zz), 1.f); R.m[1] = fmaf(oc, xy, -o.s * k.z); R.m[2] = fmaf(oc, xz, o.s * k.y);
+  R.m[3] = fmaf(oc, xy, o.s * k.z); R.m[4] = fmaf(-oc, fmaf(k.x, k.x, zz), 1.f); R.m[5] = fmaf(oc, yz, -o.s * k.x);
+  R.m[6] = fmaf(oc, xz, -o.s * k.y); R.m[7] = fmaf(oc, yz, o.s * k.x); R.m[8] = fmaf(-oc, fmaf(k.x, k.x, yy), 1.f);
   return R;
 }
 
