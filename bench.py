@@ -471,7 +471,7 @@ def run_ours(args):
     if chain:
         # let fit_chain's event-timed mesh-overlap policy finish its trial calls (one cold call + one per candidate share)
         # before the warm-up steps, so that the timed steps all run with the share it settled on
-        for _ in range(6):
+        for _ in range(12):
             pol = fitter.overlap_policy()
             if pol and all(v["fraction"] is not None for v in pol.values()):
                 break

@@ -77,16 +77,26 @@ class _OverlapTuner:
     of the finished ones can either be held to the SMs the fit leaves free (slower mesh, undisturbed fit) or run
     everywhere (its long-lived CTAs delay the next window's fit); which share of the windows to hold back depends on
     how long a window's fit takes relative to its mesh pass (optimiser, iteration budgets, model).  Each candidate share
-    is tried on one call (after a first, cold call that is not measured), timed by two events on the caller's stream; the timing is read at the start of the next call
-    (by then the work has long finished), so the policy adds no synchronisation to the call it measures."""
+    is tried on whole calls (after a first, cold call that is not measured), timed by two events on the caller's stream;
+    the timing is read at the start of the next call (by then the work has long finished), so the policy adds no
+    synchronisation to the call it measures."""
 
-    CANDIDATES = (0.55, 0.75, 0.9)
+    CANDIDATES = (0.55, 0.65, 0.75, 0.85)
+    REPEATS = 2           # each candidate is timed twice, the faster run counts (one disturbed call must not decide)
 
     def __init__(self):
         self.times = {}
+        self.counts = {}
         self.best = None
         self.pending = None
         self.calls = 0          # the first call of a problem shape is cold (allocations, first launches): not measured
+
+    def _next_candidate(self):
+        for r in range(1, self.REPEATS + 1):
+            for c in self.CANDIDATES:
+                if self.counts.get(c, 0) < r:
+                    return c
+        return None
 
     def collect(self):
         if self.pending is not None:
@@ -94,8 +104,9 @@ class _OverlapTuner:
             e1.synchronize()
             ms = e0.elapsed_time(e1)
             self.times[frac] = min(ms, self.times.get(frac, ms))
+            self.counts[frac] = self.counts.get(frac, 0) + 1
             self.pending = None
-            if self.best is None and all(c in self.times for c in self.CANDIDATES):
+            if self.best is None and self._next_candidate() is None:
                 self.best = min(self.CANDIDATES, key=lambda c: self.times[c])
 
     def next_fraction(self):
@@ -104,8 +115,8 @@ class _OverlapTuner:
         if self.best is not None:
             return self.best
         if self.calls == 1:
-            return self.CANDIDATES[-1]
-        return next(c for c in self.CANDIDATES if c not in self.times)
+            return self.CANDIDATES[-2]
+        return self._next_candidate()
 
     def begin(self, stream):
         self._frac_e0 = torch.cuda.Event(enable_timing=True)
@@ -115,8 +126,7 @@ class _OverlapTuner:
         if self.best is None and self.calls > 1:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record(stream)
-            frac = next(c for c in self.CANDIDATES if c not in self.times)
-            self.pending = (frac, self._frac_e0, e1)
+            self.pending = (self._next_candidate(), self._frac_e0, e1)
 
 
 class WorldSpaceFitter:
@@ -564,7 +574,7 @@ class WorldSpaceFitter:
         ``mesh_capped_fraction``: share of the windows whose mesh pass is held to the SMs the fit leaves free
         (the rest, at the end, run on all SMs).  Default (None): chosen by measurement -- the first calls of a
         problem shape (S, T, chunks, optimiser) each run with one candidate share and are timed with CUDA events
-        on the caller's stream (four calls: a cold one and three candidates), later calls use the fastest (``overlap_policy()`` reports what was measured);
+        on the caller's stream (nine calls: a cold one, then four candidates twice), later calls use the fastest (``overlap_policy()`` reports what was measured);
         a number, or the environment variable K2B_MESH_CAPPED_FRACTION, pins it.  ``fit_joints=False``: the fit kernel does not return the posed kinematic joints
         (``out["fit_joints"]`` is None; the mesh pass returns all joints anyway), which also spares the L-BFGS fit its
         extra forward pass at the returned parameters -- the returned loss is the accepted trial's, bit for bit.
