@@ -117,7 +117,9 @@ typedef struct k2b_fit_args {
   float* out_expr;           /* [B][10] or NULL */
   float* out_loss;           /* [B] (L-BFGS: loss at the returned params; Adam: loss of the
                                 last iteration before its step, world_space.py:246-256) */
-  float* out_joints;         /* [B][K][3] posed kinematic joints incl. transl, or NULL */
+  float* out_joints;         /* [B][K][3] posed kinematic joints incl. transl, or NULL.  NULL (with final_loss_mode 0)
+                              * also spares an L-BFGS fit the forward pass at the returned parameters
+                              * (world_space.py:246-247): they are the accepted trial point, whose loss is returned */
   int32_t* out_evals;        /* [B] closure evaluations performed, or NULL */
   /* scratch (device) */
   void* workspace;
@@ -181,7 +183,7 @@ typedef struct k2b_chain_args {
   float* out_transl;            /* [S][T][3] */
   float* out_expr;              /* [S][T][10] or NULL */
   float* out_loss;              /* [S][T] */
-  float* out_joints;            /* [S][T][K][3] or NULL */
+  float* out_joints;            /* [S][T][K][3] or NULL (NULL: no forward pass at the returned parameters, as in k2b_fit_args) */
   int32_t* out_evals;           /* [S][T] or NULL */
   void* workspace;              /* L-BFGS history; may be NULL for Adam */
   size_t workspace_bytes;       /* >= k2b_chain_workspace_bytes(m, S, optimizer, max(num_iters_*)) */
