@@ -654,9 +654,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) blend_skin_vt_kernel(const __gr
               T2.x = fmaf(wk[k], r2.x, T2.x); T2.y = fmaf(wk[k], r2.y, T2.y); T2.z = fmaf(wk[k], r2.z, T2.z); T2.w = fmaf(wk[k], r2.w, T2.w);
             }
             if (i < nvalid) {
-              o[0] = fmaf(T0.x, px, fmaf(T0.y, py, fmaf(T0.z, pz, T0.w)));
-              o[1] = fmaf(T1.x, px, fmaf(T1.y, py, fmaf(T1.z, pz, T1.w)));
-              o[2] = fmaf(T2.x, px, fmaf(T2.y, py, fmaf(T2.z, pz, T2.w)));
+              // streaming stores (evict-first): 83 KB per frame that nothing on the GPU reads again must not push the fit
+              // kernel's L2-resident L-BFGS history (it runs beside this kernel) out of the cache
+              __stcs(o + 0, fmaf(T0.x, px, fmaf(T0.y, py, fmaf(T0.z, pz, T0.w))));
+              __stcs(o + 1, fmaf(T1.x, px, fmaf(T1.y, py, fmaf(T1.z, pz, T1.w))));
+              __stcs(o + 2, fmaf(T2.x, px, fmaf(T2.y, py, fmaf(T2.z, pz, T2.w))));
             }
             o += ncols;
           }
