@@ -1,16 +1,9 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "overlap or windows" 2>&1 | tail -2
-for i in 1 2; do
-timeout 600 python bench.py --skip-cpu-baseline --no-e2e-vertices --no-frame-parallel > gpurun_out/r2_bench_tuner2.json 2> gpurun_out/r2_bench_tuner2.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r2_bench_tuner2.json'))
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['mesh_overlap'])
+for ppc in 0 1 2 4 0 2; do
+  K2B_MESH_PASSES_PER_CTA=$ppc timeout 600 python bench.py --skip-cpu-baseline --no-e2e-vertices --no-frame-parallel > gpurun_out/r2_x.json 2> gpurun_out/r2_x.err
+  python - "$ppc" <<'PY'
+import json,sys
+d=json.load(open('gpurun_out/r2_x.json'))
+print('ppc', sys.argv[1], round(d['value']), round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), 'fit ms', round(d['roofline']['ms_per_step_in_kernel'],2), 'mesh', round(d['roofline_mesh']['ms'],2), d['mesh_overlap'])
 PY
 done
-timeout 600 python bench.py --optimizer adam --skip-cpu-baseline --no-e2e-vertices --no-frame-parallel > gpurun_out/r2_bench_tuner2_adam.json 2> gpurun_out/r2_bench_tuner2_adam.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r2_bench_tuner2_adam.json'))
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['mesh_overlap'])
-PY
