@@ -1087,7 +1087,9 @@ K2B_HD void load_frame_obs(const ChainParams& p, long f, bool stage1, FrameObs& 
 // CAM: camera sequences (ChainParams::camera_seq) -- a separate instantiation, because the per-frame stage state costs the
 // world-space kernel registers it does not have (168 of 168 used: the L-BFGS build went from 36 to 130 bytes of spills
 // and 16 % slower with the stage as run-time state).
-template <int NS, int K, bool LB, bool CAM = false>
+// FIN: the launch may want the forward pass at the returned parameters (joints out, the camera stage's loss, the
+// evaluation-only launch); without it every evaluation has a gradient and the final phase is compiled out.
+template <int NS, int K, bool LB, bool CAM = false, bool FIN = true>
 K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const WarpMem& wm, const TeamMem& tm, int idx,
                           long first_seq, long seq_stride, float* hist) {
   const int lane = lane_id();
@@ -1248,7 +1250,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
           phase = iters > 0 ? kAdam : kAdamFinal;
         }
       }
-      float* jframe = p.out_joints ? p.out_joints + frow * K * 3 : nullptr;
+      float* jframe = (FIN && p.out_joints) ? p.out_joints + frow * K * 3 : nullptr;
       if (!LB && phase == kEvalOnly) {
         jout = jframe;
         want_comp = true;
@@ -1257,6 +1259,8 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         with_grad = false;
         with_priors = false;
         jout = jframe;
+      } else if (!LB && !FIN && phase == kAdamFinal) {
+        do_eval = false;
       } else if (!LB && phase == kAdamFinal) {
         // joints at the final parameters (world_space.py:258-278); camera stage 2 also re-evaluates the loss there
         do_eval = jframe != nullptr || p.final_mode != 0;
@@ -1265,7 +1269,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         final_obs = true;
         jout = jframe;
       } else if (LB && (phase == kRound || phase == kFinal)) {
-        const bool fin = phase == kFinal;
+        const bool fin = FIN && phase == kFinal;
 #if !defined(__CUDA_ARCH__) && defined(K2B_WARP_EMUL)
         if (lane == 0 && !fin) ++k2b_emul_rounds;
 #endif
@@ -1322,7 +1326,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         cur_row = row;
       }
       ob.keep_w2 = (flags & kFlagKeep) ? p.keep_w2 : 0.f;
-      with_grad = (flags & kFlagGrad) != 0;
+      with_grad = FIN ? (flags & kFlagGrad) != 0 : true;
       with_priors = (flags & kFlagPriors) != 0;
       use_line = with_priors;
       do_eval = idx < n_c;
@@ -1479,7 +1483,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         if (CAM && cstage == 2) {          // camera stage 1 is over: stage 2 starts from its result
           evals_prev = st.evals;
           if constexpr (CAM) begin_camera_stage(false);
-        } else if (p.out_joints || p.final_mode) {
+        } else if (FIN && (p.out_joints || p.final_mode)) {
           phase = kFinal;
         } else {
           out_loss = (float)st.loss;
@@ -1487,7 +1491,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
           frame_done = true;
         }
       }
-    } else if (LB) {        // kFinal
+    } else if (FIN && LB) {        // kFinal
       if (teamed) bar_sync(tm.bar_done, 32 * tm.E);
       out_loss = loss;
       evals = st.evals;

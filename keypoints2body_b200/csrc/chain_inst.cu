@@ -13,17 +13,21 @@ cudaError_t launch_chain<K2B_NS, K2B_K>(const wc::ChainParams& p, const ChainTab
                                         cudaStream_t st) {
   // the optimiser is a template parameter of the kernel (the other optimiser's state would only cost registers)
   const bool lb = p.lbfgs != 0 && !p.eval_only;
-  auto kern = lb ? chain_kernel<K2B_NS, K2B_K, true, false> : chain_kernel<K2B_NS, K2B_K, false, false>;
+  // launches that want no forward pass at the returned parameters (no joints out, no camera-stage loss, not an
+  // evaluation-only launch) get the instantiation without the final phase: every evaluation has a gradient
+  const bool fin = p.out_joints != nullptr || p.final_mode != 0 || p.eval_only != 0 || p.camera_seq != 0;
+  auto kern = lb ? (fin ? chain_kernel<K2B_NS, K2B_K, true, false, true> : chain_kernel<K2B_NS, K2B_K, true, false, false>)
+                 : (fin ? chain_kernel<K2B_NS, K2B_K, false, false, true> : chain_kernel<K2B_NS, K2B_K, false, false, false>);
 #if K2B_NS == 10
   // camera sequences (SMPL only, like the reference's CameraSpaceFitter) are their own instantiation
-  if (p.camera_seq) kern = lb ? chain_kernel<K2B_NS, K2B_K, true, true> : chain_kernel<K2B_NS, K2B_K, false, true>;
+  if (p.camera_seq) kern = lb ? chain_kernel<K2B_NS, K2B_K, true, true, true> : chain_kernel<K2B_NS, K2B_K, false, true, true>;
 #else
   if (p.camera_seq) return cudaErrorInvalidValue;
 #endif
   const int warps = teams * p.team * (1 + p.helpers);
   const size_t smem = chain_smem_bytes(K2B_NS, teams, p.team, p.helpers, p.hmax);
-  static size_t configured[4] = {0, 0, 0, 0};
-  const int variant = (lb ? 1 : 0) + (p.camera_seq ? 2 : 0);
+  static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int variant = (lb ? 1 : 0) + (p.camera_seq ? 2 : 0) + (fin ? 0 : 4);
   if (smem > configured[variant]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -37,7 +37,7 @@ inline size_t chain_smem_bytes(int ns, int teams, int E, int H, int hmax) {
   return sizeof(float) * (tab + (size_t)teams * wc::team_floats(E, H, hmax));
 }
 
-template <int NS, int K, bool LB, bool CAM>
+template <int NS, int K, bool LB, bool CAM, bool FIN>
 __global__ void __launch_bounds__(32 * kChainMaxWarps, 1)
 chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
   extern __shared__ __align__(16) float smem[];
@@ -86,7 +86,7 @@ chain_kernel(const __grid_constant__ wc::ChainParams p, const ChainTables tab) {
     wm.helper_stride = wc::kEvalMemFloats;
     const long slot = (long)blockIdx.x * nteams + team;
     float* hist = p.hist ? p.hist + slot * wc::hist_floats(p.hmax) : nullptr;
-    wc::run_evaluator<NS, K, LB, CAM>(p, tb, wm, tm, member, slot, (long)gridDim.x * nteams, hist);
+    wc::run_evaluator<NS, K, LB, CAM, FIN>(p, tb, wm, tm, member, slot, (long)gridDim.x * nteams, hist);
   } else {
     const int e = (member - E) / H, h = (member - E) % H;
     float* own = base + (size_t)member * wc::kEvalMemFloats;

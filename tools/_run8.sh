@@ -1,7 +1,8 @@
 cd $GRAFT_REPO_ROOT
 for rep in 1 2; do
-for v in head TABLES MACHINE; do
-  echo "== $v"
-  K2B_LIB=$GRAFT_REPO_ROOT/variants/libk2b_$v.so timeout 600 python tools/window_tail.py 256 4096 1 2>&1 | grep lbfgs
+for lib in variants/libk2b_head.so keypoints2body_b200/libk2b_b200.so; do
+  echo "== $lib"
+  K2B_LIB=$GRAFT_REPO_ROOT/$lib timeout 600 python tools/window_tail.py 256 4096 1 2>&1 | grep "S=256"
 done
 done
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_lbfgs_parity.py tests/test_gpu_api.py -q -x 2>&1 | tail -2
