@@ -1233,7 +1233,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
           stage1 = false;
           priors_on = false;
           phase = kCamGuess;
-        } else if (!LB && p.eval_only) {      // evaluation-only launches use the Adam instantiation (chain_inst.cu)
+        } else if (!LB && FIN && p.eval_only) {      // evaluation-only launches use the Adam instantiation (chain_inst.cu)
           phase = kEvalOnly;
         } else if (lbfgs) {
 #pragma unroll
@@ -1251,7 +1251,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         }
       }
       float* jframe = (FIN && p.out_joints) ? p.out_joints + frow * K * 3 : nullptr;
-      if (!LB && phase == kEvalOnly) {
+      if (!LB && FIN && phase == kEvalOnly) {
         jout = jframe;
         want_comp = true;
       } else if (CAM && phase == kCamGuess) {
@@ -1394,7 +1394,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
         for (int c = 0; c < 3; ++c) { xr[c] = ct[c]; ob.dref[c] = ct[c]; }
       }
       if constexpr (CAM) begin_camera_stage(true);
-    } else if (!LB && phase == kEvalOnly) {
+    } else if (!LB && FIN && phase == kEvalOnly) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) store_elem<NS>(p, frow, 3 * lane + c, gr[c]);
       if (lane == 0) {
