@@ -1099,7 +1099,8 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
   const bool teamed = LB && tm.E > 1;
   // camera-space stage 1: only global_orient and the translation move, no priors.  A launch constant for the two-launch
   // camera fit (loss_kind), a per-frame state of the leader when both stages run inside the launch (camera_seq).
-  bool stage1 = p.loss_kind == 1;
+  // the instantiation without a final phase is the plain world-space fit: no camera stage either (chain_inst.cu)
+  bool stage1 = FIN ? p.loss_kind == 1 : false;
   bool priors_on = !stage1;
   constexpr bool lbfgs = LB;
   const bool body_owner = lane >= 1 && lane < 24;
@@ -1327,7 +1328,7 @@ K2B_HD void run_evaluator(const ChainParams& p, const WarpTables& tb, const Warp
       }
       ob.keep_w2 = (flags & kFlagKeep) ? p.keep_w2 : 0.f;
       with_grad = FIN ? (flags & kFlagGrad) != 0 : true;
-      with_priors = (flags & kFlagPriors) != 0;
+      with_priors = FIN ? (flags & kFlagPriors) != 0 : true;
       use_line = with_priors;
       do_eval = idx < n_c;
       if (do_eval) {

@@ -13,9 +13,9 @@ cudaError_t launch_chain<K2B_NS, K2B_K>(const wc::ChainParams& p, const ChainTab
                                         cudaStream_t st) {
   // the optimiser is a template parameter of the kernel (the other optimiser's state would only cost registers)
   const bool lb = p.lbfgs != 0 && !p.eval_only;
-  // launches that want no forward pass at the returned parameters (no joints out, no camera-stage loss, not an
-  // evaluation-only launch) get the instantiation without the final phase: every evaluation has a gradient
-  const bool fin = p.out_joints != nullptr || p.final_mode != 0 || p.eval_only != 0 || p.camera_seq != 0;
+  // plain world-space fits that want no forward pass at the returned parameters (no joints out, no camera stage, not an
+  // evaluation-only launch) get the instantiation without the final phase: every evaluation has a gradient and priors
+  const bool fin = p.out_joints != nullptr || p.final_mode != 0 || p.eval_only != 0 || p.camera_seq != 0 || p.loss_kind != 0;
   auto kern = lb ? (fin ? chain_kernel<K2B_NS, K2B_K, true, false, true> : chain_kernel<K2B_NS, K2B_K, true, false, false>)
                  : (fin ? chain_kernel<K2B_NS, K2B_K, false, false, true> : chain_kernel<K2B_NS, K2B_K, false, false, false>);
 #if K2B_NS == 10

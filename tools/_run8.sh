@@ -5,4 +5,4 @@ for lib in variants/libk2b_head.so keypoints2body_b200/libk2b_b200.so; do
   K2B_LIB=$GRAFT_REPO_ROOT/$lib timeout 600 python tools/window_tail.py 256 4096 1 2>&1 | grep "S=256"
 done
 done
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_api.py -q -x 2>&1 | tail -2
+timeout 900 python -m pytest tests -q -x -m gpu 2>&1 | tail -2
