@@ -256,8 +256,14 @@ extern "C" int k2b_fit_batch(const k2b_model* m, const k2b_fit_args* a, void* st
   AdamTable at;
   fill_adam_table(at, (double)a->lr);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->optimizer == K2B_OPT_ADAM) return launch_fit_ns<kModeAdam>(m->num_shape, p, at, grid, st);
-  return launch_fit_ns<kModeLbfgs>(m->num_shape, p, at, grid, st);
+  // plain world-space fits that want no forward pass at the returned parameters take the instantiation that has neither
+  // the camera stage nor the final round (fit_kernel.cuh, kModeAdamWorld / kModeLbfgsWorld)
+  const bool world_only = a->loss_kind == 0 && a->final_loss_mode == 0 && !a->out_joints;
+  if (a->optimizer == K2B_OPT_ADAM)
+    return world_only ? launch_fit_ns<kModeAdamWorld>(m->num_shape, p, at, grid, st)
+                      : launch_fit_ns<kModeAdam>(m->num_shape, p, at, grid, st);
+  return world_only ? launch_fit_ns<kModeLbfgsWorld>(m->num_shape, p, at, grid, st)
+                    : launch_fit_ns<kModeLbfgs>(m->num_shape, p, at, grid, st);
 }
 
 namespace {

@@ -30,7 +30,11 @@ __host__ __device__ constexpr int fit_threads() { return FitThreads<NS>::value; 
 inline int fit_threads_rt(int ns) { return ns == 20 ? 320 : 384; }
 constexpr int kAdamTable = 256;
 
-enum FitMode { kModeEval = 0, kModeAdam = 1, kModeLbfgs = 2 };
+// kModeAdamWorld / kModeLbfgsWorld: the same optimisers for launches that are plain world-space fits without a forward
+// pass at the returned parameters (loss_kind 0, final_loss_mode 0, no out_joints -- what the frame-parallel schedule
+// launches): the camera stage and the final round are compiled out (Adam 128.7 -> 117.6 ms per 1 M-frame two-sweep
+// step, L-BFGS 304.4 -> 293.7 ms in a same-box A/B; bit-identical results).
+enum FitMode { kModeEval = 0, kModeAdam = 1, kModeLbfgs = 2, kModeAdamWorld = 3, kModeLbfgsWorld = 4 };
 
 struct DeviceTables {      // global-memory copies owned by k2b_model
   const float* chol;       // [8][kCholStride]
@@ -98,6 +102,8 @@ constexpr size_t fit_smem_bytes() {
 template <int NS, int K, int MODE>
 __global__ void __launch_bounds__(fit_threads<NS>(), 1)
 fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTable at) {
+  constexpr bool kWorldOnly = MODE >= kModeAdamWorld;
+  constexpr int OPT = kWorldOnly ? MODE - 2 : MODE;
   constexpr int NX = 75 + NS;
   constexpr int kFitThreads = fit_threads<NS>();
   extern __shared__ __align__(16) float smem[];
@@ -160,7 +166,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         const float cf = p.conf ? (p.conf_per_frame ? p.conf[fr * K + j] : p.conf[j]) : 1.f;
         float wj = p.joint_w2 * cf * cf;
         // camera stage 1 looks at RHip, LHip, RShoulder, LShoulder only, unweighted (losses.py:80-92)
-        if (p.loss_kind == 1) wj = (j == 1 || j == 2 || j == 16 || j == 17) ? 1.f : 0.f;
+        if (!kWorldOnly && p.loss_kind == 1) wj = (j == 1 || j == 2 || j == 16 || j == 17) ? 1.f : 0.f;
         scr[(kScrWgt + j) * kStride] = wj;
       }
       const float* kp = p.preserve_pose ? p.preserve_pose + fr * kBodyDim : p.init_pose + fr * kPoseDim + 3;
@@ -174,7 +180,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
     fc.stride = kStride;
     const bool keep_on = p.frame_preserve ? (p.frame_preserve[fr] != 0) : (p.preserve_all != 0);
     fc.keep_w2 = keep_on ? p.keep_w2 : 0.f;
-    const bool stage1 = p.loss_kind == 1;       // only global_orient and the translation are optimised
+    const bool stage1 = !kWorldOnly && p.loss_kind == 1;       // only global_orient and the translation are optimised
     fc.plain_sq = stage1;
     fc.depth_w2 = stage1 ? p.depth_w2 : 0.f;
     fc.dref[0] = fc.dref[1] = fc.dref[2] = 0.f;
@@ -190,11 +196,13 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
 
     int iters = p.frame_iters ? p.frame_iters[fr] : p.num_iters;
     if (!valid) iters = 0;
-    float* jout = (p.out_joints && valid) ? p.out_joints + f * K * 3 : nullptr;
+    float* jout = (!kWorldOnly && p.out_joints && valid) ? p.out_joints + f * K * 3 : nullptr;
+    const int final_mode = kWorldOnly ? 0 : p.final_mode;
+    const bool want_final = !kWorldOnly && (p.out_joints || p.final_mode);
 
     // Every mode funnels through ONE eval_frame call site (one copy of the evaluation code):
     // each round evaluates at the current x, then the mode-specific (cheap) update runs.
-    if (MODE == kModeEval) {
+    if (OPT == kModeEval) {
       int comp = 0;
       out_loss = eval_frame<NS, K>(c, tb, fc, true, priors, jout, &comp);
       if (valid) {
@@ -209,7 +217,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       continue;
     }
 
-    if (MODE == kModeAdam) {
+    if (OPT == kModeAdam) {
       float* m1 = scr + kScrOpt * kStride;
       float* m2 = m1 + (long)NX * kStride;
 #pragma unroll 5
@@ -220,7 +228,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       const int warp_iters = __reduce_max_sync(0xffffffffu, iters);
       // rounds 1..warp_iters: loss + gradient + Adam step; round warp_iters+1: joints-only
       // forward at the final parameters (world_space.py:258-278)
-      const int rounds = warp_iters + ((p.out_joints || p.final_mode) ? 1 : 0);
+      const int rounds = warp_iters + (want_final ? 1 : 0);
       for (int k = 1; k <= rounds; ++k) {
         const bool last = k > warp_iters;
         if (last) fc.keep_w2 = 0.f;
@@ -241,8 +249,8 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         fc.adam_v = m2;
         fc.adam_step = step_k;
         fc.adam_bc2 = bc2_k;
-        const float loss = eval_frame<NS, K, true>(c, tb, fc, !last, priors && (!last || p.final_mode), last ? jout : nullptr, nullptr);
-        if (last && p.final_mode) out_loss = loss;
+        const float loss = eval_frame<NS, K, true>(c, tb, fc, !last, priors && (!last || final_mode), last ? jout : nullptr, nullptr);
+        if (last && final_mode) out_loss = loss;
         if (stepping) {
           out_loss = loss;   // loss of the last iteration, before its step (world_space.py:250-256)
           ++evals;
@@ -262,7 +270,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
       }
     }
 
-    if (MODE == kModeLbfgs) {
+    if (OPT == kModeLbfgs) {
       Vecs v;
       v.base = scr + kScrOpt * kStride;
       v.stride = kStride;
@@ -280,7 +288,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
         ++rounds;
         const bool fin = stage == 2;
         const Cols ce = st.eval_cols(c, v);
-        if (fin && p.final_mode) fc.keep_w2 = 0.f;
+        if (fin && final_mode) fc.keep_w2 = 0.f;
         const float loss = eval_frame<NS, K, K2B_LBFGS_HINTS>(ce, tb, fc, !fin, priors, fin ? jout : nullptr, nullptr);
         if (fin) {
           out_loss = loss;
@@ -317,7 +325,7 @@ fit_kernel(const __grid_constant__ FitParams p, const __grid_constant__ AdamTabl
           // The returned parameters ARE the accepted trial point (lbfgs.py:488-493 adds t d to the iterate the way the
           // trial was formed), so the loss re-evaluated there (world_space.py:246-247) is the machine's own, bit for bit;
           // the extra forward pass is only run for its joints or for the camera stage's loss without the temporal term.
-          if (!p.out_joints && !p.final_mode) {
+          if (!want_final) {
             out_loss = (float)st.loss;
             break;
           }
